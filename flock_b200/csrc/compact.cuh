@@ -1,0 +1,134 @@
+// compact.cuh -- the single-pass stable compaction skeleton shared by FilterExec (filter_project.cu),
+// the hash-table emitters (hash_agg.cu) and the join pair writer (hash_join.cu).
+//
+// A persistent CTA takes TILE-row tiles from an atomic ticket.  For each tile it gets one bit per
+// item ("survives"), ranks the survivors in row order with warp ballots, obtains the tile's global
+// output offset by decoupled look-back (device_utils.cuh) and hands every survivor its output
+// position.  The last CTA to finish resets the scratch, so back-to-back launches need no memset.
+#pragma once
+
+#include "device_utils.cuh"
+
+namespace fg {
+
+constexpr int CP_THREADS = 256;
+constexpr int CP_WARPS = CP_THREADS / 32;
+constexpr int CP_ITEMS = 16;                      // items per thread per tile
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;    // 4096 items
+
+struct CompactScratch {
+  unsigned long long* tile_state;  // look-back words, zero between launches
+  unsigned int* counters;          // [0] ticket, [1] done
+  unsigned long long* out_count;   // receives the total number of survivors
+  long long num_tiles;
+};
+
+// Item k of thread `tid` is item index  ((k / E) * CP_THREADS + tid) * E + k % E  of the tile: E = items
+// a thread loads contiguously (vector width).  Survivors are ordered (group = k / E, thread, k % E),
+// which is ascending item index.
+template <int E>
+__device__ __forceinline__ long long cp_item_index(int k, int tid) {
+  return ((long long)(k / E) * CP_THREADS + tid) * E + (k % E);
+}
+
+template <int E>
+struct CompactSmem {
+  static constexpr int G = CP_ITEMS / E;
+  unsigned group_warp[G][CP_WARPS];
+  long long tile;
+  unsigned long long excl;
+  unsigned tile_total;
+  int last;
+};
+
+// Fetches the next tile index for the CTA (or -1 when the work is exhausted).
+template <int E>
+__device__ __forceinline__ long long cp_next_tile(CompactSmem<E>& s, const CompactScratch& sc) {
+  if (threadIdx.x == 0) s.tile = (long long)atomicAdd(sc.counters, 1u);
+  __syncthreads();
+  long long t = s.tile;
+  return t < sc.num_tiles ? t : -1;
+}
+
+// Ranks the survivors of one tile.  On return (after the internal barriers) `lane_prefix[g]` +
+// s.group_warp[g][warp] + popc(earlier own bits in group g) + s.excl is the output position of an item
+// of group g, and s.tile_total the number of survivors of the tile.
+template <int E>
+__device__ __forceinline__ void cp_rank_tile(CompactSmem<E>& s, const CompactScratch& sc, long long tile, unsigned bits,
+                                             unsigned (&lane_prefix)[CP_ITEMS / E]) {
+  constexpr int G = CP_ITEMS / E;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    unsigned pre = 0, tot = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      unsigned b = __ballot_sync(FULL_MASK, (bits >> (g * E + e)) & 1u);
+      pre += __popc(b & lt);
+      tot += __popc(b);
+    }
+    lane_prefix[g] = pre;
+    if (lane == 0) s.group_warp[g][warp] = tot;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    constexpr int N = G * CP_WARPS;
+    constexpr int PER = (N + 31) / 32;
+    unsigned* flat = &s.group_warp[0][0];
+    unsigned v[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int idx = lane * PER + i;
+      v[i] = idx < N ? flat[idx] : 0u;
+      sum += v[i];
+    }
+    unsigned incl = warp_inclusive_sum(sum);
+    unsigned run = incl - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int idx = lane * PER + i;
+      if (idx < N) flat[idx] = run;
+      run += v[i];
+    }
+    unsigned total = __shfl_sync(FULL_MASK, incl, 31);
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st_relaxed_u64(sc.tile_state, LB_PREFIX | (unsigned long long)total);
+    } else {
+      if (lane == 0) st_relaxed_u64(sc.tile_state + tile, LB_PARTIAL | (unsigned long long)total);
+      excl = lookback_exclusive_prefix(sc.tile_state, tile);
+      if (lane == 0) st_relaxed_u64(sc.tile_state + tile, LB_PREFIX | (excl + total));
+    }
+    if (lane == 0) {
+      s.excl = excl;
+      s.tile_total = total;
+      if (tile == sc.num_tiles - 1) *sc.out_count = excl + total;
+    }
+  }
+  __syncthreads();
+}
+
+template <int E>
+__device__ __forceinline__ long long cp_position(const CompactSmem<E>& s, unsigned bits, int k, const unsigned (&lane_prefix)[CP_ITEMS / E]) {
+  const int g = k / E, e = k % E;
+  const unsigned within = __popc(bits & (((1u << e) - 1u) << (g * E)));
+  return (long long)s.excl + s.group_warp[g][threadIdx.x >> 5] + lane_prefix[g] + within;
+}
+
+// Call once per CTA after its tile loop: the last CTA to arrive clears the scratch.
+template <int E>
+__device__ __forceinline__ void cp_finish(CompactSmem<E>& s, const CompactScratch& sc) {
+  __threadfence();
+  if (threadIdx.x == 0) s.last = (atomicAdd(sc.counters + 1, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s.last) {
+    for (long long i = threadIdx.x; i < sc.num_tiles; i += CP_THREADS) sc.tile_state[i] = LB_INVALID;
+    if (threadIdx.x == 0) {
+      sc.counters[0] = 0;
+      sc.counters[1] = 0;
+    }
+  }
+}
+
+}  // namespace fg

@@ -1,0 +1,826 @@
+// core.cu -- context, HBM buffers, and the Arrow C Data Interface boundary (host <-> HBM).
+//
+// Replaces, on the reference side: MemoryExec::set_partitions fed by
+// ExecutionContext::feed_data_sources (flock/src/runtime/context.rs:257-325) for the way in, and the
+// Vec<RecordBatch> returned by `collect` (context.rs:172-191) for the way out.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+
+#include "device_utils.cuh"
+#include "internal.h"
+
+namespace fg {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error{code, buf};
+}
+
+// ------------------------------------------------------------------------------------------------
+// dtypes
+// ------------------------------------------------------------------------------------------------
+int dtype_width(int dtype) {
+  switch (dtype) {
+    case FLOCKGPU_BOOL: return 1;
+    case FLOCKGPU_INT32: case FLOCKGPU_UINT32: return 4;
+    case FLOCKGPU_INT64: case FLOCKGPU_UINT64: case FLOCKGPU_FLOAT64: case FLOCKGPU_TIMESTAMP: return 8;
+    default: return 0;
+  }
+}
+
+const char* dtype_name(int dtype) {
+  switch (dtype) {
+    case FLOCKGPU_BOOL: return "Boolean";
+    case FLOCKGPU_INT32: return "Int32";
+    case FLOCKGPU_UINT32: return "UInt32";
+    case FLOCKGPU_INT64: return "Int64";
+    case FLOCKGPU_UINT64: return "UInt64";
+    case FLOCKGPU_FLOAT64: return "Float64";
+    case FLOCKGPU_TIMESTAMP: return "Timestamp";
+    case FLOCKGPU_UTF8: return "Utf8";
+    default: return "?";
+  }
+}
+
+int dtype_from_format(const char* f) {
+  if (!f) return -1;
+  if (!strcmp(f, "i")) return FLOCKGPU_INT32;
+  if (!strcmp(f, "I")) return FLOCKGPU_UINT32;
+  if (!strcmp(f, "l")) return FLOCKGPU_INT64;
+  if (!strcmp(f, "L")) return FLOCKGPU_UINT64;
+  if (!strcmp(f, "g")) return FLOCKGPU_FLOAT64;
+  if (!strcmp(f, "u")) return FLOCKGPU_UTF8;
+  if (!strncmp(f, "ts", 2) && strlen(f) >= 4 && f[3] == ':') return FLOCKGPU_TIMESTAMP;
+  return -1;
+}
+
+std::string default_format(int dtype) {
+  switch (dtype) {
+    case FLOCKGPU_INT32: return "i";
+    case FLOCKGPU_UINT32: return "I";
+    case FLOCKGPU_INT64: return "l";
+    case FLOCKGPU_UINT64: return "L";
+    case FLOCKGPU_FLOAT64: return "g";
+    case FLOCKGPU_UTF8: return "u";
+    case FLOCKGPU_TIMESTAMP: return "tsm:";
+    default: return "n";
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+CtxCore::~CtxCore() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  for (auto& kv : pinned) cudaFreeHost(kv.first);
+  pinned.clear();
+  if (scan.tile_state) cudaFree(scan.tile_state);
+  if (scan.counters) cudaFree(scan.counters);
+  if (l2_flush) cudaFree(l2_flush);
+  if (h_scalars) cudaFreeHost(h_scalars);
+  if (d_scalars) cudaFree(d_scalars);
+  for (int i = 0; i < 16; ++i) {
+    if (timer_start[i]) cudaEventDestroy(timer_start[i]);
+    if (timer_stop[i]) cudaEventDestroy(timer_stop[i]);
+  }
+  if (stream) cudaStreamDestroy(stream);
+}
+
+Buffer::Buffer(CtxPtr c, size_t n) : ctx(std::move(c)), bytes(n) {
+  size_t want = n ? n : 16;
+  want = (want + 255) & ~size_t(255);  // room for vector tails: kernels may read up to 16 B past the end
+  FG_CUDA(cudaMallocAsync(&ptr, want + 256, ctx->stream));
+}
+
+Buffer::~Buffer() {
+  if (ptr) cudaFreeAsync(ptr, ctx->stream);
+}
+
+BufferPtr alloc(const CtxPtr& ctx, size_t bytes) { return std::make_shared<Buffer>(ctx, bytes); }
+
+void ensure_scan_scratch(const CtxPtr& ctx, int64_t tiles) {
+  ScanScratch& s = ctx->scan;
+  if (!s.counters) {
+    FG_CUDA(cudaMalloc(&s.counters, 64 * sizeof(unsigned int)));
+    FG_CUDA(cudaMemsetAsync(s.counters, 0, 64 * sizeof(unsigned int), ctx->stream));
+  }
+  if (tiles > s.capacity) {
+    int64_t cap = 1 << 16;
+    while (cap < tiles) cap <<= 1;
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s.tile_state) FG_CUDA(cudaFree(s.tile_state));
+    FG_CUDA(cudaMalloc(&s.tile_state, cap * sizeof(unsigned long long)));
+    FG_CUDA(cudaMemsetAsync(s.tile_state, 0, cap * sizeof(unsigned long long), ctx->stream));
+    s.capacity = cap;
+  }
+}
+
+void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out) {
+  FG_CUDA(cudaMemcpyAsync(ctx->h_scalars + first, ctx->d_scalars + first, sizeof(unsigned long long) * n,
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  FG_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) out[i] = ctx->h_scalars[first + i];
+}
+
+int64_t Table::nbytes() const {
+  int64_t n = 0;
+  for (const Column& c : cols) {
+    if (c.dtype == FLOCKGPU_UTF8)
+      n += c.values_bytes + (c.length + 1) * 4;
+    else
+      n += c.length * c.width();
+  }
+  return n;
+}
+
+flockgpu_table* wrap_table(TablePtr t) {
+  auto* h = new flockgpu_table();
+  h->table = std::move(t);
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels used by import / concat
+// ------------------------------------------------------------------------------------------------
+__global__ void rebase_offsets_kernel(int32_t* __restrict__ offs, int64_t n, int32_t delta) {
+  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) offs[i] += delta;
+}
+
+__global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
+
+static void rebase_offsets(const CtxPtr& ctx, int32_t* offs, int64_t n, int32_t delta) {
+  if (n <= 0 || delta == 0) return;
+  int blocks = int(std::min<int64_t>((n + 255) / 256, ctx->sm_count * 8));
+  rebase_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(offs, n, delta);
+  count_launch(ctx);
+}
+
+static void set_i32(const CtxPtr& ctx, int32_t* p, int32_t v) {
+  set_i32_kernel<<<1, 1, 0, ctx->stream>>>(p, v);
+  count_launch(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// import: Arrow C Data (host) -> Table (HBM)
+// ------------------------------------------------------------------------------------------------
+static bool range_has_null(const uint8_t* bitmap, int64_t off, int64_t len) {
+  for (int64_t i = off; i < off + len; ++i)
+    if (!((bitmap[i >> 3] >> (i & 7)) & 1)) return true;
+  return false;
+}
+
+static std::string copy_metadata(const char* md) {
+  // Arrow metadata block: int32 n, then n x (int32 klen, key, int32 vlen, value)
+  if (!md) return std::string();
+  const char* p = md;
+  int32_t n;
+  memcpy(&n, p, 4);
+  p += 4;
+  for (int32_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 2; ++k) {
+      int32_t l;
+      memcpy(&l, p, 4);
+      p += 4 + l;
+    }
+  }
+  return std::string(md, p - md);
+}
+
+TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const ArrowArray* const* batches,
+                        int n_batches, const int* projection, int n_projection) {
+  FG_CHECK(schema && schema->format && !strcmp(schema->format, "+s"), FLOCKGPU_ERR_INVALID,
+           "table_import: schema must be a struct (\"+s\"), got \"%s\"", schema && schema->format ? schema->format : "null");
+  FG_CHECK(n_batches >= 0 && (n_batches == 0 || batches), FLOCKGPU_ERR_INVALID, "table_import: bad batch list");
+  std::vector<int> proj;
+  if (projection) {
+    proj.assign(projection, projection + n_projection);
+  } else {
+    for (int i = 0; i < schema->n_children; ++i) proj.push_back(i);
+  }
+  int64_t total = 0;
+  for (int b = 0; b < n_batches; ++b) {
+    FG_CHECK(batches[b] && batches[b]->n_children == schema->n_children, FLOCKGPU_ERR_INVALID,
+             "table_import: batch %d has %lld children, schema has %lld", b,
+             (long long)(batches[b] ? batches[b]->n_children : -1), (long long)schema->n_children);
+    FG_CHECK(batches[b]->null_count <= 0, FLOCKGPU_ERR_UNSUPPORTED, "table_import: struct-level nulls");
+    total += batches[b]->length;
+  }
+  FG_CHECK(total < (int64_t(1) << 32) - 1, FLOCKGPU_ERR_UNSUPPORTED, "table_import: more than 2^32-2 rows in one relation");
+
+  auto t = std::make_shared<Table>();
+  t->ctx = ctx;
+  t->num_rows = total;
+  t->metadata = copy_metadata(schema->metadata);
+  for (int p : proj) {
+    FG_CHECK(p >= 0 && p < schema->n_children, FLOCKGPU_ERR_INVALID, "table_import: projection index %d out of range", p);
+    const ArrowSchema* cs = schema->children[p];
+    int dt = dtype_from_format(cs->format);
+    FG_CHECK(dt >= 0, FLOCKGPU_ERR_UNSUPPORTED, "table_import: column \"%s\" has unsupported Arrow format \"%s\"",
+             cs->name ? cs->name : "", cs->format ? cs->format : "");
+    FG_CHECK(cs->dictionary == nullptr, FLOCKGPU_ERR_UNSUPPORTED, "table_import: dictionary-encoded column \"%s\"", cs->name);
+    Column col;
+    col.dtype = dt;
+    col.name = cs->name ? cs->name : "";
+    col.format = cs->format;
+    col.nullable = (cs->flags & ARROW_FLAG_NULLABLE) != 0;
+    col.length = total;
+    // validity check (no nulls on the GPU path)
+    for (int b = 0; b < n_batches; ++b) {
+      const ArrowArray* a = batches[b]->children[p];
+      int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
+      bool has_null = a->null_count > 0;
+      if (a->null_count < 0 && a->n_buffers > 0 && a->buffers[0])
+        has_null = range_has_null(static_cast<const uint8_t*>(a->buffers[0]), off, len);
+      FG_CHECK(!has_null, FLOCKGPU_ERR_UNSUPPORTED,
+               "table_import: column \"%s\" contains nulls; the GPU path handles non-null columns only", col.name.c_str());
+    }
+    if (dt != FLOCKGPU_UTF8) {
+      int w = dtype_width(dt);
+      col.data = alloc(ctx, size_t(total) * w);
+      int64_t row = 0;
+      for (int b = 0; b < n_batches; ++b) {
+        const ArrowArray* a = batches[b]->children[p];
+        int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
+        if (len == 0) continue;
+        FG_CHECK(a->n_buffers >= 2 && a->buffers[1], FLOCKGPU_ERR_INVALID, "table_import: column \"%s\" has no data buffer", col.name.c_str());
+        FG_CUDA(cudaMemcpyAsync(static_cast<char*>(col.data->ptr) + row * w,
+                                static_cast<const char*>(a->buffers[1]) + off * w, size_t(len) * w,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        row += len;
+      }
+    } else {
+      int64_t bytes = 0;
+      for (int b = 0; b < n_batches; ++b) {
+        const ArrowArray* a = batches[b]->children[p];
+        int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
+        if (len == 0) continue;
+        FG_CHECK(a->n_buffers >= 3 && a->buffers[1], FLOCKGPU_ERR_INVALID, "table_import: Utf8 column \"%s\" has no offsets", col.name.c_str());
+        const int32_t* o = static_cast<const int32_t*>(a->buffers[1]) + off;
+        bytes += int64_t(o[len]) - int64_t(o[0]);
+      }
+      FG_CHECK(bytes < (int64_t(1) << 31), FLOCKGPU_ERR_UNSUPPORTED,
+               "table_import: Utf8 column \"%s\" holds %lld bytes; at most 2^31-1 per relation", col.name.c_str(), (long long)bytes);
+      col.offsets = alloc(ctx, size_t(total + 1) * 4);
+      col.data = alloc(ctx, size_t(bytes));
+      col.values_bytes = bytes;
+      int64_t row = 0, byte = 0;
+      for (int b = 0; b < n_batches; ++b) {
+        const ArrowArray* a = batches[b]->children[p];
+        int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
+        if (len == 0) continue;
+        const int32_t* o = static_cast<const int32_t*>(a->buffers[1]) + off;
+        int64_t nb = int64_t(o[len]) - int64_t(o[0]);
+        FG_CUDA(cudaMemcpyAsync(col.offsets->as<int32_t>() + row, o, size_t(len) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        rebase_offsets(ctx, col.offsets->as<int32_t>() + row, len, int32_t(byte - int64_t(o[0])));
+        if (nb > 0) {
+          FG_CHECK(a->buffers[2], FLOCKGPU_ERR_INVALID, "table_import: Utf8 column \"%s\" has no value buffer", col.name.c_str());
+          FG_CUDA(cudaMemcpyAsync(static_cast<char*>(col.data->ptr) + byte, static_cast<const char*>(a->buffers[2]) + o[0],
+                                  size_t(nb), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        row += len;
+        byte += nb;
+      }
+      set_i32(ctx, col.offsets->as<int32_t>() + total, int32_t(bytes));
+    }
+    t->cols.push_back(std::move(col));
+  }
+  // inputs are only borrowed for the call: every copy must have left the host buffers before we return
+  FG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// export: Table (HBM) -> Arrow C Data (host)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// Pinned blocks are recycled through a per-context cache: cudaHostAlloc costs ~1 ms per call.
+struct PinCache {
+  std::mutex mu;
+  std::unordered_multimap<size_t, void*> free_blocks;  // rounded size -> block
+  ~PinCache() {
+    for (auto& kv : free_blocks) cudaFreeHost(kv.second);
+  }
+};
+std::shared_ptr<PinCache> pin_cache() {
+  static std::shared_ptr<PinCache> c = std::make_shared<PinCache>();
+  return c;
+}
+size_t round_pin(size_t n) {
+  size_t r = 4096;
+  while (r < n) r <<= 1;
+  return r;
+}
+void* pin_get(size_t bytes) {
+  size_t r = round_pin(bytes);
+  auto c = pin_cache();
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->free_blocks.find(r);
+    if (it != c->free_blocks.end()) {
+      void* p = it->second;
+      c->free_blocks.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  FG_CUDA(cudaHostAlloc(&p, r, cudaHostAllocDefault));
+  return p;
+}
+void pin_put(void* p, size_t bytes) {
+  auto c = pin_cache();
+  std::lock_guard<std::mutex> g(c->mu);
+  c->free_blocks.emplace(round_pin(bytes), p);
+}
+
+struct ArrayPrivate {
+  std::vector<std::pair<void*, size_t>> blocks;  // pinned blocks owned by this array
+  std::vector<const void*> buffers;
+  std::vector<ArrowArray*> child_ptrs;
+  std::vector<ArrowArray> children;
+};
+
+void release_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  auto* priv = static_cast<ArrayPrivate*>(a->private_data);
+  if (priv) {
+    for (auto& ch : priv->children)
+      if (ch.release) ch.release(&ch);
+    for (auto& b : priv->blocks) pin_put(b.first, b.second);
+    delete priv;
+  }
+  a->release = nullptr;
+}
+
+struct SchemaPrivate {
+  std::string format, name, metadata;
+  std::vector<ArrowSchema*> child_ptrs;
+  std::vector<ArrowSchema> children;
+};
+
+void release_schema(ArrowSchema* s) {
+  if (!s || !s->release) return;
+  auto* priv = static_cast<SchemaPrivate*>(s->private_data);
+  if (priv) {
+    for (auto& ch : priv->children)
+      if (ch.release) ch.release(&ch);
+    delete priv;
+  }
+  s->release = nullptr;
+}
+
+void fill_schema(ArrowSchema* s, const std::string& format, const std::string& name, const std::string& metadata,
+                 bool nullable, size_t n_children) {
+  auto* priv = new SchemaPrivate();
+  priv->format = format;
+  priv->name = name;
+  priv->metadata = metadata;
+  priv->children.resize(n_children);
+  for (auto& c : priv->children) {
+    memset(&c, 0, sizeof c);
+    priv->child_ptrs.push_back(&c);
+  }
+  memset(s, 0, sizeof *s);
+  s->format = priv->format.c_str();
+  s->name = priv->name.c_str();
+  s->metadata = priv->metadata.empty() ? nullptr : priv->metadata.data();
+  s->flags = nullable ? ARROW_FLAG_NULLABLE : 0;
+  s->n_children = int64_t(n_children);
+  s->children = n_children ? priv->child_ptrs.data() : nullptr;
+  s->release = release_schema;
+  s->private_data = priv;
+}
+
+}  // namespace
+
+void export_schema(const Table& t, ArrowSchema* out) {
+  fill_schema(out, "+s", "", t.metadata, false, t.cols.size());
+  auto* priv = static_cast<SchemaPrivate*>(out->private_data);
+  for (size_t i = 0; i < t.cols.size(); ++i) {
+    const Column& c = t.cols[i];
+    fill_schema(&priv->children[i], c.format.empty() ? default_format(c.dtype) : c.format, c.name, "", c.nullable || c.all_null, 0);
+  }
+}
+
+__global__ void shift_offsets_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n) {
+  int32_t base = src[0];
+  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[i] - base;
+}
+
+void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t row_count, ArrowSchema* out_schema,
+                  ArrowArray* out_array) {
+  FG_CHECK(out_schema && out_array, FLOCKGPU_ERR_INVALID, "table_export: null output");
+  if (row_count < 0) row_count = t.num_rows - row_begin;
+  FG_CHECK(row_begin >= 0 && row_begin + row_count <= t.num_rows, FLOCKGPU_ERR_INVALID,
+           "table_export: rows [%lld, %lld) outside table of %lld rows", (long long)row_begin,
+           (long long)(row_begin + row_count), (long long)t.num_rows);
+  auto top = std::make_unique<ArrayPrivate>();
+  top->children.resize(t.cols.size());
+  for (auto& c : top->children) memset(&c, 0, sizeof c);
+
+  // Utf8: the first/last offsets of the exported row range decide how many bytes travel
+  std::vector<int32_t> first_off(t.cols.size(), 0), last_off(t.cols.size(), 0);
+  bool need_sync = false;
+  int32_t* h_i32 = reinterpret_cast<int32_t*>(ctx->h_scalars);
+  int k = 0;
+  for (size_t i = 0; i < t.cols.size(); ++i) {
+    const Column& c = t.cols[i];
+    if (c.dtype == FLOCKGPU_UTF8 && row_count > 0) {
+      FG_CHECK(k + 2 <= 512, FLOCKGPU_ERR_UNSUPPORTED, "table_export: too many Utf8 columns");
+      FG_CUDA(cudaMemcpyAsync(h_i32 + k, c.offs() + row_begin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      FG_CUDA(cudaMemcpyAsync(h_i32 + k + 1, c.offs() + row_begin + row_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      k += 2;
+      need_sync = true;
+    }
+  }
+  if (need_sync) {
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    k = 0;
+    for (size_t i = 0; i < t.cols.size(); ++i)
+      if (t.cols[i].dtype == FLOCKGPU_UTF8 && row_count > 0) {
+        first_off[i] = h_i32[k];
+        last_off[i] = h_i32[k + 1];
+        k += 2;
+      }
+  }
+
+  std::vector<BufferPtr> keep;  // device temporaries alive until the final sync
+  for (size_t i = 0; i < t.cols.size(); ++i) {
+    const Column& c = t.cols[i];
+    auto priv = std::make_unique<ArrayPrivate>();
+    ArrowArray& a = top->children[i];
+    a.length = row_count;
+    a.null_count = 0;
+    a.offset = 0;
+    void* validity = nullptr;
+    if (c.all_null && row_count > 0) {
+      size_t nb = size_t((row_count + 7) / 8);
+      validity = pin_get(nb);
+      memset(validity, 0, nb);
+      priv->blocks.emplace_back(validity, nb);
+      a.null_count = row_count;
+    }
+    if (c.dtype != FLOCKGPU_UTF8) {
+      int w = c.width();
+      size_t nb = size_t(row_count) * w;
+      void* h = pin_get(nb ? nb : 8);
+      priv->blocks.emplace_back(h, nb ? nb : 8);
+      if (nb) {
+        if (c.all_null)
+          memset(h, 0, nb);
+        else
+          FG_CUDA(cudaMemcpyAsync(h, static_cast<const char*>(c.values()) + row_begin * w, nb, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      priv->buffers = {validity, h};
+    } else {
+      size_t nb_off = size_t(row_count + 1) * 4;
+      int32_t* h_off = static_cast<int32_t*>(pin_get(nb_off));
+      priv->blocks.emplace_back(h_off, nb_off);
+      size_t nb_val = size_t(last_off[i] - first_off[i]);
+      void* h_val = pin_get(nb_val ? nb_val : 8);
+      priv->blocks.emplace_back(h_val, nb_val ? nb_val : 8);
+      if (row_count > 0) {
+        if (first_off[i] == 0) {
+          FG_CUDA(cudaMemcpyAsync(h_off, c.offs() + row_begin, nb_off, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+          BufferPtr tmp = alloc(ctx, nb_off);
+          keep.push_back(tmp);
+          int blocks = int(std::min<int64_t>((row_count + 256) / 256, ctx->sm_count * 8));
+          shift_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(c.offs() + row_begin, tmp->as<int32_t>(), row_count + 1);
+          count_launch(ctx);
+          FG_CUDA(cudaMemcpyAsync(h_off, tmp->ptr, nb_off, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (nb_val)
+          FG_CUDA(cudaMemcpyAsync(h_val, static_cast<const char*>(c.values()) + first_off[i], nb_val, cudaMemcpyDeviceToHost, ctx->stream));
+      } else {
+        h_off[0] = 0;
+      }
+      priv->buffers = {validity, h_off, h_val};
+    }
+    a.n_buffers = int64_t(priv->buffers.size());
+    a.buffers = priv->buffers.data();
+    a.n_children = 0;
+    a.children = nullptr;
+    a.dictionary = nullptr;
+    a.release = release_array;
+    a.private_data = priv.release();
+  }
+  FG_CUDA(cudaStreamSynchronize(ctx->stream));
+
+  for (auto& c : top->children) top->child_ptrs.push_back(&c);
+  top->buffers = {nullptr};
+  memset(out_array, 0, sizeof *out_array);
+  out_array->length = row_count;
+  out_array->null_count = 0;
+  out_array->offset = 0;
+  out_array->n_buffers = 1;
+  out_array->buffers = top->buffers.data();
+  out_array->n_children = int64_t(t.cols.size());
+  out_array->children = top->child_ptrs.data();
+  out_array->release = release_array;
+  out_array->private_data = top.release();
+  export_schema(t, out_schema);
+}
+
+// ------------------------------------------------------------------------------------------------
+// concat / empty
+// ------------------------------------------------------------------------------------------------
+TablePtr empty_like(const CtxPtr& ctx, const Table& src) {
+  auto t = std::make_shared<Table>();
+  t->ctx = ctx;
+  t->metadata = src.metadata;
+  t->num_rows = 0;
+  for (const Column& c : src.cols) {
+    Column e;
+    e.dtype = c.dtype;
+    e.name = c.name;
+    e.format = c.format;
+    e.nullable = c.nullable;
+    e.length = 0;
+    e.data = alloc(ctx, 0);
+    if (c.dtype == FLOCKGPU_UTF8) {
+      e.offsets = alloc(ctx, 4);
+      FG_CUDA(cudaMemsetAsync(e.offsets->ptr, 0, 4, ctx->stream));
+    }
+    t->cols.push_back(std::move(e));
+  }
+  return t;
+}
+
+TablePtr concat_tables(const CtxPtr& ctx, const std::vector<TablePtr>& tables) {
+  FG_CHECK(!tables.empty(), FLOCKGPU_ERR_INVALID, "concat: no tables");
+  if (tables.size() == 1) return tables[0];
+  const Table& first = *tables[0];
+  int64_t total = 0;
+  for (const TablePtr& t : tables) {
+    FG_CHECK(t->cols.size() == first.cols.size(), FLOCKGPU_ERR_INVALID, "concat: column count differs");
+    for (size_t i = 0; i < first.cols.size(); ++i)
+      FG_CHECK(t->cols[i].dtype == first.cols[i].dtype, FLOCKGPU_ERR_INVALID, "concat: column %zu type differs", i);
+    total += t->num_rows;
+  }
+  FG_CHECK(total < (int64_t(1) << 32) - 1, FLOCKGPU_ERR_UNSUPPORTED, "concat: more than 2^32-2 rows");
+  auto out = std::make_shared<Table>();
+  out->ctx = ctx;
+  out->metadata = first.metadata;
+  out->num_rows = total;
+  for (size_t i = 0; i < first.cols.size(); ++i) {
+    Column c;
+    c.dtype = first.cols[i].dtype;
+    c.name = first.cols[i].name;
+    c.format = first.cols[i].format;
+    c.nullable = first.cols[i].nullable;
+    c.length = total;
+    if (c.dtype != FLOCKGPU_UTF8) {
+      int w = c.width();
+      c.data = alloc(ctx, size_t(total) * w);
+      int64_t row = 0;
+      for (const TablePtr& t : tables) {
+        const Column& s = t->cols[i];
+        FG_CHECK(!s.all_null, FLOCKGPU_ERR_UNSUPPORTED, "concat: NULL column");
+        if (s.length)
+          FG_CUDA(cudaMemcpyAsync(static_cast<char*>(c.data->ptr) + row * w, s.values(), size_t(s.length) * w,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        row += s.length;
+      }
+    } else {
+      // value-byte totals are host-known (values_bytes), so no read-back is needed
+      int64_t bytes = 0;
+      for (const TablePtr& t : tables) bytes += t->cols[i].values_bytes;
+      FG_CHECK(bytes < (int64_t(1) << 31), FLOCKGPU_ERR_UNSUPPORTED, "concat: Utf8 column exceeds 2^31-1 bytes");
+      c.offsets = alloc(ctx, size_t(total + 1) * 4);
+      c.data = alloc(ctx, size_t(bytes));
+      c.values_bytes = bytes;
+      int64_t row = 0, byte = 0;
+      for (const TablePtr& t : tables) {
+        const Column& s = t->cols[i];
+        if (s.length) {
+          // s.offsets may start at a non-zero base: shift to `byte`
+          int blocks = int(std::min<int64_t>((s.length + 255) / 256, ctx->sm_count * 8));
+          shift_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(s.offs(), c.offsets->as<int32_t>() + row, s.length);
+          count_launch(ctx);
+          rebase_offsets(ctx, c.offsets->as<int32_t>() + row, s.length, int32_t(byte));
+          if (s.values_bytes) {
+            // value bytes of `s` start at s.offsets[0]; tables built by this library always start at 0
+            FG_CUDA(cudaMemcpyAsync(static_cast<char*>(c.data->ptr) + byte, s.values(), size_t(s.values_bytes),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+          }
+        }
+        row += s.length;
+        byte += s.values_bytes;
+      }
+      set_i32(ctx, c.offsets->as<int32_t>() + total, int32_t(bytes));
+    }
+    out->cols.push_back(std::move(c));
+  }
+  return out;
+}
+
+}  // namespace fg
+
+// ================================================================================================
+// extern "C": context + table entry points
+// ================================================================================================
+using namespace fg;
+
+extern "C" {
+
+const char* flockgpu_last_error(void) { return g_last_error.c_str(); }
+
+const char* flockgpu_version(void) { return "flockgpu 0.1 (sm_100a, CUDA " FG_STR(CUDART_VERSION) ")"; }
+
+int flockgpu_open(int device, flockgpu_ctx** out) {
+  return guarded([&] {
+    FG_CHECK(out, FLOCKGPU_ERR_INVALID, "open: null out pointer");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      fail(FLOCKGPU_ERR_NO_DEVICE, "open: no CUDA device available (%s); this library has no CPU fallback",
+           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    FG_CHECK(device >= 0 && device < n, FLOCKGPU_ERR_INVALID, "open: device %d out of range (have %d)", device, n);
+    FG_CUDA(cudaSetDevice(device));
+    auto core = std::make_shared<CtxCore>();
+    core->device = device;
+    cudaDeviceProp prop;
+    FG_CUDA(cudaGetDeviceProperties(&prop, device));
+    core->sm_count = prop.multiProcessorCount;
+    FG_CUDA(cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking));
+    FG_CUDA(cudaDeviceGetDefaultMemPool(&core->pool, device));
+    uint64_t threshold = UINT64_MAX;  // keep freed blocks in the pool: allocation is on the hot path
+    FG_CUDA(cudaMemPoolSetAttribute(core->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    FG_CUDA(cudaHostAlloc(&core->h_scalars, 512 * sizeof(unsigned long long), cudaHostAllocDefault));
+    FG_CUDA(cudaMalloc(&core->d_scalars, 512 * sizeof(unsigned long long)));
+    FG_CUDA(cudaMemset(core->d_scalars, 0, 512 * sizeof(unsigned long long)));
+    for (int i = 0; i < 16; ++i) {
+      FG_CUDA(cudaEventCreate(&core->timer_start[i]));
+      FG_CUDA(cudaEventCreate(&core->timer_stop[i]));
+    }
+    ensure_scan_scratch(core, 1);
+    *out = new flockgpu_ctx{core};
+  });
+}
+
+int flockgpu_close(flockgpu_ctx* ctx) {
+  return guarded([&] {
+    if (!ctx) return;
+    if (ctx->core && ctx->core->stream) {
+      cudaSetDevice(ctx->core->device);
+      cudaStreamSynchronize(ctx->core->stream);
+    }
+    delete ctx;
+  });
+}
+
+int flockgpu_synchronize(flockgpu_ctx* ctx) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int flockgpu_timer_start(flockgpu_ctx* ctx, int slot) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(slot >= 0 && slot < 16, FLOCKGPU_ERR_INVALID, "timer slot out of range");
+    FG_CUDA(cudaEventRecord(c->timer_start[slot], c->stream));
+  });
+}
+
+int flockgpu_timer_stop(flockgpu_ctx* ctx, int slot) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(slot >= 0 && slot < 16, FLOCKGPU_ERR_INVALID, "timer slot out of range");
+    FG_CUDA(cudaEventRecord(c->timer_stop[slot], c->stream));
+  });
+}
+
+int flockgpu_timer_elapsed_ms(flockgpu_ctx* ctx, int slot, float* ms) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(slot >= 0 && slot < 16 && ms, FLOCKGPU_ERR_INVALID, "timer slot out of range");
+    FG_CUDA(cudaEventSynchronize(c->timer_stop[slot]));
+    FG_CUDA(cudaEventElapsedTime(ms, c->timer_start[slot], c->timer_stop[slot]));
+  });
+}
+
+int64_t flockgpu_kernel_launches(flockgpu_ctx* ctx) { return ctx && ctx->core ? ctx->core->launches.load() : -1; }
+
+int flockgpu_host_alloc(flockgpu_ctx* ctx, int64_t bytes, void** out) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(out && bytes >= 0, FLOCKGPU_ERR_INVALID, "host_alloc: bad arguments");
+    void* p = nullptr;
+    FG_CUDA(cudaHostAlloc(&p, size_t(bytes ? bytes : 8), cudaHostAllocDefault));
+    std::lock_guard<std::mutex> g(c->pin_mu);
+    c->pinned.emplace(p, size_t(bytes));
+    *out = p;
+  });
+}
+
+int flockgpu_host_free(flockgpu_ctx* ctx, void* ptr) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    std::lock_guard<std::mutex> g(c->pin_mu);
+    auto it = c->pinned.find(ptr);
+    FG_CHECK(it != c->pinned.end(), FLOCKGPU_ERR_INVALID, "host_free: pointer was not allocated by host_alloc");
+    c->pinned.erase(it);
+    FG_CUDA(cudaFreeHost(ptr));
+  });
+}
+
+int flockgpu_flush_l2(flockgpu_ctx* ctx) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    if (!c->l2_flush) {
+      c->l2_flush_bytes = size_t(384) << 20;  // 3x the 126 MB L2
+      FG_CUDA(cudaMalloc(&c->l2_flush, c->l2_flush_bytes));
+    }
+    FG_CUDA(cudaMemsetAsync(c->l2_flush, 0x5a, c->l2_flush_bytes, c->stream));
+  });
+}
+
+int flockgpu_table_import(flockgpu_ctx* ctx, const struct ArrowSchema* schema, const struct ArrowArray* const* batches,
+                          int32_t n_batches, const int32_t* projection, int32_t n_projection, flockgpu_table** out) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(out, FLOCKGPU_ERR_INVALID, "table_import: null out pointer");
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    FG_CUDA(cudaSetDevice(c->device));
+    *out = wrap_table(import_batches(c, schema, batches, n_batches, projection, n_projection));
+  });
+}
+
+int flockgpu_table_export(flockgpu_ctx* ctx, const flockgpu_table* table, int64_t row_begin, int64_t row_count,
+                          struct ArrowSchema* out_schema, struct ArrowArray* out_array) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    FG_CUDA(cudaSetDevice(c->device));
+    export_table(c, deref(table), row_begin, row_count, out_schema, out_array);
+  });
+}
+
+int flockgpu_table_schema(flockgpu_ctx* ctx, const flockgpu_table* table, struct ArrowSchema* out_schema) {
+  return guarded([&] {
+    (void)ctx;
+    FG_CHECK(out_schema, FLOCKGPU_ERR_INVALID, "table_schema: null output");
+    export_schema(deref(table), out_schema);
+  });
+}
+
+int flockgpu_table_retain(flockgpu_table* table) {
+  return guarded([&] {
+    FG_CHECK(table, FLOCKGPU_ERR_INVALID, "null table handle");
+    table->refs.fetch_add(1);
+  });
+}
+
+int flockgpu_table_release(flockgpu_table* table) {
+  return guarded([&] {
+    if (!table) return;
+    if (table->refs.fetch_sub(1) == 1) {
+      if (table->table && table->table->ctx) cudaSetDevice(table->table->ctx->device);
+      delete table;
+    }
+  });
+}
+
+int64_t flockgpu_table_num_rows(const flockgpu_table* table) { return table && table->table ? table->table->num_rows : -1; }
+
+int32_t flockgpu_table_num_columns(const flockgpu_table* table) {
+  return table && table->table ? int32_t(table->table->cols.size()) : -1;
+}
+
+int64_t flockgpu_table_nbytes(const flockgpu_table* table) { return table && table->table ? table->table->nbytes() : -1; }
+
+int flockgpu_table_concat(flockgpu_ctx* ctx, flockgpu_table* const* tables, int32_t n, flockgpu_table** out) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(out && tables && n > 0, FLOCKGPU_ERR_INVALID, "table_concat: bad arguments");
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    FG_CUDA(cudaSetDevice(c->device));
+    std::vector<TablePtr> ts;
+    for (int i = 0; i < n; ++i) ts.push_back(tables[i] ? tables[i]->table : nullptr);
+    for (auto& t : ts) FG_CHECK(t, FLOCKGPU_ERR_INVALID, "table_concat: null table");
+    *out = wrap_table(concat_tables(c, ts));
+  });
+}
+
+}  // extern "C"

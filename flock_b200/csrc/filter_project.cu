@@ -1,0 +1,478 @@
+// filter_project.cu -- K1: FilterExec + CoalesceBatchesExec + ProjectionExec as one pass over HBM.
+//
+// Reference operators replaced (DataFusion fork, not in tree; shapes evidenced at
+// flock/src/distributed_plan/planner.rs:90-92 (q1), :120-124 (q2), :151-163 (q3 filters)):
+//   FilterExec:     predicate.evaluate(batch) -> BooleanArray -> arrow filter_record_batch (stable)
+//   ProjectionExec: per-batch expression evaluation; plain Column exprs are zero-copy
+//
+// filter_compact_kernel: ONE launch for the whole relation (all 64 Ki-row batches: a 1.3 MB batch is
+// 0.2 us of HBM traffic, far below launch latency, so per-batch launches cannot work).  Persistent
+// CTAs take 4096-row tiles from an atomic ticket, evaluate the predicate (a hand-specialised functor
+// for the NEXMark shapes, the generic term interpreter otherwise), rank the survivors with warp
+// ballots, obtain the tile's global output offset by decoupled look-back (each input byte is read
+// once, no second pass), and write the surviving rows of every fixed-width output column in input
+// order.  Utf8 outputs leave through the selection vector and gather.cu.
+#include <algorithm>
+
+#include "compact.cuh"
+#include "expr_compile.h"
+#include "internal.h"
+
+namespace fg {
+
+constexpr int FP_THREADS = CP_THREADS;
+constexpr int FP_ITEMS = CP_ITEMS;   // rows per thread per tile
+constexpr int FP_TILE = CP_TILE;     // 4096 rows
+
+struct FilterArgs {
+  int64_t n_rows;
+  int64_t num_tiles;
+  int32_t n_out;
+  int32_t pad;
+  uint32_t* sel_out;                 // optional: indices of surviving rows
+  unsigned long long* tile_state;    // look-back scratch (self-resetting)
+  unsigned int* counters;            // [0] ticket, [1] done
+  unsigned long long* out_count;     // total surviving rows
+  int* err_flag;                     // set to 1 on divide-by-zero
+  ColRef cols[MAX_IN_COLS];
+  OutCol outs[MAX_OUT_COLS];
+};
+
+// ---- predicate functors ---------------------------------------------------------------------------
+// A functor evaluates this thread's FP_ITEMS rows of a tile and returns one bit per item.  E = rows a
+// thread loads contiguously (vector width); item k is row
+//   tile_base + ((k / E) * FP_THREADS + tid) * E + k % E.
+struct PredGeneric {
+  static constexpr int E = 1;
+  Predicate p;
+  __device__ __forceinline__ unsigned eval(const ColRef* cols, int64_t tile_base, int64_t n_rows, int tid, int* err) const {
+    int64_t rows[FP_ITEMS];
+#pragma unroll
+    for (int k = 0; k < FP_ITEMS; ++k) {
+      int64_t r = tile_base + int64_t(k) * FP_THREADS + tid;
+      rows[k] = r < n_rows ? r : -1;
+    }
+    return eval_predicate<FP_ITEMS>(p, cols, rows, err);
+  }
+};
+
+__device__ __forceinline__ bool cmp_i64(int cmp, int64_t a, int64_t b) {
+  switch (cmp) {
+    case FLOCKGPU_OP_EQ: return a == b;
+    case FLOCKGPU_OP_NE: return a != b;
+    case FLOCKGPU_OP_LT: return a < b;
+    case FLOCKGPU_OP_LE: return a <= b;
+    case FLOCKGPU_OP_GT: return a > b;
+    default: return a >= b;
+  }
+}
+
+// CAST(i32col AS Int64) [% m] CMP rhs, 128-bit loads.  MODE 0: plain compare; MODE 1: `% m` via
+// Lemire's fastmod (M = 2^64/m + 1: two multiplies instead of a software division); MODE 2: `% m = 0`
+// via the divisibility test n * M <= M - 1 (one multiply).
+template <int MODE>
+struct PredI32 {
+  static constexpr int E = 4;
+  const int32_t* col;
+  uint64_t M;
+  uint32_t d;
+  int32_t cmp;
+  int64_t rhs;
+  __device__ __forceinline__ bool test(int32_t x) const {
+    if (MODE == 0) return cmp_i64(cmp, int64_t(x), rhs);
+    uint32_t ax = x < 0 ? 0u - uint32_t(x) : uint32_t(x);
+    uint64_t low = M * uint64_t(ax);
+    if (MODE == 2) return low <= M - 1;
+    int64_t r = int64_t(__umul64hi(low, uint64_t(d)));
+    if (x < 0) r = -r;
+    return cmp_i64(cmp, r, rhs);
+  }
+  __device__ __forceinline__ unsigned eval(const ColRef*, int64_t tile_base, int64_t n_rows, int tid, int*) const {
+    unsigned bits = 0;
+    int4 v[FP_ITEMS / 4];
+    int64_t row0[FP_ITEMS / 4];
+#pragma unroll
+    for (int g = 0; g < FP_ITEMS / 4; ++g) {
+      row0[g] = tile_base + (int64_t(g) * FP_THREADS + tid) * 4;
+      if (row0[g] + 3 < n_rows) {
+        v[g] = ldg_stream_v4(col + row0[g]);
+      } else {
+        v[g] = make_int4(0, 0, 0, 0);
+        if (row0[g] + 0 < n_rows) v[g].x = col[row0[g] + 0];
+        if (row0[g] + 1 < n_rows) v[g].y = col[row0[g] + 1];
+        if (row0[g] + 2 < n_rows) v[g].z = col[row0[g] + 2];
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < FP_ITEMS / 4; ++g) {
+      unsigned b = unsigned(test(v[g].x)) | (unsigned(test(v[g].y)) << 1) | (unsigned(test(v[g].z)) << 2) | (unsigned(test(v[g].w)) << 3);
+      // mask rows past the end
+      int64_t left = n_rows - row0[g];
+      if (left < 4) b &= left <= 0 ? 0u : ((1u << left) - 1u);
+      bits |= b << (4 * g);
+    }
+    return bits;
+  }
+};
+
+__device__ __forceinline__ void copy_value(void* dst, const void* src, int width, int64_t pos, int64_t row) {
+  if (width == 4) static_cast<uint32_t*>(dst)[pos] = static_cast<const uint32_t*>(src)[row];
+  else static_cast<uint64_t*>(dst)[pos] = static_cast<const uint64_t*>(src)[row];
+}
+
+template <class PredFn>
+__global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid_constant__ PredFn pred, const __grid_constant__ FilterArgs a) {
+  constexpr int E = PredFn::E;
+  __shared__ CompactSmem<E> sm;
+  const int tid = threadIdx.x;
+  const CompactScratch sc{a.tile_state, a.counters, a.out_count, a.num_tiles};
+  int err = 0;
+
+  for (long long tile = cp_next_tile(sm, sc); tile >= 0; tile = cp_next_tile(sm, sc)) {
+    const int64_t tile_base = tile * FP_TILE;
+    const unsigned bits = pred.eval(a.cols, tile_base, a.n_rows, tid, &err);
+    unsigned lane_prefix[FP_ITEMS / E];
+    cp_rank_tile<E>(sm, sc, tile, bits, lane_prefix);
+
+    // ---- write survivors in input order
+    if (bits && sm.tile_total) {
+      unsigned m = bits;
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t pos = cp_position<E>(sm, bits, k, lane_prefix);
+        const int64_t row = tile_base + cp_item_index<E>(k, tid);
+        if (a.sel_out) a.sel_out[pos] = uint32_t(row);
+        for (int c = 0; c < a.n_out; ++c) {
+          const OutCol& oc = a.outs[c];
+          if (oc.kind == OUT_PASS) {
+            copy_value(oc.dst, a.cols[oc.src_col].data, oc.width, pos, row);
+          } else {
+            int64_t rows1[1] = {row};
+            Val acc[1];
+            eval_chain<1>(oc.chain, a.cols, rows1, acc, &err);
+            store_val(oc.dst, oc.out_dtype, pos, acc[0]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // sm is reused by the next tile
+  }
+  if (err) *a.err_flag = 1;
+  cp_finish(sm, sc);
+}
+
+// ---- pure projection (no predicate): streaming evaluation of the computed columns ----------------
+struct ProjectArgs {
+  int64_t n_rows;
+  int32_t n_out;
+  int32_t pad;
+  int* err_flag;
+  ColRef cols[MAX_IN_COLS];
+  OutCol outs[MAX_OUT_COLS];
+};
+
+constexpr int PJ_THREADS = 256;
+constexpr int PJ_ROWS = 4;
+
+__global__ void __launch_bounds__(PJ_THREADS) project_generic_kernel(const __grid_constant__ ProjectArgs a) {
+  int err = 0;
+  const int64_t stride = int64_t(gridDim.x) * PJ_THREADS * PJ_ROWS;
+  for (int64_t base = int64_t(blockIdx.x) * PJ_THREADS * PJ_ROWS; base < a.n_rows; base += stride) {
+    int64_t rows[PJ_ROWS];
+#pragma unroll
+    for (int j = 0; j < PJ_ROWS; ++j) {
+      int64_t r = base + int64_t(j) * PJ_THREADS + threadIdx.x;
+      rows[j] = r < a.n_rows ? r : -1;
+    }
+    for (int c = 0; c < a.n_out; ++c) {
+      const OutCol& oc = a.outs[c];
+      Val acc[PJ_ROWS];
+      eval_chain<PJ_ROWS>(oc.chain, a.cols, rows, acc, &err);
+#pragma unroll
+      for (int j = 0; j < PJ_ROWS; ++j)
+        if (rows[j] >= 0) store_val(oc.dst, oc.out_dtype, rows[j], acc[j]);
+    }
+  }
+  if (err) *a.err_flag = 1;
+}
+
+// NEXMark q1: price' = lit * CAST(price AS Float64).  One IEEE multiply per row (__dmul_rn: the i32 ->
+// f64 conversion is exact, so the product has a single rounding).
+// 16 B in, 32 B out per thread-iteration; 4 B + 8 B per row is all the traffic there is.
+__global__ void __launch_bounds__(PJ_THREADS) project_i32_to_f64_mul_kernel(const int32_t* __restrict__ in, double* __restrict__ out,
+                                                                            int64_t n_rows, double lit) {
+  const int64_t n4 = n_rows >> 2;
+  const int64_t stride = int64_t(gridDim.x) * PJ_THREADS;
+  for (int64_t i = int64_t(blockIdx.x) * PJ_THREADS + threadIdx.x; i < n4; i += stride) {
+    int4 v = ldg_stream_v4(in + i * 4);
+    stg_stream_v2f64(out + i * 4, __dmul_rn(lit, double(v.x)), __dmul_rn(lit, double(v.y)));
+    stg_stream_v2f64(out + i * 4 + 2, __dmul_rn(lit, double(v.z)), __dmul_rn(lit, double(v.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n_rows & 3)) {
+    int64_t r = (n4 << 2) + threadIdx.x;
+    out[r] = __dmul_rn(lit, double(in[r]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static std::vector<ColInfo> col_infos(const Table& t) {
+  std::vector<ColInfo> v;
+  for (const Column& c : t.cols) v.push_back({c.dtype, c.name, c.format});
+  return v;
+}
+
+static void fill_colrefs(const Table& t, ColRef* refs) {
+  FG_CHECK(t.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "filter_project: more than %d input columns", MAX_IN_COLS);
+  for (size_t i = 0; i < t.cols.size(); ++i) {
+    FG_CHECK(!t.cols[i].all_null, FLOCKGPU_ERR_UNSUPPORTED, "filter_project: NULL input column \"%s\"", t.cols[i].name.c_str());
+    refs[i].data = t.cols[i].values();
+    refs[i].offsets = t.cols[i].offs();
+    refs[i].dtype = t.cols[i].dtype;
+    refs[i].pad = 0;
+  }
+}
+
+static int persistent_grid(const CtxPtr& ctx, const void* kernel, int threads, int64_t work_items) {
+  int per_sm = 1;
+  FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  if (per_sm < 1) per_sm = 1;
+  int64_t g = int64_t(ctx->sm_count) * per_sm;
+  return int(std::max<int64_t>(1, std::min<int64_t>(g, work_items)));
+}
+
+template <class PredFn>
+static void launch_filter(const CtxPtr& ctx, const PredFn& pred, const FilterArgs& args) {
+  const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
+  int grid = persistent_grid(ctx, k, FP_THREADS, args.num_tiles);
+  filter_compact_kernel<PredFn><<<grid, FP_THREADS, 0, ctx->stream>>>(pred, args);
+  FG_CUDA(cudaGetLastError());
+  count_launch(ctx);
+}
+
+TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* predicate, const std::vector<Expr>& projections,
+                        const std::vector<std::string>& names) {
+  const Table& in = *in_ptr;
+  std::vector<ColInfo> infos = col_infos(in);
+  // ---- compile
+  std::vector<CompiledValue> vals;
+  if (projections.empty()) {
+    for (size_t i = 0; i < in.cols.size(); ++i) {
+      CompiledValue v;
+      v.passthrough = true;
+      v.src_col = int(i);
+      v.dtype = in.cols[i].dtype;
+      v.format = in.cols[i].format;
+      vals.push_back(v);
+    }
+  } else {
+    for (const Expr& e : projections) vals.push_back(compile_value(e, infos));
+  }
+  auto out_name = [&](size_t i) -> std::string {
+    if (i < names.size() && !names[i].empty()) return names[i];
+    if (vals[i].passthrough) return in.cols[vals[i].src_col].name;
+    return projections.empty() ? std::string() : expr_to_string(projections[i], infos);
+  };
+
+  auto out = std::make_shared<Table>();
+  out->ctx = ctx;
+  out->metadata = in.metadata;
+
+  int* err_flag = reinterpret_cast<int*>(ctx->d_scalars + 8);
+  bool check_err = false;
+
+  if (!predicate) {
+    // ------------------------------------------------------------------ ProjectionExec only
+    out->num_rows = in.num_rows;
+    ProjectArgs pa{};
+    pa.n_rows = in.num_rows;
+    pa.err_flag = err_flag;
+    fill_colrefs(in, pa.cols);
+    for (size_t i = 0; i < vals.size(); ++i) {
+      const CompiledValue& v = vals[i];
+      Column c;
+      c.name = out_name(i);
+      c.dtype = v.dtype;
+      c.format = v.format;
+      c.length = in.num_rows;
+      if (v.passthrough) {
+        const Column& s = in.cols[v.src_col];
+        c.nullable = s.nullable;
+        c.data = s.data;  // zero-copy, like the Arc clone in ProjectionExec
+        c.offsets = s.offsets;
+        c.values_bytes = s.values_bytes;
+        c.all_null = s.all_null;
+      } else {
+        c.data = alloc(ctx, size_t(in.num_rows) * dtype_width(v.dtype));
+        if (in.num_rows > 0) {
+          if (v.fast == FAST_VAL_I32_TO_F64_MUL) {
+            int64_t n4 = std::max<int64_t>(1, in.num_rows / 4);
+            int grid = int(std::min<int64_t>((n4 + PJ_THREADS - 1) / PJ_THREADS, int64_t(ctx->sm_count) * 8));
+            project_i32_to_f64_mul_kernel<<<grid, PJ_THREADS, 0, ctx->stream>>>(
+                static_cast<const int32_t*>(in.cols[v.chain.start_col].values()), c.data->as<double>(), in.num_rows, v.fast_lit);
+            FG_CUDA(cudaGetLastError());
+            count_launch(ctx);
+          } else {
+            FG_CHECK(pa.n_out < MAX_OUT_COLS, FLOCKGPU_ERR_UNSUPPORTED, "projection: more than %d computed columns", MAX_OUT_COLS);
+            OutCol& oc = pa.outs[pa.n_out++];
+            oc.kind = OUT_COMPUTED;
+            oc.src_col = -1;
+            oc.out_dtype = v.dtype;
+            oc.width = dtype_width(v.dtype);
+            oc.dst = c.data->ptr;
+            oc.chain = v.chain;
+            check_err |= v.has_div_by_col;
+          }
+        }
+      }
+      out->cols.push_back(std::move(c));
+    }
+    if (pa.n_out > 0 && in.num_rows > 0) {
+      int64_t per_block = int64_t(PJ_THREADS) * PJ_ROWS;
+      int grid = int(std::min<int64_t>((in.num_rows + per_block - 1) / per_block, int64_t(ctx->sm_count) * 8));
+      if (check_err) FG_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int), ctx->stream));
+      project_generic_kernel<<<grid, PJ_THREADS, 0, ctx->stream>>>(pa);
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+      if (check_err) {
+        unsigned long long flag = 0;
+        read_scalars(ctx, 8, 1, &flag);
+        FG_CHECK((flag & 0xffffffffull) == 0, FLOCKGPU_ERR_EXECUTION, "Divide by zero");
+      }
+    }
+    return out;
+  }
+
+  // -------------------------------------------------------------------- FilterExec (+ projection)
+  CompiledPredicate cp = compile_predicate(*predicate, infos);
+  check_err = cp.prog.has_div_by_col != 0;
+  if (in.num_rows == 0) {
+    // nothing to scan: an empty table with the output schema
+    out->num_rows = 0;
+    for (size_t i = 0; i < vals.size(); ++i) {
+      Column c;
+      c.name = out_name(i);
+      c.dtype = vals[i].dtype;
+      c.format = vals[i].format;
+      c.length = 0;
+      c.data = alloc(ctx, 0);
+      if (c.dtype == FLOCKGPU_UTF8) {
+        c.offsets = alloc(ctx, 4);
+        FG_CUDA(cudaMemsetAsync(c.offsets->ptr, 0, 4, ctx->stream));
+      }
+      out->cols.push_back(std::move(c));
+    }
+    return out;
+  }
+
+  FilterArgs fa{};
+  fa.n_rows = in.num_rows;
+  fa.num_tiles = (in.num_rows + FP_TILE - 1) / FP_TILE;
+  ensure_scan_scratch(ctx, fa.num_tiles);
+  fa.tile_state = ctx->scan.tile_state;
+  fa.counters = ctx->scan.counters;
+  fa.out_count = ctx->d_scalars + 0;
+  fa.err_flag = err_flag;
+  fill_colrefs(in, fa.cols);
+
+  bool need_sel = false;
+  std::vector<int> utf8_outs;
+  for (size_t i = 0; i < vals.size(); ++i) {
+    const CompiledValue& v = vals[i];
+    Column c;
+    c.name = out_name(i);
+    c.dtype = v.dtype;
+    c.format = v.format;
+    if (v.passthrough) c.nullable = in.cols[v.src_col].nullable;
+    if (v.dtype == FLOCKGPU_UTF8) {
+      need_sel = true;
+      utf8_outs.push_back(int(i));
+    } else {
+      FG_CHECK(fa.n_out < MAX_OUT_COLS, FLOCKGPU_ERR_UNSUPPORTED, "filter: more than %d fixed-width output columns", MAX_OUT_COLS);
+      c.data = alloc(ctx, size_t(in.num_rows) * dtype_width(v.dtype));  // worst case: every row survives
+      OutCol& oc = fa.outs[fa.n_out++];
+      oc.kind = v.passthrough ? OUT_PASS : OUT_COMPUTED;
+      oc.src_col = v.src_col;
+      oc.out_dtype = v.dtype;
+      oc.width = dtype_width(v.dtype);
+      oc.dst = c.data->ptr;
+      oc.chain = v.chain;
+      check_err |= v.has_div_by_col;
+    }
+    out->cols.push_back(std::move(c));
+  }
+  BufferPtr sel;
+  if (need_sel) {
+    sel = alloc(ctx, size_t(in.num_rows) * 4);
+    fa.sel_out = sel->as<uint32_t>();
+  }
+  if (check_err) FG_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int), ctx->stream));
+
+  switch (cp.fast.kind) {
+    case FAST_PRED_I32_MOD_CMP: {
+      uint32_t d = uint32_t(cp.fast.modulus);
+      uint64_t M = ~uint64_t(0) / d + 1;
+      const int32_t* col = static_cast<const int32_t*>(in.cols[cp.fast.col].values());
+      if (cp.fast.cmp == FLOCKGPU_OP_EQ && cp.fast.rhs == 0) {
+        PredI32<2> p{col, M, d, cp.fast.cmp, cp.fast.rhs};
+        launch_filter(ctx, p, fa);
+      } else {
+        PredI32<1> p{col, M, d, cp.fast.cmp, cp.fast.rhs};
+        launch_filter(ctx, p, fa);
+      }
+      break;
+    }
+    case FAST_PRED_I32_CMP: {
+      PredI32<0> p{static_cast<const int32_t*>(in.cols[cp.fast.col].values()), 0, 1, cp.fast.cmp, cp.fast.rhs};
+      launch_filter(ctx, p, fa);
+      break;
+    }
+    default: {
+      PredGeneric p{cp.prog};
+      launch_filter(ctx, p, fa);
+    }
+  }
+
+  unsigned long long scalars[9];
+  read_scalars(ctx, 0, 9, scalars);
+  if (check_err) FG_CHECK((scalars[8] & 0xffffffffull) == 0, FLOCKGPU_ERR_EXECUTION, "Divide by zero");
+  int64_t n_sel = int64_t(scalars[0]);
+  FG_CHECK(n_sel >= 0 && n_sel <= in.num_rows, FLOCKGPU_ERR_CUDA, "filter: corrupt survivor count %lld", (long long)n_sel);
+  out->num_rows = n_sel;
+  for (Column& c : out->cols) c.length = n_sel;
+  for (int i : utf8_outs) {
+    Column g = gather_column(ctx, in.cols[vals[i].src_col], fa.sel_out, n_sel);
+    g.name = out->cols[i].name;
+    out->cols[i] = std::move(g);
+  }
+  return out;
+}
+
+}  // namespace fg
+
+// ================================================================================================
+using namespace fg;
+
+extern "C" int flockgpu_filter_project(flockgpu_ctx* ctx, const flockgpu_table* in, const flockgpu_expr* predicate,
+                                       const flockgpu_expr* projections, const char* const* out_names, int32_t n_projections,
+                                       flockgpu_table** out) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(out, FLOCKGPU_ERR_INVALID, "filter_project: null out pointer");
+    FG_CHECK(in && in->table, FLOCKGPU_ERR_INVALID, "filter_project: null input table");
+    FG_CHECK(n_projections >= 0 && (n_projections == 0 || projections), FLOCKGPU_ERR_INVALID, "filter_project: bad projection list");
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    FG_CUDA(cudaSetDevice(c->device));
+    Expr pred;
+    if (predicate) pred = tokens_to_expr(predicate);
+    std::vector<Expr> projs;
+    std::vector<std::string> names;
+    for (int i = 0; i < n_projections; ++i) {
+      projs.push_back(tokens_to_expr(&projections[i]));
+      names.push_back(out_names && out_names[i] ? out_names[i] : "");
+    }
+    *out = wrap_table(filter_project(c, in->table, predicate ? &pred : nullptr, projs, names));
+  });
+}

@@ -1,0 +1,236 @@
+// gather.cu -- row gather through an index vector: the arrow `take` kernel of the reference's
+// HashJoinExec output construction and RepartitionExec (call shape in
+// playground/src/distributed_plan/shuffle_writer.rs:129-146), and the Utf8 half of `filter`.
+//
+//   fixed width : out[i] = in[idx[i]]
+//   Utf8        : lengths -> exclusive scan (single pass, decoupled look-back) -> byte copy where each
+//                 warp owns 32 consecutive OUTPUT rows, so output bytes are written densely in order.
+#include <algorithm>
+
+#include "device_utils.cuh"
+#include "internal.h"
+
+namespace fg {
+
+constexpr int GA_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(GA_THREADS) gather_fixed_kernel(const T* __restrict__ in, const uint32_t* __restrict__ idx,
+                                                                   T* __restrict__ out, int64_t n) {
+  const int64_t stride = int64_t(gridDim.x) * GA_THREADS;
+  int64_t i = int64_t(blockIdx.x) * GA_THREADS + threadIdx.x;
+  // 4 independent gathers in flight per thread
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    uint32_t a = idx[i], b = idx[i + stride], c = idx[i + 2 * stride], d = idx[i + 3 * stride];
+    T va = in[a], vb = in[b], vc = in[c], vd = in[d];
+    out[i] = va;
+    out[i + stride] = vb;
+    out[i + 2 * stride] = vc;
+    out[i + 3 * stride] = vd;
+  }
+  for (; i < n; i += stride) out[i] = in[idx[i]];
+}
+
+// ---- Utf8 pass 1: out_off[i] = sum_{j<i} len(idx[j]); out_off[n] = total ---------------------------
+constexpr int GL_ITEMS = 8;
+constexpr int GL_TILE = GA_THREADS * GL_ITEMS;
+
+struct GatherLenArgs {
+  const int32_t* in_off;
+  const uint32_t* idx;  // may be NULL: identity (plain offsets rebuild)
+  int32_t* out_off;
+  int64_t n;
+  int64_t num_tiles;
+  unsigned long long* tile_state;
+  unsigned int* counters;
+  unsigned long long* out_total;
+};
+
+__global__ void __launch_bounds__(GA_THREADS) gather_lengths_scan_kernel(const __grid_constant__ GatherLenArgs a) {
+  __shared__ unsigned long long s_warp[GA_THREADS / 32];
+  __shared__ long long s_tile;
+  __shared__ unsigned long long s_excl;
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  while (true) {
+    if (tid == 0) s_tile = (long long)atomicAdd(a.counters, 1u);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= a.num_tiles) break;
+    const int64_t i0 = tile * GL_TILE + int64_t(tid) * GL_ITEMS;
+    unsigned len[GL_ITEMS];
+    unsigned long long local = 0;
+#pragma unroll
+    for (int k = 0; k < GL_ITEMS; ++k) {
+      len[k] = 0;
+      if (i0 + k < a.n) {
+        int64_t r = a.idx ? int64_t(a.idx[i0 + k]) : i0 + k;
+        len[k] = unsigned(a.in_off[r + 1] - a.in_off[r]);
+      }
+      local += len[k];
+    }
+    unsigned long long incl = warp_inclusive_sum(local);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < GA_THREADS / 32; ++w) {
+      unsigned long long v = s_warp[w];
+      if (w < warp) warp_base += v;
+      tile_total += v;
+    }
+    if (warp == 0) {
+      unsigned long long excl = 0;
+      if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(a.tile_state, LB_PREFIX | tile_total);
+      } else {
+        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PARTIAL | tile_total);
+        excl = lookback_exclusive_prefix(a.tile_state, tile);
+        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PREFIX | (excl + tile_total));
+      }
+      if (lane == 0) {
+        s_excl = excl;
+        if (tile == a.num_tiles - 1) {
+          *a.out_total = excl + tile_total;
+          a.out_off[a.n] = int32_t(excl + tile_total);
+        }
+      }
+    }
+    __syncthreads();
+    unsigned long long run = s_excl + warp_base + (incl - local);
+#pragma unroll
+    for (int k = 0; k < GL_ITEMS; ++k) {
+      if (i0 + k < a.n) a.out_off[i0 + k] = int32_t(run);
+      run += len[k];
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  if (tid == 0) s_last = (atomicAdd(a.counters + 1, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    for (int64_t i = tid; i < a.num_tiles; i += GA_THREADS) a.tile_state[i] = LB_INVALID;
+    if (tid == 0) {
+      a.counters[0] = 0;
+      a.counters[1] = 0;
+    }
+  }
+}
+
+// ---- Utf8 pass 2: byte copy, one warp per 32 output rows -------------------------------------------
+__global__ void __launch_bounds__(GA_THREADS) gather_utf8_copy_kernel(const uint8_t* __restrict__ in_data, const int32_t* __restrict__ in_off,
+                                                                       const uint32_t* __restrict__ idx, const int32_t* __restrict__ out_off,
+                                                                       uint8_t* __restrict__ out_data, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t(gridDim.x) * GA_THREADS) >> 5;
+  const int64_t chunks = (n + 31) >> 5;
+  for (int64_t chunk = (int64_t(blockIdx.x) * GA_THREADS + threadIdx.x) >> 5; chunk < chunks; chunk += warps_total) {
+    const int64_t r0 = chunk << 5;
+    const int rows = (n - r0) < 32 ? int(n - r0) : 32;
+    int32_t dst_start = 0x7fffffff, src_start = 0;
+    if (lane < rows) {
+      dst_start = out_off[r0 + lane];
+      int64_t r = idx ? int64_t(idx[r0 + lane]) : r0 + lane;
+      src_start = in_off[r];
+    }
+    const int32_t d0 = __shfl_sync(FULL_MASK, dst_start, 0);
+    const int32_t d1 = out_off[r0 + rows];
+    for (int32_t b0 = d0; b0 < d1; b0 += 32) {
+      const int32_t b = b0 + lane;
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        int cand = lo + step;
+        int32_t ds = __shfl_sync(FULL_MASK, dst_start, cand & 31);
+        if (cand < rows && ds <= b) lo = cand;
+      }
+      const int32_t ds = __shfl_sync(FULL_MASK, dst_start, lo);
+      const int32_t ss = __shfl_sync(FULL_MASK, src_start, lo);
+      if (b < d1) out_data[b] = in_data[ss + (b - ds)];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int stream_grid(const CtxPtr& ctx, int64_t items, int per_block, int blocks_per_sm = 8) {
+  int64_t g = (items + per_block - 1) / per_block;
+  return int(std::max<int64_t>(1, std::min<int64_t>(g, int64_t(ctx->sm_count) * blocks_per_sm)));
+}
+
+Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx, int64_t n) {
+  FG_CHECK(!in.all_null, FLOCKGPU_ERR_UNSUPPORTED, "gather: NULL column \"%s\"", in.name.c_str());
+  Column out;
+  out.dtype = in.dtype;
+  out.name = in.name;
+  out.format = in.format;
+  out.nullable = in.nullable;
+  out.length = n;
+  if (in.dtype != FLOCKGPU_UTF8) {
+    int w = in.width();
+    out.data = alloc(ctx, size_t(n) * w);
+    if (n > 0) {
+      int grid = stream_grid(ctx, n, GA_THREADS * 4);
+      if (w == 4)
+        gather_fixed_kernel<uint32_t><<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint32_t*>(in.values()), d_idx,
+                                                                            out.data->as<uint32_t>(), n);
+      else
+        gather_fixed_kernel<uint64_t><<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint64_t*>(in.values()), d_idx,
+                                                                            out.data->as<uint64_t>(), n);
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    }
+    return out;
+  }
+  out.offsets = alloc(ctx, size_t(n + 1) * 4);
+  if (n == 0) {
+    FG_CUDA(cudaMemsetAsync(out.offsets->ptr, 0, 4, ctx->stream));
+    out.data = alloc(ctx, 0);
+    out.values_bytes = 0;
+    return out;
+  }
+  GatherLenArgs a{};
+  a.in_off = in.offs();
+  a.idx = d_idx;
+  a.out_off = out.offsets->as<int32_t>();
+  a.n = n;
+  a.num_tiles = (n + GL_TILE - 1) / GL_TILE;
+  ensure_scan_scratch(ctx, a.num_tiles);
+  a.tile_state = ctx->scan.tile_state;
+  a.counters = ctx->scan.counters;
+  a.out_total = ctx->d_scalars + 1;
+  {
+    int per_sm = 1;
+    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_lengths_scan_kernel, GA_THREADS, 0));
+    int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), a.num_tiles)));
+    gather_lengths_scan_kernel<<<grid, GA_THREADS, 0, ctx->stream>>>(a);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
+  unsigned long long total = 0;
+  read_scalars(ctx, 1, 1, &total);
+  FG_CHECK(total < (1ull << 31), FLOCKGPU_ERR_UNSUPPORTED, "gather: Utf8 result column \"%s\" exceeds 2^31-1 bytes", in.name.c_str());
+  out.values_bytes = int64_t(total);
+  out.data = alloc(ctx, size_t(total));
+  if (total > 0) {
+    int grid = stream_grid(ctx, (n + 31) / 32, GA_THREADS / 32);
+    gather_utf8_copy_kernel<<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint8_t*>(in.values()), in.offs(), d_idx,
+                                                                  out.offsets->as<int32_t>(), out.data->as<uint8_t>(), n);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
+  return out;
+}
+
+TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx, int64_t n_idx) {
+  auto out = std::make_shared<Table>();
+  out->ctx = ctx;
+  out->metadata = in.metadata;
+  out->num_rows = n_idx;
+  for (int c : cols) {
+    FG_CHECK(c >= 0 && c < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "gather: column %d out of range", c);
+    out->cols.push_back(gather_column(ctx, in.cols[c], d_idx, n_idx));
+  }
+  return out;
+}
+
+}  // namespace fg

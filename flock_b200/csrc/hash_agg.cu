@@ -1,0 +1,883 @@
+// hash_agg.cu -- K5/K6/K7: HashAggregateExec {Partial, Final, FinalPartitioned} (+ the fused SINGLE mode).
+//
+// Reference operator (DataFusion fork, not in tree): group-by hash table over the group columns with
+// per-group accumulators; Partial emits (keys, state columns "<name>[count|sum|max|min]"), Final*
+// merges states (COUNT = sum of counts, AVG = sum / count) -- shapes at
+// flock/src/distributed_plan/stage.rs:535-543, :597-600, planner.rs:235, :246-254; state-column names
+// in flock/src/tests/data/plan/aggregate.json.
+//
+// GPU design
+//   packed keys   up to two fixed-width group columns (<= 8 bytes together) become one 64-bit key.
+//     level 1     agg_local_kernel: every CTA owns a contiguous row range and pre-aggregates it in a
+//                 SHARED-MEMORY hash table (NEXMark keys are local in time: a 64 Ki-row bid batch
+//                 touches ~4 300 auctions, half of the rows one "hot" id), flushing (key, state)
+//                 partials to HBM when the table is 3/4 full.  This is the reference's Partial stage,
+//                 with the CTA in the role of the partition.
+//     level 2     agg_insert_kernel: partials (or raw rows when the input is small) are merged into a
+//                 global open-addressing table with 64-bit CAS + atomics; its size is known from the
+//                 partial count, not from the row count.
+//     emit        agg_emit_kernel: stable single-pass compaction of the occupied slots (compact.cuh).
+//   row keys      Utf8 or wide group keys: the table stores the index of a representative input row
+//                 (agg_insert_rows_kernel); key equality is checked against the input columns.
+//   no keys       agg_global_kernel: register accumulators -> warp shuffle -> one atomic per warp.
+#include <algorithm>
+
+#include "compact.cuh"
+#include "expr_program.h"
+#include "internal.h"
+#include "rowkeys.cuh"
+
+namespace fg {
+
+constexpr int MAX_ACC = 8;
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+constexpr unsigned EMPTY_OWNER = ~0u;
+
+enum AccOp : int32_t { ACC_COUNT = 0, ACC_ADD_I, ACC_ADD_F, ACC_MIN_I, ACC_MAX_I, ACC_MIN_U, ACC_MAX_U, ACC_MIN_F, ACC_MAX_F };
+
+struct AccDesc {
+  int32_t op;   // AccOp applied to raw input rows
+  int32_t col;  // input column (-1: none, COUNT(*))
+  int32_t cvt;  // Cvt applied to the loaded value (AVG / SUM over ints into f64)
+  int32_t pad;
+};
+
+enum EmitKind : int32_t { EMIT_RAW = 0, EMIT_AVG = 1 };
+struct EmitDesc {
+  int32_t kind;
+  int32_t a0, a1;     // accumulator indices (AVG: a0 = count, a1 = sum)
+  int32_t out_dtype;
+  void* dst;
+};
+
+__host__ __device__ __forceinline__ unsigned long long acc_identity(int op) {
+  switch (op) {
+    case ACC_MIN_I: return 0x7fffffffffffffffull;
+    case ACC_MAX_I: return 0x8000000000000000ull;
+    case ACC_MIN_U: return ~0ull;
+    case ACC_MIN_F: return 0x7ff0000000000000ull;  // +inf
+    case ACC_MAX_F: return 0xfff0000000000000ull;  // -inf
+    default: return 0ull;                          // COUNT / ADD_I / ADD_F (0.0) / MAX_U
+  }
+}
+
+// The operation that merges two partial states of accumulator `op`.
+__host__ __device__ __forceinline__ int acc_merge_op(int op) { return op == ACC_COUNT ? ACC_ADD_I : op; }
+
+__device__ __forceinline__ void atomic_minmax_f64(unsigned long long* p, double v, bool is_min) {
+  unsigned long long old = *p;
+  while (true) {
+    double cur = __longlong_as_double((long long)old);
+    if (is_min ? !(v < cur) : !(v > cur)) break;
+    unsigned long long prev = atomicCAS(p, old, (unsigned long long)__double_as_longlong(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+// Atomic accumulate into a (shared or global) 64-bit state word.
+__device__ __forceinline__ void acc_apply(unsigned long long* p, int op, Val v) {
+  switch (op) {
+    case ACC_COUNT: atomicAdd(p, 1ull); break;
+    case ACC_ADD_I: atomicAdd(p, v.u); break;
+    case ACC_ADD_F: atomicAdd(reinterpret_cast<double*>(p), v.d); break;
+    case ACC_MIN_I: atomicMin(reinterpret_cast<long long*>(p), (long long)v.i); break;
+    case ACC_MAX_I: atomicMax(reinterpret_cast<long long*>(p), (long long)v.i); break;
+    case ACC_MIN_U: atomicMin(p, (unsigned long long)v.u); break;
+    case ACC_MAX_U: atomicMax(p, (unsigned long long)v.u); break;
+    case ACC_MIN_F: atomic_minmax_f64(p, v.d, true); break;
+    default: atomic_minmax_f64(p, v.d, false); break;
+  }
+}
+
+// Non-atomic combine (register accumulators of the no-group kernel).
+__device__ __forceinline__ Val acc_combine(int op, Val a, Val b) {
+  Val r = a;
+  switch (op) {
+    case ACC_COUNT: r.u = a.u + 1; break;
+    case ACC_ADD_I: r.u = a.u + b.u; break;
+    case ACC_ADD_F: r.d = a.d + b.d; break;
+    case ACC_MIN_I: r.i = b.i < a.i ? b.i : a.i; break;
+    case ACC_MAX_I: r.i = b.i > a.i ? b.i : a.i; break;
+    case ACC_MIN_U: r.u = b.u < a.u ? b.u : a.u; break;
+    case ACC_MAX_U: r.u = b.u > a.u ? b.u : a.u; break;
+    case ACC_MIN_F: r.d = b.d < a.d ? b.d : a.d; break;
+    default: r.d = b.d > a.d ? b.d : a.d; break;
+  }
+  return r;
+}
+
+__device__ __forceinline__ Val load_acc_input(const AccDesc& d, const ColRef* cols, int64_t row) {
+  Val v;
+  v.u = 0;
+  if (d.col >= 0) {
+    v = load_val(cols[d.col], row);
+    if (d.cvt == CVT_I2F) v.d = __ll2double_rn(v.i);
+    else if (d.cvt == CVT_U2F) v.d = __ull2double_rn(v.u);
+  }
+  return v;
+}
+
+__device__ __forceinline__ unsigned hash_key(unsigned long long k) { return unsigned(fmix64(k) >> 20); }
+
+// ================================================================================================
+// level 1: CTA-local pre-aggregation in shared memory
+// ================================================================================================
+constexpr int AL_THREADS = 256;
+constexpr int AL_UNROLL = 4;
+constexpr int AL_SLOTS = 4096;  // >= 4 * AL_THREADS * AL_UNROLL so a 3/4-full table absorbs one iteration
+
+struct AggLocalArgs {
+  int64_t n_rows;
+  KeyPack keys;
+  int32_t n_acc;
+  int32_t pad;
+  AccDesc acc[MAX_ACC];
+  ColRef cols[MAX_IN_COLS];
+  unsigned long long* part_keys;    // [part_capacity]
+  unsigned long long* part_acc;     // [n_acc][part_capacity]
+  int64_t part_capacity;
+  unsigned long long* part_cursor;  // number of partial entries written so far
+};
+
+__device__ __forceinline__ void local_flush(const AggLocalArgs& a, unsigned long long* s_keys, unsigned long long* s_acc, unsigned* s_warp,
+                                            unsigned long long* s_base, unsigned* s_occ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PER = AL_SLOTS / AL_THREADS;
+  // thread owns slots [tid * PER, tid * PER + PER)
+  unsigned cnt = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) cnt += s_keys[tid * PER + j] != EMPTY_KEY;
+  unsigned incl = warp_inclusive_sum(cnt);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  unsigned warp_base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < AL_THREADS / 32; ++w) {
+    unsigned v = s_warp[w];
+    if (w < warp) warp_base += v;
+    total += v;
+  }
+  if (tid == 0) *s_base = total ? atomicAdd(a.part_cursor, (unsigned long long)total) : 0ull;
+  __syncthreads();
+  unsigned long long pos = *s_base + warp_base + (incl - cnt);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int slot = tid * PER + j;
+    const unsigned long long k = s_keys[slot];
+    if (k != EMPTY_KEY) {
+      a.part_keys[pos] = k;
+      for (int c = 0; c < a.n_acc; ++c) {
+        a.part_acc[int64_t(c) * a.part_capacity + pos] = s_acc[c * AL_SLOTS + slot];
+        s_acc[c * AL_SLOTS + slot] = acc_identity(a.acc[c].op);
+      }
+      s_keys[slot] = EMPTY_KEY;
+      ++pos;
+    }
+  }
+  if (tid == 0) *s_occ = 0;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(AL_THREADS) agg_local_kernel(const __grid_constant__ AggLocalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned long long* s_acc = s_keys + AL_SLOTS;  // [n_acc][AL_SLOTS]
+  __shared__ unsigned s_warp[AL_THREADS / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned s_occ;
+  const int tid = threadIdx.x;
+
+  for (int s = tid; s < AL_SLOTS; s += AL_THREADS) {
+    s_keys[s] = EMPTY_KEY;
+    for (int c = 0; c < a.n_acc; ++c) s_acc[c * AL_SLOTS + s] = acc_identity(a.acc[c].op);
+  }
+  if (tid == 0) s_occ = 0;
+  __syncthreads();
+
+  constexpr int STEP = AL_THREADS * AL_UNROLL;
+  int64_t per_cta = (a.n_rows + gridDim.x - 1) / gridDim.x;
+  per_cta = (per_cta + STEP - 1) / STEP * STEP;
+  const int64_t begin = int64_t(blockIdx.x) * per_cta;
+  const int64_t end = begin + per_cta < a.n_rows ? begin + per_cta : a.n_rows;
+
+  for (int64_t base = begin; base < end; base += STEP) {
+    unsigned long long key[AL_UNROLL];
+    int64_t row[AL_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AL_UNROLL; ++u) {
+      row[u] = base + int64_t(u) * AL_THREADS + tid;
+      if (row[u] < end) key[u] = pack_key(a.keys, a.cols, row[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < AL_UNROLL; ++u) {
+      if (row[u] >= end) continue;
+      if (key[u] == EMPTY_KEY) {
+        // the one key value that collides with the empty marker bypasses the shared table
+        unsigned long long pos = atomicAdd(a.part_cursor, 1ull);
+        a.part_keys[pos] = key[u];
+        for (int c = 0; c < a.n_acc; ++c) {
+          Val v = load_acc_input(a.acc[c], a.cols, row[u]);
+          Val id;
+          id.u = acc_identity(a.acc[c].op);
+          a.part_acc[int64_t(c) * a.part_capacity + pos] = acc_combine(a.acc[c].op, id, v).u;
+        }
+        continue;
+      }
+      unsigned slot = hash_key(key[u]) & (AL_SLOTS - 1);
+      while (true) {
+        unsigned long long cur = s_keys[slot];
+        if (cur == key[u]) break;
+        if (cur == EMPTY_KEY) {
+          unsigned long long old = atomicCAS(&s_keys[slot], EMPTY_KEY, key[u]);
+          if (old == EMPTY_KEY) {
+            atomicAdd(&s_occ, 1u);
+            break;
+          }
+          if (old == key[u]) break;
+        }
+        slot = (slot + 1) & (AL_SLOTS - 1);
+      }
+      for (int c = 0; c < a.n_acc; ++c) acc_apply(&s_acc[c * AL_SLOTS + slot], a.acc[c].op, load_acc_input(a.acc[c], a.cols, row[u]));
+    }
+    __syncthreads();
+    if (s_occ > AL_SLOTS * 3 / 4 - STEP) local_flush(a, s_keys, s_acc, s_warp, &s_base, &s_occ);
+  }
+  local_flush(a, s_keys, s_acc, s_warp, &s_base, &s_occ);
+}
+
+// ================================================================================================
+// level 2: global table (packed 64-bit keys)
+// ================================================================================================
+struct AggTable {
+  unsigned long long* keys;  // [cap + 1]; slot `cap` is reserved for the key equal to EMPTY_KEY
+  unsigned long long* acc;   // [n_acc][cap + 1]
+  unsigned long long cap;    // power of two
+};
+
+__global__ void agg_init_kernel(AggTable t, int n_acc, unsigned long long ident0, unsigned long long ident1, unsigned long long ident2,
+                                unsigned long long ident3, unsigned long long ident4, unsigned long long ident5, unsigned long long ident6,
+                                unsigned long long ident7) {
+  const unsigned long long ident[MAX_ACC] = {ident0, ident1, ident2, ident3, ident4, ident5, ident6, ident7};
+  const unsigned long long n = t.cap + 1;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    t.keys[i] = EMPTY_KEY;
+    for (int c = 0; c < n_acc; ++c) t.acc[c * n + i] = ident[c];
+  }
+}
+
+struct AggInsertArgs {
+  int64_t n;  // rows or partial entries
+  KeyPack keys;
+  int32_t n_acc;
+  int32_t from_partials;
+  AccDesc acc[MAX_ACC];
+  ColRef cols[MAX_IN_COLS];
+  const unsigned long long* part_keys;
+  const unsigned long long* part_acc;
+  int64_t part_capacity;
+  AggTable table;
+};
+
+__device__ __forceinline__ unsigned long long table_find_or_insert(const AggTable& t, unsigned long long key) {
+  if (key == EMPTY_KEY) {
+    t.keys[t.cap] = 0;  // marks the reserved slot occupied (idempotent plain store)
+    return t.cap;
+  }
+  unsigned long long slot = fmix64(key) & (t.cap - 1);
+  while (true) {
+    unsigned long long cur = t.keys[slot];
+    if (cur == key) return slot;
+    if (cur == EMPTY_KEY) {
+      unsigned long long old = atomicCAS(&t.keys[slot], EMPTY_KEY, key);
+      if (old == EMPTY_KEY || old == key) return slot;
+    }
+    slot = (slot + 1) & (t.cap - 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) agg_insert_kernel(const __grid_constant__ AggInsertArgs a) {
+  const unsigned long long stride_n = a.table.cap + 1;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < a.n; i += int64_t(gridDim.x) * blockDim.x) {
+    const unsigned long long key = a.from_partials ? a.part_keys[i] : pack_key(a.keys, a.cols, i);
+    const unsigned long long slot = table_find_or_insert(a.table, key);
+    for (int c = 0; c < a.n_acc; ++c) {
+      Val v;
+      int op;
+      if (a.from_partials) {
+        v.u = a.part_acc[int64_t(c) * a.part_capacity + i];
+        op = acc_merge_op(a.acc[c].op);
+      } else {
+        v = load_acc_input(a.acc[c], a.cols, i);
+        op = a.acc[c].op;
+      }
+      acc_apply(&a.table.acc[c * stride_n + slot], op, v);
+    }
+  }
+}
+
+// ================================================================================================
+// row-representative table (Utf8 / wide keys)
+// ================================================================================================
+struct AggRowsArgs {
+  int64_t n_rows;
+  RowKeys keys;
+  int32_t n_acc;
+  AccDesc acc[MAX_ACC];
+  ColRef cols[MAX_IN_COLS];
+  unsigned* owner;          // [cap]
+  unsigned long long* tacc; // [n_acc][cap]
+  unsigned long long cap;
+};
+
+__global__ void agg_rows_init_kernel(unsigned* owner, unsigned long long* tacc, unsigned long long cap, int n_acc, unsigned long long ident0,
+                                     unsigned long long ident1, unsigned long long ident2, unsigned long long ident3, unsigned long long ident4,
+                                     unsigned long long ident5, unsigned long long ident6, unsigned long long ident7) {
+  const unsigned long long ident[MAX_ACC] = {ident0, ident1, ident2, ident3, ident4, ident5, ident6, ident7};
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+    owner[i] = EMPTY_OWNER;
+    for (int c = 0; c < n_acc; ++c) tacc[c * cap + i] = ident[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) agg_insert_rows_kernel(const __grid_constant__ AggRowsArgs a) {
+  for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+    unsigned long long slot = hash_row(a.keys, a.cols, row) & (a.cap - 1);
+    while (true) {
+      unsigned cur = a.owner[slot];
+      if (cur == EMPTY_OWNER) {
+        cur = atomicCAS(&a.owner[slot], EMPTY_OWNER, unsigned(row));
+        if (cur == EMPTY_OWNER) break;  // we own the slot: `row` is the group's representative
+      }
+      if (rows_equal(a.keys, a.cols, int64_t(cur), a.keys, a.cols, row)) break;
+      slot = (slot + 1) & (a.cap - 1);
+    }
+    for (int c = 0; c < a.n_acc; ++c) acc_apply(&a.tacc[c * a.cap + slot], a.acc[c].op, load_acc_input(a.acc[c], a.cols, row));
+  }
+}
+
+// ================================================================================================
+// emit: compaction of the occupied slots
+// ================================================================================================
+struct AggEmitArgs {
+  CompactScratch sc;
+  unsigned long long n_slots;       // slots to scan (cap + 1 packed, cap rows mode)
+  const unsigned long long* keys;   // packed mode (NULL in rows mode)
+  const unsigned* owner;            // rows mode
+  const unsigned long long* acc;    // [n_acc][n_slots]
+  int32_t n_emit;
+  int32_t n_key_out;                // packed mode: 1 or 2 key columns
+  int32_t key_width[2];
+  void* key_dst[2];
+  unsigned* rep_rows;               // rows mode: representative row per group
+  EmitDesc emit[2 * MAX_ACC];
+};
+
+__device__ __forceinline__ void emit_values(const EmitDesc* emit, int n_emit, const unsigned long long* acc, unsigned long long stride,
+                                            unsigned long long slot, int64_t pos) {
+  for (int e = 0; e < n_emit; ++e) {
+    const EmitDesc& d = emit[e];
+    Val v;
+    v.u = acc[d.a0 * stride + slot];
+    if (d.kind == EMIT_AVG) {
+      Val s;
+      s.u = acc[d.a1 * stride + slot];
+      v.d = __ddiv_rn(s.d, __ull2double_rn(v.u));
+    }
+    store_val(d.dst, d.out_dtype, pos, v);
+  }
+}
+
+__global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_constant__ AggEmitArgs a) {
+  constexpr int E = 1;
+  __shared__ CompactSmem<E> sm;
+  const int tid = threadIdx.x;
+  for (long long tile = cp_next_tile(sm, a.sc); tile >= 0; tile = cp_next_tile(sm, a.sc)) {
+    const unsigned long long tile_base = (unsigned long long)tile * CP_TILE;
+    unsigned bits = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) {
+      unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
+      bool occ = false;
+      if (slot < a.n_slots) occ = a.keys ? a.keys[slot] != EMPTY_KEY : a.owner[slot] != EMPTY_OWNER;
+      bits |= unsigned(occ) << k;
+    }
+    unsigned lane_prefix[CP_ITEMS / E];
+    cp_rank_tile<E>(sm, a.sc, tile, bits, lane_prefix);
+    if (bits && sm.tile_total) {
+      unsigned m = bits;
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t pos = cp_position<E>(sm, bits, k, lane_prefix);
+        const unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
+        if (a.keys) {
+          unsigned long long key = slot == a.n_slots - 1 ? EMPTY_KEY : a.keys[slot];
+          if (a.n_key_out == 2) {
+            static_cast<uint32_t*>(a.key_dst[0])[pos] = uint32_t(key >> 32);
+            static_cast<uint32_t*>(a.key_dst[1])[pos] = uint32_t(key);
+          } else if (a.key_width[0] == 4) {
+            static_cast<uint32_t*>(a.key_dst[0])[pos] = uint32_t(key);
+          } else {
+            static_cast<unsigned long long*>(a.key_dst[0])[pos] = key;
+          }
+        } else {
+          a.rep_rows[pos] = a.owner[slot];
+        }
+        emit_values(a.emit, a.n_emit, a.acc, a.n_slots, slot, pos);
+      }
+    }
+    __syncthreads();
+  }
+  cp_finish(sm, a.sc);
+}
+
+// ================================================================================================
+// no group columns: one global accumulator row
+// ================================================================================================
+struct AggGlobalArgs {
+  int64_t n_rows;
+  int32_t n_acc;
+  int32_t pad;
+  AccDesc acc[MAX_ACC];
+  ColRef cols[MAX_IN_COLS];
+  unsigned long long* state;  // [n_acc], pre-initialised to the identities
+};
+
+__global__ void __launch_bounds__(256) agg_global_kernel(const __grid_constant__ AggGlobalArgs a) {
+  Val local[MAX_ACC];
+#pragma unroll
+  for (int c = 0; c < MAX_ACC; ++c) local[c].u = c < a.n_acc ? acc_identity(a.acc[c].op) : 0ull;
+  for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < MAX_ACC; ++c)
+      if (c < a.n_acc) local[c] = acc_combine(a.acc[c].op, local[c], load_acc_input(a.acc[c], a.cols, row));
+  }
+#pragma unroll
+  for (int c = 0; c < MAX_ACC; ++c) {
+    if (c >= a.n_acc) break;
+    const int mop = acc_merge_op(a.acc[c].op);
+    Val v = local[c];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      Val o;
+      o.u = __shfl_xor_sync(FULL_MASK, v.u, d);
+      v = acc_combine(mop, v, o);
+    }
+    if ((threadIdx.x & 31) == 0) acc_apply(&a.state[c], mop, v);
+  }
+}
+
+struct AggEmitOneArgs {
+  const unsigned long long* state;
+  int32_t n_emit;
+  EmitDesc emit[2 * MAX_ACC];
+};
+__global__ void agg_emit_one_kernel(const __grid_constant__ AggEmitOneArgs a) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) emit_values(a.emit, a.n_emit, a.state, 1, 0, 0);
+}
+
+// ================================================================================================
+// host
+// ================================================================================================
+namespace {
+
+bool is_unsigned_dt(int dt) { return dt == FLOCKGPU_UINT32 || dt == FLOCKGPU_UINT64; }
+bool is_signed_dt(int dt) { return dt == FLOCKGPU_INT32 || dt == FLOCKGPU_INT64 || dt == FLOCKGPU_TIMESTAMP; }
+
+struct OutPlan {
+  std::string name;
+  int dtype;
+  std::string format;
+  int kind, a0, a1;
+};
+
+const char* func_name(int f) {
+  switch (f) {
+    case FLOCKGPU_AGG_COUNT: return "COUNT";
+    case FLOCKGPU_AGG_SUM: return "SUM";
+    case FLOCKGPU_AGG_MIN: return "MIN";
+    case FLOCKGPU_AGG_MAX: return "MAX";
+    default: return "AVG";
+  }
+}
+
+int minmax_op(int dtype, bool is_min, const char* what) {
+  if (dtype == FLOCKGPU_FLOAT64) return is_min ? ACC_MIN_F : ACC_MAX_F;
+  if (is_unsigned_dt(dtype)) return is_min ? ACC_MIN_U : ACC_MAX_U;
+  if (is_signed_dt(dtype)) return is_min ? ACC_MIN_I : ACC_MAX_I;
+  fail(FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: %s over %s", what, dtype_name(dtype));
+}
+
+// Translates (mode, aggregate list) into accumulators + output columns.
+void plan_aggregates(const Table& in, int mode, const std::vector<AggSpec>& aggs, std::vector<AccDesc>* accs, std::vector<OutPlan>* outs) {
+  const bool from_states = mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED;
+  const bool partial_out = mode == FLOCKGPU_AGG_PARTIAL;
+  auto add_acc = [&](int op, int col, int cvt) {
+    FG_CHECK(accs->size() < size_t(MAX_ACC), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: more than %d accumulators", MAX_ACC);
+    accs->push_back(AccDesc{op, col, cvt, 0});
+    return int(accs->size()) - 1;
+  };
+  auto col_dtype = [&](int col, const char* what) {
+    FG_CHECK(col >= 0 && col < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_aggregate: %s column %d out of range", what, col);
+    FG_CHECK(!in.cols[col].all_null, FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: NULL input column");
+    return in.cols[col].dtype;
+  };
+  for (const AggSpec& s : aggs) {
+    const std::string base = s.name.empty() ? std::string(func_name(s.func)) : s.name;
+    switch (s.func) {
+      case FLOCKGPU_AGG_COUNT: {
+        int a;
+        if (from_states) {
+          FG_CHECK(col_dtype(s.col, "COUNT state") == FLOCKGPU_UINT64, FLOCKGPU_ERR_INVALID, "hash_aggregate: COUNT state must be UInt64");
+          a = add_acc(ACC_ADD_I, s.col, CVT_NONE);
+        } else {
+          if (s.col >= 0) col_dtype(s.col, "COUNT");
+          a = add_acc(ACC_COUNT, -1, CVT_NONE);
+        }
+        outs->push_back({partial_out ? base + "[count]" : base, FLOCKGPU_UINT64, "L", EMIT_RAW, a, 0});
+        break;
+      }
+      case FLOCKGPU_AGG_SUM: {
+        int dt = col_dtype(s.col, "SUM");
+        int out_dt, op;
+        if (dt == FLOCKGPU_FLOAT64) { out_dt = FLOCKGPU_FLOAT64; op = ACC_ADD_F; }
+        else if (is_unsigned_dt(dt)) { out_dt = FLOCKGPU_UINT64; op = ACC_ADD_I; }
+        else if (dt == FLOCKGPU_INT32 || dt == FLOCKGPU_INT64) { out_dt = FLOCKGPU_INT64; op = ACC_ADD_I; }
+        else fail(FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: SUM over %s", dtype_name(dt));
+        int a = add_acc(op, s.col, CVT_NONE);
+        outs->push_back({partial_out ? base + "[sum]" : base, out_dt, default_format(out_dt), EMIT_RAW, a, 0});
+        break;
+      }
+      case FLOCKGPU_AGG_MIN:
+      case FLOCKGPU_AGG_MAX: {
+        bool is_min = s.func == FLOCKGPU_AGG_MIN;
+        int dt = col_dtype(s.col, is_min ? "MIN" : "MAX");
+        int a = add_acc(minmax_op(dt, is_min, is_min ? "MIN" : "MAX"), s.col, CVT_NONE);
+        outs->push_back({partial_out ? base + (is_min ? "[min]" : "[max]") : base, dt, in.cols[s.col].format, EMIT_RAW, a, 0});
+        break;
+      }
+      case FLOCKGPU_AGG_AVG: {
+        int a_cnt, a_sum;
+        if (from_states) {
+          FG_CHECK(col_dtype(s.col, "AVG count state") == FLOCKGPU_UINT64 && col_dtype(s.col + 1, "AVG sum state") == FLOCKGPU_FLOAT64,
+                   FLOCKGPU_ERR_INVALID, "hash_aggregate: AVG states must be (UInt64 count, Float64 sum)");
+          a_cnt = add_acc(ACC_ADD_I, s.col, CVT_NONE);
+          a_sum = add_acc(ACC_ADD_F, s.col + 1, CVT_NONE);
+        } else {
+          int dt = col_dtype(s.col, "AVG");
+          FG_CHECK(dt != FLOCKGPU_UTF8 && dt != FLOCKGPU_TIMESTAMP, FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: AVG over %s", dtype_name(dt));
+          a_cnt = add_acc(ACC_COUNT, -1, CVT_NONE);
+          a_sum = add_acc(ACC_ADD_F, s.col, dt == FLOCKGPU_FLOAT64 ? CVT_NONE : (is_unsigned_dt(dt) ? CVT_U2F : CVT_I2F));
+        }
+        if (partial_out) {
+          outs->push_back({base + "[count]", FLOCKGPU_UINT64, "L", EMIT_RAW, a_cnt, 0});
+          outs->push_back({base + "[sum]", FLOCKGPU_FLOAT64, "g", EMIT_RAW, a_sum, 0});
+        } else {
+          outs->push_back({base, FLOCKGPU_FLOAT64, "g", EMIT_AVG, a_cnt, a_sum});
+        }
+        break;
+      }
+      default:
+        fail(FLOCKGPU_ERR_INVALID, "hash_aggregate: unknown aggregate function %d", s.func);
+    }
+  }
+}
+
+void fill_cols(const Table& t, ColRef* refs) {
+  FG_CHECK(t.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: more than %d input columns", MAX_IN_COLS);
+  for (size_t i = 0; i < t.cols.size(); ++i) {
+    refs[i].data = t.cols[i].values();
+    refs[i].offsets = t.cols[i].offs();
+    refs[i].dtype = t.cols[i].dtype;
+    refs[i].pad = 0;
+  }
+}
+
+int grid_for(const CtxPtr& ctx, int64_t items, int threads, int per_sm) {
+  return int(std::max<int64_t>(1, std::min<int64_t>((items + threads - 1) / threads, int64_t(ctx->sm_count) * per_sm)));
+}
+
+unsigned long long pow2_at_least(unsigned long long n) {
+  unsigned long long c = 1024;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+}  // namespace
+
+TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs) {
+  const Table& in = *in_ptr;
+  FG_CHECK(mode >= FLOCKGPU_AGG_PARTIAL && mode <= FLOCKGPU_AGG_SINGLE, FLOCKGPU_ERR_INVALID, "hash_aggregate: bad mode %d", mode);
+  for (int g : group_cols) {
+    FG_CHECK(g >= 0 && g < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_aggregate: group column %d out of range", g);
+    FG_CHECK(!in.cols[g].all_null, FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: NULL group column");
+  }
+  std::vector<AccDesc> accs;
+  std::vector<OutPlan> outs;
+  plan_aggregates(in, mode, aggs, &accs, &outs);
+  const int n_acc = int(accs.size());
+  const int64_t n = in.num_rows;
+
+  auto out = std::make_shared<Table>();
+  out->ctx = ctx;
+  out->metadata = in.metadata;
+
+  auto make_out_col = [&](const OutPlan& p, int64_t rows) {
+    Column c;
+    c.name = p.name;
+    c.dtype = p.dtype;
+    c.format = p.format;
+    c.nullable = true;  // aggregate outputs are nullable in the reference schema (aggregate.json)
+    c.length = rows;
+    c.data = alloc(ctx, size_t(rows) * dtype_width(p.dtype));
+    return c;
+  };
+  auto fill_emit = [&](EmitDesc* emit, int* n_emit, std::vector<Column>& cols) {
+    FG_CHECK(outs.size() <= size_t(2 * MAX_ACC), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: too many output columns");
+    *n_emit = int(outs.size());
+    for (size_t i = 0; i < outs.size(); ++i) emit[i] = EmitDesc{outs[i].kind, outs[i].a0, outs[i].a1, outs[i].dtype, cols[i].data->ptr};
+  };
+  unsigned long long ident[MAX_ACC] = {};
+  for (int c = 0; c < n_acc; ++c) ident[c] = acc_identity(accs[c].op);
+
+  // ------------------------------------------------------------------ no group columns
+  if (group_cols.empty()) {
+    out->num_rows = 1;
+    std::vector<Column> cols;
+    for (const OutPlan& p : outs) cols.push_back(make_out_col(p, 1));
+    BufferPtr state = alloc(ctx, sizeof(unsigned long long) * MAX_ACC);
+    FG_CUDA(cudaMemcpyAsync(state->ptr, ident, sizeof ident, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+      AggGlobalArgs ga{};
+      ga.n_rows = n;
+      ga.n_acc = n_acc;
+      for (int c = 0; c < n_acc; ++c) ga.acc[c] = accs[c];
+      fill_cols(in, ga.cols);
+      ga.state = state->as<unsigned long long>();
+      agg_global_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ga);
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    }
+    AggEmitOneArgs ea{};
+    ea.state = state->as<unsigned long long>();
+    fill_emit(ea.emit, &ea.n_emit, cols);
+    agg_emit_one_kernel<<<1, 32, 0, ctx->stream>>>(ea);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    // aggregates other than COUNT over zero rows are NULL
+    bool from_states = mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED;
+    if (n == 0 && !from_states)
+      for (size_t i = 0; i < cols.size(); ++i)
+        if (accs[outs[i].a0].op != ACC_COUNT || outs[i].kind == EMIT_AVG) cols[i].all_null = true;
+    out->cols = std::move(cols);
+    // keep `state` alive until the kernels have run: stream-ordered free does that
+    return out;
+  }
+
+  // ------------------------------------------------------------------ empty input: empty output
+  auto key_out_col = [&](int g, int64_t rows) {
+    Column c;
+    c.name = in.cols[g].name;
+    c.dtype = in.cols[g].dtype;
+    c.format = in.cols[g].format;
+    c.nullable = in.cols[g].nullable;
+    c.length = rows;
+    return c;
+  };
+  if (n == 0) {
+    out->num_rows = 0;
+    for (int g : group_cols) {
+      Column c = key_out_col(g, 0);
+      c.data = alloc(ctx, 0);
+      if (c.dtype == FLOCKGPU_UTF8) {
+        c.offsets = alloc(ctx, 4);
+        FG_CUDA(cudaMemsetAsync(c.offsets->ptr, 0, 4, ctx->stream));
+      }
+      out->cols.push_back(std::move(c));
+    }
+    for (const OutPlan& p : outs) out->cols.push_back(make_out_col(p, 0));
+    return out;
+  }
+
+  // ------------------------------------------------------------------ choose key representation
+  bool packed = group_cols.size() <= 2;
+  int key_bytes = 0;
+  for (int g : group_cols) {
+    int w = in.cols[g].width();
+    if (w == 0) packed = false;
+    key_bytes += w;
+  }
+  if (group_cols.size() == 2 && key_bytes != 8) packed = false;
+  if (key_bytes > 8) packed = false;
+
+  AggEmitArgs ea{};
+  BufferPtr tkeys, tacc, towner, rep_rows;
+  unsigned long long n_slots = 0;
+
+  if (packed) {
+    KeyPack kp{};
+    kp.n = int(group_cols.size());
+    for (int i = 0; i < kp.n; ++i) {
+      kp.col[i] = group_cols[i];
+      kp.width[i] = in.cols[group_cols[i]].width();
+    }
+    // ---- level 1 (large inputs): CTA-local pre-aggregation into partials
+    BufferPtr pkeys, pacc;
+    int64_t n_entries = n;
+    bool from_partials = false;
+    const size_t local_smem = size_t(AL_SLOTS) * 8 * (1 + n_acc);
+    if (n >= (int64_t(1) << 18) && local_smem <= 200 * 1024) {
+      AggLocalArgs la{};
+      la.n_rows = n;
+      la.keys = kp;
+      la.n_acc = n_acc;
+      for (int c = 0; c < n_acc; ++c) la.acc[c] = accs[c];
+      fill_cols(in, la.cols);
+      pkeys = alloc(ctx, size_t(n) * 8);
+      pacc = alloc(ctx, size_t(n) * 8 * std::max(n_acc, 1));
+      la.part_keys = pkeys->as<unsigned long long>();
+      la.part_acc = pacc->as<unsigned long long>();
+      la.part_capacity = n;
+      la.part_cursor = ctx->d_scalars + 2;
+      FG_CUDA(cudaMemsetAsync(la.part_cursor, 0, 8, ctx->stream));
+      FG_CUDA(cudaFuncSetAttribute(agg_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(local_smem)));
+      int per_sm = 1;
+      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_local_kernel, AL_THREADS, local_smem));
+      int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + AL_THREADS * AL_UNROLL - 1) / (AL_THREADS * AL_UNROLL))));
+      agg_local_kernel<<<grid, AL_THREADS, local_smem, ctx->stream>>>(la);
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+      unsigned long long cnt = 0;
+      read_scalars(ctx, 2, 1, &cnt);
+      FG_CHECK(int64_t(cnt) <= n, FLOCKGPU_ERR_CUDA, "hash_aggregate: corrupt partial count");
+      n_entries = int64_t(cnt);
+      from_partials = true;
+    }
+    // ---- level 2: global table
+    const unsigned long long cap = pow2_at_least(2ull * (unsigned long long)n_entries);
+    n_slots = cap + 1;
+    tkeys = alloc(ctx, size_t(n_slots) * 8);
+    tacc = alloc(ctx, size_t(n_slots) * 8 * std::max(n_acc, 1));
+    AggTable tab{tkeys->as<unsigned long long>(), tacc->as<unsigned long long>(), cap};
+    agg_init_kernel<<<grid_for(ctx, int64_t(n_slots), 256, 8), 256, 0, ctx->stream>>>(tab, n_acc, ident[0], ident[1], ident[2], ident[3], ident[4],
+                                                                                       ident[5], ident[6], ident[7]);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    AggInsertArgs ia{};
+    ia.n = n_entries;
+    ia.keys = kp;
+    ia.n_acc = n_acc;
+    ia.from_partials = from_partials ? 1 : 0;
+    for (int c = 0; c < n_acc; ++c) ia.acc[c] = accs[c];
+    fill_cols(in, ia.cols);
+    ia.part_keys = pkeys ? pkeys->as<unsigned long long>() : nullptr;
+    ia.part_acc = pacc ? pacc->as<unsigned long long>() : nullptr;
+    ia.part_capacity = n;
+    ia.table = tab;
+    if (n_entries > 0) {
+      agg_insert_kernel<<<grid_for(ctx, n_entries, 256, 8), 256, 0, ctx->stream>>>(ia);
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    }
+    ea.keys = tab.keys;
+    ea.acc = tab.acc;
+    ea.n_key_out = kp.n;
+    ea.key_width[0] = kp.width[0];
+    ea.key_width[1] = kp.width[1];
+  } else {
+    FG_CHECK(group_cols.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: more than %d group columns", MAX_KEY_COLS);
+    const unsigned long long cap = pow2_at_least(2ull * (unsigned long long)n);
+    n_slots = cap;
+    towner = alloc(ctx, size_t(cap) * 4);
+    tacc = alloc(ctx, size_t(cap) * 8 * std::max(n_acc, 1));
+    agg_rows_init_kernel<<<grid_for(ctx, int64_t(cap), 256, 8), 256, 0, ctx->stream>>>(towner->as<unsigned>(), tacc->as<unsigned long long>(), cap, n_acc,
+                                                                                       ident[0], ident[1], ident[2], ident[3], ident[4], ident[5],
+                                                                                       ident[6], ident[7]);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    AggRowsArgs ra{};
+    ra.n_rows = n;
+    ra.keys.n = int(group_cols.size());
+    for (size_t i = 0; i < group_cols.size(); ++i) ra.keys.col[i] = group_cols[i];
+    ra.n_acc = n_acc;
+    for (int c = 0; c < n_acc; ++c) ra.acc[c] = accs[c];
+    fill_cols(in, ra.cols);
+    ra.owner = towner->as<unsigned>();
+    ra.tacc = tacc->as<unsigned long long>();
+    ra.cap = cap;
+    agg_insert_rows_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ra);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    ea.owner = towner->as<unsigned>();
+    ea.acc = tacc->as<unsigned long long>();
+    rep_rows = alloc(ctx, size_t(std::min<unsigned long long>(cap, (unsigned long long)n)) * 4);
+    ea.rep_rows = rep_rows->as<unsigned>();
+  }
+
+  // ---- emit (worst case: every input row is its own group)
+  const int64_t max_groups = n;
+  std::vector<Column> key_cols, val_cols;
+  if (packed) {
+    for (size_t i = 0; i < group_cols.size(); ++i) {
+      Column c = key_out_col(group_cols[i], 0);
+      c.data = alloc(ctx, size_t(max_groups) * c.width());
+      ea.key_dst[i] = c.data->ptr;
+      key_cols.push_back(std::move(c));
+    }
+  }
+  for (const OutPlan& p : outs) val_cols.push_back(make_out_col(p, max_groups));
+  fill_emit(ea.emit, &ea.n_emit, val_cols);
+  ea.n_slots = n_slots;
+  ea.sc.num_tiles = (long long)((n_slots + CP_TILE - 1) / CP_TILE);
+  ensure_scan_scratch(ctx, ea.sc.num_tiles);
+  ea.sc.tile_state = ctx->scan.tile_state;
+  ea.sc.counters = ctx->scan.counters;
+  ea.sc.out_count = ctx->d_scalars + 3;
+  {
+    int per_sm = 1;
+    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_emit_kernel, CP_THREADS, 0));
+    int grid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), ea.sc.num_tiles)));
+    agg_emit_kernel<<<grid, CP_THREADS, 0, ctx->stream>>>(ea);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
+  unsigned long long n_groups = 0;
+  read_scalars(ctx, 3, 1, &n_groups);
+  FG_CHECK(int64_t(n_groups) <= n, FLOCKGPU_ERR_CUDA, "hash_aggregate: corrupt group count %llu", n_groups);
+  out->num_rows = int64_t(n_groups);
+  if (packed) {
+    for (Column& c : key_cols) {
+      c.length = int64_t(n_groups);
+      out->cols.push_back(std::move(c));
+    }
+  } else {
+    for (int g : group_cols) out->cols.push_back(gather_column(ctx, in.cols[g], rep_rows->as<uint32_t>(), int64_t(n_groups)));
+  }
+  for (Column& c : val_cols) {
+    c.length = int64_t(n_groups);
+    out->cols.push_back(std::move(c));
+  }
+  return out;
+}
+
+}  // namespace fg
+
+// ================================================================================================
+using namespace fg;
+
+extern "C" int flockgpu_hash_aggregate(flockgpu_ctx* ctx, const flockgpu_table* in, int32_t mode, const int32_t* group_cols, int32_t n_group_cols,
+                                       const flockgpu_agg_spec* aggs, int32_t n_aggs, flockgpu_table** out) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(out && in && in->table, FLOCKGPU_ERR_INVALID, "hash_aggregate: null argument");
+    FG_CHECK(n_group_cols >= 0 && n_aggs >= 0 && (n_group_cols == 0 || group_cols) && (n_aggs == 0 || aggs), FLOCKGPU_ERR_INVALID,
+             "hash_aggregate: bad column lists");
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    FG_CUDA(cudaSetDevice(c->device));
+    std::vector<int> gc(group_cols, group_cols + n_group_cols);
+    std::vector<AggSpec> as;
+    for (int i = 0; i < n_aggs; ++i) as.push_back(AggSpec{aggs[i].func, aggs[i].col, aggs[i].name ? aggs[i].name : ""});
+    *out = wrap_table(hash_aggregate(c, in->table, mode, gc, as));
+  });
+}

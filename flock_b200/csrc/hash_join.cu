@@ -1,0 +1,311 @@
+// hash_join.cu -- K3/K4: HashJoinExec { mode: Partitioned, join_type: Inner }.
+//
+// Reference operator (DataFusion fork, not in tree; used at flock/src/distributed_plan/planner.rs:169,
+// :239 and serialised in flock/src/tests/data/plan/join.json): build a hash map over ALL left batches
+// (hash -> row indices), then for every right batch emit (left_idx, right_idx) for each pair of equal
+// keys and materialise `take(left columns) ++ take(right columns)`.  NULL keys never match (no NULLs on
+// this path); duplicate keys on both sides give the full cross product.
+//
+// GPU design: an open-addressing table of build ROW IDS (one slot per build row, duplicates simply
+// occupy further slots of the probe sequence), plus the 64-bit packed key next to it when the key
+// packs (rowkeys.cuh) so that a probe compares words without touching the build columns.
+//   join_build_kernel        CAS row ids into the table
+//   join_count_scan_kernel   per probe row: number of matches -> exclusive offsets (decoupled
+//                            look-back, single pass) and the total pair count
+//   join_emit_kernel         second walk (table lines are L2-hot) writes the (build, probe) index pairs
+// and gather.cu materialises the output columns (Utf8 included).
+#include <algorithm>
+
+#include "device_utils.cuh"
+#include "internal.h"
+#include "rowkeys.cuh"
+
+namespace fg {
+
+constexpr unsigned JOIN_EMPTY = ~0u;
+
+struct JoinSide {
+  int64_t n_rows;
+  int32_t packed;
+  int32_t pad;
+  KeyPack pack;
+  RowKeys rk;
+  ColRef cols[MAX_IN_COLS];
+};
+
+struct JoinTable {
+  unsigned* rows;            // [cap] build row ids, JOIN_EMPTY = free
+  unsigned long long* keys;  // [cap] packed keys (packed mode only)
+  unsigned long long cap;    // power of two
+};
+
+__device__ __forceinline__ unsigned long long side_hash(const JoinSide& s, int64_t row, unsigned long long* key) {
+  if (s.packed) {
+    *key = pack_key(s.pack, s.cols, row);
+    return fmix64(*key);
+  }
+  *key = 0;
+  return hash_row(s.rk, s.cols, row);
+}
+
+__global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__ JoinSide build, const JoinTable t) {
+  for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < build.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+    unsigned long long key;
+    unsigned long long slot = side_hash(build, row, &key) & (t.cap - 1);
+    while (atomicCAS(&t.rows[slot], JOIN_EMPTY, unsigned(row)) != JOIN_EMPTY) slot = (slot + 1) & (t.cap - 1);
+    if (build.packed) t.keys[slot] = key;
+  }
+}
+
+// Calls f(build_row) for every build row whose key equals the key of probe row `row`.
+template <class F>
+__device__ __forceinline__ void for_each_match(const JoinSide& build, const JoinSide& probe, const JoinTable& t, int64_t row, F&& f) {
+  unsigned long long key;
+  unsigned long long slot = side_hash(probe, row, &key) & (t.cap - 1);
+  while (true) {
+    const unsigned r = t.rows[slot];
+    if (r == JOIN_EMPTY) return;
+    const bool match = probe.packed ? (t.keys[slot] == key) : rows_equal(build.rk, build.cols, int64_t(r), probe.rk, probe.cols, row);
+    if (match) f(r);
+    slot = (slot + 1) & (t.cap - 1);
+  }
+}
+
+constexpr int JC_THREADS = 256;
+constexpr int JC_ITEMS = 4;
+constexpr int JC_TILE = JC_THREADS * JC_ITEMS;
+
+struct JoinCountArgs {
+  JoinSide build, probe;
+  JoinTable table;
+  unsigned* out_off;  // [probe rows + 1] exclusive pair offsets
+  int64_t num_tiles;
+  unsigned long long* tile_state;
+  unsigned int* counters;
+  unsigned long long* out_total;
+};
+
+__global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __grid_constant__ JoinCountArgs a) {
+  __shared__ unsigned long long s_warp[JC_THREADS / 32];
+  __shared__ long long s_tile;
+  __shared__ unsigned long long s_excl;
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = a.probe.n_rows;
+  while (true) {
+    if (tid == 0) s_tile = (long long)atomicAdd(a.counters, 1u);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= a.num_tiles) break;
+    const int64_t i0 = tile * JC_TILE + int64_t(tid) * JC_ITEMS;
+    unsigned cnt[JC_ITEMS];
+    unsigned long long local = 0;
+#pragma unroll
+    for (int k = 0; k < JC_ITEMS; ++k) {
+      unsigned c = 0;
+      if (i0 + k < n) for_each_match(a.build, a.probe, a.table, i0 + k, [&](unsigned) { ++c; });
+      cnt[k] = c;
+      local += c;
+    }
+    unsigned long long incl = warp_inclusive_sum(local);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < JC_THREADS / 32; ++w) {
+      unsigned long long v = s_warp[w];
+      if (w < warp) warp_base += v;
+      tile_total += v;
+    }
+    if (warp == 0) {
+      unsigned long long excl = 0;
+      if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(a.tile_state, LB_PREFIX | tile_total);
+      } else {
+        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PARTIAL | tile_total);
+        excl = lookback_exclusive_prefix(a.tile_state, tile);
+        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PREFIX | (excl + tile_total));
+      }
+      if (lane == 0) {
+        s_excl = excl;
+        if (tile == a.num_tiles - 1) {
+          *a.out_total = excl + tile_total;
+          a.out_off[n] = unsigned(excl + tile_total);
+        }
+      }
+    }
+    __syncthreads();
+    unsigned long long run = s_excl + warp_base + (incl - local);
+#pragma unroll
+    for (int k = 0; k < JC_ITEMS; ++k) {
+      if (i0 + k < n) a.out_off[i0 + k] = unsigned(run);
+      run += cnt[k];
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  if (tid == 0) s_last = (atomicAdd(a.counters + 1, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    for (int64_t i = tid; i < a.num_tiles; i += JC_THREADS) a.tile_state[i] = LB_INVALID;
+    if (tid == 0) {
+      a.counters[0] = 0;
+      a.counters[1] = 0;
+    }
+  }
+}
+
+struct JoinEmitArgs {
+  JoinSide build, probe;
+  JoinTable table;
+  const unsigned* off;
+  unsigned* build_idx;
+  unsigned* probe_idx;
+};
+
+__global__ void __launch_bounds__(256) join_emit_kernel(const __grid_constant__ JoinEmitArgs a) {
+  for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.probe.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+    unsigned pos = a.off[row];
+    if (a.off[row + 1] == pos) continue;
+    for_each_match(a.build, a.probe, a.table, row, [&](unsigned r) {
+      a.build_idx[pos] = r;
+      a.probe_idx[pos] = unsigned(row);
+      ++pos;
+    });
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static void fill_side(const Table& t, const std::vector<int>& keys, bool packed, JoinSide* s) {
+  FG_CHECK(t.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_join: more than %d columns on one side", MAX_IN_COLS);
+  s->n_rows = t.num_rows;
+  s->packed = packed ? 1 : 0;
+  for (size_t i = 0; i < t.cols.size(); ++i) {
+    s->cols[i].data = t.cols[i].values();
+    s->cols[i].offsets = t.cols[i].offs();
+    s->cols[i].dtype = t.cols[i].dtype;
+    s->cols[i].pad = 0;
+  }
+  s->rk.n = int(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) s->rk.col[i] = keys[i];
+  if (packed) {
+    s->pack.n = int(keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) {
+      s->pack.col[i] = keys[i];
+      s->pack.width[i] = t.cols[keys[i]].width();
+    }
+  }
+}
+
+static int grid_for(const CtxPtr& ctx, int64_t items, int threads, int per_sm) {
+  return int(std::max<int64_t>(1, std::min<int64_t>((items + threads - 1) / threads, int64_t(ctx->sm_count) * per_sm)));
+}
+
+TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& right_ptr, const std::vector<int>& left_keys,
+                   const std::vector<int>& right_keys) {
+  const Table& L = *left_ptr;
+  const Table& R = *right_ptr;
+  FG_CHECK(!left_keys.empty() && left_keys.size() == right_keys.size(), FLOCKGPU_ERR_INVALID, "hash_join: key lists must be non-empty and of equal length");
+  FG_CHECK(left_keys.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_join: more than %d key columns", MAX_KEY_COLS);
+  std::vector<int> widths;
+  for (size_t i = 0; i < left_keys.size(); ++i) {
+    int lk = left_keys[i], rk = right_keys[i];
+    FG_CHECK(lk >= 0 && lk < int(L.cols.size()) && rk >= 0 && rk < int(R.cols.size()), FLOCKGPU_ERR_INVALID, "hash_join: key column out of range");
+    const Column& lc = L.cols[lk];
+    const Column& rc = R.cols[rk];
+    FG_CHECK(lc.dtype == rc.dtype, FLOCKGPU_ERR_UNSUPPORTED, "hash_join: key types differ (%s vs %s); DataFusion inserts casts before the join",
+             dtype_name(lc.dtype), dtype_name(rc.dtype));
+    widths.push_back(lc.width());
+  }
+  const bool packed = keys_packable(widths.data(), int(widths.size()));
+
+  auto out = std::make_shared<Table>();
+  out->ctx = ctx;
+  out->metadata = L.metadata;
+
+  // a NULL key column (one-row global aggregate over empty input) matches nothing
+  bool null_key = false;
+  for (size_t i = 0; i < left_keys.size(); ++i) null_key |= L.cols[left_keys[i]].all_null || R.cols[right_keys[i]].all_null;
+
+  int64_t n_pairs = 0;
+  BufferPtr build_idx, probe_idx;
+  if (L.num_rows > 0 && R.num_rows > 0 && !null_key) {
+    JoinSide bs{}, ps{};
+    fill_side(L, left_keys, packed, &bs);
+    fill_side(R, right_keys, packed, &ps);
+    unsigned long long cap = 1024;
+    while (cap < 2ull * (unsigned long long)L.num_rows) cap <<= 1;
+    BufferPtr trows = alloc(ctx, size_t(cap) * 4);
+    BufferPtr tkeys = packed ? alloc(ctx, size_t(cap) * 8) : nullptr;
+    FG_CUDA(cudaMemsetAsync(trows->ptr, 0xff, size_t(cap) * 4, ctx->stream));
+    JoinTable tab{trows->as<unsigned>(), tkeys ? tkeys->as<unsigned long long>() : nullptr, cap};
+    join_build_kernel<<<grid_for(ctx, L.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab);
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+
+    BufferPtr off = alloc(ctx, size_t(R.num_rows + 1) * 4);
+    JoinCountArgs ca{};
+    ca.build = bs;
+    ca.probe = ps;
+    ca.table = tab;
+    ca.out_off = off->as<unsigned>();
+    ca.num_tiles = (R.num_rows + JC_TILE - 1) / JC_TILE;
+    ensure_scan_scratch(ctx, ca.num_tiles);
+    ca.tile_state = ctx->scan.tile_state;
+    ca.counters = ctx->scan.counters;
+    ca.out_total = ctx->d_scalars + 4;
+    {
+      int per_sm = 1;
+      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_count_scan_kernel, JC_THREADS, 0));
+      int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), ca.num_tiles)));
+      join_count_scan_kernel<<<grid, JC_THREADS, 0, ctx->stream>>>(ca);
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    }
+    unsigned long long total = 0;
+    read_scalars(ctx, 4, 1, &total);
+    FG_CHECK(total < (1ull << 32) - 1, FLOCKGPU_ERR_UNSUPPORTED, "hash_join: %llu output rows exceed 2^32-2", total);
+    n_pairs = int64_t(total);
+    if (n_pairs > 0) {
+      build_idx = alloc(ctx, size_t(n_pairs) * 4);
+      probe_idx = alloc(ctx, size_t(n_pairs) * 4);
+      JoinEmitArgs ea{};
+      ea.build = bs;
+      ea.probe = ps;
+      ea.table = tab;
+      ea.off = off->as<unsigned>();
+      ea.build_idx = build_idx->as<unsigned>();
+      ea.probe_idx = probe_idx->as<unsigned>();
+      join_emit_kernel<<<grid_for(ctx, R.num_rows, 256, 8), 256, 0, ctx->stream>>>(ea);
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    }
+  }
+  out->num_rows = n_pairs;
+  if (n_pairs == 0) {
+    TablePtr le = empty_like(ctx, L), re = empty_like(ctx, R);
+    for (const Column& c : le->cols) out->cols.push_back(c);
+    for (const Column& c : re->cols) out->cols.push_back(c);
+    return out;
+  }
+  for (const Column& c : L.cols) out->cols.push_back(gather_column(ctx, c, build_idx->as<uint32_t>(), n_pairs));
+  for (const Column& c : R.cols) out->cols.push_back(gather_column(ctx, c, probe_idx->as<uint32_t>(), n_pairs));
+  return out;
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+extern "C" int flockgpu_hash_join(flockgpu_ctx* ctx, const flockgpu_table* left, const flockgpu_table* right, const int32_t* left_keys,
+                                  const int32_t* right_keys, int32_t n_keys, flockgpu_table** out) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(out && left && left->table && right && right->table && left_keys && right_keys && n_keys > 0, FLOCKGPU_ERR_INVALID,
+             "hash_join: null or empty argument");
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    FG_CUDA(cudaSetDevice(c->device));
+    std::vector<int> lk(left_keys, left_keys + n_keys), rk(right_keys, right_keys + n_keys);
+    *out = wrap_table(hash_join(c, left->table, right->table, lk, rk));
+  });
+}

@@ -1,0 +1,228 @@
+// internal.h -- host-side C++ types shared by every translation unit of libflockgpu.
+//
+// Nothing here is part of the ABI (include/flockgpu.h is).  Data model:
+//   Ctx      one CUDA device + stream + stream-ordered memory pool + scratch state
+//   Buffer   a reference-counted HBM allocation (freed stream-ordered when the last owner drops it)
+//   Column   one Arrow column resident in HBM: fixed-width values, or Utf8 = int32 offsets + bytes
+//   Table    an immutable relation = columns of equal length (the device form of Vec<RecordBatch>)
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/flockgpu.h"
+
+namespace fg {
+
+// ------------------------------------------------------------------------------------------------
+// errors: thrown inside the library, converted to return codes at the extern "C" boundary
+// ------------------------------------------------------------------------------------------------
+struct Error {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+void set_last_error(const std::string& msg);
+
+#define FG_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      ::fg::fail(FLOCKGPU_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                 cudaGetErrorString(_e));                                                      \
+  } while (0)
+
+#define FG_CHECK(cond, code, ...)                 \
+  do {                                            \
+    if (!(cond)) ::fg::fail((code), __VA_ARGS__); \
+  } while (0)
+
+// Runs `body` and maps fg::Error / std::exception to an ABI return code.
+template <typename F>
+int guarded(F&& body) noexcept {
+  try {
+    body();
+    return FLOCKGPU_OK;
+  } catch (const Error& e) {
+    set_last_error(e.msg);
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(std::string("internal error: ") + e.what());
+    return FLOCKGPU_ERR_INVALID;
+  } catch (...) {
+    set_last_error("internal error: unknown exception");
+    return FLOCKGPU_ERR_INVALID;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct Comm;  // comm.cc
+
+// Scratch for the single-pass (decoupled look-back) compaction/scan kernels; self-resetting.
+struct ScanScratch {
+  unsigned long long* tile_state = nullptr;  // [capacity] packed {flag:2, value:62}
+  unsigned int* counters = nullptr;          // [0]=ticket, [1]=done, [2..] spare
+  int64_t capacity = 0;
+};
+
+struct CtxCore {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;
+  int sm_count = 148;
+  std::recursive_mutex mu;
+
+  // small pinned buffer for device->host scalar read-backs and device scalars
+  unsigned long long* h_scalars = nullptr;  // pinned, 512 x u64
+  unsigned long long* d_scalars = nullptr;  // device, 512 x u64
+
+  ScanScratch scan;
+  void* l2_flush = nullptr;
+  size_t l2_flush_bytes = 0;
+
+  cudaEvent_t timer_start[16] = {};
+  cudaEvent_t timer_stop[16] = {};
+  std::atomic<int64_t> launches{0};
+
+  // pinned host blocks handed out by flockgpu_host_alloc and by table export
+  std::mutex pin_mu;
+  std::unordered_map<void*, size_t> pinned;
+
+  std::shared_ptr<Comm> comm;  // comm.cc (shared_ptr: Comm is incomplete here)
+
+  ~CtxCore();
+};
+using CtxPtr = std::shared_ptr<CtxCore>;
+
+struct Buffer {
+  CtxPtr ctx;
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  Buffer(CtxPtr c, size_t n);
+  ~Buffer();
+  Buffer(const Buffer&) = delete;
+  Buffer& operator=(const Buffer&) = delete;
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(ptr);
+  }
+};
+using BufferPtr = std::shared_ptr<Buffer>;
+BufferPtr alloc(const CtxPtr& ctx, size_t bytes);  // bytes == 0 still yields a valid (tiny) buffer
+
+// Grows the look-back scratch to at least `tiles` entries (zero-initialised once).
+void ensure_scan_scratch(const CtxPtr& ctx, int64_t tiles);
+// Copies `n` u64 scalars from d_scalars[first..] to the host and waits.
+void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out);
+
+// ------------------------------------------------------------------------------------------------
+// columns and tables
+// ------------------------------------------------------------------------------------------------
+int dtype_width(int dtype);                 // bytes per value; 0 for Utf8
+const char* dtype_name(int dtype);
+int dtype_from_format(const char* format);  // -1 if unsupported
+std::string default_format(int dtype);
+
+struct Column {
+  int dtype = FLOCKGPU_INT32;
+  std::string name;
+  std::string format;  // Arrow C format string ("i", "tsm:", "u", ...)
+  bool nullable = false;
+  int64_t length = 0;
+  BufferPtr data;      // fixed width: values; Utf8: value bytes
+  BufferPtr offsets;   // Utf8 only: int32[length + 1]; offsets[0] may be > 0
+  int64_t values_bytes = 0;  // Utf8: number of value bytes addressed by offsets
+  // Only the one-row result of a global aggregate over empty input carries a NULL.
+  bool all_null = false;
+
+  const void* values() const { return data ? data->ptr : nullptr; }
+  const int32_t* offs() const { return offsets ? offsets->as<int32_t>() : nullptr; }
+  int width() const { return dtype_width(dtype); }
+};
+
+struct Table {
+  CtxPtr ctx;
+  std::vector<Column> cols;
+  int64_t num_rows = 0;
+  std::string metadata;  // raw Arrow schema metadata block (may be empty)
+  int64_t nbytes() const;
+};
+using TablePtr = std::shared_ptr<const Table>;
+
+}  // namespace fg
+
+// ABI handles ------------------------------------------------------------------------------------
+struct flockgpu_ctx {
+  fg::CtxPtr core;
+};
+struct flockgpu_table {
+  fg::TablePtr table;
+  std::atomic<int> refs{1};
+};
+
+namespace fg {
+flockgpu_table* wrap_table(TablePtr t);
+inline const Table& deref(const flockgpu_table* t) {
+  if (!t || !t->table) fail(FLOCKGPU_ERR_INVALID, "null table handle");
+  return *t->table;
+}
+inline CtxPtr core_of(flockgpu_ctx* c) {
+  if (!c || !c->core) fail(FLOCKGPU_ERR_INVALID, "null context handle");
+  return c->core;
+}
+
+// ---- operators (implemented in the .cu files; called by the ABI layer and by the plan layer) ----
+struct ExprTok {
+  int op, dtype, col;
+  int64_t i64;
+  double f64;
+  std::string str;
+};
+using Expr = std::vector<ExprTok>;  // postfix
+
+TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const ArrowArray* const* batches,
+                        int n_batches, const int* projection, int n_projection);
+void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t row_count,
+                  ArrowSchema* out_schema, ArrowArray* out_array);
+void export_schema(const Table& t, ArrowSchema* out_schema);
+TablePtr concat_tables(const CtxPtr& ctx, const std::vector<TablePtr>& tables);
+TablePtr empty_like(const CtxPtr& ctx, const Table& t);
+
+TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in, const Expr* predicate,
+                        const std::vector<Expr>& projections, const std::vector<std::string>& names);
+
+struct AggSpec {
+  int func;
+  int col;
+  std::string name;
+};
+TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in, int mode, const std::vector<int>& group_cols,
+                        const std::vector<AggSpec>& aggs);
+TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left, const TablePtr& right,
+                   const std::vector<int>& left_keys, const std::vector<int>& right_keys);
+std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in, const std::vector<int>& keys,
+                                     int n_parts);
+// Row gather: out.col[c][i] = in.col[c][idx[i]] for every column (fixed width and Utf8).
+TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx,
+                     int64_t n_idx);
+// Gathers single columns (used by filter for Utf8 pass-through and by join).
+Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx, int64_t n_idx);
+
+TablePtr all_to_all(const CtxPtr& ctx, const std::vector<TablePtr>& parts);
+void comm_unique_id(uint8_t* out);
+void comm_init(const CtxPtr& ctx, const uint8_t* id, int rank, int world);
+int comm_world(const CtxPtr& ctx);  // 1 when no communicator is attached
+
+inline void count_launch(const CtxPtr& ctx, int n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace fg

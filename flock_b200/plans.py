@@ -1,0 +1,195 @@
+"""NEXMark physical plans in the reference's own serde-JSON plan format.
+
+The reference serialises ``Arc<dyn ExecutionPlan>`` with typetag tags ("execution_plan": "filter_exec",
+"physical_expr": "binary_expr", ...; fixtures flock/src/tests/data/plan/{simple_select,aggregate,join}.json)
+and ships the string in the Lambda environment (flock/src/runtime/context.rs:366-398).  No Rust
+toolchain exists here, so these builders write the same JSON by hand, following the physical plans the
+reference's own tests print (flock/src/distributed_plan/planner.rs:86-255) and SURVEY.md Appendix B.
+Both the GPU executor (flock_b200.ExecutionContext) and the CPU oracle execute exactly this JSON.
+"""
+from __future__ import annotations
+
+import pyarrow as pa
+
+from . import nexgen
+
+TARGET_PARTITIONS = 8     # flock/src/configs/flock.toml:113
+TARGET_BATCH_SIZE = 4096  # CoalesceBatchesExec default seen in every plan dump
+
+
+# ---- data types / schema ---------------------------------------------------------------------------
+def data_type_json(t: pa.DataType):
+    if pa.types.is_int32(t): return "Int32"
+    if pa.types.is_uint32(t): return "UInt32"
+    if pa.types.is_int64(t): return "Int64"
+    if pa.types.is_uint64(t): return "UInt64"
+    if pa.types.is_float64(t): return "Float64"
+    if pa.types.is_string(t): return "Utf8"
+    if pa.types.is_timestamp(t):
+        unit = {"s": "Second", "ms": "Millisecond", "us": "Microsecond", "ns": "Nanosecond"}[t.unit]
+        return {"Timestamp": [unit, t.tz]}
+    raise TypeError(f"unsupported type {t}")
+
+
+def schema_json(schema: pa.Schema) -> dict:
+    md = {k.decode(): v.decode() for k, v in (schema.metadata or {}).items()}
+    return {"fields": [{"name": f.name, "data_type": data_type_json(f.type), "nullable": f.nullable,
+                        "dict_id": 0, "dict_is_ordered": False} for f in schema],
+            "metadata": md}
+
+
+# ---- physical expressions ----------------------------------------------------------------------------
+def column(name: str, index: int) -> dict:
+    return {"physical_expr": "column", "name": name, "index": index}
+
+
+def literal(type_name: str, value) -> dict:
+    return {"physical_expr": "literal", "value": {type_name: value}}
+
+
+def binary(left: dict, op: str, right: dict) -> dict:
+    return {"physical_expr": "binary_expr", "left": left, "op": op, "right": right}
+
+
+def cast(expr: dict, type_json) -> dict:
+    return {"physical_expr": "cast_expr", "expr": expr, "cast_type": type_json}
+
+
+def try_cast(expr: dict, type_json) -> dict:
+    return {"physical_expr": "try_cast_expr", "expr": expr, "cast_type": type_json}
+
+
+# ---- execution plans -------------------------------------------------------------------------------------
+def memory_exec(schema: pa.Schema, projection: list[int] | None) -> dict:
+    return {"execution_plan": "memory_exec", "schema": schema_json(schema), "projection": projection}
+
+
+def projection_exec(exprs: list[tuple[dict, str]], input: dict) -> dict:
+    return {"execution_plan": "projection_exec", "expr": [[e, n] for e, n in exprs], "input": input}
+
+
+def filter_exec(predicate: dict, input: dict) -> dict:
+    return {"execution_plan": "filter_exec", "predicate": predicate, "input": input}
+
+
+def coalesce_batches_exec(input: dict, target_batch_size: int = TARGET_BATCH_SIZE) -> dict:
+    return {"execution_plan": "coalesce_batches_exec", "input": input, "target_batch_size": target_batch_size}
+
+
+def coalesce_partitions_exec(input: dict) -> dict:
+    return {"execution_plan": "coalesce_partitions_exec", "input": input}
+
+
+def repartition_rr(input: dict, n: int = TARGET_PARTITIONS) -> dict:
+    return {"execution_plan": "repartition_exec", "input": input, "partitioning": {"RoundRobinBatch": n}}
+
+
+def repartition_hash(input: dict, exprs: list[dict], n: int = TARGET_PARTITIONS) -> dict:
+    return {"execution_plan": "repartition_exec", "input": input, "partitioning": {"Hash": [exprs, n]}}
+
+
+def aggregate_expr(func: str, name: str, expr: dict, data_type) -> dict:
+    return {"aggregate_expr": func, "name": name, "expr": expr, "data_type": data_type, "nullable": True}
+
+
+def hash_aggregate_exec(mode: str, group_expr: list[tuple[dict, str]], aggr_expr: list[dict], input: dict) -> dict:
+    return {"execution_plan": "hash_aggregate_exec", "mode": mode, "group_expr": [[e, n] for e, n in group_expr],
+            "aggr_expr": aggr_expr, "input": input}
+
+
+def hash_join_exec(left: dict, right: dict, on: list[tuple[dict, dict]], mode: str = "Partitioned") -> dict:
+    return {"execution_plan": "hash_join_exec", "join_type": "Inner", "mode": mode, "left": left, "right": right,
+            "on": [[{"name": l["name"], "index": l["index"]}, {"name": r["name"], "index": r["index"]}] for l, r in on]}
+
+
+def two_phase_aggregate(group: list[tuple[str, int]], aggrs: list[dict], input: dict, n: int = TARGET_PARTITIONS) -> dict:
+    """Partial -> RepartitionExec(Hash[group]) -> CoalesceBatches -> FinalPartitioned (stage.rs:597-601);
+    without group columns: Partial -> CoalescePartitions -> Final (stage.rs:535-537)."""
+    gexpr = [(column(nm, ix), nm) for nm, ix in group]
+    partial = hash_aggregate_exec("Partial", gexpr, aggrs, input)
+    if not group:
+        return hash_aggregate_exec("Final", [], aggrs, coalesce_partitions_exec(partial))
+    gfinal = [(column(nm, i), nm) for i, (nm, _) in enumerate(group)]
+    shuffled = coalesce_batches_exec(repartition_hash(partial, [column(nm, i) for i, (nm, _) in enumerate(group)], n))
+    return hash_aggregate_exec("FinalPartitioned", gfinal, aggrs, shuffled)
+
+
+# ---- NEXMark q1..q8 (benchmarks/src/nexmark/query/qN.sql) -------------------------------------------------
+BID, AUCTION, PERSON = nexgen.bid_schema(), nexgen.auction_schema(), nexgen.person_schema()
+TS_MS = {"Timestamp": ["Millisecond", None]}
+
+
+def q1(n: int = TARGET_PARTITIONS) -> dict:
+    """planner.rs:90-92  SELECT auction, bidder, 0.908 * price AS price, b_date_time FROM bid"""
+    scan = repartition_rr(memory_exec(BID, [0, 1, 2, 3]), n)
+    return projection_exec([
+        (column("auction", 0), "auction"), (column("bidder", 1), "bidder"),
+        (binary(literal("Float64", 0.908), "Multiply", cast(column("price", 2), "Float64")), "price"),
+        (column("b_date_time", 3), "b_date_time")], scan)
+
+
+def q2(n: int = TARGET_PARTITIONS) -> dict:
+    """planner.rs:120-124  SELECT auction, price FROM bid WHERE auction % 123 = 0"""
+    scan = repartition_rr(memory_exec(BID, [0, 2]), n)
+    pred = binary(binary(cast(column("auction", 0), "Int64"), "Modulo", literal("Int64", 123)), "Eq", literal("Int64", 0))
+    return projection_exec([(column("auction", 0), "auction"), (column("price", 1), "price")],
+                           coalesce_batches_exec(filter_exec(pred, scan)))
+
+
+def q3_stage0(n: int = TARGET_PARTITIONS) -> list[dict]:
+    """planner.rs:151-163: the two shuffle stages (auction side, person side)."""
+    a_scan = repartition_rr(memory_exec(AUCTION, [0, 7, 8]), n)
+    a_pred = binary(cast(column("category", 2), "Int64"), "Eq", literal("Int64", 10))
+    a = coalesce_batches_exec(repartition_hash(coalesce_batches_exec(filter_exec(a_pred, a_scan)), [column("seller", 1)], n))
+    p_scan = repartition_rr(memory_exec(PERSON, [0, 1, 4, 5]), n)
+    st = column("state", 3)
+    p_pred = binary(binary(binary(st, "Eq", literal("Utf8", "or")), "Or", binary(st, "Eq", literal("Utf8", "id"))),
+                    "Or", binary(st, "Eq", literal("Utf8", "ca")))
+    p = coalesce_batches_exec(repartition_hash(coalesce_batches_exec(filter_exec(p_pred, p_scan)), [column("p_id", 0)], n))
+    return [a, p]
+
+
+def q3(n: int = TARGET_PARTITIONS) -> dict:
+    """planner.rs:151-171 as ONE plan (centralized mode runs the whole plan in one worker,
+    benchmarks/src/nexmark/main.rs:209-214): auction JOIN person ON seller = p_id."""
+    a, p = q3_stage0(n)
+    join = hash_join_exec(a, p, [(column("seller", 1), column("p_id", 0))])
+    return projection_exec([(column("name", 4), "name"), (column("city", 5), "city"), (column("state", 6), "state"),
+                            (column("a_id", 0), "a_id")], coalesce_batches_exec(join))
+
+
+def _count_by_auction(n: int) -> dict:
+    scan = repartition_rr(memory_exec(BID, [0]), n)
+    cnt = aggregate_expr("count", "COUNT(UInt8(1))", literal("UInt8", 1), "UInt64")
+    return two_phase_aggregate([("auction", 0)], [cnt], scan, n)
+
+
+def q5(n: int = TARGET_PARTITIONS) -> dict:
+    """SURVEY.md Appendix B (types q5_plan.fmt): AuctionBids JOIN MaxBids ON num = maxn.  The COUNT-by-auction
+    subtree appears twice, exactly as DataFusion 6 plans it (no common-subexpression elimination)."""
+    left = projection_exec([(column("auction", 0), "auction"), (column("COUNT(UInt8(1))", 1), "num")], _count_by_auction(n))
+    nums = projection_exec([(column("COUNT(UInt8(1))", 1), "num")], _count_by_auction(n))
+    mx = aggregate_expr("max", "MAX(CountBids.num)", column("num", 0), "UInt64")
+    right = projection_exec([(column("MAX(CountBids.num)", 0), "maxn")], two_phase_aggregate([], [mx], nums, n))
+    lsh = coalesce_batches_exec(repartition_hash(left, [column("num", 1)], n))
+    rsh = coalesce_batches_exec(repartition_hash(right, [column("maxn", 0)], n))
+    join = hash_join_exec(lsh, rsh, [(column("num", 1), column("maxn", 0))])
+    return projection_exec([(column("auction", 0), "auction"), (column("num", 1), "num")], coalesce_batches_exec(join))
+
+
+def q8(n: int = TARGET_PARTITIONS) -> dict:
+    """SURVEY.md Appendix B (q8_plan.fmt): P(p_id, name GROUP BY) JOIN A(seller GROUP BY) ON p_id = seller."""
+    p_scan = repartition_rr(memory_exec(PERSON, [0, 1]), n)
+    P = two_phase_aggregate([("p_id", 0), ("name", 1)], [], p_scan, n)
+    a_scan = repartition_rr(memory_exec(AUCTION, [7]), n)
+    A = two_phase_aggregate([("seller", 0)], [], a_scan, n)
+    lsh = coalesce_batches_exec(repartition_hash(P, [column("p_id", 0)], n))
+    rsh = coalesce_batches_exec(repartition_hash(A, [column("seller", 0)], n))
+    join = hash_join_exec(lsh, rsh, [(column("p_id", 0), column("seller", 0))])
+    return projection_exec([(column("p_id", 0), "p_id"), (column("name", 1), "name")], coalesce_batches_exec(join))
+
+
+QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q5": q5, "q8": q8}
+# relations each query feeds, in feed order (flock/src/datasource/nexmark/nexmark.rs:181-203); q5 scans bid
+# twice, and feed_data_sources hands one source to one leaf (context.rs:293-303), so bid is fed twice.
+SOURCES = {"q1": ["bid"], "q2": ["bid"], "q3": ["auction", "person"], "q5": ["bid", "bid"], "q8": ["person", "auction"]}

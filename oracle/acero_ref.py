@@ -1,0 +1,63 @@
+"""Second, independent CPU implementation of the NEXMark queries on Arrow C++ compute / Acero (pyarrow).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  It exists to pin the C++ restatement: two
+implementations written against different libraries must agree bit-exactly (after the canonical sort)
+before either is trusted as the oracle.  It works from the SQL text
+(benchmarks/src/nexmark/query/qN.sql), not from the physical plan JSON, so it also cross-checks the
+hand-written plans in flock_b200/plans.py.  Label: "Arrow C++ kernels -- not DataFusion".
+"""
+from __future__ import annotations
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+
+
+def _table(batches) -> pa.Table:
+    return pa.Table.from_batches(list(batches)).combine_chunks()
+
+
+def q1(bid) -> pa.Table:
+    """SELECT auction, bidder, 0.908 * price AS price, b_date_time FROM bid"""
+    t = _table(bid)
+    price = pc.multiply(pa.scalar(0.908, pa.float64()), pc.cast(t["price"], pa.float64()))
+    return pa.table({"auction": t["auction"], "bidder": t["bidder"], "price": price, "b_date_time": t["b_date_time"]})
+
+
+def q2(bid) -> pa.Table:
+    """SELECT auction, price FROM bid WHERE auction % 123 = 0  (truncated remainder, like Rust's %)"""
+    t = _table(bid)
+    a = t["auction"].to_numpy().astype(np.int64)
+    mask = np.fmod(a, 123) == 0
+    return t.select(["auction", "price"]).filter(pa.array(mask))
+
+
+def q3(auction, person) -> pa.Table:
+    """SELECT name, city, state, a_id FROM auction JOIN person ON seller = p_id
+       WHERE category = 10 AND (state = 'or' OR state = 'id' OR state = 'ca')"""
+    a = _table(auction).select(["a_id", "seller", "category"])
+    p = _table(person).select(["p_id", "name", "city", "state"])
+    a = a.filter(pc.equal(pc.cast(a["category"], pa.int64()), 10))
+    p = p.filter(pc.is_in(p["state"], value_set=pa.array(["or", "id", "ca"])))
+    j = a.join(p, keys="seller", right_keys="p_id", join_type="inner")
+    return j.select(["name", "city", "state", "a_id"])
+
+
+def q5(bid) -> pa.Table:
+    """AuctionBids(auction, COUNT(*) num) JOIN MaxBids(MAX(num) maxn) ON num = maxn"""
+    t = _table(bid)
+    counts = t.group_by("auction").aggregate([([], "count_all")])
+    num = pc.cast(counts["count_all"], pa.uint64())
+    mx = pc.max(num)
+    out = pa.table({"auction": counts["auction"], "num": num})
+    return out.filter(pc.equal(num, mx))
+
+
+def q8(person, auction) -> pa.Table:
+    """P(SELECT p_id, name GROUP BY p_id, name) JOIN A(SELECT seller GROUP BY seller) ON p_id = seller"""
+    p = _table(person).select(["p_id", "name"]).group_by(["p_id", "name"]).aggregate([])
+    sellers = pc.unique(_table(auction)["seller"].combine_chunks())
+    return p.filter(pc.is_in(p["p_id"], value_set=sellers)).select(["p_id", "name"])
+
+
+QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q5": q5, "q8": q8}

@@ -1,0 +1,527 @@
+// oracle.cc -- CPU restatement of the DataFusion-6 operators on Flock's per-batch hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked, imported or executed by the product
+// (flock_b200/, libflockgpu.so); only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// `--impl reference` legs use it -- as the checker, never as the thing shipped.
+//
+// PARITY UNPINNED for NEXMark outputs: the reference's operators live in an un-vendored git dependency
+// (datafusion = { git = "https://github.com/flock-lab/arrow-datafusion", branch = "flock" },
+// flock/Cargo.toml:21, no Cargo.lock) and no Rust toolchain exists here, so the reference binary was
+// never executed.  This file restates the PUBLISHED algorithms of apache/arrow-datafusion 6.0 /
+// arrow-rs 6 and is pinned against (a) the reference's own toy goldens
+// (flock/src/runtime/context.rs:428-592, flock/src/launcher/local.rs:169-234) and (b) an independent
+// second implementation on Arrow C++ compute (oracle/acero_ref.py); see tests/test_oracle.py.
+//
+// Algorithms restated (each function cites the reference call site that exercises it):
+//   eval_expr        PhysicalExpr::evaluate, vector-at-a-time with materialised intermediates like the
+//                    arrow-rs kernels (cast / arithmetic / comparison / boolean), planner.rs:90,122,155,162
+//   filter           arrow `filter` (order preserving), FilterExec
+//   partition_ids    RepartitionExec::Hash: hash(keys) % n (shuffle_writer.rs:105-146); ahash is replaced
+//                    by SplitMix64 -- hash values are unobservable (Appendix C.6)
+//   group_by         HashAggregateExec: hash map keyed by the group values, groups in first-seen order,
+//                    accumulators COUNT(u64) / SUM / MIN / MAX / AVG(sum f64, count u64) (Appendix C.7)
+//   hash_join        HashJoinExec Inner: build map on the left, probe right rows in order, verify equality,
+//                    emit (left, right) index pairs probe-row-major (Appendix C.8)
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+extern "C" {
+
+enum { T_BOOL = 0, T_I32 = 1, T_I64 = 2, T_U64 = 3, T_F64 = 4, T_TS = 5, T_UTF8 = 6, T_U32 = 7 };
+enum {
+  OP_COLUMN = 1, OP_LIT_I64 = 2, OP_LIT_F64 = 3, OP_LIT_UTF8 = 4, OP_CAST = 5,
+  OP_ADD = 10, OP_SUB = 11, OP_MUL = 12, OP_DIV = 13, OP_MOD = 14,
+  OP_EQ = 20, OP_NE = 21, OP_LT = 22, OP_LE = 23, OP_GT = 24, OP_GE = 25,
+  OP_AND = 30, OP_OR = 31, OP_NOT = 32
+};
+
+struct OCol {
+  int32_t dtype;
+  int32_t pad;
+  int64_t len;
+  const void* data;        // values, or Utf8 bytes
+  const int32_t* offsets;  // Utf8: offsets[0..len] (absolute into data)
+};
+
+struct OTok {
+  int32_t op, dtype, col, str_len;
+  int64_t i64;
+  double f64;
+  const char* str;
+};
+
+}  // extern "C"
+
+namespace {
+
+// A materialised intermediate array (or a scalar literal broadcast lazily).
+struct Arr {
+  int dtype = T_I64;
+  bool scalar = false;
+  int64_t si = 0;
+  double sd = 0;
+  std::string ss;
+  std::vector<int64_t> i;   // I32 (widened) / I64 / U64 (bit pattern) / TS / U32 / BOOL(0,1)
+  std::vector<double> d;    // F64
+  const OCol* utf8 = nullptr;
+};
+
+bool is_float(int t) { return t == T_F64; }
+bool is_unsigned(int t) { return t == T_U64 || t == T_U32; }
+
+inline int64_t geti(const Arr& a, int64_t r) { return a.scalar ? a.si : a.i[r]; }
+inline double getd(const Arr& a, int64_t r) { return a.scalar ? a.sd : a.d[r]; }
+
+Arr load_col(const OCol& c) {
+  Arr a;
+  a.dtype = c.dtype;
+  switch (c.dtype) {
+    case T_I32: {
+      a.i.resize(c.len);
+      const int32_t* p = static_cast<const int32_t*>(c.data);
+      for (int64_t r = 0; r < c.len; ++r) a.i[r] = p[r];
+      break;
+    }
+    case T_U32: {
+      a.i.resize(c.len);
+      const uint32_t* p = static_cast<const uint32_t*>(c.data);
+      for (int64_t r = 0; r < c.len; ++r) a.i[r] = p[r];
+      break;
+    }
+    case T_I64: case T_U64: case T_TS: {
+      a.i.assign(static_cast<const int64_t*>(c.data), static_cast<const int64_t*>(c.data) + c.len);
+      break;
+    }
+    case T_F64:
+      a.d.assign(static_cast<const double*>(c.data), static_cast<const double*>(c.data) + c.len);
+      break;
+    case T_UTF8:
+      a.utf8 = &c;
+      break;
+    default: break;
+  }
+  return a;
+}
+
+// arrow-rs `cast` kernel for the numeric pairs DataFusion's coercion inserts
+Arr cast_to(const Arr& x, int to, int64_t n) {
+  Arr r;
+  r.dtype = to;
+  r.scalar = x.scalar;
+  auto conv_i = [&](int64_t v) -> int64_t {
+    if (to == T_I32) return int64_t(int32_t(uint32_t(uint64_t(v))));
+    if (to == T_U32) return int64_t(uint64_t(uint32_t(uint64_t(v))));
+    return v;
+  };
+  if (is_float(to)) {
+    if (is_float(x.dtype)) return x;
+    if (x.scalar) { r.sd = is_unsigned(x.dtype) ? double(uint64_t(x.si)) : double(x.si); return r; }
+    r.d.resize(n);
+    if (is_unsigned(x.dtype)) for (int64_t k = 0; k < n; ++k) r.d[k] = double(uint64_t(x.i[k]));
+    else for (int64_t k = 0; k < n; ++k) r.d[k] = double(x.i[k]);
+    return r;
+  }
+  if (is_float(x.dtype)) {
+    if (x.scalar) { r.si = conv_i(int64_t(x.sd)); return r; }
+    r.i.resize(n);
+    for (int64_t k = 0; k < n; ++k) r.i[k] = conv_i(int64_t(x.d[k]));
+    return r;
+  }
+  if (x.scalar) { r.si = conv_i(x.si); return r; }
+  r.i.resize(n);
+  for (int64_t k = 0; k < n; ++k) r.i[k] = conv_i(x.i[k]);
+  return r;
+}
+
+int promote(int a, int b) {
+  if (a == b) return a;
+  if (a == T_F64 || b == T_F64) return T_F64;
+  auto rank = [](int t) { return t == T_I32 ? 1 : t == T_U32 ? 2 : (t == T_I64 || t == T_TS) ? 3 : 4; };
+  return rank(a) >= rank(b) ? a : b;
+}
+
+int arith(int op, const Arr& l0, const Arr& r0, int64_t n, Arr* out) {
+  int T = promote(l0.dtype, r0.dtype);
+  Arr l = cast_to(l0, T, n), r = cast_to(r0, T, n);
+  out->dtype = T;
+  out->scalar = false;
+  if (T == T_F64) {
+    if (op == OP_MOD) return -2;
+    out->d.resize(n);
+    for (int64_t k = 0; k < n; ++k) {
+      double a = getd(l, k), b = getd(r, k);
+      out->d[k] = op == OP_ADD ? a + b : op == OP_SUB ? a - b : op == OP_MUL ? a * b : a / b;
+    }
+    return 0;
+  }
+  out->i.resize(n);
+  const bool u = is_unsigned(T);
+  for (int64_t k = 0; k < n; ++k) {
+    int64_t a = geti(l, k), b = geti(r, k), v;
+    switch (op) {
+      case OP_ADD: v = int64_t(uint64_t(a) + uint64_t(b)); break;
+      case OP_SUB: v = int64_t(uint64_t(a) - uint64_t(b)); break;
+      case OP_MUL: v = int64_t(uint64_t(a) * uint64_t(b)); break;
+      case OP_DIV:
+        if (b == 0) return -5;  // DataFusion: "Divide by zero"
+        v = u ? int64_t(uint64_t(a) / uint64_t(b)) : (b == -1 ? int64_t(0 - uint64_t(a)) : a / b);
+        break;
+      default:
+        if (b == 0) return -5;
+        v = u ? int64_t(uint64_t(a) % uint64_t(b)) : (b == -1 ? 0 : a % b);  // truncated remainder (Rust %)
+    }
+    if (T == T_I32) v = int64_t(int32_t(uint32_t(uint64_t(v))));
+    if (T == T_U32) v = int64_t(uint64_t(uint32_t(uint64_t(v))));
+    out->i[k] = v;
+  }
+  return 0;
+}
+
+template <typename T>
+inline bool cmp_op(int op, T a, T b) {
+  switch (op) {
+    case OP_EQ: return a == b;
+    case OP_NE: return a != b;
+    case OP_LT: return a < b;
+    case OP_LE: return a <= b;
+    case OP_GT: return a > b;
+    default: return a >= b;
+  }
+}
+
+inline int cmp_bytes(const char* a, int64_t na, const char* b, int64_t nb) {
+  int c = memcmp(a, b, size_t(std::min(na, nb)));
+  if (c) return c;
+  return na < nb ? -1 : na > nb ? 1 : 0;
+}
+
+int compare(int op, const Arr& l0, const Arr& r0, int64_t n, Arr* out) {
+  out->dtype = T_BOOL;
+  out->scalar = false;
+  out->i.resize(n);
+  if (l0.dtype == T_UTF8 || r0.dtype == T_UTF8) {
+    if (l0.dtype != T_UTF8 || r0.dtype != T_UTF8) return -2;
+    auto str_at = [](const Arr& a, int64_t k, const char** p, int64_t* len) {
+      if (a.utf8) {
+        *p = static_cast<const char*>(a.utf8->data) + a.utf8->offsets[k];
+        *len = a.utf8->offsets[k + 1] - a.utf8->offsets[k];
+      } else {
+        *p = a.ss.data();
+        *len = int64_t(a.ss.size());
+      }
+    };
+    for (int64_t k = 0; k < n; ++k) {
+      const char *pa, *pb;
+      int64_t la, lb;
+      str_at(l0, k, &pa, &la);
+      str_at(r0, k, &pb, &lb);
+      out->i[k] = cmp_op<int>(op, cmp_bytes(pa, la, pb, lb), 0);
+    }
+    return 0;
+  }
+  int T = promote(l0.dtype, r0.dtype);
+  Arr l = cast_to(l0, T, n), r = cast_to(r0, T, n);
+  if (T == T_F64) for (int64_t k = 0; k < n; ++k) out->i[k] = cmp_op<double>(op, getd(l, k), getd(r, k));
+  else if (is_unsigned(T)) for (int64_t k = 0; k < n; ++k) out->i[k] = cmp_op<uint64_t>(op, uint64_t(geti(l, k)), uint64_t(geti(r, k)));
+  else for (int64_t k = 0; k < n; ++k) out->i[k] = cmp_op<int64_t>(op, geti(l, k), geti(r, k));
+  return 0;
+}
+
+int eval_tokens(const OCol* cols, int n_cols, int64_t n, const OTok* toks, int n_toks, Arr* result) {
+  std::vector<Arr> st;
+  for (int t = 0; t < n_toks; ++t) {
+    const OTok& k = toks[t];
+    switch (k.op) {
+      case OP_COLUMN:
+        if (k.col < 0 || k.col >= n_cols) return -1;
+        st.push_back(load_col(cols[k.col]));
+        break;
+      case OP_LIT_I64: {
+        Arr a;
+        a.scalar = true;
+        a.dtype = (k.dtype == T_I32 || k.dtype == T_U32 || k.dtype == T_U64 || k.dtype == T_TS) ? k.dtype : T_I64;
+        a.si = k.i64;
+        st.push_back(a);
+        break;
+      }
+      case OP_LIT_F64: {
+        Arr a;
+        a.scalar = true;
+        a.dtype = T_F64;
+        a.sd = k.f64;
+        st.push_back(a);
+        break;
+      }
+      case OP_LIT_UTF8: {
+        Arr a;
+        a.scalar = true;
+        a.dtype = T_UTF8;
+        a.ss.assign(k.str ? k.str : "", size_t(k.str_len));
+        st.push_back(a);
+        break;
+      }
+      case OP_CAST: {
+        if (st.empty()) return -1;
+        Arr x = std::move(st.back());
+        st.pop_back();
+        if (x.dtype == T_UTF8 || k.dtype == T_UTF8 || k.dtype == T_BOOL) return -2;
+        st.push_back(cast_to(x, k.dtype, n));
+        break;
+      }
+      case OP_NOT: {
+        if (st.empty()) return -1;
+        Arr& x = st.back();
+        for (auto& v : x.i) v = !v;
+        break;
+      }
+      default: {
+        if (st.size() < 2) return -1;
+        Arr r = std::move(st.back());
+        st.pop_back();
+        Arr l = std::move(st.back());
+        st.pop_back();
+        Arr o;
+        int rc = 0;
+        if (k.op >= OP_ADD && k.op <= OP_MOD) rc = arith(k.op, l, r, n, &o);
+        else if (k.op >= OP_EQ && k.op <= OP_GE) rc = compare(k.op, l, r, n, &o);
+        else if (k.op == OP_AND || k.op == OP_OR) {
+          o.dtype = T_BOOL;
+          o.i.resize(n);
+          for (int64_t q = 0; q < n; ++q) o.i[q] = k.op == OP_AND ? (geti(l, q) && geti(r, q)) : (geti(l, q) || geti(r, q));
+        } else return -1;
+        if (rc) return rc;
+        st.push_back(std::move(o));
+      }
+    }
+  }
+  if (st.size() != 1) return -1;
+  *result = std::move(st[0]);
+  return 0;
+}
+
+inline uint64_t splitmix(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+// Serialises the key columns of row r into a byte string (fixed width raw, Utf8 length-prefixed).
+inline void key_bytes(const OCol* cols, const int32_t* keys, int n_keys, int64_t r, std::string* out) {
+  out->clear();
+  for (int k = 0; k < n_keys; ++k) {
+    const OCol& c = cols[keys[k]];
+    if (c.dtype == T_UTF8) {
+      int32_t lo = c.offsets[r], len = c.offsets[r + 1] - lo;
+      out->append(reinterpret_cast<const char*>(&len), 4);
+      out->append(static_cast<const char*>(c.data) + lo, size_t(len));
+    } else if (c.dtype == T_I32 || c.dtype == T_U32) {
+      out->append(static_cast<const char*>(c.data) + r * 4, 4);
+    } else {
+      out->append(static_cast<const char*>(c.data) + r * 8, 8);
+    }
+  }
+}
+
+inline uint64_t hash_bytes(const std::string& s) {
+  uint64_t h = 0x243f6a8885a308d3ull;
+  size_t i = 0;
+  for (; i + 8 <= s.size(); i += 8) {
+    uint64_t w;
+    memcpy(&w, s.data() + i, 8);
+    h = splitmix(h ^ w);
+  }
+  uint64_t w = 0;
+  memcpy(&w, s.data() + i, s.size() - i);
+  return splitmix(h ^ w ^ (uint64_t(s.size()) << 56));
+}
+
+struct StrHash {
+  size_t operator()(const std::string& s) const { return size_t(hash_bytes(s)); }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---- PhysicalExpr::evaluate ---------------------------------------------------------------------------
+// Predicate: out_mask[n] (0/1).  Returns 0, or <0 (-1 malformed, -2 unsupported, -5 divide by zero).
+int orc_eval_predicate(const OCol* cols, int n_cols, int64_t n, const OTok* toks, int n_toks, uint8_t* out_mask) {
+  Arr r;
+  int rc = eval_tokens(cols, n_cols, n, toks, n_toks, &r);
+  if (rc) return rc;
+  if (r.dtype != T_BOOL) return -1;
+  for (int64_t k = 0; k < n; ++k) out_mask[k] = uint8_t(r.scalar ? r.si != 0 : r.i[k] != 0);
+  return 0;
+}
+
+// Value expression: writes the result with its natural storage width; *out_dtype receives the type.
+int orc_eval_value(const OCol* cols, int n_cols, int64_t n, const OTok* toks, int n_toks, void* out, int32_t* out_dtype) {
+  Arr r;
+  int rc = eval_tokens(cols, n_cols, n, toks, n_toks, &r);
+  if (rc) return rc;
+  *out_dtype = r.dtype;
+  if (r.dtype == T_F64) {
+    double* o = static_cast<double*>(out);
+    for (int64_t k = 0; k < n; ++k) o[k] = getd(r, k);
+  } else if (r.dtype == T_I32 || r.dtype == T_U32) {
+    int32_t* o = static_cast<int32_t*>(out);
+    for (int64_t k = 0; k < n; ++k) o[k] = int32_t(geti(r, k));
+  } else if (r.dtype == T_UTF8 || r.dtype == T_BOOL) {
+    return -2;
+  } else {
+    int64_t* o = static_cast<int64_t*>(out);
+    for (int64_t k = 0; k < n; ++k) o[k] = geti(r, k);
+  }
+  return 0;
+}
+
+int32_t orc_infer_dtype(const OCol* cols, int n_cols, const OTok* toks, int n_toks) {
+  Arr r;
+  // evaluate on zero rows: types propagate without touching data
+  std::vector<OCol> empty(cols, cols + n_cols);
+  for (auto& c : empty) c.len = 0;
+  if (eval_tokens(empty.data(), n_cols, 0, toks, n_toks, &r)) return -1;
+  return r.dtype;
+}
+
+// ---- arrow `filter`: indices of the set mask entries ---------------------------------------------------
+int64_t orc_mask_to_indices(const uint8_t* mask, int64_t n, int64_t* out_idx) {
+  int64_t m = 0;
+  for (int64_t k = 0; k < n; ++k)
+    if (mask[k]) out_idx[m++] = k;
+  return m;
+}
+
+// ---- RepartitionExec::Hash ------------------------------------------------------------------------------
+int orc_partition_ids(const OCol* cols, const int32_t* keys, int n_keys, int64_t n, int n_parts, int32_t* out_pid) {
+  std::string kb;
+  for (int64_t r = 0; r < n; ++r) {
+    key_bytes(cols, keys, n_keys, r, &kb);
+    out_pid[r] = int32_t(hash_bytes(kb) % uint64_t(n_parts));
+  }
+  return 0;
+}
+
+// ---- HashAggregateExec -----------------------------------------------------------------------------------
+// accumulator kinds
+enum { A_COUNT = 0, A_SUM_I = 1, A_SUM_F = 2, A_MIN_I = 3, A_MAX_I = 4, A_MIN_U = 5, A_MAX_U = 6, A_MIN_F = 7, A_MAX_F = 8 };
+struct OAcc {
+  int32_t kind;
+  int32_t col;  // value column (-1: COUNT(*)); int columns are read widened to int64, f64 as double
+};
+
+// Groups rows by the key columns (first-seen order).  out_first_row[g] = first row of group g;
+// out_state[a * n + g] = accumulator a of group g (int64 / uint64 / double bit patterns).
+// Returns the number of groups.
+int64_t orc_group_by(const OCol* cols, const int32_t* keys, int n_keys, int64_t n, const OAcc* accs, int n_accs, int64_t* out_first_row,
+                     uint64_t* out_state) {
+  std::unordered_map<std::string, int64_t, StrHash> map;
+  map.reserve(size_t(n / 4 + 16));
+  std::string kb;
+  int64_t n_groups = 0;
+  auto load_i = [&](const OCol& c, int64_t r) -> int64_t {
+    switch (c.dtype) {
+      case T_I32: return static_cast<const int32_t*>(c.data)[r];
+      case T_U32: return static_cast<const uint32_t*>(c.data)[r];
+      default: return static_cast<const int64_t*>(c.data)[r];
+    }
+  };
+  auto load_d = [&](const OCol& c, int64_t r) -> double {
+    if (c.dtype == T_F64) return static_cast<const double*>(c.data)[r];
+    if (c.dtype == T_U64 || c.dtype == T_U32) return double(uint64_t(load_i(c, r)));
+    return double(load_i(c, r));
+  };
+  for (int64_t r = 0; r < n; ++r) {
+    int64_t g;
+    if (n_keys == 0) {
+      g = 0;
+      if (n_groups == 0) {
+        n_groups = 1;
+        out_first_row[0] = r;
+        g = -1;
+      }
+    } else {
+      key_bytes(cols, keys, n_keys, r, &kb);
+      auto it = map.find(kb);
+      if (it == map.end()) {
+        map.emplace(kb, n_groups);
+        out_first_row[n_groups] = r;
+        g = -1;
+      } else {
+        g = it->second;
+      }
+    }
+    const bool fresh = g < 0;
+    if (fresh) g = n_keys == 0 ? 0 : n_groups++;
+    for (int a = 0; a < n_accs; ++a) {
+      uint64_t* s = &out_state[int64_t(a) * n + g];
+      const OAcc& ac = accs[a];
+      switch (ac.kind) {
+        case A_COUNT: *s = fresh ? 1 : *s + 1; break;
+        case A_SUM_I: { int64_t v = load_i(cols[ac.col], r); *s = fresh ? uint64_t(v) : *s + uint64_t(v); break; }
+        case A_SUM_F: { double v = load_d(cols[ac.col], r), cur; memcpy(&cur, s, 8); cur = fresh ? v : cur + v; memcpy(s, &cur, 8); break; }
+        case A_MIN_I: { int64_t v = load_i(cols[ac.col], r); if (fresh || v < int64_t(*s)) *s = uint64_t(v); break; }
+        case A_MAX_I: { int64_t v = load_i(cols[ac.col], r); if (fresh || v > int64_t(*s)) *s = uint64_t(v); break; }
+        case A_MIN_U: { uint64_t v = uint64_t(load_i(cols[ac.col], r)); if (fresh || v < *s) *s = v; break; }
+        case A_MAX_U: { uint64_t v = uint64_t(load_i(cols[ac.col], r)); if (fresh || v > *s) *s = v; break; }
+        case A_MIN_F: { double v = load_d(cols[ac.col], r), cur; memcpy(&cur, s, 8); if (fresh || v < cur) memcpy(s, &v, 8); break; }
+        case A_MAX_F: { double v = load_d(cols[ac.col], r), cur; memcpy(&cur, s, 8); if (fresh || v > cur) memcpy(s, &v, 8); break; }
+      }
+    }
+  }
+  return n_groups;
+}
+
+// ---- HashJoinExec (Inner) ------------------------------------------------------------------------------------
+// Returns the number of pairs; writes up to `cap` pairs (call once with cap = 0 to size the output).
+int64_t orc_hash_join(const OCol* lcols, const int32_t* lkeys, int64_t ln, const OCol* rcols, const int32_t* rkeys, int64_t rn, int n_keys,
+                      int64_t* out_left, int64_t* out_right, int64_t cap) {
+  std::unordered_map<std::string, std::vector<int64_t>, StrHash> map;
+  map.reserve(size_t(ln + 16));
+  std::string kb;
+  for (int64_t r = 0; r < ln; ++r) {
+    key_bytes(lcols, lkeys, n_keys, r, &kb);
+    map[kb].push_back(r);
+  }
+  int64_t m = 0;
+  for (int64_t r = 0; r < rn; ++r) {
+    key_bytes(rcols, rkeys, n_keys, r, &kb);
+    auto it = map.find(kb);
+    if (it == map.end()) continue;
+    for (int64_t l : it->second) {
+      if (m < cap) {
+        out_left[m] = l;
+        out_right[m] = r;
+      }
+      ++m;
+    }
+  }
+  return m;
+}
+
+// ---- fused CPU pipelines timed as bench.py's cpu_baseline ----------------------------------------------------
+// NEXMark q2 on ONE record batch, step by step as DataFusion executes it (planner.rs:120-124):
+//   CAST(auction AS Int64) -> `% 123` -> `= 0` (three materialised arrow kernels) -> filter(auction), filter(price).
+// Returns the number of surviving rows; out_* need room for n values.
+int64_t orc_q2_batch(const int32_t* auction, const int32_t* price, int64_t n, int64_t modulus, int64_t rhs, int64_t* scratch_i64,
+                     uint8_t* scratch_mask, int32_t* out_auction, int32_t* out_price) {
+  for (int64_t k = 0; k < n; ++k) scratch_i64[k] = int64_t(auction[k]);          // cast kernel
+  for (int64_t k = 0; k < n; ++k) scratch_i64[k] = scratch_i64[k] % modulus;      // modulus kernel
+  for (int64_t k = 0; k < n; ++k) scratch_mask[k] = scratch_i64[k] == rhs;        // eq kernel
+  int64_t m = 0;
+  for (int64_t k = 0; k < n; ++k)                                                 // filter kernel, column 1
+    if (scratch_mask[k]) out_auction[m++] = auction[k];
+  m = 0;
+  for (int64_t k = 0; k < n; ++k)                                                 // filter kernel, column 2
+    if (scratch_mask[k]) out_price[m++] = price[k];
+  return m;
+}
+
+}  // extern "C"
