@@ -227,6 +227,14 @@ class Context:
         check(lib.flockgpu_timer_elapsed_ms(self.handle, slot, C.byref(ms)))
         return ms.value
 
+    def profile_begin(self) -> None:
+        check(lib.flockgpu_profile_begin(self.handle))
+
+    def profile_end(self) -> dict:
+        buf = C.create_string_buffer(1 << 16)
+        check(lib.flockgpu_profile_end(self.handle, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     @property
     def kernel_launches(self) -> int:
         return lib.flockgpu_kernel_launches(self.handle)

@@ -108,6 +108,7 @@ TablePtr all_to_all(const CtxPtr& ctx, const std::vector<TablePtr>& parts) {
   Comm& cm = *ctx->comm;
   const int W = cm.world;
   FG_CHECK(int(parts.size()) == W, FLOCKGPU_ERR_INVALID, "all_to_all: %zu partitions for %d ranks", parts.size(), W);
+  for (const TablePtr& p : parts) p->resolve();
   const Table& proto = *parts[0];
   const size_t ncol = proto.cols.size();
   std::vector<int> utf8_cols;
@@ -196,11 +197,17 @@ TablePtr all_to_all(const CtxPtr& ctx, const std::vector<TablePtr>& parts) {
     for (int s = 0; s < W; ++s) {
       if (recv_rows[s] && byte_base[u][s]) {
         int blocks = int(std::min<int64_t>((recv_rows[s] + 255) / 256, int64_t(ctx->sm_count) * 8));
-        add_offset_kernel<<<blocks, 256, 0, ctx->stream>>>(oc.offsets->as<int32_t>() + row_base[s], recv_rows[s], int32_t(byte_base[u][s]));
+        {
+          LaunchTimer lt(ctx, "add_offset_kernel");
+          add_offset_kernel<<<blocks, 256, 0, ctx->stream>>>(oc.offsets->as<int32_t>() + row_base[s], recv_rows[s], int32_t(byte_base[u][s]));
+        }
         count_launch(ctx);
       }
     }
-    store_i32_kernel<<<1, 1, 0, ctx->stream>>>(oc.offsets->as<int32_t>() + total_rows, int32_t(byte_base[u][W]));
+    {
+      LaunchTimer lt(ctx, "store_i32_kernel");
+      store_i32_kernel<<<1, 1, 0, ctx->stream>>>(oc.offsets->as<int32_t>() + total_rows, int32_t(byte_base[u][W]));
+    }
     count_launch(ctx);
   }
   // the send buffers (parts) must stay alive until the exchange has run

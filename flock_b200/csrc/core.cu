@@ -3,6 +3,7 @@
 // Replaces, on the reference side: MemoryExec::set_partitions fed by
 // ExecutionContext::feed_data_sources (flock/src/runtime/context.rs:257-325) for the way in, and the
 // Vec<RecordBatch> returned by `collect` (context.rs:172-191) for the way out.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -135,7 +136,53 @@ void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out) 
   for (int i = 0; i < n; ++i) out[i] = ctx->h_scalars[first + i];
 }
 
+// ---- row counts in flight ------------------------------------------------------------------------
+int64_t PendingRows::wait() {
+  if (!done) {
+    cudaSetDevice(ctx->device);
+    FG_CUDA(cudaEventSynchronize(ev));
+    value = int64_t(ctx->h_scalars[256 + slot]);
+    done = true;
+  }
+  return value;
+}
+
+PendingRows::~PendingRows() {
+  if (ev) cudaEventDestroy(ev);
+}
+
+std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned long long* d_count) {
+  const int slot = ctx->pending_next;
+  ctx->pending_next = (ctx->pending_next + 1) % CtxCore::kPendingSlots;
+  if (auto old = ctx->pending_owner[slot].lock()) old->wait();  // the pinned slot is about to be overwritten
+  auto p = std::make_shared<PendingRows>();
+  p->ctx = ctx;
+  p->slot = slot;
+  FG_CUDA(cudaEventCreateWithFlags(&p->ev, cudaEventDisableTiming));
+  FG_CUDA(cudaMemcpyAsync(ctx->h_scalars + 256 + slot, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  FG_CUDA(cudaEventRecord(p->ev, ctx->stream));
+  ctx->pending_owner[slot] = p;
+  return p;
+}
+
+// ---- per-kernel profile ----------------------------------------------------------------------------
+LaunchTimer::LaunchTimer(const CtxPtr& c, const char* kernel) : ctx(c.get()) {
+  if (!ctx->profiling) return;
+  cudaEvent_t start;
+  if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) {
+    stop = nullptr;
+    return;
+  }
+  cudaEventRecord(start, ctx->stream);
+  ctx->profile.push_back({kernel, start, stop});
+}
+
+LaunchTimer::~LaunchTimer() {
+  if (stop) cudaEventRecord(stop, ctx->stream);
+}
+
 int64_t Table::nbytes() const {
+  resolve();
   int64_t n = 0;
   for (const Column& c : cols) {
     if (c.dtype == FLOCKGPU_UTF8)
@@ -166,12 +213,18 @@ __global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
 static void rebase_offsets(const CtxPtr& ctx, int32_t* offs, int64_t n, int32_t delta) {
   if (n <= 0 || delta == 0) return;
   int blocks = int(std::min<int64_t>((n + 255) / 256, ctx->sm_count * 8));
-  rebase_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(offs, n, delta);
+  {
+    LaunchTimer lt(ctx, "rebase_offsets_kernel");
+    rebase_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(offs, n, delta);
+  }
   count_launch(ctx);
 }
 
 static void set_i32(const CtxPtr& ctx, int32_t* p, int32_t v) {
-  set_i32_kernel<<<1, 1, 0, ctx->stream>>>(p, v);
+  {
+    LaunchTimer lt(ctx, "set_i32_kernel");
+    set_i32_kernel<<<1, 1, 0, ctx->stream>>>(p, v);
+  }
   count_launch(ctx);
 }
 
@@ -427,6 +480,7 @@ __global__ void shift_offsets_kernel(const int32_t* __restrict__ src, int32_t* _
 void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t row_count, ArrowSchema* out_schema,
                   ArrowArray* out_array) {
   FG_CHECK(out_schema && out_array, FLOCKGPU_ERR_INVALID, "table_export: null output");
+  t.resolve();
   if (row_count < 0) row_count = t.num_rows - row_begin;
   FG_CHECK(row_begin >= 0 && row_begin + row_count <= t.num_rows, FLOCKGPU_ERR_INVALID,
            "table_export: rows [%lld, %lld) outside table of %lld rows", (long long)row_begin,
@@ -503,7 +557,10 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
           BufferPtr tmp = alloc(ctx, nb_off);
           keep.push_back(tmp);
           int blocks = int(std::min<int64_t>((row_count + 256) / 256, ctx->sm_count * 8));
-          shift_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(c.offs() + row_begin, tmp->as<int32_t>(), row_count + 1);
+          {
+            LaunchTimer lt(ctx, "shift_offsets_kernel");
+            shift_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(c.offs() + row_begin, tmp->as<int32_t>(), row_count + 1);
+          }
           count_launch(ctx);
           FG_CUDA(cudaMemcpyAsync(h_off, tmp->ptr, nb_off, cudaMemcpyDeviceToHost, ctx->stream));
         }
@@ -567,6 +624,7 @@ TablePtr empty_like(const CtxPtr& ctx, const Table& src) {
 TablePtr concat_tables(const CtxPtr& ctx, const std::vector<TablePtr>& tables) {
   FG_CHECK(!tables.empty(), FLOCKGPU_ERR_INVALID, "concat: no tables");
   if (tables.size() == 1) return tables[0];
+  for (const TablePtr& t : tables) t->resolve();
   const Table& first = *tables[0];
   int64_t total = 0;
   for (const TablePtr& t : tables) {
@@ -613,7 +671,10 @@ TablePtr concat_tables(const CtxPtr& ctx, const std::vector<TablePtr>& tables) {
         if (s.length) {
           // s.offsets may start at a non-zero base: shift to `byte`
           int blocks = int(std::min<int64_t>((s.length + 255) / 256, ctx->sm_count * 8));
-          shift_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(s.offs(), c.offsets->as<int32_t>() + row, s.length);
+          {
+            LaunchTimer lt(ctx, "shift_offsets_kernel");
+            shift_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(s.offs(), c.offsets->as<int32_t>() + row, s.length);
+          }
           count_launch(ctx);
           rebase_offsets(ctx, c.offsets->as<int32_t>() + row, s.length, int32_t(byte));
           if (s.values_bytes) {
@@ -802,7 +863,68 @@ int flockgpu_table_release(flockgpu_table* table) {
   });
 }
 
-int64_t flockgpu_table_num_rows(const flockgpu_table* table) { return table && table->table ? table->table->num_rows : -1; }
+int64_t flockgpu_table_num_rows(const flockgpu_table* table) {
+  if (!table || !table->table) return -1;
+  int64_t n = -1;
+  guarded([&] {
+    table->table->resolve();  // waits for a survivor count that is still in flight
+    n = table->table->num_rows;
+  });
+  return n;
+}
+
+int flockgpu_profile_begin(flockgpu_ctx* ctx) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    for (auto& p : c->profile) {
+      cudaEventDestroy(p.start);
+      cudaEventDestroy(p.stop);
+    }
+    c->profile.clear();
+    c->profiling = true;
+  });
+}
+
+int flockgpu_profile_end(flockgpu_ctx* ctx, char* out_json, int32_t capacity) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(out_json && capacity > 2, FLOCKGPU_ERR_INVALID, "profile_end: bad output buffer");
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    FG_CUDA(cudaSetDevice(c->device));
+    c->profiling = false;
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    struct Acc {
+      double ms = 0;
+      int64_t n = 0;
+    };
+    std::vector<std::pair<std::string, Acc>> acc;
+    for (auto& p : c->profile) {
+      float ms = 0;
+      FG_CUDA(cudaEventElapsedTime(&ms, p.start, p.stop));
+      auto it = std::find_if(acc.begin(), acc.end(), [&](const std::pair<std::string, Acc>& kv) { return kv.first == p.kernel; });
+      if (it == acc.end()) {
+        acc.emplace_back(p.kernel, Acc{});
+        it = acc.end() - 1;
+      }
+      it->second.ms += ms;
+      it->second.n += 1;
+      cudaEventDestroy(p.start);
+      cudaEventDestroy(p.stop);
+    }
+    c->profile.clear();
+    std::string s = "{";
+    for (size_t i = 0; i < acc.size(); ++i) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", i ? ", " : "", acc[i].first.c_str(), (long long)acc[i].second.n,
+               acc[i].second.ms);
+      s += buf;
+    }
+    s += "}";
+    FG_CHECK(int(s.size()) < capacity, FLOCKGPU_ERR_INVALID, "profile_end: output buffer too small (%zu bytes needed)", s.size() + 1);
+    memcpy(out_json, s.c_str(), s.size() + 1);
+  });
+}
 
 int32_t flockgpu_table_num_columns(const flockgpu_table* table) {
   return table && table->table ? int32_t(table->table->cols.size()) : -1;

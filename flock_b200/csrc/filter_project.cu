@@ -247,7 +247,10 @@ template <class PredFn>
 static void launch_filter(const CtxPtr& ctx, const PredFn& pred, const FilterArgs& args) {
   const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
   int grid = persistent_grid(ctx, k, FP_THREADS, args.num_tiles);
-  filter_compact_kernel<PredFn><<<grid, FP_THREADS, 0, ctx->stream>>>(pred, args);
+  {
+    LaunchTimer lt(ctx, "filter_compact_kernel");
+    filter_compact_kernel<PredFn><<<grid, FP_THREADS, 0, ctx->stream>>>(pred, args);
+  }
   FG_CUDA(cudaGetLastError());
   count_launch(ctx);
 }
@@ -255,6 +258,7 @@ static void launch_filter(const CtxPtr& ctx, const PredFn& pred, const FilterArg
 TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* predicate, const std::vector<Expr>& projections,
                         const std::vector<std::string>& names) {
   const Table& in = *in_ptr;
+  in.resolve();
   std::vector<ColInfo> infos = col_infos(in);
   // ---- compile
   std::vector<CompiledValue> vals;
@@ -310,8 +314,11 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
           if (v.fast == FAST_VAL_I32_TO_F64_MUL) {
             int64_t n4 = std::max<int64_t>(1, in.num_rows / 4);
             int grid = int(std::min<int64_t>((n4 + PJ_THREADS - 1) / PJ_THREADS, int64_t(ctx->sm_count) * 8));
-            project_i32_to_f64_mul_kernel<<<grid, PJ_THREADS, 0, ctx->stream>>>(
+            {
+              LaunchTimer lt(ctx, "project_i32_to_f64_mul_kernel");
+              project_i32_to_f64_mul_kernel<<<grid, PJ_THREADS, 0, ctx->stream>>>(
                 static_cast<const int32_t*>(in.cols[v.chain.start_col].values()), c.data->as<double>(), in.num_rows, v.fast_lit);
+            }
             FG_CUDA(cudaGetLastError());
             count_launch(ctx);
           } else {
@@ -333,7 +340,10 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
       int64_t per_block = int64_t(PJ_THREADS) * PJ_ROWS;
       int grid = int(std::min<int64_t>((in.num_rows + per_block - 1) / per_block, int64_t(ctx->sm_count) * 8));
       if (check_err) FG_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int), ctx->stream));
-      project_generic_kernel<<<grid, PJ_THREADS, 0, ctx->stream>>>(pa);
+      {
+        LaunchTimer lt(ctx, "project_generic_kernel");
+        project_generic_kernel<<<grid, PJ_THREADS, 0, ctx->stream>>>(pa);
+      }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
       if (check_err) {
@@ -435,6 +445,14 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
     }
   }
 
+  if (!check_err && utf8_outs.empty()) {
+    // fixed-width outputs only: the survivor count stays in flight (one async 8-byte copy into a pinned
+    // slot); the first consumer that needs the number waits for it (Table::resolve)
+    out->pending = enqueue_row_count(ctx, fa.out_count);
+    out->num_rows = -1;
+    for (Column& c : out->cols) c.length = -1;
+    return out;
+  }
   unsigned long long scalars[9];
   read_scalars(ctx, 0, 9, scalars);
   if (check_err) FG_CHECK((scalars[8] & 0xffffffffull) == 0, FLOCKGPU_ERR_EXECUTION, "Divide by zero");

@@ -171,11 +171,17 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
     if (n > 0) {
       int grid = stream_grid(ctx, n, GA_THREADS * 4);
       if (w == 4)
-        gather_fixed_kernel<uint32_t><<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint32_t*>(in.values()), d_idx,
+        {
+          LaunchTimer lt(ctx, "gather_fixed_kernel<uint32_t>");
+          gather_fixed_kernel<uint32_t><<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint32_t*>(in.values()), d_idx,
                                                                             out.data->as<uint32_t>(), n);
+        }
       else
-        gather_fixed_kernel<uint64_t><<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint64_t*>(in.values()), d_idx,
+        {
+          LaunchTimer lt(ctx, "gather_fixed_kernel<uint64_t>");
+          gather_fixed_kernel<uint64_t><<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint64_t*>(in.values()), d_idx,
                                                                             out.data->as<uint64_t>(), n);
+        }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
     }
@@ -202,7 +208,10 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
     int per_sm = 1;
     FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_lengths_scan_kernel, GA_THREADS, 0));
     int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), a.num_tiles)));
-    gather_lengths_scan_kernel<<<grid, GA_THREADS, 0, ctx->stream>>>(a);
+    {
+      LaunchTimer lt(ctx, "gather_lengths_scan_kernel");
+      gather_lengths_scan_kernel<<<grid, GA_THREADS, 0, ctx->stream>>>(a);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
   }
@@ -213,8 +222,11 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
   out.data = alloc(ctx, size_t(total));
   if (total > 0) {
     int grid = stream_grid(ctx, (n + 31) / 32, GA_THREADS / 32);
-    gather_utf8_copy_kernel<<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint8_t*>(in.values()), in.offs(), d_idx,
+    {
+      LaunchTimer lt(ctx, "gather_utf8_copy_kernel");
+      gather_utf8_copy_kernel<<<grid, GA_THREADS, 0, ctx->stream>>>(static_cast<const uint8_t*>(in.values()), in.offs(), d_idx,
                                                                   out.offsets->as<int32_t>(), out.data->as<uint8_t>(), n);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
   }
@@ -222,6 +234,7 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
 }
 
 TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx, int64_t n_idx) {
+  in.resolve();
   auto out = std::make_shared<Table>();
   out->ctx = ctx;
   out->metadata = in.metadata;

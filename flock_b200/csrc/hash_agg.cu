@@ -608,6 +608,7 @@ unsigned long long pow2_at_least(unsigned long long n) {
 
 TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs) {
   const Table& in = *in_ptr;
+  in.resolve();
   FG_CHECK(mode >= FLOCKGPU_AGG_PARTIAL && mode <= FLOCKGPU_AGG_SINGLE, FLOCKGPU_ERR_INVALID, "hash_aggregate: bad mode %d", mode);
   for (int g : group_cols) {
     FG_CHECK(g >= 0 && g < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_aggregate: group column %d out of range", g);
@@ -655,14 +656,20 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       for (int c = 0; c < n_acc; ++c) ga.acc[c] = accs[c];
       fill_cols(in, ga.cols);
       ga.state = state->as<unsigned long long>();
-      agg_global_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ga);
+      {
+        LaunchTimer lt(ctx, "agg_global_kernel");
+        agg_global_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ga);
+      }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
     }
     AggEmitOneArgs ea{};
     ea.state = state->as<unsigned long long>();
     fill_emit(ea.emit, &ea.n_emit, cols);
-    agg_emit_one_kernel<<<1, 32, 0, ctx->stream>>>(ea);
+    {
+      LaunchTimer lt(ctx, "agg_emit_one_kernel");
+      agg_emit_one_kernel<<<1, 32, 0, ctx->stream>>>(ea);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
     // aggregates other than COUNT over zero rows are NULL
@@ -745,7 +752,10 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       int per_sm = 1;
       FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_local_kernel, AL_THREADS, local_smem));
       int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + AL_THREADS * AL_UNROLL - 1) / (AL_THREADS * AL_UNROLL))));
-      agg_local_kernel<<<grid, AL_THREADS, local_smem, ctx->stream>>>(la);
+      {
+        LaunchTimer lt(ctx, "agg_local_kernel");
+        agg_local_kernel<<<grid, AL_THREADS, local_smem, ctx->stream>>>(la);
+      }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
       unsigned long long cnt = 0;
@@ -760,8 +770,11 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     tkeys = alloc(ctx, size_t(n_slots) * 8);
     tacc = alloc(ctx, size_t(n_slots) * 8 * std::max(n_acc, 1));
     AggTable tab{tkeys->as<unsigned long long>(), tacc->as<unsigned long long>(), cap};
-    agg_init_kernel<<<grid_for(ctx, int64_t(n_slots), 256, 8), 256, 0, ctx->stream>>>(tab, n_acc, ident[0], ident[1], ident[2], ident[3], ident[4],
+    {
+      LaunchTimer lt(ctx, "agg_init_kernel");
+      agg_init_kernel<<<grid_for(ctx, int64_t(n_slots), 256, 8), 256, 0, ctx->stream>>>(tab, n_acc, ident[0], ident[1], ident[2], ident[3], ident[4],
                                                                                        ident[5], ident[6], ident[7]);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
     AggInsertArgs ia{};
@@ -776,7 +789,10 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     ia.part_capacity = n;
     ia.table = tab;
     if (n_entries > 0) {
-      agg_insert_kernel<<<grid_for(ctx, n_entries, 256, 8), 256, 0, ctx->stream>>>(ia);
+      {
+        LaunchTimer lt(ctx, "agg_insert_kernel");
+        agg_insert_kernel<<<grid_for(ctx, n_entries, 256, 8), 256, 0, ctx->stream>>>(ia);
+      }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
     }
@@ -791,9 +807,12 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     n_slots = cap;
     towner = alloc(ctx, size_t(cap) * 4);
     tacc = alloc(ctx, size_t(cap) * 8 * std::max(n_acc, 1));
-    agg_rows_init_kernel<<<grid_for(ctx, int64_t(cap), 256, 8), 256, 0, ctx->stream>>>(towner->as<unsigned>(), tacc->as<unsigned long long>(), cap, n_acc,
+    {
+      LaunchTimer lt(ctx, "agg_rows_init_kernel");
+      agg_rows_init_kernel<<<grid_for(ctx, int64_t(cap), 256, 8), 256, 0, ctx->stream>>>(towner->as<unsigned>(), tacc->as<unsigned long long>(), cap, n_acc,
                                                                                        ident[0], ident[1], ident[2], ident[3], ident[4], ident[5],
                                                                                        ident[6], ident[7]);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
     AggRowsArgs ra{};
@@ -806,7 +825,10 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     ra.owner = towner->as<unsigned>();
     ra.tacc = tacc->as<unsigned long long>();
     ra.cap = cap;
-    agg_insert_rows_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ra);
+    {
+      LaunchTimer lt(ctx, "agg_insert_rows_kernel");
+      agg_insert_rows_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ra);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
     ea.owner = towner->as<unsigned>();
@@ -838,7 +860,10 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     int per_sm = 1;
     FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_emit_kernel, CP_THREADS, 0));
     int grid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), ea.sc.num_tiles)));
-    agg_emit_kernel<<<grid, CP_THREADS, 0, ctx->stream>>>(ea);
+    {
+      LaunchTimer lt(ctx, "agg_emit_kernel");
+      agg_emit_kernel<<<grid, CP_THREADS, 0, ctx->stream>>>(ea);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
   }

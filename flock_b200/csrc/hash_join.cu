@@ -205,6 +205,8 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
                    const std::vector<int>& right_keys) {
   const Table& L = *left_ptr;
   const Table& R = *right_ptr;
+  L.resolve();
+  R.resolve();
   FG_CHECK(!left_keys.empty() && left_keys.size() == right_keys.size(), FLOCKGPU_ERR_INVALID, "hash_join: key lists must be non-empty and of equal length");
   FG_CHECK(left_keys.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_join: more than %d key columns", MAX_KEY_COLS);
   std::vector<int> widths;
@@ -239,7 +241,10 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     BufferPtr tkeys = packed ? alloc(ctx, size_t(cap) * 8) : nullptr;
     FG_CUDA(cudaMemsetAsync(trows->ptr, 0xff, size_t(cap) * 4, ctx->stream));
     JoinTable tab{trows->as<unsigned>(), tkeys ? tkeys->as<unsigned long long>() : nullptr, cap};
-    join_build_kernel<<<grid_for(ctx, L.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab);
+    {
+      LaunchTimer lt(ctx, "join_build_kernel");
+      join_build_kernel<<<grid_for(ctx, L.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
 
@@ -258,7 +263,10 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       int per_sm = 1;
       FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_count_scan_kernel, JC_THREADS, 0));
       int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), ca.num_tiles)));
-      join_count_scan_kernel<<<grid, JC_THREADS, 0, ctx->stream>>>(ca);
+      {
+        LaunchTimer lt(ctx, "join_count_scan_kernel");
+        join_count_scan_kernel<<<grid, JC_THREADS, 0, ctx->stream>>>(ca);
+      }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
     }
@@ -276,7 +284,10 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       ea.off = off->as<unsigned>();
       ea.build_idx = build_idx->as<unsigned>();
       ea.probe_idx = probe_idx->as<unsigned>();
-      join_emit_kernel<<<grid_for(ctx, R.num_rows, 256, 8), 256, 0, ctx->stream>>>(ea);
+      {
+        LaunchTimer lt(ctx, "join_emit_kernel");
+        join_emit_kernel<<<grid_for(ctx, R.num_rows, 256, 8), 256, 0, ctx->stream>>>(ea);
+      }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
     }

@@ -346,6 +346,7 @@ static TablePtr rename_columns(const ExecEnv& env, const TablePtr& t, const std:
   bool same = true;
   for (size_t i = 0; i < names.size() && i < t->cols.size(); ++i) same &= names[i].empty() || t->cols[i].name == names[i];
   if (same) return t;
+  t->resolve();
   auto r = std::make_shared<fg::Table>(*t);
   for (size_t i = 0; i < names.size() && i < r->cols.size(); ++i)
     if (!names[i].empty()) r->cols[i].name = names[i];
@@ -595,6 +596,7 @@ static bool compare_schema(const std::vector<std::string>& a, const std::vector<
 }
 
 static TablePtr project_by_name(const CtxPtr& ctx, const TablePtr& t, const std::vector<std::string>& names) {
+  t->resolve();
   auto out = std::make_shared<fg::Table>();
   out->ctx = ctx;
   out->metadata = t->metadata;

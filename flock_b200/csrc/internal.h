@@ -100,9 +100,43 @@ struct CtxCore {
 
   std::shared_ptr<Comm> comm;  // comm.cc (shared_ptr: Comm is incomplete here)
 
+  // row counts still in flight (see PendingRows): pinned slots h_scalars[256 + i]
+  static constexpr int kPendingSlots = 256;
+  std::weak_ptr<struct PendingRows> pending_owner[kPendingSlots];
+  int pending_next = 0;
+
+  // per-kernel CUDA-event profile (flockgpu_profile_begin / _end; bench.py's roofline numerator)
+  bool profiling = false;
+  struct ProfiledLaunch {
+    const char* kernel;
+    cudaEvent_t start, stop;
+  };
+  std::vector<ProfiledLaunch> profile;
+
   ~CtxCore();
 };
 using CtxPtr = std::shared_ptr<CtxCore>;
+
+// RAII: when profiling is on, brackets ONE kernel launch with events on the context stream.
+struct LaunchTimer {
+  CtxCore* ctx;
+  cudaEvent_t stop = nullptr;
+  LaunchTimer(const CtxPtr& c, const char* kernel);
+  ~LaunchTimer();
+};
+
+// A survivor count that a kernel is still producing.  The operator enqueues an async copy of the device
+// counter into a pinned slot and returns at once; the first consumer that needs the number waits.
+struct PendingRows {
+  CtxPtr ctx;
+  int slot = 0;
+  cudaEvent_t ev = nullptr;
+  bool done = false;
+  int64_t value = 0;
+  int64_t wait();
+  ~PendingRows();
+};
+std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned long long* d_count);
 
 struct Buffer {
   CtxPtr ctx;
@@ -152,10 +186,19 @@ struct Column {
 
 struct Table {
   CtxPtr ctx;
-  std::vector<Column> cols;
-  int64_t num_rows = 0;
+  // `cols[i].length` and `num_rows` are -1 while `pending` is set (a filter's survivor count that has not
+  // been read back yet); resolve() waits for it and fills them in.  Every operator resolves its inputs.
+  mutable std::vector<Column> cols;
+  mutable int64_t num_rows = 0;
+  mutable std::shared_ptr<PendingRows> pending;
   std::string metadata;  // raw Arrow schema metadata block (may be empty)
   int64_t nbytes() const;
+  void resolve() const {
+    if (!pending) return;
+    num_rows = pending->wait();
+    for (Column& c : cols) c.length = num_rows;
+    pending.reset();
+  }
 };
 using TablePtr = std::shared_ptr<const Table>;
 
@@ -174,6 +217,7 @@ namespace fg {
 flockgpu_table* wrap_table(TablePtr t);
 inline const Table& deref(const flockgpu_table* t) {
   if (!t || !t->table) fail(FLOCKGPU_ERR_INVALID, "null table handle");
+  t->table->resolve();
   return *t->table;
 }
 inline CtxPtr core_of(flockgpu_ctx* c) {

@@ -95,6 +95,7 @@ __global__ void partition_advance_kernel(unsigned long long* bases, int part, co
 
 std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vector<int>& keys, int n_parts) {
   const Table& in = *in_ptr;
+  in.resolve();
   FG_CHECK(n_parts >= 1 && n_parts <= 255, FLOCKGPU_ERR_INVALID, "hash_partition: n_parts must be in [1, 255], got %d", n_parts);
   FG_CHECK(!keys.empty() && keys.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_INVALID, "hash_partition: 1..%d key columns", MAX_KEY_COLS);
   FG_CHECK(in.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d columns", MAX_IN_COLS);
@@ -135,7 +136,10 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   }
   ia.pid = pid->as<uint8_t>();
   int grid = int(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, int64_t(ctx->sm_count) * 8)));
-  partition_ids_kernel<<<grid, 256, 0, ctx->stream>>>(ia);
+  {
+    LaunchTimer lt(ctx, "partition_ids_kernel");
+    partition_ids_kernel<<<grid, 256, 0, ctx->stream>>>(ia);
+  }
   FG_CUDA(cudaGetLastError());
   count_launch(ctx);
 
@@ -159,9 +163,15 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   int sgrid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), sa.sc.num_tiles)));
   for (int p = 0; p < n_parts; ++p) {
     sa.part = p;
-    partition_select_kernel<<<sgrid, CP_THREADS, 0, ctx->stream>>>(sa);
+    {
+      LaunchTimer lt(ctx, "partition_select_kernel");
+      partition_select_kernel<<<sgrid, CP_THREADS, 0, ctx->stream>>>(sa);
+    }
     FG_CUDA(cudaGetLastError());
-    partition_advance_kernel<<<1, 1, 0, ctx->stream>>>(bases, p, ctx->d_scalars + 5);
+    {
+      LaunchTimer lt(ctx, "partition_advance_kernel");
+      partition_advance_kernel<<<1, 1, 0, ctx->stream>>>(bases, p, ctx->d_scalars + 5);
+    }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx, 2);
   }

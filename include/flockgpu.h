@@ -94,6 +94,11 @@ int flockgpu_timer_stop(flockgpu_ctx* ctx, int slot);              /* records th
 int flockgpu_timer_elapsed_ms(flockgpu_ctx* ctx, int slot, float* ms); /* syncs on the stop event  */
 /* Number of kernels this library has launched on the ctx since it was opened.                     */
 int64_t flockgpu_kernel_launches(flockgpu_ctx* ctx);
+/* Per-kernel device timing: between _begin and _end every kernel this library launches on the ctx is
+ * bracketed by its own pair of CUDA events on the ctx stream.  _end waits for the stream and writes a JSON
+ * object {"<kernel>": {"launches": n, "ms": total}, ...} into out_json (bench.py's roofline numerator).  */
+int flockgpu_profile_begin(flockgpu_ctx* ctx);
+int flockgpu_profile_end(flockgpu_ctx* ctx, char* out_json, int32_t capacity);
 /* Pinned host memory (page-locked) for staging Arrow buffers: bench.py's e2e leg and the Rust shim
  * allocate record-batch buffers here so that host<->device copies are true DMA.                    */
 int flockgpu_host_alloc(flockgpu_ctx* ctx, int64_t bytes, void** out);

@@ -280,7 +280,7 @@ def hash_aggregate(batch: pa.RecordBatch, mode: str, group: list[tuple[int, str]
         t = batch.schema.field(col).type if col is not None and col >= 0 else None
         if f == "count":
             accs.append((A_SUM_I, col) if final else (A_COUNT, -1))
-            outs.append((name if final else name + "[count]", "raw", len(accs) - 1, None, pa.uint64()))
+            outs.append((name if final or mode == "Single" else name + "[count]", "raw", len(accs) - 1, None, pa.uint64()))
         elif f == "sum":
             if pa.types.is_float64(t):
                 accs.append((A_SUM_F, col)); ot = pa.float64()

@@ -1,0 +1,243 @@
+"""Operator-level parity on the GPU (`-m gpu`), every call through the C ABI (ctypes), checked against the
+CPU oracle on the same seeded inputs.  Bit-exact: integers, bytes and indices everywhere; the only
+floating-point kernels (q1's 0.908 * CAST(price AS Float64) and AVG) are also compared bit for bit
+because each value is produced by a single IEEE operation."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+import flock_b200 as fb
+import oracle
+from flock_b200 import col, lit, nexgen, plans, sharding
+
+pytestmark = pytest.mark.gpu
+
+
+def rb(**cols):
+    return pa.RecordBatch.from_arrays(list(cols.values()), names=list(cols.keys()))
+
+
+def mixed_batch(n, seed):
+    rng = np.random.default_rng(seed)
+    words = ["", "a", "or", "id", "ca", "portland", "san francisco", "x" * 37, "émile", "日本"]
+    return pa.RecordBatch.from_arrays([
+        pa.array(rng.integers(-1000, 1000, n).astype(np.int32)),
+        pa.array(rng.integers(-(1 << 50), 1 << 50, n)),
+        pa.array(rng.integers(0, 1 << 62, n).astype(np.uint64)),
+        pa.array(rng.normal(0, 1e6, n)),
+        pa.array(rng.integers(1_436_918_400_000, 1_436_918_500_000, n), pa.timestamp("ms")),
+        pa.array([words[k] for k in rng.integers(0, len(words), n)]),
+        pa.array(rng.integers(0, 50, n).astype(np.int32)),
+    ], schema=pa.schema([pa.field("i32", pa.int32(), False), pa.field("i64", pa.int64(), False), pa.field("u64", pa.uint64(), False),
+                         pa.field("f64", pa.float64(), False), pa.field("ts", pa.timestamp("ms"), False), pa.field("s", pa.utf8(), False),
+                         pa.field("k", pa.int32(), False)], metadata={"name": "mixed"}))
+
+
+# ---- host <-> HBM ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 31, 4097, 100_003])
+def test_import_export_roundtrip(gpu_ctx, n):
+    b = mixed_batch(n, seed=n)
+    pieces = [b] if n < 10 else [b.slice(0, 7), b.slice(7, 0), b.slice(7, n // 2), b.slice(7 + n // 2)]   # ragged + sliced (offset != 0)
+    t = gpu_ctx.import_batches(pieces)
+    assert t.num_rows == n and t.num_columns == 7
+    out = t.to_batch()
+    assert out.schema.equals(b.schema, check_metadata=True)
+    assert out.equals(b)
+    if n > 100:
+        assert t.to_batch(50, 40).equals(b.slice(50, 40))          # Utf8 offsets are rebased on export
+        proj = gpu_ctx.import_batches(pieces, projection=[5, 0])
+        assert proj.to_batch().equals(b.select(["s", "i32"]))
+        both = gpu_ctx.concat([t, proj]) if False else gpu_ctx.concat([t, t])
+        assert both.to_batch().equals(pa.Table.from_batches([b, b]).combine_chunks().to_batches()[0])
+
+
+def test_import_rejects_nulls_and_unknown_types(gpu_ctx):
+    with pytest.raises(fb.FlockGpuError) as info:
+        gpu_ctx.import_batches([rb(x=pa.array([1, None, 3], pa.int32()))])
+    assert info.value.code == -2 and "nulls" in info.value.message
+    with pytest.raises(fb.FlockGpuError) as info:
+        gpu_ctx.import_batches([rb(x=pa.array([1.0, 2.0], pa.float32()))])
+    assert info.value.code == -2
+
+
+# ---- FilterExec / ProjectionExec ----------------------------------------------------------------------------
+PREDICATES = [
+    lambda: col(0).cast("int64") % 123 == 0,
+    lambda: col(0).cast("int64") % 7 == -3,
+    lambda: col(0).cast("int64") == 10,
+    lambda: col(0).cast("int64") < 0,
+    lambda: (col(5) == "or") | (col(5) == "id") | (col(5) == "ca"),
+    lambda: col(5) >= "id",
+    lambda: (col(1) > 0) & ~(col(3) < lit(0).cast("float64")),
+    lambda: (col(4) >= lit(1_436_918_450_000, "timestamp")) & (col(2) > lit(1 << 61, "uint64")),
+    lambda: (col(0) * 2 + 1).cast("int64") % (col(6) + 1).cast("int64") == 1,
+    lambda: col(0).cast("int64") > 5000,        # nothing survives
+    lambda: col(0).cast("int64") >= -5000,      # everything survives
+]
+
+
+def oracle_filter(b, pred_e, proj_es=None, names=None):
+    """Reference result through the oracle's own evaluator, driven by the same postfix tokens."""
+    import ctypes as C
+    cols = oracle.Cols(b)
+    toks, keep = oracle._ctoks(pred_e.tokens)
+    mask = np.zeros(max(b.num_rows, 1), np.uint8)
+    oracle._check(oracle.lib().orc_eval_predicate(cols.arr, b.num_columns, C.c_int64(b.num_rows), toks, len(toks), mask.ctypes.data_as(C.c_void_p)), "pred")
+    return b.filter(pa.array(mask[:b.num_rows].astype(bool)))
+
+
+@pytest.mark.parametrize("case", range(len(PREDICATES)))
+@pytest.mark.parametrize("n", [1, 4096, 70_001])
+def test_filter_matches_oracle(gpu_ctx, case, n):
+    b = mixed_batch(n, seed=100 + case)
+    pred = PREDICATES[case]()
+    t = gpu_ctx.import_batches([b.slice(0, n // 3), b.slice(n // 3)])
+    got = gpu_ctx.filter_project(t, pred).to_batch()
+    want = oracle_filter(b, pred)
+    assert got.num_rows == want.num_rows
+    assert got.equals(want)                                   # stable: surviving rows keep their input order
+
+
+def test_filter_with_projection_and_computed_columns(gpu_ctx):
+    b = mixed_batch(50_000, seed=9)
+    t = gpu_ctx.import_batches([b])
+    got = gpu_ctx.filter_project(t, col(0).cast("int64") % 5 == 0,
+                                 [col(5), col(0), 0.908 * col(0).cast("float64"), col(1) - col(0).cast("int64"), col(4)],
+                                 ["s", "i32", "scaled", "diff", "ts"]).to_batch()
+    keep = np.fmod(b["i32"].to_numpy().astype(np.int64), 5) == 0
+    w = b.filter(pa.array(keep))
+    i32 = w["i32"].to_numpy()
+    assert got.schema.names == ["s", "i32", "scaled", "diff", "ts"]
+    assert got["s"].equals(w["s"]) and got["i32"].equals(w["i32"]) and got["ts"].equals(w["ts"])
+    assert np.array_equal(got["scaled"].to_numpy().view(np.int64), (np.float64(0.908) * i32.astype(np.float64)).view(np.int64))
+    assert np.array_equal(got["diff"].to_numpy(), w["i64"].to_numpy() - i32)
+
+
+def test_projection_only_is_zero_copy_and_exact(gpu_ctx):
+    bids = nexgen.bids(65536 + 3, seed=11)
+    t = gpu_ctx.import_batches([bids])
+    k0 = gpu_ctx.kernel_launches
+    out = gpu_ctx.filter_project(t, None, [col(0), col(1), 0.908 * col(2).cast("float64"), col(3)], ["auction", "bidder", "price", "b_date_time"])
+    assert gpu_ctx.kernel_launches - k0 == 1                  # only the computed column costs a kernel
+    got = out.to_batch()
+    price = bids["price"].to_numpy().astype(np.float64)
+    assert np.array_equal(got["price"].to_numpy().view(np.int64), (np.float64(0.908) * price).view(np.int64))
+    assert got["auction"].equals(bids["auction"]) and got["b_date_time"].equals(bids["b_date_time"])
+    gen = gpu_ctx.filter_project(t, None, [(col(2) + 7) * 3, col(2).cast("int64") % 1000], ["a", "b"]).to_batch()   # generic interpreter
+    p = bids["price"].to_numpy()
+    assert np.array_equal(gen["a"].to_numpy(), ((p + 7) * 3).astype(np.int32)) and np.array_equal(gen["b"].to_numpy(), p.astype(np.int64) % 1000)
+
+
+def test_divide_by_zero_is_reported(gpu_ctx):
+    b = rb(a=pa.array([1, 2, 3], pa.int64()), z=pa.array([1, 0, 2], pa.int64()))
+    t = gpu_ctx.import_batches([b])
+    with pytest.raises(fb.FlockGpuError, match="Divide by zero") as info:
+        gpu_ctx.filter_project(t, col(0) % col(1) == 0)
+    assert info.value.code == -5
+    assert gpu_ctx.filter_project(t, col(0) % 2 == 1).num_rows == 2      # the context stays usable
+
+
+# ---- HashAggregateExec ---------------------------------------------------------------------------------------
+def oracle_agg(b, mode, group, aggs):
+    return oracle.hash_aggregate(b, mode, [(g, b.schema.names[g]) for g in group], [{"func": f, "col": c, "name": n} for f, c, n in aggs])
+
+
+AGGS = [("count", -1, "COUNT(UInt8(1))"), ("sum", 1, "SUM(i64)"), ("min", 0, "MIN(i32)"), ("max", 2, "MAX(u64)"),
+        ("avg", 0, "AVG(i32)"), ("max", 4, "MAX(ts)"), ("min", 3, "MIN(f64)"), ("sum", 0, "SUM(i32)")]
+
+
+@pytest.mark.parametrize("group", [[6], [6, 0], [1], [5], [6, 5], [4, 2, 5]])
+@pytest.mark.parametrize("n", [3, 5000, 300_000])
+def test_hash_aggregate_single(gpu_ctx, group, n):
+    b = mixed_batch(n, seed=n + len(group))
+    t = gpu_ctx.import_batches([b])
+    aggs = AGGS[:6] if len(group) < 3 else AGGS[:2]
+    got = gpu_ctx.hash_aggregate(t, group, aggs, "single").to_arrow()
+    want = pa.Table.from_batches([oracle_agg(b, "Single", group, aggs)])
+    oracle.assert_tables_equal(got, want)
+
+
+def test_hash_aggregate_partial_then_final(gpu_ctx):
+    b = mixed_batch(200_000, seed=77)
+    halves = [gpu_ctx.import_batches([b.slice(0, 90_000)]), gpu_ctx.import_batches([b.slice(90_000)])]
+    aggs = [("count", -1, "c"), ("avg", 3, "a"), ("max", 0, "m"), ("sum", 2, "s")]
+    partials = [gpu_ctx.hash_aggregate(h, [6, 5], aggs, "partial") for h in halves]
+    p0 = partials[0].to_batch()
+    assert p0.schema.names == ["k", "s", "c[count]", "a[count]", "a[sum]", "m[max]", "s[sum]"]          # aggregate.json naming
+    merged = gpu_ctx.concat(partials)
+    final_aggs = [("count", 2, "c"), ("avg", 3, "a"), ("max", 5, "m"), ("sum", 6, "s")]
+    got = gpu_ctx.hash_aggregate(merged, [0, 1], final_aggs, "final_partitioned").to_arrow()
+    want = pa.Table.from_batches([oracle_agg(b, "Single", [6, 5], aggs)])
+    oracle.assert_tables_equal(got, want)
+
+
+def test_global_aggregate_and_empty_input(gpu_ctx):
+    b = mixed_batch(123_457, seed=5)
+    t = gpu_ctx.import_batches([b])
+    aggs = [("min", 1, "MIN"), ("avg", 2, "AVG"), ("count", 5, "COUNT"), ("max", 3, "MAXF")]
+    got = gpu_ctx.hash_aggregate(t, [], aggs, "single").to_arrow()
+    want = pa.Table.from_batches([oracle_agg(b, "Single", [], aggs)])
+    oracle.assert_tables_equal(got, want)
+    e = gpu_ctx.hash_aggregate(gpu_ctx.import_batches([b.slice(0, 0)]), [], aggs, "single").to_arrow()
+    assert e.num_rows == 1 and e["COUNT"].to_pylist() == [0] and e["MIN"].to_pylist() == [None] and e["AVG"].to_pylist() == [None]
+    assert gpu_ctx.hash_aggregate(gpu_ctx.import_batches([b.slice(0, 0)]), [6], aggs, "single").num_rows == 0
+
+
+def test_aggregate_key_edge_cases(gpu_ctx):
+    # the packed-key table reserves ~0 as its empty marker: a real key with that bit pattern must still group
+    keys = np.array([-1, -1, 0, 5, -1, 0], np.int64)
+    t = gpu_ctx.import_batches([rb(k=pa.array(keys), v=pa.array(np.arange(6, dtype=np.int64)))])
+    got = gpu_ctx.hash_aggregate(t, [0], [("count", -1, "n"), ("sum", 1, "s")], "single").to_arrow()
+    assert sorted(zip(*[got.column(i).to_pylist() for i in range(3)])) == [(-1, 3, 5), (0, 2, 7), (5, 1, 3)]
+    big = np.full(400_000, -1, np.int64)
+    big[::1000] = 7
+    t = gpu_ctx.import_batches([rb(k=pa.array(big), v=pa.array(np.ones(400_000, np.int64)))])
+    got = gpu_ctx.hash_aggregate(t, [0], [("count", -1, "n")], "single").to_arrow()
+    assert sorted(zip(got["k"].to_pylist(), got["n"].to_pylist())) == [(-1, 399_600), (7, 400)]
+
+
+# ---- HashJoinExec -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("keys", [([0], [0]), ([5], [5]), ([6, 0], [6, 0]), ([6, 5], [6, 5]), ([1], [1])])
+def test_hash_join_matches_oracle(gpu_ctx, keys):
+    l = mixed_batch(20_000, seed=1)
+    r = mixed_batch(30_000, seed=2)
+    if keys[0] == [1]:
+        r = r.set_column(1, r.schema.field(1), l["i64"].take(pa.array(np.random.default_rng(3).integers(0, 20_000, 30_000))))
+    got = gpu_ctx.hash_join(gpu_ctx.import_batches([l]), gpu_ctx.import_batches([r]), *keys).to_arrow()
+    want = pa.Table.from_batches([oracle.hash_join(l, r, *keys)])
+    assert got.num_rows == want.num_rows and got.num_rows > 0
+    oracle.assert_tables_equal(got, want, check_names=False)
+
+
+def test_hash_join_edge_cases(gpu_ctx):
+    l = rb(a=pa.array([1, 1, 2, 3], pa.int32()), x=pa.array(["p", "q", "r", "s"]))
+    r = rb(b=pa.array([1, 1, 3, 4], pa.int32()), y=pa.array([10, 20, 30, 40], pa.int64()))
+    got = gpu_ctx.hash_join(gpu_ctx.import_batches([l]), gpu_ctx.import_batches([r]), [0], [0]).to_arrow()
+    assert got.schema.names == ["a", "x", "b", "y"]                      # left ++ right
+    assert sorted(zip(*[got.column(i).to_pylist() for i in range(4)])) == [(1, "p", 1, 10), (1, "p", 1, 20), (1, "q", 1, 10), (1, "q", 1, 20), (3, "s", 3, 30)]
+    empty = gpu_ctx.hash_join(gpu_ctx.import_batches([l.slice(0, 0)]), gpu_ctx.import_batches([r]), [0], [0])
+    assert empty.num_rows == 0 and empty.num_columns == 4
+    none = gpu_ctx.hash_join(gpu_ctx.import_batches([l]), gpu_ctx.import_batches([r.slice(3)]), [0], [0])
+    assert none.num_rows == 0
+    with pytest.raises(fb.FlockGpuError):
+        gpu_ctx.hash_join(gpu_ctx.import_batches([l]), gpu_ctx.import_batches([r]), [0], [1])   # Int32 vs Int64 keys
+
+
+# ---- RepartitionExec: Hash -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("keys", [[0], [5], [6, 0], [1]])
+@pytest.mark.parametrize("n_parts", [2, 8])
+def test_hash_partition(gpu_ctx, keys, n_parts):
+    b = mixed_batch(100_001, seed=42)
+    parts = [p.to_batch() for p in gpu_ctx.hash_partition(gpu_ctx.import_batches([b]), keys, n_parts)]
+    assert len(parts) == n_parts and sum(p.num_rows for p in parts) == b.num_rows
+    if all(pa.types.is_integer(b.schema.field(k).type) for k in keys):
+        pid = sharding.partition_ids(b, keys, n_parts)                   # the numpy model of the device hash
+        for q, p in enumerate(parts):
+            assert p.equals(b.filter(pa.array(pid == q)))                # membership AND input order inside a partition
+    else:
+        seen = {}
+        for q, p in enumerate(parts):
+            for key in zip(*[p.column(k).to_pylist() for k in keys]):
+                assert seen.setdefault(key, q) == q
+        oracle.assert_tables_equal(pa.Table.from_batches(parts), pa.Table.from_batches([b]))

@@ -1,0 +1,201 @@
+"""Host logic that runs without a GPU (`-m "not gpu"`): the C ABI library loads and exports every symbol
+include/flockgpu.h declares, fails loudly without a device, parses the reference's serde-JSON plans,
+and lowers DataFusion expressions to the term/chain programs the kernels interpret."""
+import ctypes as C
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import flock_b200 as fb
+from flock_b200 import _ffi, nexgen, plans
+from flock_b200 import col, lit
+
+ROOT = Path(__file__).resolve().parent.parent
+REFERENCE_PLANS = Path("/root/reference/flock/src/tests/data/plan")
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "flockgpu.h").read_text()
+    declared = set(re.findall(r"\b(flockgpu_[a-z0-9_]+|flock_context_[a-z0-9_]+)\s*\(", header))
+    declared -= {"flockgpu_ctx", "flockgpu_table"}
+    assert len(declared) >= 40
+    lib = C.CDLL(str(_ffi.LIB_PATH))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"libflockgpu.so does not export: {missing}"
+    assert set(_ffi.PROTOTYPES) == declared, set(_ffi.PROTOTYPES) ^ declared
+
+
+def test_version_and_no_cpu_fallback():
+    assert b"sm_100a" in fb.lib.flockgpu_version()
+    try:
+        ctx = fb.Context(0)
+    except fb.FlockGpuError as e:
+        # CPU-only box: opening a context must fail loudly -- there is no CPU execution path
+        assert e.code == _ffi.ERR_NO_DEVICE and "no CPU fallback" in e.message
+        ec = fb.ExecutionContext(None, plans.q2())
+        with pytest.raises(fb.FlockGpuError) as info:
+            ec.execute_device(0)
+        assert info.value.code == _ffi.ERR_NO_DEVICE
+    else:
+        ctx.close()
+
+
+@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q5", "q8"])
+def test_unmarshal_nexmark_plans(query):
+    ec = fb.ExecutionContext(None, plans.QUERIES[query]())
+    assert ec.num_plans == 1 and not ec.is_shuffling()
+    s = ec.plan_str(0)
+    assert s.splitlines()[0].startswith("ProjectionExec: expr=[")
+    assert "MemoryExec" in s
+    if query == "q2":
+        # the rendering of planner.rs:120-124
+        assert "FilterExec: CAST(auction@0 AS Int64) % 123 = 0" in s
+        assert "CoalesceBatchesExec: target_batch_size=4096" in s and "RepartitionExec: partitioning=RoundRobinBatch(8)" in s
+    if query == "q3":
+        assert "HashJoinExec: mode=Partitioned, join_type=Inner, on=[(seller, p_id)]" in s
+        assert "FilterExec: state@3 = or OR state@3 = id OR state@3 = ca" in s
+        assert s.count("RepartitionExec: partitioning=Hash") == 2 and s.count("FilterExec") == 2
+    if query == "q5":
+        assert s.count("HashAggregateExec: mode=Partial") == 3 and s.count("MemoryExec") == 2
+
+
+def test_shuffle_stage_and_marshalled_context():
+    a, p = plans.q3_stage0()
+    ec = fb.ExecutionContext(None, [a, p])
+    assert ec.num_plans == 2 and ec.is_shuffling()       # context.rs:328-337
+    wrapped = {"plan": {"execution_plans": [plans.q1()], "object_storage": None}, "name": "q1-00", "next": {"Sink": "Blackhole"}}
+    assert fb.ExecutionContext(None, wrapped).num_plans == 1
+
+
+def test_unsupported_nodes_fail_loudly():
+    sort = {"execution_plan": "sort_exec", "input": plans.q2(), "expr": []}
+    with pytest.raises(fb.FlockGpuError) as info:
+        fb.ExecutionContext(None, sort)
+    assert info.value.code == _ffi.ERR_UNSUPPORTED and "sort_exec" in info.value.message
+    with pytest.raises(fb.FlockGpuError):
+        fb.ExecutionContext(None, "{not json")
+
+
+@pytest.mark.skipif(not REFERENCE_PLANS.exists(), reason="reference checkout not present (GPU box)")
+def test_reference_plan_fixtures_parse():
+    """The reference's own serialised plans (older serde dialect: columns without index, on=[[\"a\",\"c\"]])."""
+    ec = fb.ExecutionContext(None, (REFERENCE_PLANS / "simple_select.json").read_text())
+    assert ec.plan_str(0).startswith("ProjectionExec: expr=[c1 as c1]")
+    ec = fb.ExecutionContext(None, (REFERENCE_PLANS / "aggregate.json").read_text())
+    s = ec.plan_str(0)
+    assert "HashAggregateExec: mode=FinalPartitioned, gby=[c3 as c3], aggr=[MAX(c1), MIN(c2)]" in s
+    assert "FilterExec: c2 < CAST(99 AS Float64)" in s
+    with pytest.raises(fb.FlockGpuError) as info:      # join.json carries global_limit_exec + sort_exec
+        fb.ExecutionContext(None, (REFERENCE_PLANS / "join.json").read_text())
+    assert info.value.code == _ffi.ERR_UNSUPPORTED
+
+
+# ---- expression lowering ---------------------------------------------------------------------------------
+def expr_batch(n=1000, seed=0):
+    rng = np.random.default_rng(seed)
+    return pa.RecordBatch.from_arrays([
+        pa.array(rng.integers(-5000, 5000, n).astype(np.int32)),
+        pa.array(rng.integers(-(1 << 40), 1 << 40, n)),
+        pa.array(rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + np.uint64(1)),
+        pa.array(rng.normal(0, 100, n)),
+        pa.array(rng.integers(1_436_918_400_000, 1_436_918_500_000, n), pa.timestamp("ms")),
+        pa.array(rng.integers(1_436_918_400_000, 1_436_918_500_000, n), pa.timestamp("ms")),
+        pa.array([["az", "ca", "id", "or", "wa", "wy", ""][k] for k in rng.integers(0, 7, n)]),
+        pa.array(rng.integers(1, 50, n).astype(np.int32)),
+    ], names=["i32", "i64", "u64", "f64", "t0", "t1", "state", "pos"])
+
+
+def cols(b):
+    return {name: b.column(i).to_numpy(zero_copy_only=False) for i, name in enumerate(b.schema.names)}
+
+
+def test_predicate_lowering_matches_numpy():
+    b = expr_batch()
+    c = cols(b)
+    i32, i64 = c["i32"].astype(np.int64), c["i64"]
+    t0, t1 = c["t0"].astype("int64"), c["t1"].astype("int64")
+    state = np.array(b.column(6).to_pylist())
+    cases = [
+        (col(0).cast("int64") % 123 == 0, np.fmod(i32, 123) == 0, 1),                       # q2, planner.rs:122
+        (col(0).cast("int64") % 7 == -3, np.fmod(i32, 7) == -3, 1),
+        (col(0).cast("int64") % -123 == 0, np.fmod(i32, 123) == 0, 1),
+        (col(0).cast("int64") == 10, i32 == 10, 2),                                           # q3, planner.rs:155
+        (col(0).cast("int64") >= -17, i32 >= -17, 2),
+        ((col(6) == "or") | (col(6) == "id") | (col(6) == "ca"), np.isin(state, ["or", "id", "ca"]), 0),  # planner.rs:162
+        ((col(4) >= col(5)) & (col(4) <= col(5) + 20000), (t0 >= t1) & (t0 <= t1 + 20000), 0),  # q4 BETWEEN, planner.rs:237
+        (col(3) < lit(99).cast("float64"), c["f64"] < 99.0, 0),                               # aggregate.json predicate
+        (~((col(1) + 5) * 3 > col(0).cast("int64")), ~((i64 + 5) * 3 > i32), 0),
+        ((col(1) - col(0).cast("int64")) / 7 != 0, np.trunc((i64 - i32) / 7).astype(np.int64) != 0, 0),
+        (col(2) > lit(1 << 63, "uint64"), c["u64"] > np.uint64(1 << 63), 0),                  # unsigned domain
+        (col(6) < "id", state < "id", 0),
+        ((col(0) * 2 + 1).cast("int64") % col(7).cast("int64") == 1, np.fmod(i32 * 2 + 1, c["pos"].astype(np.int64)) == 1, 0),
+        (lit(100) - col(0).cast("int64") > 5000, 100 - i32 > 5000, 0),
+    ]
+    for e, want, fast in cases:
+        got, kind = fb.selftest_eval_predicate(b, e)
+        assert kind == fast
+        assert np.array_equal(got, want), fb.E.wrap(e).tokens
+
+
+def test_truth_table_covers_and_or_not():
+    b = expr_batch(256, seed=1)
+    i32 = cols(b)["i32"].astype(np.int64)
+    t = [i32 > 0, np.fmod(i32, 2) == 0, i32 < 1000, np.fmod(i32, 3) == 0]
+    e = [col(0).cast("int64") > 0, col(0).cast("int64") % 2 == 0, col(0).cast("int64") < 1000, col(0).cast("int64") % 3 == 0]
+    got, _ = fb.selftest_eval_predicate(b, (e[0] & ~e[1]) | (e[2] & (e[3] | ~e[0])))
+    assert np.array_equal(got, (t[0] & ~t[1]) | (t[2] & (t[3] | ~t[0])))
+
+
+def test_value_lowering_matches_numpy():
+    b = expr_batch(500, seed=2)
+    c = cols(b)
+    i32 = c["i32"]
+    v, dt = fb.selftest_eval_value(b, 0.908 * col(0).cast("float64"))                        # q1, planner.rs:90
+    assert dt == fb.FLOAT64 and np.array_equal(v.view(np.int64), (np.float64(0.908) * i32.astype(np.float64)).view(np.int64))
+    v, dt = fb.selftest_eval_value(b, col(0) * col(7) + 7)                                   # Int32 arithmetic wraps to Int32
+    assert dt == fb.INT64 or dt == fb.INT32
+    v, dt = fb.selftest_eval_value(b, (col(1) - 3) * 2)
+    assert dt == fb.INT64 and np.array_equal(v, (c["i64"] - 3) * 2)
+    v, dt = fb.selftest_eval_value(b, col(3) / 4.0 - col(0).cast("float64"))
+    assert dt == fb.FLOAT64 and np.array_equal(v.view(np.int64), (c["f64"] / 4.0 - i32.astype(np.float64)).view(np.int64))
+    v, dt = fb.selftest_eval_value(b, col(4))
+    assert v is None and dt == fb.TIMESTAMP                                                  # plain columns stay zero-copy
+    v, dt = fb.selftest_eval_value(b, (col(3) * 2.5).cast("int64"))
+    assert dt == fb.INT64 and np.array_equal(v, np.trunc(c["f64"] * 2.5).astype(np.int64))
+
+
+def test_expression_errors():
+    b = expr_batch(16)
+    with pytest.raises(fb.FlockGpuError, match="Divide by zero") as info:
+        fb.selftest_eval_predicate(b, col(0).cast("int64") % 0 == 0)
+    assert info.value.code == _ffi.ERR_EXECUTION
+    z = b.set_column(7, "pos", pa.array(np.zeros(16, np.int32)))
+    with pytest.raises(fb.FlockGpuError, match="Divide by zero"):
+        fb.selftest_eval_predicate(z, col(0).cast("int64") % col(7).cast("int64") == 0)
+    with pytest.raises(fb.FlockGpuError) as info:      # (a+b)*(c+d): not a left-deep chain
+        fb.selftest_eval_value(b, (col(0) + col(7)) * (col(0) - col(7)))
+    assert info.value.code == _ffi.ERR_UNSUPPORTED
+    with pytest.raises(fb.FlockGpuError) as info:
+        fb.selftest_eval_predicate(b, col(99) == 1)
+    assert info.value.code == _ffi.ERR_INVALID
+    with pytest.raises(fb.FlockGpuError):
+        fb.selftest_eval_predicate(b, col(0) + 1)      # not boolean
+
+
+def test_nexgen_invariants():
+    # generator counts (nexmark.rs:427-454 analogue): event mix 1:3:46
+    assert nexgen.relation_counts(10_000) == (200, 600, 9200)
+    ev = nexgen.generate(10_000, seed=5, batch_rows=4096)
+    assert [sum(b.num_rows for b in ev[r]) for r in ("person", "auction", "bid")] == [200, 600, 9200]
+    assert ev["bid"][0].schema.equals(nexgen.bid_schema()) and ev["bid"][0].num_rows == 4096
+    assert ev["person"][0].schema.equals(nexgen.person_schema()) and ev["auction"][0].schema.equals(nexgen.auction_schema())
+    p = pa.Table.from_batches(ev["person"])
+    assert p["p_id"].to_pylist() == list(range(1000, 1200))
+    assert set(p["state"].to_pylist()) <= set(nexgen.US_STATES)
+    a = pa.Table.from_batches(ev["auction"])
+    assert set(a["category"].to_pylist()) <= set(range(10, 15))
+    assert all(1000 <= s < 1000 + 200 + 10 for s in a["seller"].to_pylist())
