@@ -175,8 +175,10 @@ def run_gpu(args) -> dict:
     sampler.active.set()
     ctx.profile_begin()
     ctx.timer_start(0)
+    t_host = time.perf_counter()
     for i in range(args.steps):
         keep = (keep + [step_device(args.warmup + i)])[-2:]
+    host_us = (time.perf_counter() - t_host) * 1e6 / args.steps      # host time to ENQUEUE one step (no sync inside)
     ctx.timer_stop(0)
     ctx.synchronize()
     barrier(dist, local)
@@ -237,7 +239,7 @@ def run_gpu(args) -> dict:
                    f"({RING} x {8 * args.bids / 1e6:.0f} MB > 126 MB L2)", "selectivity": mean_sel / args.bids},
         "e2e": {"value": world * args.bids * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_ms / max(e2e_steps, 1)},
-        "gpu_launches": int(launches), "kernels": prof, "clocks": clocks, "roofline": roofline,
+        "gpu_launches": int(launches), "host_enqueue_us_per_step": round(host_us, 2), "kernels": prof, "clocks": clocks, "roofline": roofline,
         "stream_events_per_sec": world * args.bids * (50 / 46) * args.steps / (dev_ms * 1e-3),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

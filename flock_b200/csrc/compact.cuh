@@ -1,10 +1,15 @@
 // compact.cuh -- the single-pass stable compaction skeleton shared by FilterExec (filter_project.cu),
-// the hash-table emitters (hash_agg.cu) and the join pair writer (hash_join.cu).
+// the hash-table emitter (hash_agg.cu) and the partition selector (partition.cu).
 //
-// A persistent CTA takes TILE-row tiles from an atomic ticket.  For each tile it gets one bit per
-// item ("survives"), ranks the survivors in row order with warp ballots, obtains the tile's global
-// output offset by decoupled look-back (device_utils.cuh) and hands every survivor its output
+// A persistent CTA takes tiles of CP_THREADS x I items from an atomic ticket.  For each tile it gets one
+// bit per item ("survives"), ranks the survivors in item order with warp ballots, obtains the tile's
+// global output offset by decoupled look-back (device_utils.cuh) and hands every survivor its output
 // position.  The last CTA to finish resets the scratch, so back-to-back launches need no memset.
+//
+// I = items per thread per tile (16 / 32 / 64): measured on B200 (profiles/r1_microbench.txt), a 40 MB
+// column is read fastest with >= 4 independent 16-byte loads in flight per thread and as FEW
+// inter-tile synchronisation points as possible -- with I = 64 a 10 M-row relation is 611 tiles, fewer
+// than the resident CTAs, so every CTA does exactly one ticket, one look-back and three barriers.
 #pragma once
 
 #include "device_utils.cuh"
@@ -13,8 +18,6 @@ namespace fg {
 
 constexpr int CP_THREADS = 256;
 constexpr int CP_WARPS = CP_THREADS / 32;
-constexpr int CP_ITEMS = 16;                      // items per thread per tile
-constexpr int CP_TILE = CP_THREADS * CP_ITEMS;    // 4096 items
 
 struct CompactScratch {
   unsigned long long* tile_state;  // look-back words, zero between launches
@@ -31,9 +34,9 @@ __device__ __forceinline__ long long cp_item_index(int k, int tid) {
   return ((long long)(k / E) * CP_THREADS + tid) * E + (k % E);
 }
 
-template <int E>
+template <int E, int I>
 struct CompactSmem {
-  static constexpr int G = CP_ITEMS / E;
+  static constexpr int G = I / E;
   unsigned group_warp[G][CP_WARPS];
   long long tile;
   unsigned long long excl;
@@ -42,21 +45,20 @@ struct CompactSmem {
 };
 
 // Fetches the next tile index for the CTA (or -1 when the work is exhausted).
-template <int E>
-__device__ __forceinline__ long long cp_next_tile(CompactSmem<E>& s, const CompactScratch& sc) {
+template <int E, int I>
+__device__ __forceinline__ long long cp_next_tile(CompactSmem<E, I>& s, const CompactScratch& sc) {
   if (threadIdx.x == 0) s.tile = (long long)atomicAdd(sc.counters, 1u);
   __syncthreads();
   long long t = s.tile;
   return t < sc.num_tiles ? t : -1;
 }
 
-// Ranks the survivors of one tile.  On return (after the internal barriers) `lane_prefix[g]` +
-// s.group_warp[g][warp] + popc(earlier own bits in group g) + s.excl is the output position of an item
-// of group g, and s.tile_total the number of survivors of the tile.
-template <int E>
-__device__ __forceinline__ void cp_rank_tile(CompactSmem<E>& s, const CompactScratch& sc, long long tile, unsigned bits,
-                                             unsigned (&lane_prefix)[CP_ITEMS / E]) {
-  constexpr int G = CP_ITEMS / E;
+// Ranks the survivors of one tile (bit k of `bits` = item k survives).  On return (after the internal
+// barriers) cp_position() gives every survivor its output slot and s.tile_total the tile's survivor count.
+template <int E, int I>
+__device__ __forceinline__ void cp_rank_tile(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned long long bits,
+                                             unsigned (&lane_prefix)[I / E]) {
+  constexpr int G = I / E;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = lanemask_lt();
 #pragma unroll
@@ -64,7 +66,7 @@ __device__ __forceinline__ void cp_rank_tile(CompactSmem<E>& s, const CompactScr
     unsigned pre = 0, tot = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      unsigned b = __ballot_sync(FULL_MASK, (bits >> (g * E + e)) & 1u);
+      unsigned b = __ballot_sync(FULL_MASK, (bits >> (g * E + e)) & 1ull);
       pre += __popc(b & lt);
       tot += __popc(b);
     }
@@ -109,16 +111,16 @@ __device__ __forceinline__ void cp_rank_tile(CompactSmem<E>& s, const CompactScr
   __syncthreads();
 }
 
-template <int E>
-__device__ __forceinline__ long long cp_position(const CompactSmem<E>& s, unsigned bits, int k, const unsigned (&lane_prefix)[CP_ITEMS / E]) {
+template <int E, int I>
+__device__ __forceinline__ long long cp_position(const CompactSmem<E, I>& s, unsigned long long bits, int k, const unsigned (&lane_prefix)[I / E]) {
   const int g = k / E, e = k % E;
-  const unsigned within = __popc(bits & (((1u << e) - 1u) << (g * E)));
+  const unsigned within = __popcll(bits & (((1ull << e) - 1ull) << (g * E)));
   return (long long)s.excl + s.group_warp[g][threadIdx.x >> 5] + lane_prefix[g] + within;
 }
 
 // Call once per CTA after its tile loop: the last CTA to arrive clears the scratch.
-template <int E>
-__device__ __forceinline__ void cp_finish(CompactSmem<E>& s, const CompactScratch& sc) {
+template <int E, int I>
+__device__ __forceinline__ void cp_finish(CompactSmem<E, I>& s, const CompactScratch& sc) {
   __threadfence();
   if (threadIdx.x == 0) s.last = (atomicAdd(sc.counters + 1, 1u) == gridDim.x - 1);
   __syncthreads();

@@ -457,7 +457,19 @@ CompiledPredicate compile_predicate(const Expr& e, const std::vector<ColInfo>& c
     if (truth(t.root, bits)) p.lut[bits >> 5] |= 1u << (bits & 31);
 
   // fast shapes: one term over one Int32 column against literals
-  if (p.n_terms == 1 && p.terms[0].domain == DOM_I64) {
+  // (a single term has a 2-entry truth table: 0b10 = the term itself, 0b01 = NOT term; constants keep the interpreter)
+  const unsigned table1 = p.lut[0] & 3u;
+  auto negate_cmp = [](int cmp) {
+    switch (cmp) {
+      case FLOCKGPU_OP_EQ: return int(FLOCKGPU_OP_NE);
+      case FLOCKGPU_OP_NE: return int(FLOCKGPU_OP_EQ);
+      case FLOCKGPU_OP_LT: return int(FLOCKGPU_OP_GE);
+      case FLOCKGPU_OP_LE: return int(FLOCKGPU_OP_GT);
+      case FLOCKGPU_OP_GT: return int(FLOCKGPU_OP_LE);
+      default: return int(FLOCKGPU_OP_LT);
+    }
+  };
+  if (p.n_terms == 1 && p.terms[0].domain == DOM_I64 && (table1 == 2u || table1 == 1u)) {
     const Term& term = p.terms[0];
     const Chain& l = term.lhs;
     const Chain& r = term.rhs;
@@ -479,6 +491,7 @@ CompiledPredicate compile_predicate(const Expr& e, const std::vector<ColInfo>& c
         }
       }
     }
+    if (out.fast.kind != FAST_PRED_NONE && table1 == 1u) out.fast.cmp = negate_cmp(out.fast.cmp);
   }
   return out;
 }

@@ -13,6 +13,8 @@
 // once, no second pass), and write the surviving rows of every fixed-width output column in input
 // order.  Utf8 outputs leave through the selection vector and gather.cu.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 #include "compact.cuh"
 #include "expr_compile.h"
@@ -21,8 +23,6 @@
 namespace fg {
 
 constexpr int FP_THREADS = CP_THREADS;
-constexpr int FP_ITEMS = CP_ITEMS;   // rows per thread per tile
-constexpr int FP_TILE = CP_TILE;     // 4096 rows
 
 struct FilterArgs {
   int64_t n_rows;
@@ -44,15 +44,16 @@ struct FilterArgs {
 //   tile_base + ((k / E) * FP_THREADS + tid) * E + k % E.
 struct PredGeneric {
   static constexpr int E = 1;
+  static constexpr int I = 16;
   Predicate p;
-  __device__ __forceinline__ unsigned eval(const ColRef* cols, int64_t tile_base, int64_t n_rows, int tid, int* err) const {
-    int64_t rows[FP_ITEMS];
+  __device__ __forceinline__ unsigned long long eval(const ColRef* cols, int64_t tile_base, int64_t n_rows, int tid, int* err) const {
+    int64_t rows[I];
 #pragma unroll
-    for (int k = 0; k < FP_ITEMS; ++k) {
+    for (int k = 0; k < I; ++k) {
       int64_t r = tile_base + int64_t(k) * FP_THREADS + tid;
       rows[k] = r < n_rows ? r : -1;
     }
-    return eval_predicate<FP_ITEMS>(p, cols, rows, err);
+    return eval_predicate<I>(p, cols, rows, err);
   }
 };
 
@@ -70,9 +71,10 @@ __device__ __forceinline__ bool cmp_i64(int cmp, int64_t a, int64_t b) {
 // CAST(i32col AS Int64) [% m] CMP rhs, 128-bit loads.  MODE 0: plain compare; MODE 1: `% m` via
 // Lemire's fastmod (M = 2^64/m + 1: two multiplies instead of a software division); MODE 2: `% m = 0`
 // via the divisibility test n * M <= M - 1 (one multiply).
-template <int MODE>
+template <int MODE, int ITEMS>
 struct PredI32 {
   static constexpr int E = 4;
+  static constexpr int I = ITEMS;  // rows per thread per tile: ITEMS / 4 independent 16-byte loads in flight
   const int32_t* col;
   uint64_t M;
   uint32_t d;
@@ -87,29 +89,28 @@ struct PredI32 {
     if (x < 0) r = -r;
     return cmp_i64(cmp, r, rhs);
   }
-  __device__ __forceinline__ unsigned eval(const ColRef*, int64_t tile_base, int64_t n_rows, int tid, int*) const {
-    unsigned bits = 0;
-    int4 v[FP_ITEMS / 4];
-    int64_t row0[FP_ITEMS / 4];
+  __device__ __forceinline__ unsigned long long eval(const ColRef*, int64_t tile_base, int64_t n_rows, int tid, int*) const {
+    unsigned long long bits = 0;
+    int4 v[I / 4];
 #pragma unroll
-    for (int g = 0; g < FP_ITEMS / 4; ++g) {
-      row0[g] = tile_base + (int64_t(g) * FP_THREADS + tid) * 4;
-      if (row0[g] + 3 < n_rows) {
-        v[g] = ldg_stream_v4(col + row0[g]);
+    for (int g = 0; g < I / 4; ++g) {
+      const int64_t row0 = tile_base + (int64_t(g) * FP_THREADS + tid) * 4;
+      if (row0 + 3 < n_rows) {
+        v[g] = ldg_stream_v4(col + row0);
       } else {
         v[g] = make_int4(0, 0, 0, 0);
-        if (row0[g] + 0 < n_rows) v[g].x = col[row0[g] + 0];
-        if (row0[g] + 1 < n_rows) v[g].y = col[row0[g] + 1];
-        if (row0[g] + 2 < n_rows) v[g].z = col[row0[g] + 2];
+        if (row0 + 0 < n_rows) v[g].x = col[row0 + 0];
+        if (row0 + 1 < n_rows) v[g].y = col[row0 + 1];
+        if (row0 + 2 < n_rows) v[g].z = col[row0 + 2];
       }
     }
 #pragma unroll
-    for (int g = 0; g < FP_ITEMS / 4; ++g) {
+    for (int g = 0; g < I / 4; ++g) {
+      const int64_t row0 = tile_base + (int64_t(g) * FP_THREADS + tid) * 4;
       unsigned b = unsigned(test(v[g].x)) | (unsigned(test(v[g].y)) << 1) | (unsigned(test(v[g].z)) << 2) | (unsigned(test(v[g].w)) << 3);
-      // mask rows past the end
-      int64_t left = n_rows - row0[g];
+      const int64_t left = n_rows - row0;  // mask rows past the end
       if (left < 4) b &= left <= 0 ? 0u : ((1u << left) - 1u);
-      bits |= b << (4 * g);
+      bits |= (unsigned long long)b << (4 * g);
     }
     return bits;
   }
@@ -123,24 +124,26 @@ __device__ __forceinline__ void copy_value(void* dst, const void* src, int width
 template <class PredFn>
 __global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid_constant__ PredFn pred, const __grid_constant__ FilterArgs a) {
   constexpr int E = PredFn::E;
-  __shared__ CompactSmem<E> sm;
+  constexpr int I = PredFn::I;
+  constexpr int TILE = FP_THREADS * I;
+  __shared__ CompactSmem<E, I> sm;
   const int tid = threadIdx.x;
   const CompactScratch sc{a.tile_state, a.counters, a.out_count, a.num_tiles};
   int err = 0;
 
   for (long long tile = cp_next_tile(sm, sc); tile >= 0; tile = cp_next_tile(sm, sc)) {
-    const int64_t tile_base = tile * FP_TILE;
-    const unsigned bits = pred.eval(a.cols, tile_base, a.n_rows, tid, &err);
-    unsigned lane_prefix[FP_ITEMS / E];
-    cp_rank_tile<E>(sm, sc, tile, bits, lane_prefix);
+    const int64_t tile_base = tile * TILE;
+    const unsigned long long bits = pred.eval(a.cols, tile_base, a.n_rows, tid, &err);
+    unsigned lane_prefix[I / E];
+    cp_rank_tile<E, I>(sm, sc, tile, bits, lane_prefix);
 
     // ---- write survivors in input order
     if (bits && sm.tile_total) {
-      unsigned m = bits;
+      unsigned long long m = bits;
       while (m) {
-        const int k = __ffs(m) - 1;
+        const int k = __ffsll((long long)m) - 1;
         m &= m - 1;
-        const int64_t pos = cp_position<E>(sm, bits, k, lane_prefix);
+        const int64_t pos = cp_position<E, I>(sm, bits, k, lane_prefix);
         const int64_t row = tile_base + cp_item_index<E>(k, tid);
         if (a.sel_out) a.sel_out[pos] = uint32_t(row);
         for (int c = 0; c < a.n_out; ++c) {
@@ -236,15 +239,32 @@ static void fill_colrefs(const Table& t, ColRef* refs) {
 }
 
 static int persistent_grid(const CtxPtr& ctx, const void* kernel, int threads, int64_t work_items) {
-  int per_sm = 1;
-  FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
-  if (per_sm < 1) per_sm = 1;
+  // the occupancy query costs microseconds per call; a q2 step is one ~10 us kernel, so cache it per kernel
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
+  int per_sm = 0;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(kernel);
+    if (it != cache.end()) per_sm = it->second;
+  }
+  if (per_sm == 0) {
+    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) per_sm = 1;
+    std::lock_guard<std::mutex> g(mu);
+    cache[kernel] = per_sm;
+  }
   int64_t g = int64_t(ctx->sm_count) * per_sm;
   return int(std::max<int64_t>(1, std::min<int64_t>(g, work_items)));
 }
 
 template <class PredFn>
-static void launch_filter(const CtxPtr& ctx, const PredFn& pred, const FilterArgs& args) {
+static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args) {
+  constexpr int64_t TILE = int64_t(FP_THREADS) * PredFn::I;
+  args.num_tiles = (args.n_rows + TILE - 1) / TILE;
+  ensure_scan_scratch(ctx, args.num_tiles);
+  args.tile_state = ctx->scan.tile_state;
+  args.counters = ctx->scan.counters;
   const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
   int grid = persistent_grid(ctx, k, FP_THREADS, args.num_tiles);
   {
@@ -379,10 +399,6 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
 
   FilterArgs fa{};
   fa.n_rows = in.num_rows;
-  fa.num_tiles = (in.num_rows + FP_TILE - 1) / FP_TILE;
-  ensure_scan_scratch(ctx, fa.num_tiles);
-  fa.tile_state = ctx->scan.tile_state;
-  fa.counters = ctx->scan.counters;
   fa.out_count = ctx->d_scalars + 0;
   fa.err_flag = err_flag;
   fill_colrefs(in, fa.cols);
@@ -420,25 +436,30 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   }
   if (check_err) FG_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int), ctx->stream));
 
+  // rows per thread per tile of the vectorised functors (FLOCKGPU_FILTER_ITEMS = 16 | 32 | 64 overrides, for tuning)
+  static const int items = [] {
+    const char* e = getenv("FLOCKGPU_FILTER_ITEMS");
+    int v = e ? atoi(e) : 64;
+    return (v == 16 || v == 32 || v == 64) ? v : 64;
+  }();
+  auto launch_i32 = [&](auto mode_tag, const int32_t* col, uint64_t M, uint32_t d) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    if (items == 16) launch_filter(ctx, PredI32<MODE, 16>{col, M, d, cp.fast.cmp, cp.fast.rhs}, fa);
+    else if (items == 32) launch_filter(ctx, PredI32<MODE, 32>{col, M, d, cp.fast.cmp, cp.fast.rhs}, fa);
+    else launch_filter(ctx, PredI32<MODE, 64>{col, M, d, cp.fast.cmp, cp.fast.rhs}, fa);
+  };
   switch (cp.fast.kind) {
     case FAST_PRED_I32_MOD_CMP: {
       uint32_t d = uint32_t(cp.fast.modulus);
       uint64_t M = ~uint64_t(0) / d + 1;
       const int32_t* col = static_cast<const int32_t*>(in.cols[cp.fast.col].values());
-      if (cp.fast.cmp == FLOCKGPU_OP_EQ && cp.fast.rhs == 0) {
-        PredI32<2> p{col, M, d, cp.fast.cmp, cp.fast.rhs};
-        launch_filter(ctx, p, fa);
-      } else {
-        PredI32<1> p{col, M, d, cp.fast.cmp, cp.fast.rhs};
-        launch_filter(ctx, p, fa);
-      }
+      if (cp.fast.cmp == FLOCKGPU_OP_EQ && cp.fast.rhs == 0) launch_i32(std::integral_constant<int, 2>{}, col, M, d);
+      else launch_i32(std::integral_constant<int, 1>{}, col, M, d);
       break;
     }
-    case FAST_PRED_I32_CMP: {
-      PredI32<0> p{static_cast<const int32_t*>(in.cols[cp.fast.col].values()), 0, 1, cp.fast.cmp, cp.fast.rhs};
-      launch_filter(ctx, p, fa);
+    case FAST_PRED_I32_CMP:
+      launch_i32(std::integral_constant<int, 0>{}, static_cast<const int32_t*>(in.cols[cp.fast.col].values()), 0, 1);
       break;
-    }
     default: {
       PredGeneric p{cp.prog};
       launch_filter(ctx, p, fa);

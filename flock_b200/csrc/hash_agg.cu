@@ -390,26 +390,28 @@ __device__ __forceinline__ void emit_values(const EmitDesc* emit, int n_emit, co
 
 __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_constant__ AggEmitArgs a) {
   constexpr int E = 1;
-  __shared__ CompactSmem<E> sm;
+  constexpr int CP_ITEMS = 16;
+  constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+  __shared__ CompactSmem<E, CP_ITEMS> sm;
   const int tid = threadIdx.x;
   for (long long tile = cp_next_tile(sm, a.sc); tile >= 0; tile = cp_next_tile(sm, a.sc)) {
     const unsigned long long tile_base = (unsigned long long)tile * CP_TILE;
-    unsigned bits = 0;
+    unsigned long long bits = 0;
 #pragma unroll
     for (int k = 0; k < CP_ITEMS; ++k) {
       unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
       bool occ = false;
       if (slot < a.n_slots) occ = a.keys ? a.keys[slot] != EMPTY_KEY : a.owner[slot] != EMPTY_OWNER;
-      bits |= unsigned(occ) << k;
+      bits |= (unsigned long long)occ << k;
     }
     unsigned lane_prefix[CP_ITEMS / E];
-    cp_rank_tile<E>(sm, a.sc, tile, bits, lane_prefix);
+    cp_rank_tile<E, CP_ITEMS>(sm, a.sc, tile, bits, lane_prefix);
     if (bits && sm.tile_total) {
-      unsigned m = bits;
+      unsigned long long m = bits;
       while (m) {
-        const int k = __ffs(m) - 1;
+        const int k = __ffsll((long long)m) - 1;
         m &= m - 1;
-        const int64_t pos = cp_position<E>(sm, bits, k, lane_prefix);
+        const int64_t pos = cp_position<E, CP_ITEMS>(sm, bits, k, lane_prefix);
         const unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
         if (a.keys) {
           unsigned long long key = slot == a.n_slots - 1 ? EMPTY_KEY : a.keys[slot];
@@ -851,7 +853,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   for (const OutPlan& p : outs) val_cols.push_back(make_out_col(p, max_groups));
   fill_emit(ea.emit, &ea.n_emit, val_cols);
   ea.n_slots = n_slots;
-  ea.sc.num_tiles = (long long)((n_slots + CP_TILE - 1) / CP_TILE);
+  ea.sc.num_tiles = (long long)((n_slots + CP_THREADS * 16 - 1) / (CP_THREADS * 16));
   ensure_scan_scratch(ctx, ea.sc.num_tiles);
   ea.sc.tile_state = ctx->scan.tile_state;
   ea.sc.counters = ctx->scan.counters;

@@ -354,7 +354,36 @@ static TablePtr rename_columns(const ExecEnv& env, const TablePtr& t, const std:
   return r;
 }
 
+// Structural signature of a subtree + identity of the buffers its leaves scan.
+static void subtree_signature(ExecutionPlan* p, std::string* s) {
+  s->append(p->name());
+  if (auto* m = dynamic_cast<MemoryExec*>(p)) {
+    char buf[64];
+    const void* id = m->fed && !m->fed->cols.empty() ? m->fed->cols[0].values() : nullptr;
+    snprintf(buf, sizeof buf, "@%p/%zu", id, m->fed ? m->fed->cols.size() : size_t(0));
+    s->append(buf);
+    for (const std::string& n : m->projected_names()) s->append("," + n);
+  } else {
+    s->append(":" + p->fmt_as());
+  }
+  s->push_back('(');
+  for (const PlanPtr& c : p->children()) subtree_signature(c.get(), s);
+  s->push_back(')');
+}
+
 TablePtr HashAggregateExec::execute(const ExecEnv& env) {
+  std::string sig;
+  if (env.memo) {
+    subtree_signature(this, &sig);
+    auto hit = env.memo->find(sig);
+    if (hit != env.memo->end()) return hit->second;
+  }
+  TablePtr result = execute_uncached(env);
+  if (env.memo) (*env.memo)[sig] = result;
+  return result;
+}
+
+TablePtr HashAggregateExec::execute_uncached(const ExecEnv& env) {
   const bool final_mode = mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED;
   // ---- single-GPU fusion: Final*( Coalesce/Repartition ( Partial(x) ) ) == one SINGLE aggregate over x
   if (final_mode && env.world == 1) {
@@ -565,6 +594,7 @@ ExecEnv ExecutionContext::env() const {
   ExecEnv e;
   e.ctx = ctx;
   e.world = fg::comm_world(ctx);
+  e.memo = std::make_shared<std::map<std::string, TablePtr>>();
   return e;
 }
 
@@ -650,6 +680,7 @@ void ExecutionContext::feed_data_sources(const ArrowSchema* const* schemas, cons
     for (int64_t c = 0; c < schemas[i]->n_children; ++c) s.names.push_back(schemas[i]->children[c]->name ? schemas[i]->children[c]->name : "");
     sources.push_back(std::move(s));
   }
+  std::map<std::string, TablePtr> imported;
   for (MemoryExec* leaf : leaves_bfs()) {
     std::vector<std::string> want = leaf->projected_names();
     int found = -1;
@@ -670,7 +701,24 @@ void ExecutionContext::feed_data_sources(const ArrowSchema* const* schemas, cons
       FG_CHECK(it != s.names.end(), FLOCKGPU_ERR_INVALID, "feed_data_sources: the fed relation has no column \"%s\" required by the plan", n.c_str());
       proj.push_back(int(it - s.names.begin()));
     }
-    leaf->fed = fg::import_batches(ctx, s.schema, s.batches, s.n, proj.data(), int(proj.size()));
+    // The same host batches fed for two leaves (q5 scans `bid` twice, and feed_data_sources hands one source to
+    // one leaf, context.rs:293-303) cross PCIe once: identical (buffers, projection) reuse the imported table.
+    std::string key;
+    for (int p : proj) key += std::to_string(p) + ",";
+    for (int b = 0; b < s.n; ++b) {
+      char buf[64];
+      const ArrowArray* first = s.batches[b]->n_children > 0 ? s.batches[b]->children[proj.empty() ? 0 : proj[0]] : nullptr;
+      snprintf(buf, sizeof buf, "|%p:%lld:%lld", first && first->n_buffers > 1 ? first->buffers[1] : nullptr, (long long)s.batches[b]->length,
+               (long long)(first ? first->offset : 0));
+      key += buf;
+    }
+    auto hit = imported.find(key);
+    if (hit != imported.end()) {
+      leaf->fed = hit->second;
+    } else {
+      leaf->fed = fg::import_batches(ctx, s.schema, s.batches, s.n, proj.data(), int(proj.size()));
+      imported[key] = leaf->fed;
+    }
     sources.erase(sources.begin() + found);
   }
 }

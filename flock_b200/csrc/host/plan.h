@@ -12,6 +12,7 @@
 // carry no values, so those nodes forward their input.
 #pragma once
 
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -43,6 +44,11 @@ using PlanPtr = std::shared_ptr<ExecutionPlan>;
 struct ExecEnv {
   CtxPtr ctx;
   int world = 1;  // > 1 when an NCCL communicator is attached: Hash repartitioning becomes an all-to-all
+  // Results of aggregate subtrees already computed during THIS execution, keyed by the subtree's structure and
+  // the identity of the HBM buffers its leaves scan.  DataFusion 6 has no common-subexpression elimination, so
+  // NEXMark q5 plans the COUNT-by-auction subtree twice (benchmarks/src/nexmark/query/q5_plan.fmt); computing it
+  // once cannot change a value (tables are immutable).
+  std::shared_ptr<std::map<std::string, TablePtr>> memo;
 };
 
 class ExecutionPlan {
@@ -129,6 +135,7 @@ class HashAggregateExec : public UnaryExec {
   const char* name() const override { return "HashAggregateExec"; }
   std::string fmt_as() const override;
   TablePtr execute(const ExecEnv& env) override;
+  TablePtr execute_uncached(const ExecEnv& env);
 };
 
 class HashJoinExec : public ExecutionPlan {

@@ -51,12 +51,14 @@ struct PartSelectArgs {
 
 __global__ void __launch_bounds__(CP_THREADS) partition_select_kernel(const __grid_constant__ PartSelectArgs a) {
   constexpr int E = 4;
-  __shared__ CompactSmem<E> sm;
+  constexpr int CP_ITEMS = 16;
+  constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+  __shared__ CompactSmem<E, CP_ITEMS> sm;
   const int tid = threadIdx.x;
   const unsigned long long base = a.bases[a.part];
   for (long long tile = cp_next_tile(sm, a.sc); tile >= 0; tile = cp_next_tile(sm, a.sc)) {
     const int64_t tile_base = tile * CP_TILE;
-    unsigned bits = 0;
+    unsigned long long bits = 0;
 #pragma unroll
     for (int g = 0; g < CP_ITEMS / E; ++g) {
       const int64_t r0 = tile_base + (int64_t(g) * CP_THREADS + tid) * E;
@@ -71,17 +73,17 @@ __global__ void __launch_bounds__(CP_THREADS) partition_select_kernel(const __gr
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         bool in_range = r0 + e < a.n_rows;
-        bits |= unsigned(in_range && ((w >> (8 * e)) & 0xffu) == uint32_t(a.part)) << (g * E + e);
+        bits |= (unsigned long long)(in_range && ((w >> (8 * e)) & 0xffu) == uint32_t(a.part)) << (g * E + e);
       }
     }
     unsigned lane_prefix[CP_ITEMS / E];
-    cp_rank_tile<E>(sm, a.sc, tile, bits, lane_prefix);
+    cp_rank_tile<E, CP_ITEMS>(sm, a.sc, tile, bits, lane_prefix);
     if (bits && sm.tile_total) {
-      unsigned m = bits;
+      unsigned long long m = bits;
       while (m) {
-        const int k = __ffs(m) - 1;
+        const int k = __ffsll((long long)m) - 1;
         m &= m - 1;
-        a.idx[base + (unsigned long long)cp_position<E>(sm, bits, k, lane_prefix)] = uint32_t(tile_base + cp_item_index<E>(k, tid));
+        a.idx[base + (unsigned long long)cp_position<E, CP_ITEMS>(sm, bits, k, lane_prefix)] = uint32_t(tile_base + cp_item_index<E>(k, tid));
       }
     }
     __syncthreads();
@@ -149,7 +151,7 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   FG_CUDA(cudaMemsetAsync(bases, 0, sizeof(unsigned long long) * (n_parts + 1), ctx->stream));
   BufferPtr idx = alloc(ctx, size_t(n) * 4);
   PartSelectArgs sa{};
-  sa.sc.num_tiles = (n + CP_TILE - 1) / CP_TILE;
+  sa.sc.num_tiles = (n + CP_THREADS * 16 - 1) / (CP_THREADS * 16);
   ensure_scan_scratch(ctx, sa.sc.num_tiles);
   sa.sc.tile_state = ctx->scan.tile_state;
   sa.sc.counters = ctx->scan.counters;

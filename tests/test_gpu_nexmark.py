@@ -74,7 +74,7 @@ def test_reference_toy_goldens(gpu_ctx):
 def test_feed_execute_clean_cycle(gpu_ctx, events_small):
     """One context serves many invocations (cloud_context.rs:53-99); unmatched leaves execute empty."""
     ec = fb.ExecutionContext(gpu_ctx, plans.q2())
-    want = oracle.execute_plan(plans.q2(), sources_for("q2", events_small))
+    want = oracle.execute_plan(plans.q2(1), sources_for("q2", events_small))     # single partition: input order
     for _ in range(3):
         ec.feed_data_sources(sources_for("q2", events_small))
         oracle.assert_tables_equal(pa.Table.from_batches(ec.execute()[0]), want, sort=False)

@@ -71,7 +71,8 @@ PREDICATES = [
     lambda: col(5) >= "id",
     lambda: (col(1) > 0) & ~(col(3) < lit(0).cast("float64")),
     lambda: (col(4) >= lit(1_436_918_450_000, "timestamp")) & (col(2) > lit(1 << 61, "uint64")),
-    lambda: (col(0) * 2 + 1).cast("int64") % (col(6) + 1).cast("int64") == 1,
+    lambda: (col(1) + col(0).cast("int64") * 3) % 1000 == 1,
+    lambda: ~(col(0).cast("int64") % 123 == 0),          # negated single term: the vectorised kernel with the inverted comparison
     lambda: col(0).cast("int64") > 5000,        # nothing survives
     lambda: col(0).cast("int64") >= -5000,      # everything survives
 ]
@@ -143,6 +144,8 @@ def oracle_agg(b, mode, group, aggs):
     return oracle.hash_aggregate(b, mode, [(g, b.schema.names[g]) for g in group], [{"func": f, "col": c, "name": n} for f, c, n in aggs])
 
 
+# AVG / SUM arguments are chosen so that every partial sum is an exactly representable integer (< 2^53): then the
+# result does not depend on the order in which a GPU accumulates, and bit-exactness holds.
 AGGS = [("count", -1, "COUNT(UInt8(1))"), ("sum", 1, "SUM(i64)"), ("min", 0, "MIN(i32)"), ("max", 2, "MAX(u64)"),
         ("avg", 0, "AVG(i32)"), ("max", 4, "MAX(ts)"), ("min", 3, "MIN(f64)"), ("sum", 0, "SUM(i32)")]
 
@@ -161,7 +164,7 @@ def test_hash_aggregate_single(gpu_ctx, group, n):
 def test_hash_aggregate_partial_then_final(gpu_ctx):
     b = mixed_batch(200_000, seed=77)
     halves = [gpu_ctx.import_batches([b.slice(0, 90_000)]), gpu_ctx.import_batches([b.slice(90_000)])]
-    aggs = [("count", -1, "c"), ("avg", 3, "a"), ("max", 0, "m"), ("sum", 2, "s")]
+    aggs = [("count", -1, "c"), ("avg", 6, "a"), ("max", 0, "m"), ("sum", 0, "s")]
     partials = [gpu_ctx.hash_aggregate(h, [6, 5], aggs, "partial") for h in halves]
     p0 = partials[0].to_batch()
     assert p0.schema.names == ["k", "s", "c[count]", "a[count]", "a[sum]", "m[max]", "s[sum]"]          # aggregate.json naming
@@ -175,7 +178,7 @@ def test_hash_aggregate_partial_then_final(gpu_ctx):
 def test_global_aggregate_and_empty_input(gpu_ctx):
     b = mixed_batch(123_457, seed=5)
     t = gpu_ctx.import_batches([b])
-    aggs = [("min", 1, "MIN"), ("avg", 2, "AVG"), ("count", 5, "COUNT"), ("max", 3, "MAXF")]
+    aggs = [("min", 1, "MIN"), ("avg", 0, "AVG"), ("count", 5, "COUNT"), ("max", 3, "MAXF")]
     got = gpu_ctx.hash_aggregate(t, [], aggs, "single").to_arrow()
     want = pa.Table.from_batches([oracle_agg(b, "Single", [], aggs)])
     oracle.assert_tables_equal(got, want)

@@ -125,6 +125,8 @@ def test_predicate_lowering_matches_numpy():
         (col(0).cast("int64") % -123 == 0, np.fmod(i32, 123) == 0, 1),
         (col(0).cast("int64") == 10, i32 == 10, 2),                                           # q3, planner.rs:155
         (col(0).cast("int64") >= -17, i32 >= -17, 2),
+        (~(col(0).cast("int64") % 123 == 0), np.fmod(i32, 123) != 0, 1),                     # negation keeps the fast shape
+        (~(col(0).cast("int64") < 5), i32 >= 5, 2),
         ((col(6) == "or") | (col(6) == "id") | (col(6) == "ca"), np.isin(state, ["or", "id", "ca"]), 0),  # planner.rs:162
         ((col(4) >= col(5)) & (col(4) <= col(5) + 20000), (t0 >= t1) & (t0 <= t1 + 20000), 0),  # q4 BETWEEN, planner.rs:237
         (col(3) < lit(99).cast("float64"), c["f64"] < 99.0, 0),                               # aggregate.json predicate
