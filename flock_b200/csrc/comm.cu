@@ -97,6 +97,7 @@ void comm_init(const CtxPtr& ctx, const uint8_t* idbytes, int rank, int world) {
 }
 
 int comm_world(const CtxPtr& ctx) { return ctx->comm ? ctx->comm->world : 1; }
+int comm_rank(const CtxPtr& ctx) { return ctx->comm ? ctx->comm->rank : 0; }
 
 __global__ void add_offset_kernel(int32_t* offs, int64_t n, int32_t delta) {
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) offs[i] += delta;

@@ -291,6 +291,16 @@ TablePtr FilterExec::execute(const ExecEnv& env) {
 
 std::string CoalesceBatchesExec::fmt_as() const { return "CoalesceBatchesExec: target_batch_size=" + std::to_string(target_batch_size); }
 
+TablePtr CoalescePartitionsExec::execute(const ExecEnv& env) {
+  TablePtr in = input->execute(env);
+  if (env.world == 1) return in;
+  // "merge every partition into one": with one partition per GPU that is a gather to rank 0 (the other ranks
+  // continue with an empty relation), done with the same all-to-all primitive as the hash shuffle
+  std::vector<TablePtr> parts;
+  for (int r = 0; r < env.world; ++r) parts.push_back(r == 0 ? in : fg::empty_like(env.ctx, *in));
+  return fg::all_to_all(env.ctx, parts);
+}
+
 std::string RepartitionExec::fmt_as() const {
   if (!hash) return "RepartitionExec: partitioning=RoundRobinBatch(" + std::to_string(n_partitions) + ")";
   std::string s = "RepartitionExec: partitioning=Hash([";
@@ -429,6 +439,9 @@ TablePtr HashAggregateExec::execute_uncached(const ExecEnv& env) {
     }
   }
   TablePtr out = fg::hash_aggregate(env.ctx, in, mode, gcols, specs);
+  // A Final aggregate without group columns runs in ONE partition (behind CoalescePartitionsExec): with several GPUs
+  // that partition lives on rank 0; the other ranks hold no partition of this node, hence no row.
+  if (final_mode && group_expr.empty() && env.world > 1 && env.rank != 0) out = fg::empty_like(env.ctx, *out);
   std::vector<std::string> names;
   for (const auto& g : group_expr) names.push_back(g.second);
   return rename_columns(env, out, names);
@@ -594,6 +607,7 @@ ExecEnv ExecutionContext::env() const {
   ExecEnv e;
   e.ctx = ctx;
   e.world = fg::comm_world(ctx);
+  e.rank = fg::comm_rank(ctx);
   e.memo = std::make_shared<std::map<std::string, TablePtr>>();
   return e;
 }

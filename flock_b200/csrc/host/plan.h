@@ -44,6 +44,7 @@ using PlanPtr = std::shared_ptr<ExecutionPlan>;
 struct ExecEnv {
   CtxPtr ctx;
   int world = 1;  // > 1 when an NCCL communicator is attached: Hash repartitioning becomes an all-to-all
+  int rank = 0;
   // Results of aggregate subtrees already computed during THIS execution, keyed by the subtree's structure and
   // the identity of the HBM buffers its leaves scan.  DataFusion 6 has no common-subexpression elimination, so
   // NEXMark q5 plans the COUNT-by-auction subtree twice (benchmarks/src/nexmark/query/q5_plan.fmt); computing it
@@ -108,7 +109,7 @@ class CoalescePartitionsExec : public UnaryExec {
  public:
   const char* name() const override { return "CoalescePartitionsExec"; }
   std::string fmt_as() const override { return "CoalescePartitionsExec"; }
-  TablePtr execute(const ExecEnv& env) override { return input->execute(env); }
+  TablePtr execute(const ExecEnv& env) override;
 };
 
 class RepartitionExec : public UnaryExec {

@@ -266,6 +266,7 @@ TablePtr all_to_all(const CtxPtr& ctx, const std::vector<TablePtr>& parts);
 void comm_unique_id(uint8_t* out);
 void comm_init(const CtxPtr& ctx, const uint8_t* id, int rank, int world);
 int comm_world(const CtxPtr& ctx);  // 1 when no communicator is attached
+int comm_rank(const CtxPtr& ctx);   // 0 when no communicator is attached
 
 inline void count_launch(const CtxPtr& ctx, int n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
 
