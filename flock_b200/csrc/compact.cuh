@@ -38,6 +38,9 @@ template <int E, int I>
 struct CompactSmem {
   static constexpr int G = I / E;
   unsigned group_warp[G][CP_WARPS];
+  unsigned long long lb_sum[CP_WARPS];
+  int lb_has[CP_WARPS];
+  int lb_done;
   long long tile;
   unsigned long long excl;
   unsigned tile_total;
@@ -51,6 +54,58 @@ __device__ __forceinline__ long long cp_next_tile(CompactSmem<E, I>& s, const Co
   __syncthreads();
   long long t = s.tile;
   return t < sc.num_tiles ? t : -1;
+}
+
+// Decoupled look-back with the WHOLE CTA: thread i inspects tile (base - i), so one step covers CP_THREADS
+// predecessors.  When a launch is a single wave (all tiles finish counting at about the same time) nearly every
+// predecessor still shows PARTIAL, and a 32-wide window would walk back serially, one L2 round trip per 32 tiles
+// (measured: 611 tiles -> ~19 dependent round trips, the dominant cost of the first version, see
+// profiles/r1_filter_ncu.md); 256-wide windows need at most ceil(tiles / 256) steps.  Leaves the exclusive
+// prefix of `tile` in s.excl (valid for every thread after the trailing barrier).
+template <int E, int I>
+__device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long excl = 0;  // meaningful in thread 0 only
+  if (tile == 0) {
+    if (tid == 0) st_relaxed_u64(sc.tile_state, LB_PREFIX | (unsigned long long)total);
+  } else {
+    if (tid == 0) st_relaxed_u64(sc.tile_state + tile, LB_PARTIAL | (unsigned long long)total);
+    long long base = tile - 1;
+    while (true) {
+      const long long t = base - tid;
+      unsigned long long st = LB_PREFIX;  // virtual tiles before the first one: inclusive prefix 0
+      if (t >= 0) {
+        do {
+          st = ld_relaxed_u64(sc.tile_state + t);
+        } while ((st & LB_FLAG_MASK) == LB_INVALID);
+      }
+      const unsigned pm = __ballot_sync(FULL_MASK, (st & LB_FLAG_MASK) == LB_PREFIX);
+      const int first = pm ? __ffs(pm) - 1 : 32;
+      const unsigned long long wsum = warp_sum(lane <= first ? (st & LB_VALUE_MASK) : 0ull);
+      if (lane == 0) {
+        s.lb_sum[warp] = wsum;
+        s.lb_has[warp] = pm != 0;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int done = 0;
+        for (int w = 0; w < CP_WARPS && !done; ++w) {  // warp 0 holds the nearest predecessors
+          excl += s.lb_sum[w];
+          done = s.lb_has[w];
+        }
+        s.lb_done = done;
+      }
+      __syncthreads();
+      if (s.lb_done) break;
+      base -= CP_THREADS;
+    }
+    if (tid == 0) st_relaxed_u64(sc.tile_state + tile, LB_PREFIX | (excl + total));
+  }
+  if (tid == 0) {
+    s.excl = excl;
+    if (tile == sc.num_tiles - 1) *sc.out_count = excl + total;
+  }
+  __syncthreads();
 }
 
 // Ranks the survivors of one tile (bit k of `bits` = item k survives).  On return (after the internal
@@ -94,21 +149,10 @@ __device__ __forceinline__ void cp_rank_tile(CompactSmem<E, I>& s, const Compact
       run += v[i];
     }
     unsigned total = __shfl_sync(FULL_MASK, incl, 31);
-    unsigned long long excl = 0;
-    if (tile == 0) {
-      if (lane == 0) st_relaxed_u64(sc.tile_state, LB_PREFIX | (unsigned long long)total);
-    } else {
-      if (lane == 0) st_relaxed_u64(sc.tile_state + tile, LB_PARTIAL | (unsigned long long)total);
-      excl = lookback_exclusive_prefix(sc.tile_state, tile);
-      if (lane == 0) st_relaxed_u64(sc.tile_state + tile, LB_PREFIX | (excl + total));
-    }
-    if (lane == 0) {
-      s.excl = excl;
-      s.tile_total = total;
-      if (tile == sc.num_tiles - 1) *sc.out_count = excl + total;
-    }
+    if (lane == 0) s.tile_total = total;
   }
   __syncthreads();
+  cp_block_lookback(s, sc, tile, s.tile_total);
 }
 
 template <int E, int I>

@@ -97,6 +97,12 @@ CtxCore::~CtxCore() {
     if (timer_start[i]) cudaEventDestroy(timer_start[i]);
     if (timer_stop[i]) cudaEventDestroy(timer_stop[i]);
   }
+  for (auto& p : profile) {
+    cudaEventDestroy(p.start);
+    cudaEventDestroy(p.stop);
+  }
+  for (cudaEvent_t e : sync_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : timing_events) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -148,7 +154,19 @@ int64_t PendingRows::wait() {
 }
 
 PendingRows::~PendingRows() {
-  if (ev) cudaEventDestroy(ev);
+  if (ev) ctx->put_event(ev, false);
+}
+
+cudaEvent_t CtxCore::get_event(bool timing) {
+  std::vector<cudaEvent_t>& pool = timing ? timing_events : sync_events;
+  if (!pool.empty()) {
+    cudaEvent_t e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  FG_CUDA(timing ? cudaEventCreate(&e) : cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return e;
 }
 
 std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned long long* d_count) {
@@ -158,7 +176,7 @@ std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned
   auto p = std::make_shared<PendingRows>();
   p->ctx = ctx;
   p->slot = slot;
-  FG_CUDA(cudaEventCreateWithFlags(&p->ev, cudaEventDisableTiming));
+  p->ev = ctx->get_event(false);
   FG_CUDA(cudaMemcpyAsync(ctx->h_scalars + 256 + slot, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   FG_CUDA(cudaEventRecord(p->ev, ctx->stream));
   ctx->pending_owner[slot] = p;
@@ -168,11 +186,8 @@ std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned
 // ---- per-kernel profile ----------------------------------------------------------------------------
 LaunchTimer::LaunchTimer(const CtxPtr& c, const char* kernel) : ctx(c.get()) {
   if (!ctx->profiling) return;
-  cudaEvent_t start;
-  if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) {
-    stop = nullptr;
-    return;
-  }
+  cudaEvent_t start = ctx->get_event(true);
+  stop = ctx->get_event(true);
   cudaEventRecord(start, ctx->stream);
   ctx->profile.push_back({kernel, start, stop});
 }
@@ -878,8 +893,8 @@ int flockgpu_profile_begin(flockgpu_ctx* ctx) {
     auto c = core_of(ctx);
     std::lock_guard<std::recursive_mutex> g(c->mu);
     for (auto& p : c->profile) {
-      cudaEventDestroy(p.start);
-      cudaEventDestroy(p.stop);
+      c->put_event(p.start, true);
+      c->put_event(p.stop, true);
     }
     c->profile.clear();
     c->profiling = true;
@@ -909,8 +924,8 @@ int flockgpu_profile_end(flockgpu_ctx* ctx, char* out_json, int32_t capacity) {
       }
       it->second.ms += ms;
       it->second.n += 1;
-      cudaEventDestroy(p.start);
-      cudaEventDestroy(p.stop);
+      c->put_event(p.start, true);
+      c->put_event(p.stop, true);
     }
     c->profile.clear();
     std::string s = "{";

@@ -89,28 +89,34 @@ struct PredI32 {
     if (x < 0) r = -r;
     return cmp_i64(cmp, r, rhs);
   }
+  // Streams the thread's rows in chunks of four 16-byte loads: only the one-bit verdicts are kept (the values of
+  // the ~1 % survivors are re-read from L2 when they are written), so the kernel needs ~48 registers and five CTAs
+  // stay resident per SM -- a 10 M-row relation (611 tiles of 16 Ki rows) is then a single wave.
   __device__ __forceinline__ unsigned long long eval(const ColRef*, int64_t tile_base, int64_t n_rows, int tid, int*) const {
     unsigned long long bits = 0;
-    int4 v[I / 4];
+#pragma unroll 1
+    for (int c = 0; c < I / 16; ++c) {
+      int4 v[4];
 #pragma unroll
-    for (int g = 0; g < I / 4; ++g) {
-      const int64_t row0 = tile_base + (int64_t(g) * FP_THREADS + tid) * 4;
-      if (row0 + 3 < n_rows) {
-        v[g] = ldg_stream_v4(col + row0);
-      } else {
-        v[g] = make_int4(0, 0, 0, 0);
-        if (row0 + 0 < n_rows) v[g].x = col[row0 + 0];
-        if (row0 + 1 < n_rows) v[g].y = col[row0 + 1];
-        if (row0 + 2 < n_rows) v[g].z = col[row0 + 2];
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row0 = tile_base + (int64_t(c * 4 + j) * FP_THREADS + tid) * 4;
+        if (row0 + 3 < n_rows) {
+          v[j] = ldg_stream_v4(col + row0);
+        } else {
+          v[j] = make_int4(0, 0, 0, 0);
+          if (row0 + 0 < n_rows) v[j].x = col[row0 + 0];
+          if (row0 + 1 < n_rows) v[j].y = col[row0 + 1];
+          if (row0 + 2 < n_rows) v[j].z = col[row0 + 2];
+        }
       }
-    }
 #pragma unroll
-    for (int g = 0; g < I / 4; ++g) {
-      const int64_t row0 = tile_base + (int64_t(g) * FP_THREADS + tid) * 4;
-      unsigned b = unsigned(test(v[g].x)) | (unsigned(test(v[g].y)) << 1) | (unsigned(test(v[g].z)) << 2) | (unsigned(test(v[g].w)) << 3);
-      const int64_t left = n_rows - row0;  // mask rows past the end
-      if (left < 4) b &= left <= 0 ? 0u : ((1u << left) - 1u);
-      bits |= (unsigned long long)b << (4 * g);
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row0 = tile_base + (int64_t(c * 4 + j) * FP_THREADS + tid) * 4;
+        unsigned b = unsigned(test(v[j].x)) | (unsigned(test(v[j].y)) << 1) | (unsigned(test(v[j].z)) << 2) | (unsigned(test(v[j].w)) << 3);
+        const int64_t left = n_rows - row0;  // mask rows past the end
+        if (left < 4) b &= left <= 0 ? 0u : ((1u << left) - 1u);
+        bits |= (unsigned long long)b << (16 * c + 4 * j);
+      }
     }
     return bits;
   }

@@ -113,6 +113,12 @@ struct CtxCore {
   };
   std::vector<ProfiledLaunch> profile;
 
+  // recycled CUDA events (creating one costs about a microsecond; a q2 step is one ~10 us kernel)
+  std::vector<cudaEvent_t> sync_events;    // cudaEventDisableTiming
+  std::vector<cudaEvent_t> timing_events;
+  cudaEvent_t get_event(bool timing);
+  void put_event(cudaEvent_t e, bool timing) { (timing ? timing_events : sync_events).push_back(e); }
+
   ~CtxCore();
 };
 using CtxPtr = std::shared_ptr<CtxCore>;
