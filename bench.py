@@ -191,7 +191,7 @@ def run_gpu(args) -> dict:
     dev_ms = dist_max(dist, local, dev_ms)
 
     # ---- e2e leg: host batches -> HBM -> plan -> host result, every step
-    src = [[pinned]]
+    src = [fb.HostRelation(pinned)]      # exported once through the C Data Interface, like FFI structs held by the Rust shim
     h2d = sum(b.num_rows for b in pinned) * 8      # projection pushdown: only auction + price (4 B each) cross PCIe
     for _ in range(min(args.warmup, 3)):
         ec.feed_data_sources(src)

@@ -24,6 +24,8 @@ struct CompactScratch {
   unsigned int* counters;          // [0] ticket, [1] done
   unsigned long long* out_count;   // receives the total number of survivors
   long long num_tiles;
+  int stride;         // u64 words between the look-back words of consecutive tiles (1 = packed; 32 = one 256-byte L2 chunk each)
+  int poll_sleep_ns;  // back-off of a polling thread that found a predecessor not yet published (0 = spin)
 };
 
 // Item k of thread `tid` is item index  ((k / E) * CP_THREADS + tid) * E + k % E  of the tile: E = items
@@ -69,15 +71,17 @@ __device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const Co
   if (tile == 0) {
     if (tid == 0) st_relaxed_u64(sc.tile_state, LB_PREFIX | (unsigned long long)total);
   } else {
-    if (tid == 0) st_relaxed_u64(sc.tile_state + tile, LB_PARTIAL | (unsigned long long)total);
+    if (tid == 0) st_relaxed_u64(sc.tile_state + tile * sc.stride, LB_PARTIAL | (unsigned long long)total);
     long long base = tile - 1;
     while (true) {
       const long long t = base - tid;
       unsigned long long st = LB_PREFIX;  // virtual tiles before the first one: inclusive prefix 0
       if (t >= 0) {
-        do {
-          st = ld_relaxed_u64(sc.tile_state + t);
-        } while ((st & LB_FLAG_MASK) == LB_INVALID);
+        while (true) {
+          st = ld_relaxed_u64(sc.tile_state + t * sc.stride);
+          if ((st & LB_FLAG_MASK) != LB_INVALID) break;
+          if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
+        }
       }
       const unsigned pm = __ballot_sync(FULL_MASK, (st & LB_FLAG_MASK) == LB_PREFIX);
       const int first = pm ? __ffs(pm) - 1 : 32;
@@ -99,7 +103,7 @@ __device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const Co
       if (s.lb_done) break;
       base -= CP_THREADS;
     }
-    if (tid == 0) st_relaxed_u64(sc.tile_state + tile, LB_PREFIX | (excl + total));
+    if (tid == 0) st_relaxed_u64(sc.tile_state + tile * sc.stride, LB_PREFIX | (excl + total));
   }
   if (tid == 0) {
     s.excl = excl;
@@ -165,11 +169,13 @@ __device__ __forceinline__ long long cp_position(const CompactSmem<E, I>& s, uns
 // Call once per CTA after its tile loop: the last CTA to arrive clears the scratch.
 template <int E, int I>
 __device__ __forceinline__ void cp_finish(CompactSmem<E, I>& s, const CompactScratch& sc) {
-  __threadfence();
-  if (threadIdx.x == 0) s.last = (atomicAdd(sc.counters + 1, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence();  // one thread: a CTA-wide fence costs ~1.5 us of L1 invalidation on every SM (profiles/r1_filter_ncu.md)
+    s.last = (atomicAdd(sc.counters + 1, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (s.last) {
-    for (long long i = threadIdx.x; i < sc.num_tiles; i += CP_THREADS) sc.tile_state[i] = LB_INVALID;
+    for (long long i = threadIdx.x; i < sc.num_tiles; i += CP_THREADS) sc.tile_state[i * sc.stride] = LB_INVALID;
     if (threadIdx.x == 0) {
       sc.counters[0] = 0;
       sc.counters[1] = 0;

@@ -124,6 +124,7 @@ void ensure_scan_scratch(const CtxPtr& ctx, int64_t tiles) {
     FG_CUDA(cudaMalloc(&s.counters, 64 * sizeof(unsigned int)));
     FG_CUDA(cudaMemsetAsync(s.counters, 0, 64 * sizeof(unsigned int), ctx->stream));
   }
+  tiles *= scan_stride();
   if (tiles > s.capacity) {
     int64_t cap = 1 << 16;
     while (cap < tiles) cap <<= 1;
@@ -133,6 +134,24 @@ void ensure_scan_scratch(const CtxPtr& ctx, int64_t tiles) {
     FG_CUDA(cudaMemsetAsync(s.tile_state, 0, cap * sizeof(unsigned long long), ctx->stream));
     s.capacity = cap;
   }
+}
+
+int scan_stride() {
+  static const int v = [] {
+    const char* e = getenv("FLOCKGPU_LB_STRIDE");
+    int x = e ? atoi(e) : 32;
+    return x >= 1 && x <= 64 ? x : 32;
+  }();
+  return v;
+}
+
+int scan_poll_sleep_ns() {
+  static const int v = [] {
+    const char* e = getenv("FLOCKGPU_LB_SLEEP");
+    int x = e ? atoi(e) : 100;
+    return x >= 0 && x <= 10000 ? x : 100;
+  }();
+  return v;
 }
 
 void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out) {

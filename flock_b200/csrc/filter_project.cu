@@ -34,6 +34,8 @@ struct FilterArgs {
   unsigned int* counters;            // [0] ticket, [1] done
   unsigned long long* out_count;     // total surviving rows
   int* err_flag;                     // set to 1 on divide-by-zero
+  unsigned long long* trace;         // debug (FLOCKGPU_TRACE): 8 globaltimer stamps per tile, else NULL
+  int32_t lb_stride, lb_sleep_ns;    // look-back tuning (internal.h: scan_stride / scan_poll_sleep_ns)
   ColRef cols[MAX_IN_COLS];
   OutCol outs[MAX_OUT_COLS];
 };
@@ -134,14 +136,27 @@ __global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid
   constexpr int TILE = FP_THREADS * I;
   __shared__ CompactSmem<E, I> sm;
   const int tid = threadIdx.x;
-  const CompactScratch sc{a.tile_state, a.counters, a.out_count, a.num_tiles};
+  const CompactScratch sc{a.tile_state, a.counters, a.out_count, a.num_tiles, a.lb_stride, a.lb_sleep_ns};
   int err = 0;
 
+  auto stamp = [&](long long tile, int k) {
+    if (a.trace && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[tile * 8 + k] = t;
+    }
+  };
+  unsigned long long t_begin = 0;
+  if (a.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
   for (long long tile = cp_next_tile(sm, sc); tile >= 0; tile = cp_next_tile(sm, sc)) {
     const int64_t tile_base = tile * TILE;
+    if (a.trace && tid == 0) a.trace[tile * 8 + 0] = t_begin;
+    stamp(tile, 1);
     const unsigned long long bits = pred.eval(a.cols, tile_base, a.n_rows, tid, &err);
+    stamp(tile, 2);
     unsigned lane_prefix[I / E];
     cp_rank_tile<E, I>(sm, sc, tile, bits, lane_prefix);
+    stamp(tile, 3);
 
     // ---- write survivors in input order
     if (bits && sm.tile_total) {
@@ -166,9 +181,21 @@ __global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid
       }
     }
     __syncthreads();  // sm is reused by the next tile
+    stamp(tile, 4);
+    if (a.trace && tid == 0) a.trace[tile * 8 + 6] = blockIdx.x;
+    if (a.trace && tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      a.trace[tile * 8 + 7] = smid;
+    }
   }
   if (err) *a.err_flag = 1;
   cp_finish(sm, sc);
+  if (a.trace && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(long long)blockIdx.x * 8 + 5] = t;   // per CTA (indexed by block, not tile)
+  }
 }
 
 // ---- pure projection (no predicate): streaming evaluation of the computed columns ----------------
@@ -271,6 +298,15 @@ static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args
   ensure_scan_scratch(ctx, args.num_tiles);
   args.tile_state = ctx->scan.tile_state;
   args.counters = ctx->scan.counters;
+  args.lb_stride = scan_stride();
+  args.lb_sleep_ns = scan_poll_sleep_ns();
+  BufferPtr trace_buf;
+  static const char* trace_path = getenv("FLOCKGPU_TRACE");
+  if (trace_path) {
+    trace_buf = alloc(ctx, size_t(args.num_tiles + 2048) * 64);
+    FG_CUDA(cudaMemsetAsync(trace_buf->ptr, 0, size_t(args.num_tiles + 2048) * 64, ctx->stream));
+    args.trace = trace_buf->as<unsigned long long>();
+  }
   const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
   int grid = persistent_grid(ctx, k, FP_THREADS, args.num_tiles);
   {
@@ -279,6 +315,20 @@ static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args
   }
   FG_CUDA(cudaGetLastError());
   count_launch(ctx);
+  if (trace_path) {
+    // debug only: dump the per-tile time stamps of this launch (overwrites the file each launch)
+    std::vector<unsigned long long> h(size_t(args.num_tiles + 2048) * 8);
+    FG_CUDA(cudaMemcpyAsync(h.data(), trace_buf->ptr, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (FILE* f = fopen(trace_path, "w")) {
+      fprintf(f, "%lld %d\n", (long long)args.num_tiles, grid);
+      for (size_t i = 0; i < h.size() / 8; ++i) {
+        for (int j = 0; j < 8; ++j) fprintf(f, "%llu ", h[i * 8 + j]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
 }
 
 TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* predicate, const std::vector<Expr>& projections,

@@ -138,6 +138,7 @@ struct AggLocalArgs {
   unsigned long long* part_acc;     // [n_acc][part_capacity]
   int64_t part_capacity;
   unsigned long long* part_cursor;  // number of partial entries written so far
+  unsigned long long* key_minmax;   // [0] = min, [1] = max packed key seen (decides the dense level-2 table)
 };
 
 __device__ __forceinline__ void local_flush(const AggLocalArgs& a, unsigned long long* s_keys, unsigned long long* s_acc, unsigned* s_warp,
@@ -201,13 +202,18 @@ __global__ void __launch_bounds__(AL_THREADS) agg_local_kernel(const __grid_cons
   const int64_t begin = int64_t(blockIdx.x) * per_cta;
   const int64_t end = begin + per_cta < a.n_rows ? begin + per_cta : a.n_rows;
 
+  unsigned long long kmin = ~0ull, kmax = 0ull;
   for (int64_t base = begin; base < end; base += STEP) {
     unsigned long long key[AL_UNROLL];
     int64_t row[AL_UNROLL];
 #pragma unroll
     for (int u = 0; u < AL_UNROLL; ++u) {
       row[u] = base + int64_t(u) * AL_THREADS + tid;
-      if (row[u] < end) key[u] = pack_key(a.keys, a.cols, row[u]);
+      if (row[u] < end) {
+        key[u] = pack_key(a.keys, a.cols, row[u]);
+        kmin = key[u] < kmin ? key[u] : kmin;
+        kmax = key[u] > kmax ? key[u] : kmax;
+      }
     }
 #pragma unroll
     for (int u = 0; u < AL_UNROLL; ++u) {
@@ -244,15 +250,208 @@ __global__ void __launch_bounds__(AL_THREADS) agg_local_kernel(const __grid_cons
     if (s_occ > AL_SLOTS * 3 / 4 - STEP) local_flush(a, s_keys, s_acc, s_warp, &s_base, &s_occ);
   }
   local_flush(a, s_keys, s_acc, s_warp, &s_base, &s_occ);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    unsigned long long o1 = __shfl_xor_sync(FULL_MASK, kmin, d), o2 = __shfl_xor_sync(FULL_MASK, kmax, d);
+    kmin = o1 < kmin ? o1 : kmin;
+    kmax = o2 > kmax ? o2 : kmax;
+  }
+  if ((tid & 31) == 0 && kmin <= kmax) {
+    atomicMin(a.key_minmax, kmin);
+    atomicMax(a.key_minmax + 1, kmax);
+  }
+}
+
+
+// ================================================================================================
+// level 1, specialised: ONE 4-byte key column, COUNT(*) or no aggregate (NEXMark q5 / q8 seller)
+// ================================================================================================
+// Same structure as agg_local_kernel, but the table is (u32 key, u32 count): native 32-bit shared atomics
+// (the generic kernel's 64-bit shared atomicAdd / CAS were measured at 20 G rows/s on q5, profiles/
+// r1_nexmark_run3.jsonl), 128-bit loads, and a per-warp HOT KEY: NEXMark's bid stream puts about half of the
+// rows of a batch on one auction id (event.rs:355-359), so every warp remembers the key that dominated its
+// last step and folds all lanes carrying it into one atomicAdd of popc(ballot).
+constexpr int A32_THREADS = 256;
+constexpr int A32_SLOTS = 8192;
+constexpr int A32_STEP = A32_THREADS * 16;  // rows per CTA iteration (4 x int4 per thread)
+constexpr unsigned EMPTY32 = ~0u;
+
+struct AggLocal32Args {
+  int64_t n_rows;
+  const uint32_t* key_col;
+  int32_t has_count;
+  int32_t pad;
+  unsigned long long* part_keys;
+  unsigned long long* part_acc;  // [1][part_capacity] (unused without COUNT)
+  int64_t part_capacity;
+  unsigned long long* part_cursor;
+  unsigned long long* key_minmax;
+};
+
+__device__ __forceinline__ unsigned a32_find_or_insert(unsigned* s_keys, unsigned* s_occ, unsigned key) {
+  unsigned slot = fmix32(key) & (A32_SLOTS - 1);
+  while (true) {
+    unsigned cur = s_keys[slot];
+    if (cur == key) return slot;
+    if (cur == EMPTY32) {
+      unsigned old = atomicCAS(&s_keys[slot], EMPTY32, key);
+      if (old == EMPTY32) {
+        atomicAdd(s_occ, 1u);
+        return slot;
+      }
+      if (old == key) return slot;
+    }
+    slot = (slot + 1) & (A32_SLOTS - 1);
+  }
+}
+
+__global__ void __launch_bounds__(A32_THREADS) agg_local32_kernel(const __grid_constant__ AggLocal32Args a) {
+  extern __shared__ __align__(16) unsigned a32_smem[];  // keys[A32_SLOTS] | counts[A32_SLOTS] = 64 KB (dynamic: > 48 KB)
+  unsigned* s_keys = a32_smem;
+  unsigned* s_cnt = a32_smem + A32_SLOTS;
+  __shared__ unsigned s_warp[A32_THREADS / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned s_occ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int s = tid; s < A32_SLOTS; s += A32_THREADS) {
+    s_keys[s] = EMPTY32;
+    s_cnt[s] = 0;
+  }
+  if (tid == 0) s_occ = 0;
+  __syncthreads();
+
+  int64_t per_cta = (a.n_rows + gridDim.x - 1) / gridDim.x;
+  per_cta = (per_cta + A32_STEP - 1) / A32_STEP * A32_STEP;
+  const int64_t begin = int64_t(blockIdx.x) * per_cta;
+  const int64_t end = begin + per_cta < a.n_rows ? begin + per_cta : a.n_rows;
+  unsigned kmin = ~0u, kmax = 0u;
+  unsigned hot = EMPTY32, hot_slot = 0;  // warp-uniform
+
+  auto flush = [&]() {
+    constexpr int PER = A32_SLOTS / A32_THREADS;
+    unsigned cnt = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) cnt += s_keys[tid * PER + j] != EMPTY32;
+    unsigned incl = warp_inclusive_sum(cnt);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned warp_base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < A32_THREADS / 32; ++w) {
+      unsigned v = s_warp[w];
+      if (w < warp) warp_base += v;
+      total += v;
+    }
+    if (tid == 0) s_base = total ? atomicAdd(a.part_cursor, (unsigned long long)total) : 0ull;
+    __syncthreads();
+    unsigned long long pos = s_base + warp_base + (incl - cnt);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int slot = tid * PER + j;
+      const unsigned k = s_keys[slot];
+      if (k != EMPTY32) {
+        a.part_keys[pos] = k;
+        if (a.has_count) a.part_acc[pos] = s_cnt[slot];
+        s_keys[slot] = EMPTY32;
+        s_cnt[slot] = 0;
+        ++pos;
+      }
+    }
+    if (tid == 0) s_occ = 0;
+    hot = EMPTY32;
+    __syncthreads();
+  };
+
+  for (int64_t base = begin; base < end; base += A32_STEP) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r0 = base + (int64_t(j) * A32_THREADS + tid) * 4;
+      if (r0 + 3 < end) {
+        int4 t = ldg_stream_v4(a.key_col + r0);
+        v[j] = make_uint4(unsigned(t.x), unsigned(t.y), unsigned(t.z), unsigned(t.w));
+      } else {
+        v[j] = make_uint4(EMPTY32, EMPTY32, EMPTY32, EMPTY32);  // EMPTY32 doubles as "no row" inside the step
+        if (r0 + 0 < end) v[j].x = a.key_col[r0 + 0];
+        if (r0 + 1 < end) v[j].y = a.key_col[r0 + 1];
+        if (r0 + 2 < end) v[j].z = a.key_col[r0 + 2];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r0 = base + (int64_t(j) * A32_THREADS + tid) * 4;
+      const unsigned ks[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned k = ks[e];
+        const bool valid = r0 + e < end;
+        if (valid) {
+          kmin = k < kmin ? k : kmin;
+          kmax = k > kmax ? k : kmax;
+        }
+        // --- hot key: all lanes carrying it become one atomic
+        unsigned m = __ballot_sync(FULL_MASK, valid && k == hot && hot != EMPTY32);
+        bool done = !valid || (m >> lane) & 1u;
+        if (m && lane == __ffs(m) - 1 && a.has_count) atomicAdd(&s_cnt[hot_slot], (unsigned)__popc(m));
+        if (__popc(m) < 8) {
+          // the remembered key no longer dominates: try the key of the first still-pending lane
+          const unsigned pending = __ballot_sync(FULL_MASK, !done && k != EMPTY32);
+          if (pending) {
+            const unsigned cand = __shfl_sync(FULL_MASK, k, __ffs(pending) - 1);
+            const unsigned m2 = __ballot_sync(FULL_MASK, !done && k == cand);
+            if (__popc(m2) >= 8) {
+              unsigned slot = 0;
+              if (lane == __ffs(m2) - 1) {
+                slot = a32_find_or_insert(s_keys, &s_occ, cand);
+                if (a.has_count) atomicAdd(&s_cnt[slot], (unsigned)__popc(m2));
+              }
+              hot = cand;
+              hot_slot = __shfl_sync(FULL_MASK, slot, __ffs(m2) - 1);
+              done = done || (m2 >> lane) & 1u;
+            }
+          }
+        }
+        if (!done) {
+          if (k == EMPTY32) {
+            // the one key equal to the empty marker bypasses the shared table
+            unsigned long long pos = atomicAdd(a.part_cursor, 1ull);
+            a.part_keys[pos] = k;
+            if (a.has_count) a.part_acc[pos] = 1;
+          } else {
+            const unsigned slot = a32_find_or_insert(s_keys, &s_occ, k);
+            if (a.has_count) atomicAdd(&s_cnt[slot], 1u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (s_occ > A32_SLOTS * 3 / 4 - A32_STEP) flush();
+  }
+  flush();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    unsigned o1 = __shfl_xor_sync(FULL_MASK, kmin, d), o2 = __shfl_xor_sync(FULL_MASK, kmax, d);
+    kmin = o1 < kmin ? o1 : kmin;
+    kmax = o2 > kmax ? o2 : kmax;
+  }
+  if (lane == 0 && kmin <= kmax) {
+    atomicMin(a.key_minmax, (unsigned long long)kmin);
+    atomicMax(a.key_minmax + 1, (unsigned long long)kmax);
+  }
 }
 
 // ================================================================================================
 // level 2: global table (packed 64-bit keys)
 // ================================================================================================
 struct AggTable {
-  unsigned long long* keys;  // [cap + 1]; slot `cap` is reserved for the key equal to EMPTY_KEY
+  unsigned long long* keys;  // [cap + 1]; slot `cap` is reserved for the key equal to EMPTY_KEY (NULL when dense)
   unsigned long long* acc;   // [n_acc][cap + 1]
-  unsigned long long cap;    // power of two
+  unsigned long long cap;    // hashed: power of two; dense: max_key - min_key + 1
+  // dense (direct-address) table: slot = key - dense_base.  NEXMark ids are dense ranges (auction ids of a window
+  // are consecutive integers), so level 2 needs no hashing, no CAS and a table small enough to live in L2
+  // (q5: 6.5 M auctions x 9 B = 58 MB), where random 64-bit atomics run at 150-190 Gop/s instead of 25 (profiles/).
+  unsigned char* present;    // [cap + 1] dense only
+  unsigned long long dense_base;
 };
 
 __global__ void agg_init_kernel(AggTable t, int n_acc, unsigned long long ident0, unsigned long long ident1, unsigned long long ident2,
@@ -261,7 +460,7 @@ __global__ void agg_init_kernel(AggTable t, int n_acc, unsigned long long ident0
   const unsigned long long ident[MAX_ACC] = {ident0, ident1, ident2, ident3, ident4, ident5, ident6, ident7};
   const unsigned long long n = t.cap + 1;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-    t.keys[i] = EMPTY_KEY;
+    if (t.keys) t.keys[i] = EMPTY_KEY;
     for (int c = 0; c < n_acc; ++c) t.acc[c * n + i] = ident[c];
   }
 }
@@ -280,6 +479,11 @@ struct AggInsertArgs {
 };
 
 __device__ __forceinline__ unsigned long long table_find_or_insert(const AggTable& t, unsigned long long key) {
+  if (t.present) {
+    const unsigned long long slot = key - t.dense_base;
+    t.present[slot] = 1;  // idempotent plain store
+    return slot;
+  }
   if (key == EMPTY_KEY) {
     t.keys[t.cap] = 0;  // marks the reserved slot occupied (idempotent plain store)
     return t.cap;
@@ -362,7 +566,9 @@ __global__ void __launch_bounds__(256) agg_insert_rows_kernel(const __grid_const
 struct AggEmitArgs {
   CompactScratch sc;
   unsigned long long n_slots;       // slots to scan (cap + 1 packed, cap rows mode)
-  const unsigned long long* keys;   // packed mode (NULL in rows mode)
+  const unsigned long long* keys;   // packed hashed mode (NULL otherwise)
+  const unsigned char* present;     // packed dense mode: key = dense_base + slot
+  unsigned long long dense_base;
   const unsigned* owner;            // rows mode
   const unsigned long long* acc;    // [n_acc][n_slots]
   int32_t n_emit;
@@ -401,7 +607,7 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
     for (int k = 0; k < CP_ITEMS; ++k) {
       unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
       bool occ = false;
-      if (slot < a.n_slots) occ = a.keys ? a.keys[slot] != EMPTY_KEY : a.owner[slot] != EMPTY_OWNER;
+      if (slot < a.n_slots) occ = a.keys ? a.keys[slot] != EMPTY_KEY : a.present ? a.present[slot] != 0 : a.owner[slot] != EMPTY_OWNER;
       bits |= (unsigned long long)occ << k;
     }
     unsigned lane_prefix[CP_ITEMS / E];
@@ -413,8 +619,8 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
         m &= m - 1;
         const int64_t pos = cp_position<E, CP_ITEMS>(sm, bits, k, lane_prefix);
         const unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
-        if (a.keys) {
-          unsigned long long key = slot == a.n_slots - 1 ? EMPTY_KEY : a.keys[slot];
+        if (a.keys || a.present) {
+          unsigned long long key = a.present ? a.dense_base + slot : (slot == a.n_slots - 1 ? EMPTY_KEY : a.keys[slot]);
           if (a.n_key_out == 2) {
             static_cast<uint32_t*>(a.key_dst[0])[pos] = uint32_t(key >> 32);
             static_cast<uint32_t*>(a.key_dst[1])[pos] = uint32_t(key);
@@ -721,7 +927,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   if (key_bytes > 8) packed = false;
 
   AggEmitArgs ea{};
-  BufferPtr tkeys, tacc, towner, rep_rows;
+  BufferPtr tkeys, tacc, towner, rep_rows, keep_alive;
   unsigned long long n_slots = 0;
 
   if (packed) {
@@ -735,6 +941,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     BufferPtr pkeys, pacc;
     int64_t n_entries = n;
     bool from_partials = false;
+    unsigned long long key_min = 1, key_max = 0;
     const size_t local_smem = size_t(AL_SLOTS) * 8 * (1 + n_acc);
     if (n >= (int64_t(1) << 18) && local_smem <= 200 * 1024) {
       AggLocalArgs la{};
@@ -749,29 +956,67 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       la.part_acc = pacc->as<unsigned long long>();
       la.part_capacity = n;
       la.part_cursor = ctx->d_scalars + 2;
+      la.key_minmax = ctx->d_scalars + 6;
       FG_CUDA(cudaMemsetAsync(la.part_cursor, 0, 8, ctx->stream));
+      FG_CUDA(cudaMemsetAsync(la.key_minmax, 0xff, 8, ctx->stream));   // min = ~0
+      FG_CUDA(cudaMemsetAsync(la.key_minmax + 1, 0, 8, ctx->stream));  // max = 0
       FG_CUDA(cudaFuncSetAttribute(agg_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(local_smem)));
-      int per_sm = 1;
-      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_local_kernel, AL_THREADS, local_smem));
-      int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + AL_THREADS * AL_UNROLL - 1) / (AL_THREADS * AL_UNROLL))));
-      {
+      const bool count32 = kp.n == 1 && kp.width[0] == 4 && (n_acc == 0 || (n_acc == 1 && accs[0].op == ACC_COUNT));
+      if (count32) {
+        AggLocal32Args l32{};
+        l32.n_rows = n;
+        l32.key_col = static_cast<const uint32_t*>(in.cols[kp.col[0]].values());
+        l32.has_count = n_acc;
+        l32.part_keys = la.part_keys;
+        l32.part_acc = la.part_acc;
+        l32.part_capacity = n;
+        l32.part_cursor = la.part_cursor;
+        l32.key_minmax = la.key_minmax;
+        constexpr size_t a32_bytes = size_t(A32_SLOTS) * 8;
+        FG_CUDA(cudaFuncSetAttribute(agg_local32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(a32_bytes)));
+        int per_sm = 1;
+        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_local32_kernel, A32_THREADS, a32_bytes));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + A32_STEP - 1) / A32_STEP)));
+        {
+          LaunchTimer lt(ctx, "agg_local32_kernel");
+          agg_local32_kernel<<<grid, A32_THREADS, a32_bytes, ctx->stream>>>(l32);
+        }
+      } else {
+        int per_sm = 1;
+        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_local_kernel, AL_THREADS, local_smem));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + AL_THREADS * AL_UNROLL - 1) / (AL_THREADS * AL_UNROLL))));
         LaunchTimer lt(ctx, "agg_local_kernel");
         agg_local_kernel<<<grid, AL_THREADS, local_smem, ctx->stream>>>(la);
       }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
-      unsigned long long cnt = 0;
-      read_scalars(ctx, 2, 1, &cnt);
+      unsigned long long sc6[6] = {};
+      read_scalars(ctx, 2, 6, sc6);
+      const unsigned long long cnt = sc6[0];
       FG_CHECK(int64_t(cnt) <= n, FLOCKGPU_ERR_CUDA, "hash_aggregate: corrupt partial count");
       n_entries = int64_t(cnt);
       from_partials = true;
+      key_min = sc6[4];
+      key_max = sc6[5];
     }
-    // ---- level 2: global table
-    const unsigned long long cap = pow2_at_least(2ull * (unsigned long long)n_entries);
+    // ---- level 2: global table.  Dense (direct-address) when the keys of a single column fill their range well.
+    bool dense = false;
+    if (from_partials && kp.n == 1 && key_max >= key_min && key_max != EMPTY_KEY) {
+      const unsigned long long range = key_max - key_min + 1;
+      dense = range <= std::max<unsigned long long>(4ull * (unsigned long long)n_entries, 1ull << 16) && range < (1ull << 31);
+    }
+    const unsigned long long cap = dense ? key_max - key_min + 1 : pow2_at_least(2ull * (unsigned long long)n_entries);
     n_slots = cap + 1;
-    tkeys = alloc(ctx, size_t(n_slots) * 8);
+    BufferPtr tpresent;
+    if (dense) {
+      tpresent = alloc(ctx, size_t(n_slots));
+      FG_CUDA(cudaMemsetAsync(tpresent->ptr, 0, size_t(n_slots), ctx->stream));
+    } else {
+      tkeys = alloc(ctx, size_t(n_slots) * 8);
+    }
     tacc = alloc(ctx, size_t(n_slots) * 8 * std::max(n_acc, 1));
-    AggTable tab{tkeys->as<unsigned long long>(), tacc->as<unsigned long long>(), cap};
+    AggTable tab{dense ? nullptr : tkeys->as<unsigned long long>(), tacc->as<unsigned long long>(), cap,
+                 dense ? tpresent->as<unsigned char>() : nullptr, key_min};
     {
       LaunchTimer lt(ctx, "agg_init_kernel");
       agg_init_kernel<<<grid_for(ctx, int64_t(n_slots), 256, 8), 256, 0, ctx->stream>>>(tab, n_acc, ident[0], ident[1], ident[2], ident[3], ident[4],
@@ -799,6 +1044,9 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       count_launch(ctx);
     }
     ea.keys = tab.keys;
+    ea.present = tab.present;
+    ea.dense_base = tab.dense_base;
+    keep_alive = tpresent;
     ea.acc = tab.acc;
     ea.n_key_out = kp.n;
     ea.key_width[0] = kp.width[0];
@@ -857,6 +1105,8 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   ensure_scan_scratch(ctx, ea.sc.num_tiles);
   ea.sc.tile_state = ctx->scan.tile_state;
   ea.sc.counters = ctx->scan.counters;
+  ea.sc.stride = scan_stride();
+  ea.sc.poll_sleep_ns = scan_poll_sleep_ns();
   ea.sc.out_count = ctx->d_scalars + 3;
   {
     int per_sm = 1;

@@ -6,10 +6,13 @@
 // keys and materialise `take(left columns) ++ take(right columns)`.  NULL keys never match (no NULLs on
 // this path); duplicate keys on both sides give the full cross product.
 //
-// GPU design: an open-addressing table of build ROW IDS (one slot per build row, duplicates simply
-// occupy further slots of the probe sequence), plus the 64-bit packed key next to it when the key
-// packs (rowkeys.cuh) so that a probe compares words without touching the build columns.
-//   join_build_kernel        CAS row ids into the table
+// GPU design: an open-addressing table with ONE slot per DISTINCT build key -- the slot holds a
+// representative build row (key equality is checked against the immutable build columns, so there is no
+// publish race), the head of a linked list threading all build rows of that key (`next[row]`), and their
+// count.  Heavily duplicated keys (NEXMark q5 joins 6.5 M (auction, num) rows on `num`, ~850 distinct
+// values; q3's hot sellers) therefore cost one probe step, not one per duplicate.  The SMALLER input is
+// the build side (the reference always builds on the left; which side is hashed is not observable).
+//   join_build_kernel        claim / find the key's slot, push the row on its list
 //   join_count_scan_kernel   per probe row: number of matches -> exclusive offsets (decoupled
 //                            look-back, single pass) and the total pair count
 //   join_emit_kernel         second walk (table lines are L2-hot) writes the (build, probe) index pairs
@@ -34,9 +37,11 @@ struct JoinSide {
 };
 
 struct JoinTable {
-  unsigned* rows;            // [cap] build row ids, JOIN_EMPTY = free
-  unsigned long long* keys;  // [cap] packed keys (packed mode only)
-  unsigned long long cap;    // power of two
+  unsigned* rep;           // [cap] representative build row of the slot's key, JOIN_EMPTY = free
+  unsigned* head;          // [cap] most recently pushed build row of that key
+  unsigned* cnt;           // [cap] number of build rows with that key
+  unsigned* next;          // [build rows] next build row with the same key, JOIN_EMPTY = end
+  unsigned long long cap;  // power of two
 };
 
 __device__ __forceinline__ unsigned long long side_hash(const JoinSide& s, int64_t row, unsigned long long* key) {
@@ -48,25 +53,37 @@ __device__ __forceinline__ unsigned long long side_hash(const JoinSide& s, int64
   return hash_row(s.rk, s.cols, row);
 }
 
+// Does build row `r` carry the key (`key` / row `row` of side `other`)?
+__device__ __forceinline__ bool build_row_matches(const JoinSide& build, unsigned r, const JoinSide& other, int64_t row, unsigned long long key) {
+  return build.packed ? pack_key(build.pack, build.cols, int64_t(r)) == key : rows_equal(build.rk, build.cols, int64_t(r), other.rk, other.cols, row);
+}
+
 __global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__ JoinSide build, const JoinTable t) {
   for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < build.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
     unsigned long long key;
     unsigned long long slot = side_hash(build, row, &key) & (t.cap - 1);
-    while (atomicCAS(&t.rows[slot], JOIN_EMPTY, unsigned(row)) != JOIN_EMPTY) slot = (slot + 1) & (t.cap - 1);
-    if (build.packed) t.keys[slot] = key;
+    while (true) {
+      unsigned r = t.rep[slot];
+      if (r == JOIN_EMPTY) {
+        r = atomicCAS(&t.rep[slot], JOIN_EMPTY, unsigned(row));
+        if (r == JOIN_EMPTY) break;  // claimed: this row represents the key
+      }
+      if (build_row_matches(build, r, build, row, key)) break;
+      slot = (slot + 1) & (t.cap - 1);
+    }
+    t.next[row] = atomicExch(&t.head[slot], unsigned(row));
+    atomicAdd(&t.cnt[slot], 1u);
   }
 }
 
-// Calls f(build_row) for every build row whose key equals the key of probe row `row`.
-template <class F>
-__device__ __forceinline__ void for_each_match(const JoinSide& build, const JoinSide& probe, const JoinTable& t, int64_t row, F&& f) {
+// Slot of the key of probe row `row`, or ~0 when no build row has it.
+__device__ __forceinline__ unsigned long long find_slot(const JoinSide& build, const JoinSide& probe, const JoinTable& t, int64_t row) {
   unsigned long long key;
   unsigned long long slot = side_hash(probe, row, &key) & (t.cap - 1);
   while (true) {
-    const unsigned r = t.rows[slot];
-    if (r == JOIN_EMPTY) return;
-    const bool match = probe.packed ? (t.keys[slot] == key) : rows_equal(build.rk, build.cols, int64_t(r), probe.rk, probe.cols, row);
-    if (match) f(r);
+    const unsigned r = t.rep[slot];
+    if (r == JOIN_EMPTY) return ~0ull;
+    if (build_row_matches(build, r, probe, row, key)) return slot;
     slot = (slot + 1) & (t.cap - 1);
   }
 }
@@ -103,7 +120,10 @@ __global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __gri
 #pragma unroll
     for (int k = 0; k < JC_ITEMS; ++k) {
       unsigned c = 0;
-      if (i0 + k < n) for_each_match(a.build, a.probe, a.table, i0 + k, [&](unsigned) { ++c; });
+      if (i0 + k < n) {
+        const unsigned long long slot = find_slot(a.build, a.probe, a.table, i0 + k);
+        if (slot != ~0ull) c = a.table.cnt[slot];
+      }
       cnt[k] = c;
       local += c;
     }
@@ -167,11 +187,12 @@ __global__ void __launch_bounds__(256) join_emit_kernel(const __grid_constant__ 
   for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.probe.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
     unsigned pos = a.off[row];
     if (a.off[row + 1] == pos) continue;
-    for_each_match(a.build, a.probe, a.table, row, [&](unsigned r) {
+    const unsigned long long slot = find_slot(a.build, a.probe, a.table, row);
+    for (unsigned r = a.table.head[slot]; r != JOIN_EMPTY; r = a.table.next[r]) {
       a.build_idx[pos] = r;
       a.probe_idx[pos] = unsigned(row);
       ++pos;
-    });
+    }
   }
 }
 
@@ -231,30 +252,36 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
 
   int64_t n_pairs = 0;
   BufferPtr build_idx, probe_idx;
+  // hash the smaller input, stream the larger one through it
+  const bool swap_sides = R.num_rows < L.num_rows;
+  const Table& B = swap_sides ? R : L;
+  const Table& P = swap_sides ? L : R;
   if (L.num_rows > 0 && R.num_rows > 0 && !null_key) {
     JoinSide bs{}, ps{};
-    fill_side(L, left_keys, packed, &bs);
-    fill_side(R, right_keys, packed, &ps);
+    fill_side(B, swap_sides ? right_keys : left_keys, packed, &bs);
+    fill_side(P, swap_sides ? left_keys : right_keys, packed, &ps);
     unsigned long long cap = 1024;
-    while (cap < 2ull * (unsigned long long)L.num_rows) cap <<= 1;
-    BufferPtr trows = alloc(ctx, size_t(cap) * 4);
-    BufferPtr tkeys = packed ? alloc(ctx, size_t(cap) * 8) : nullptr;
-    FG_CUDA(cudaMemsetAsync(trows->ptr, 0xff, size_t(cap) * 4, ctx->stream));
-    JoinTable tab{trows->as<unsigned>(), tkeys ? tkeys->as<unsigned long long>() : nullptr, cap};
+    while (cap < 2ull * (unsigned long long)B.num_rows) cap <<= 1;
+    // rep | head | cnt in one allocation (cap words each), then next[build rows]
+    BufferPtr tbuf = alloc(ctx, size_t(cap) * 12 + size_t(B.num_rows) * 4);
+    FG_CUDA(cudaMemsetAsync(tbuf->ptr, 0xff, size_t(cap) * 8, ctx->stream));                                  // rep, head = EMPTY
+    FG_CUDA(cudaMemsetAsync(static_cast<char*>(tbuf->ptr) + size_t(cap) * 8, 0, size_t(cap) * 4, ctx->stream));  // cnt = 0
+    unsigned* w = tbuf->as<unsigned>();
+    JoinTable tab{w, w + cap, w + 2 * cap, w + 3 * cap, cap};
     {
       LaunchTimer lt(ctx, "join_build_kernel");
-      join_build_kernel<<<grid_for(ctx, L.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab);
+      join_build_kernel<<<grid_for(ctx, B.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab);
     }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
 
-    BufferPtr off = alloc(ctx, size_t(R.num_rows + 1) * 4);
+    BufferPtr off = alloc(ctx, size_t(P.num_rows + 1) * 4);
     JoinCountArgs ca{};
     ca.build = bs;
     ca.probe = ps;
     ca.table = tab;
     ca.out_off = off->as<unsigned>();
-    ca.num_tiles = (R.num_rows + JC_TILE - 1) / JC_TILE;
+    ca.num_tiles = (P.num_rows + JC_TILE - 1) / JC_TILE;
     ensure_scan_scratch(ctx, ca.num_tiles);
     ca.tile_state = ctx->scan.tile_state;
     ca.counters = ctx->scan.counters;
@@ -286,7 +313,7 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       ea.probe_idx = probe_idx->as<unsigned>();
       {
         LaunchTimer lt(ctx, "join_emit_kernel");
-        join_emit_kernel<<<grid_for(ctx, R.num_rows, 256, 8), 256, 0, ctx->stream>>>(ea);
+        join_emit_kernel<<<grid_for(ctx, P.num_rows, 256, 8), 256, 0, ctx->stream>>>(ea);
       }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
@@ -299,8 +326,11 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     for (const Column& c : re->cols) out->cols.push_back(c);
     return out;
   }
-  for (const Column& c : L.cols) out->cols.push_back(gather_column(ctx, c, build_idx->as<uint32_t>(), n_pairs));
-  for (const Column& c : R.cols) out->cols.push_back(gather_column(ctx, c, probe_idx->as<uint32_t>(), n_pairs));
+  // output schema is always left ++ right, whichever side was hashed
+  const uint32_t* l_idx = (swap_sides ? probe_idx : build_idx)->as<uint32_t>();
+  const uint32_t* r_idx = (swap_sides ? build_idx : probe_idx)->as<uint32_t>();
+  for (const Column& c : L.cols) out->cols.push_back(gather_column(ctx, c, l_idx, n_pairs));
+  for (const Column& c : R.cols) out->cols.push_back(gather_column(ctx, c, r_idx, n_pairs));
   return out;
 }
 

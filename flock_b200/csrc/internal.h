@@ -162,6 +162,9 @@ BufferPtr alloc(const CtxPtr& ctx, size_t bytes);  // bytes == 0 still yields a 
 
 // Grows the look-back scratch to at least `tiles` entries (zero-initialised once).
 void ensure_scan_scratch(const CtxPtr& ctx, int64_t tiles);
+// Look-back tuning (FLOCKGPU_LB_STRIDE / FLOCKGPU_LB_SLEEP override): words between tile entries, poll back-off in ns.
+int scan_stride();
+int scan_poll_sleep_ns();
 // Copies `n` u64 scalars from d_scalars[first..] to the host and waits.
 void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out);
 

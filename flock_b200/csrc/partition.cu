@@ -155,6 +155,8 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   ensure_scan_scratch(ctx, sa.sc.num_tiles);
   sa.sc.tile_state = ctx->scan.tile_state;
   sa.sc.counters = ctx->scan.counters;
+  sa.sc.stride = scan_stride();
+  sa.sc.poll_sleep_ns = scan_poll_sleep_ns();
   sa.sc.out_count = ctx->d_scalars + 5;
   sa.pid = pid->as<uint8_t>();
   sa.n_rows = n;
