@@ -3,29 +3,51 @@
 //
 // A persistent CTA takes tiles of CP_THREADS x I items from an atomic ticket.  For each tile it gets one
 // bit per item ("survives"), ranks the survivors in item order with warp ballots, obtains the tile's
-// global output offset by decoupled look-back (device_utils.cuh) and hands every survivor its output
-// position.  The last CTA to finish resets the scratch, so back-to-back launches need no memset.
+// global output offset and hands every survivor its output position.  Two ways to get that offset:
 //
-// I = items per thread per tile (16 / 32 / 64): measured on B200 (profiles/r1_microbench.txt), a 40 MB
-// column is read fastest with >= 4 independent 16-byte loads in flight per thread and as FEW
-// inter-tile synchronisation points as possible -- with I = 64 a 10 M-row relation is 611 tiles, fewer
-// than the resident CTAs, so every CTA does exactly one ticket, one look-back and three barriers.
+//   single wave   (tiles <= resident CTAs; NEXMark q2's 10 M rows = 611 tiles): every tile needs the counts of
+//                 ALL its predecessors and they all finish counting at about the same time, so a chained
+//                 look-back degenerates into everybody polling everybody (measured: 43 % of the stall samples,
+//                 profiles/r1_filter_ncu.md).  Instead each CTA stores its count, bumps ONE arrival counter
+//                 (release), ONE thread per CTA polls that counter (acquire) until all tiles have arrived, then
+//                 the CTA sums its predecessors' counts with one strided read.
+//   many waves    decoupled look-back with the whole CTA (thread i inspects predecessor i): earlier waves have
+//                 long published their inclusive prefixes, so one 256-wide window almost always suffices.
+//
+// Nothing is reset between launches: tickets and arrivals are monotonic counters (the host passes the base
+// value of the launch), look-back words carry a 20-bit launch epoch and a stale epoch reads as "invalid".
+// That removes the end-of-kernel fence + atomic + reset loop (~2 us of a ~30 us kernel).
 #pragma once
 
+#include <utility>
+
 #include "device_utils.cuh"
+#include "internal.h"
 
 namespace fg {
 
 constexpr int CP_THREADS = 256;
 constexpr int CP_WARPS = CP_THREADS / 32;
 
+// look-back word: [63:44] launch epoch, [43:42] flag (1 = partial, 2 = inclusive prefix), [41:0] value
+constexpr int EP_VALUE_BITS = 42;
+constexpr unsigned long long EP_VALUE_MASK = (1ull << EP_VALUE_BITS) - 1;
+constexpr unsigned long long EP_PARTIAL = 1ull << EP_VALUE_BITS;
+constexpr unsigned long long EP_PREFIX = 2ull << EP_VALUE_BITS;
+constexpr unsigned long long EP_FLAG_MASK = 3ull << EP_VALUE_BITS;
+
 struct CompactScratch {
-  unsigned long long* tile_state;  // look-back words, zero between launches
-  unsigned int* counters;          // [0] ticket, [1] done
+  unsigned long long* tile_state;  // epoch-tagged look-back words (many-wave mode)
+  unsigned* counts;                // per-tile survivor counts (single-wave mode)
+  unsigned int* counters;          // [0] tickets issued, [1] tiles arrived -- both monotonic across launches
   unsigned long long* out_count;   // receives the total number of survivors
   long long num_tiles;
-  int stride;         // u64 words between the look-back words of consecutive tiles (1 = packed; 32 = one 256-byte L2 chunk each)
-  int poll_sleep_ns;  // back-off of a polling thread that found a predecessor not yet published (0 = spin)
+  unsigned ticket_base;            // value of counters[0] when this launch starts
+  unsigned arrived_base;           // value of counters[1] when this launch starts
+  unsigned epoch;                  // 20-bit launch epoch of the look-back words
+  int single_wave;
+  int stride;                      // u64 words between look-back words of consecutive tiles (32 = one 256-byte L2 chunk each)
+  int poll_sleep_ns;               // back-off of a polling thread (0 = spin)
 };
 
 // Item k of thread `tid` is item index  ((k / E) * CP_THREADS + tid) * E + k % E  of the tile: E = items
@@ -46,46 +68,86 @@ struct CompactSmem {
   long long tile;
   unsigned long long excl;
   unsigned tile_total;
-  int last;
 };
 
-// Fetches the next tile index for the CTA (or -1 when the work is exhausted).
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Fetches the next tile index for the CTA (or -1 when the work is exhausted).  Every CTA draws exactly one
+// ticket past the end, so a launch consumes num_tiles + gridDim.x tickets (the host advances its base by that).
 template <int E, int I>
 __device__ __forceinline__ long long cp_next_tile(CompactSmem<E, I>& s, const CompactScratch& sc) {
-  if (threadIdx.x == 0) s.tile = (long long)atomicAdd(sc.counters, 1u);
+  if (threadIdx.x == 0) s.tile = (long long)(atomicAdd(sc.counters, 1u) - sc.ticket_base);
   __syncthreads();
   long long t = s.tile;
   return t < sc.num_tiles ? t : -1;
 }
 
-// Decoupled look-back with the WHOLE CTA: thread i inspects tile (base - i), so one step covers CP_THREADS
-// predecessors.  When a launch is a single wave (all tiles finish counting at about the same time) nearly every
-// predecessor still shows PARTIAL, and a 32-wide window would walk back serially, one L2 round trip per 32 tiles
-// (measured: 611 tiles -> ~19 dependent round trips, the dominant cost of the first version, see
-// profiles/r1_filter_ncu.md); 256-wide windows need at most ceil(tiles / 256) steps.  Leaves the exclusive
-// prefix of `tile` in s.excl (valid for every thread after the trailing barrier).
+template <int E, int I>
+__device__ __forceinline__ unsigned long long cp_block_sum(CompactSmem<E, I>& s, unsigned long long v) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) s.lb_sum[warp] = v;
+  __syncthreads();
+  unsigned long long tot = 0;
+#pragma unroll
+  for (int w = 0; w < CP_WARPS; ++w) tot += s.lb_sum[w];
+  return tot;
+}
+
+// ---- single wave: counts + one arrival counter ------------------------------------------------------------
+template <int E, int I>
+__device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned total) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    sc.counts[tile] = total;
+    red_release_add_u32(sc.counters + 1, 1u);  // release: the count is visible before the arrival
+    const unsigned target = sc.arrived_base + unsigned(sc.num_tiles);
+    while (int(ld_acquire_u32(sc.counters + 1) - target) < 0) {
+      if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
+    }
+  }
+  __syncthreads();  // thread 0's acquire + this barrier: every predecessor's count is visible to the CTA
+  unsigned long long part = 0;
+  for (long long i = tid; i < tile; i += CP_THREADS) part += __ldcg(sc.counts + i);
+  const unsigned long long excl = cp_block_sum(s, part);
+  if (tid == 0) {
+    s.excl = excl;
+    if (tile == sc.num_tiles - 1) *sc.out_count = excl + total;
+  }
+  __syncthreads();
+}
+
+// ---- many waves: decoupled look-back, 256 predecessors per step, epoch-tagged words -------------------------
 template <int E, int I>
 __device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned total) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
   unsigned long long excl = 0;  // meaningful in thread 0 only
   if (tile == 0) {
-    if (tid == 0) st_relaxed_u64(sc.tile_state, LB_PREFIX | (unsigned long long)total);
+    if (tid == 0) st_relaxed_u64(sc.tile_state, tag | EP_PREFIX | (unsigned long long)total);
   } else {
-    if (tid == 0) st_relaxed_u64(sc.tile_state + tile * sc.stride, LB_PARTIAL | (unsigned long long)total);
+    if (tid == 0) st_relaxed_u64(sc.tile_state + tile * sc.stride, tag | EP_PARTIAL | (unsigned long long)total);
     long long base = tile - 1;
     while (true) {
       const long long t = base - tid;
-      unsigned long long st = LB_PREFIX;  // virtual tiles before the first one: inclusive prefix 0
+      unsigned long long st = tag | EP_PREFIX;  // virtual tiles before the first one: inclusive prefix 0
       if (t >= 0) {
         while (true) {
           st = ld_relaxed_u64(sc.tile_state + t * sc.stride);
-          if ((st & LB_FLAG_MASK) != LB_INVALID) break;
+          if ((st >> 44) == (tag >> 44) && (st & EP_FLAG_MASK) != 0) break;  // published in THIS launch
           if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
         }
       }
-      const unsigned pm = __ballot_sync(FULL_MASK, (st & LB_FLAG_MASK) == LB_PREFIX);
+      const unsigned pm = __ballot_sync(FULL_MASK, (st & EP_FLAG_MASK) == EP_PREFIX);
       const int first = pm ? __ffs(pm) - 1 : 32;
-      const unsigned long long wsum = warp_sum(lane <= first ? (st & LB_VALUE_MASK) : 0ull);
+      const unsigned long long wsum = warp_sum(lane <= first ? (st & EP_VALUE_MASK) : 0ull);
       if (lane == 0) {
         s.lb_sum[warp] = wsum;
         s.lb_has[warp] = pm != 0;
@@ -103,7 +165,7 @@ __device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const Co
       if (s.lb_done) break;
       base -= CP_THREADS;
     }
-    if (tid == 0) st_relaxed_u64(sc.tile_state + tile * sc.stride, LB_PREFIX | (excl + total));
+    if (tid == 0) st_relaxed_u64(sc.tile_state + tile * sc.stride, tag | EP_PREFIX | (excl + total));
   }
   if (tid == 0) {
     s.excl = excl;
@@ -156,7 +218,30 @@ __device__ __forceinline__ void cp_rank_tile(CompactSmem<E, I>& s, const Compact
     if (lane == 0) s.tile_total = total;
   }
   __syncthreads();
-  cp_block_lookback(s, sc, tile, s.tile_total);
+  if (sc.single_wave) cp_grid_prefix(s, sc, tile, s.tile_total);
+  else cp_block_lookback(s, sc, tile, s.tile_total);
+}
+
+// Host side (core.cu): sizes the scratch and fills a CompactScratch for ONE launch of `grid` CTAs over `num_tiles`
+// tiles; advances the context's ticket / arrival / epoch bookkeeping.  Call it right before the launch.
+CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, int grid, unsigned long long* out_count);
+
+// Launches a compaction kernel.  Single-wave launches wait on an arrival counter that only completes when EVERY CTA
+// of the grid is running, so they go through the cooperative-launch path: the driver then guarantees co-residency
+// (or fails the launch) instead of us assuming the GPU is otherwise idle.
+template <class Kernel, class... Args>
+inline void launch_compact(const CtxPtr& ctx, Kernel kernel, int grid, const CompactScratch& sc, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(CP_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = sc.single_wave ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FG_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
 template <int E, int I>
@@ -164,23 +249,6 @@ __device__ __forceinline__ long long cp_position(const CompactSmem<E, I>& s, uns
   const int g = k / E, e = k % E;
   const unsigned within = __popcll(bits & (((1ull << e) - 1ull) << (g * E)));
   return (long long)s.excl + s.group_warp[g][threadIdx.x >> 5] + lane_prefix[g] + within;
-}
-
-// Call once per CTA after its tile loop: the last CTA to arrive clears the scratch.
-template <int E, int I>
-__device__ __forceinline__ void cp_finish(CompactSmem<E, I>& s, const CompactScratch& sc) {
-  if (threadIdx.x == 0) {
-    __threadfence();  // one thread: a CTA-wide fence costs ~1.5 us of L1 invalidation on every SM (profiles/r1_filter_ncu.md)
-    s.last = (atomicAdd(sc.counters + 1, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s.last) {
-    for (long long i = threadIdx.x; i < sc.num_tiles; i += CP_THREADS) sc.tile_state[i * sc.stride] = LB_INVALID;
-    if (threadIdx.x == 0) {
-      sc.counters[0] = 0;
-      sc.counters[1] = 0;
-    }
-  }
 }
 
 }  // namespace fg

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "compact.cuh"
 #include "device_utils.cuh"
 #include "internal.h"
 
@@ -89,6 +90,9 @@ CtxCore::~CtxCore() {
   for (auto& kv : pinned) cudaFreeHost(kv.first);
   pinned.clear();
   if (scan.tile_state) cudaFree(scan.tile_state);
+  if (scan.ep_state) cudaFree(scan.ep_state);
+  if (scan.ep_counts) cudaFree(scan.ep_counts);
+  if (scan.ep_counters) cudaFree(scan.ep_counters);
   if (scan.counters) cudaFree(scan.counters);
   if (l2_flush) cudaFree(l2_flush);
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -152,6 +156,48 @@ int scan_poll_sleep_ns() {
     return x >= 0 && x <= 10000 ? x : 100;
   }();
   return v;
+}
+
+CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, int grid, unsigned long long* out_count) {
+  ScanScratch& s = ctx->scan;
+  const int stride = scan_stride();
+  if (!s.ep_counters) {
+    FG_CUDA(cudaMalloc(&s.ep_counters, 16 * sizeof(unsigned)));
+    FG_CUDA(cudaMemsetAsync(s.ep_counters, 0, 16 * sizeof(unsigned), ctx->stream));
+  }
+  if (num_tiles > s.ep_capacity) {
+    int64_t cap = 1 << 12;
+    while (cap < num_tiles) cap <<= 1;
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s.ep_state) FG_CUDA(cudaFree(s.ep_state));
+    if (s.ep_counts) FG_CUDA(cudaFree(s.ep_counts));
+    FG_CUDA(cudaMalloc(&s.ep_state, size_t(cap) * stride * sizeof(unsigned long long)));
+    FG_CUDA(cudaMalloc(&s.ep_counts, size_t(cap) * sizeof(unsigned)));
+    FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(cap) * stride * sizeof(unsigned long long), ctx->stream));
+    s.ep_capacity = cap;
+  }
+  s.epoch = (s.epoch + 1) & 0xfffffu;
+  if (s.epoch == 0) {
+    // 2^20 launches later a stale word could carry the current epoch again: wipe them once per wrap
+    FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(s.ep_capacity) * stride * sizeof(unsigned long long), ctx->stream));
+    s.epoch = 1;
+  }
+  CompactScratch sc{};
+  sc.tile_state = s.ep_state;
+  sc.counts = s.ep_counts;
+  sc.counters = s.ep_counters;
+  sc.out_count = out_count;
+  sc.num_tiles = num_tiles;
+  sc.ticket_base = s.tickets_issued;
+  sc.arrived_base = s.arrived;
+  sc.epoch = s.epoch;
+  static const bool force_lookback = getenv("FLOCKGPU_FORCE_LOOKBACK") != nullptr;
+  sc.single_wave = (num_tiles <= grid && !force_lookback) ? 1 : 0;
+  sc.stride = stride;
+  sc.poll_sleep_ns = scan_poll_sleep_ns();
+  s.tickets_issued += unsigned(num_tiles) + unsigned(grid);  // every CTA draws exactly one ticket past the end
+  if (sc.single_wave) s.arrived += unsigned(num_tiles);
+  return sc;
 }
 
 void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out) {

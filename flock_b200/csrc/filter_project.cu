@@ -26,16 +26,13 @@ constexpr int FP_THREADS = CP_THREADS;
 
 struct FilterArgs {
   int64_t n_rows;
-  int64_t num_tiles;
   int32_t n_out;
   int32_t pad;
+  CompactScratch sc;                 // tickets / prefix scratch of this launch (compact.cuh)
   uint32_t* sel_out;                 // optional: indices of surviving rows
-  unsigned long long* tile_state;    // look-back scratch (self-resetting)
-  unsigned int* counters;            // [0] ticket, [1] done
   unsigned long long* out_count;     // total surviving rows
   int* err_flag;                     // set to 1 on divide-by-zero
   unsigned long long* trace;         // debug (FLOCKGPU_TRACE): 8 globaltimer stamps per tile, else NULL
-  int32_t lb_stride, lb_sleep_ns;    // look-back tuning (internal.h: scan_stride / scan_poll_sleep_ns)
   ColRef cols[MAX_IN_COLS];
   OutCol outs[MAX_OUT_COLS];
 };
@@ -136,7 +133,7 @@ __global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid
   constexpr int TILE = FP_THREADS * I;
   __shared__ CompactSmem<E, I> sm;
   const int tid = threadIdx.x;
-  const CompactScratch sc{a.tile_state, a.counters, a.out_count, a.num_tiles, a.lb_stride, a.lb_sleep_ns};
+  const CompactScratch& sc = a.sc;
   int err = 0;
 
   auto stamp = [&](long long tile, int k) {
@@ -190,7 +187,6 @@ __global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid
     }
   }
   if (err) *a.err_flag = 1;
-  cp_finish(sm, sc);
   if (a.trace && tid == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -294,34 +290,30 @@ static int persistent_grid(const CtxPtr& ctx, const void* kernel, int threads, i
 template <class PredFn>
 static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args) {
   constexpr int64_t TILE = int64_t(FP_THREADS) * PredFn::I;
-  args.num_tiles = (args.n_rows + TILE - 1) / TILE;
-  ensure_scan_scratch(ctx, args.num_tiles);
-  args.tile_state = ctx->scan.tile_state;
-  args.counters = ctx->scan.counters;
-  args.lb_stride = scan_stride();
-  args.lb_sleep_ns = scan_poll_sleep_ns();
+  const int64_t num_tiles = (args.n_rows + TILE - 1) / TILE;
+  const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
+  const int grid = persistent_grid(ctx, k, FP_THREADS, num_tiles);
+  args.sc = prepare_compact(ctx, num_tiles, grid, args.out_count);
   BufferPtr trace_buf;
   static const char* trace_path = getenv("FLOCKGPU_TRACE");
   if (trace_path) {
-    trace_buf = alloc(ctx, size_t(args.num_tiles + 2048) * 64);
-    FG_CUDA(cudaMemsetAsync(trace_buf->ptr, 0, size_t(args.num_tiles + 2048) * 64, ctx->stream));
+    trace_buf = alloc(ctx, size_t(num_tiles + 2048) * 64);
+    FG_CUDA(cudaMemsetAsync(trace_buf->ptr, 0, size_t(num_tiles + 2048) * 64, ctx->stream));
     args.trace = trace_buf->as<unsigned long long>();
   }
-  const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
-  int grid = persistent_grid(ctx, k, FP_THREADS, args.num_tiles);
   {
     LaunchTimer lt(ctx, "filter_compact_kernel");
-    filter_compact_kernel<PredFn><<<grid, FP_THREADS, 0, ctx->stream>>>(pred, args);
+    launch_compact(ctx, filter_compact_kernel<PredFn>, grid, args.sc, pred, args);
   }
   FG_CUDA(cudaGetLastError());
   count_launch(ctx);
   if (trace_path) {
     // debug only: dump the per-tile time stamps of this launch (overwrites the file each launch)
-    std::vector<unsigned long long> h(size_t(args.num_tiles + 2048) * 8);
+    std::vector<unsigned long long> h(size_t(num_tiles + 2048) * 8);
     FG_CUDA(cudaMemcpyAsync(h.data(), trace_buf->ptr, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (FILE* f = fopen(trace_path, "w")) {
-      fprintf(f, "%lld %d\n", (long long)args.num_tiles, grid);
+      fprintf(f, "%lld %d\n", (long long)num_tiles, grid);
       for (size_t i = 0; i < h.size() / 8; ++i) {
         for (int j = 0; j < 8; ++j) fprintf(f, "%llu ", h[i * 8 + j]);
         fprintf(f, "\n");

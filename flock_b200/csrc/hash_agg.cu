@@ -637,7 +637,6 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
     }
     __syncthreads();
   }
-  cp_finish(sm, a.sc);
 }
 
 // ================================================================================================
@@ -1101,20 +1100,15 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   for (const OutPlan& p : outs) val_cols.push_back(make_out_col(p, max_groups));
   fill_emit(ea.emit, &ea.n_emit, val_cols);
   ea.n_slots = n_slots;
-  ea.sc.num_tiles = (long long)((n_slots + CP_THREADS * 16 - 1) / (CP_THREADS * 16));
-  ensure_scan_scratch(ctx, ea.sc.num_tiles);
-  ea.sc.tile_state = ctx->scan.tile_state;
-  ea.sc.counters = ctx->scan.counters;
-  ea.sc.stride = scan_stride();
-  ea.sc.poll_sleep_ns = scan_poll_sleep_ns();
-  ea.sc.out_count = ctx->d_scalars + 3;
   {
+    const long long tiles = (long long)((n_slots + CP_THREADS * 16 - 1) / (CP_THREADS * 16));
     int per_sm = 1;
     FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_emit_kernel, CP_THREADS, 0));
-    int grid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), ea.sc.num_tiles)));
+    int grid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), tiles)));
+    ea.sc = prepare_compact(ctx, tiles, grid, ctx->d_scalars + 3);
     {
       LaunchTimer lt(ctx, "agg_emit_kernel");
-      agg_emit_kernel<<<grid, CP_THREADS, 0, ctx->stream>>>(ea);
+      launch_compact(ctx, agg_emit_kernel, grid, ea.sc, ea);
     }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);

@@ -73,6 +73,12 @@ struct ScanScratch {
   unsigned long long* tile_state = nullptr;  // [capacity] packed {flag:2, value:62}
   unsigned int* counters = nullptr;          // [0]=ticket, [1]=done, [2..] spare
   int64_t capacity = 0;
+  // compact.cuh kernels (never reset between launches: monotonic counters + epoch-tagged words)
+  unsigned long long* ep_state = nullptr;    // [ep_capacity * stride] {epoch:20, flag:2, value:42}
+  unsigned* ep_counts = nullptr;             // [ep_capacity] per-tile counts (single-wave mode)
+  unsigned* ep_counters = nullptr;           // [0] tickets issued, [1] tiles arrived
+  int64_t ep_capacity = 0;
+  unsigned tickets_issued = 0, arrived = 0, epoch = 0;
 };
 
 struct CtxCore {

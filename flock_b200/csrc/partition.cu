@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(CP_THREADS) partition_select_kernel(const __gr
     }
     __syncthreads();
   }
-  cp_finish(sm, a.sc);
 }
 
 __global__ void partition_advance_kernel(unsigned long long* bases, int part, const unsigned long long* count) {
@@ -151,25 +150,20 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   FG_CUDA(cudaMemsetAsync(bases, 0, sizeof(unsigned long long) * (n_parts + 1), ctx->stream));
   BufferPtr idx = alloc(ctx, size_t(n) * 4);
   PartSelectArgs sa{};
-  sa.sc.num_tiles = (n + CP_THREADS * 16 - 1) / (CP_THREADS * 16);
-  ensure_scan_scratch(ctx, sa.sc.num_tiles);
-  sa.sc.tile_state = ctx->scan.tile_state;
-  sa.sc.counters = ctx->scan.counters;
-  sa.sc.stride = scan_stride();
-  sa.sc.poll_sleep_ns = scan_poll_sleep_ns();
-  sa.sc.out_count = ctx->d_scalars + 5;
+  const long long tiles = (n + CP_THREADS * 16 - 1) / (CP_THREADS * 16);
   sa.pid = pid->as<uint8_t>();
   sa.n_rows = n;
   sa.bases = bases;
   sa.idx = idx->as<uint32_t>();
   int per_sm = 1;
   FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_select_kernel, CP_THREADS, 0));
-  int sgrid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), sa.sc.num_tiles)));
+  int sgrid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), tiles)));
   for (int p = 0; p < n_parts; ++p) {
     sa.part = p;
+    sa.sc = prepare_compact(ctx, tiles, sgrid, ctx->d_scalars + 5);
     {
       LaunchTimer lt(ctx, "partition_select_kernel");
-      partition_select_kernel<<<sgrid, CP_THREADS, 0, ctx->stream>>>(sa);
+      launch_compact(ctx, partition_select_kernel, sgrid, sa.sc, sa);
     }
     FG_CUDA(cudaGetLastError());
     {
