@@ -79,10 +79,15 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Fetches the next tile index for the CTA (or -1 when the work is exhausted).  Every CTA draws exactly one
-// ticket past the end, so a launch consumes num_tiles + gridDim.x tickets (the host advances its base by that).
+// Fetches the next tile index for the CTA (or -1 when the work is exhausted); `iteration` counts the CTA's calls.
+// Many-wave mode: every CTA draws exactly one ticket past the end, so a launch consumes num_tiles + gridDim.x
+// tickets (the host advances its base by that).
 template <int E, int I>
-__device__ __forceinline__ long long cp_next_tile(CompactSmem<E, I>& s, const CompactScratch& sc) {
+__device__ __forceinline__ long long cp_next_tile(CompactSmem<E, I>& s, const CompactScratch& sc, int iteration) {
+  if (sc.single_wave) {
+    // one tile per CTA, all CTAs resident (cooperative launch, grid == num_tiles): the block index is the tile
+    return iteration == 0 && (long long)blockIdx.x < sc.num_tiles ? (long long)blockIdx.x : -1;
+  }
   if (threadIdx.x == 0) s.tile = (long long)(atomicAdd(sc.counters, 1u) - sc.ticket_base);
   __syncthreads();
   long long t = s.tile;

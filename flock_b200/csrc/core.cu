@@ -195,8 +195,8 @@ CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, int grid,
   sc.single_wave = (num_tiles <= grid && !force_lookback) ? 1 : 0;
   sc.stride = stride;
   sc.poll_sleep_ns = scan_poll_sleep_ns();
-  s.tickets_issued += unsigned(num_tiles) + unsigned(grid);  // every CTA draws exactly one ticket past the end
-  if (sc.single_wave) s.arrived += unsigned(num_tiles);
+  if (sc.single_wave) s.arrived += unsigned(num_tiles);                  // one arrival per tile, no tickets
+  else s.tickets_issued += unsigned(num_tiles) + unsigned(grid);          // every CTA draws exactly one ticket past the end
   return sc;
 }
 

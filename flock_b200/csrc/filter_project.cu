@@ -44,6 +44,7 @@ struct FilterArgs {
 struct PredGeneric {
   static constexpr int E = 1;
   static constexpr int I = 16;
+  static constexpr int MIN_CTAS = 1;
   Predicate p;
   __device__ __forceinline__ unsigned long long eval(const ColRef* cols, int64_t tile_base, int64_t n_rows, int tid, int* err) const {
     int64_t rows[I];
@@ -73,7 +74,8 @@ __device__ __forceinline__ bool cmp_i64(int cmp, int64_t a, int64_t b) {
 template <int MODE, int ITEMS>
 struct PredI32 {
   static constexpr int E = 4;
-  static constexpr int I = ITEMS;  // rows per thread per tile: ITEMS / 4 independent 16-byte loads in flight
+  static constexpr int I = ITEMS;  // rows per thread per tile
+  static constexpr int MIN_CTAS = 5;  // <= 51 registers: 740 resident CTAs, so 10 M rows (611 tiles) are one wave
   const int32_t* col;
   uint64_t M;
   uint32_t d;
@@ -93,12 +95,13 @@ struct PredI32 {
   // stay resident per SM -- a 10 M-row relation (611 tiles of 16 Ki rows) is then a single wave.
   __device__ __forceinline__ unsigned long long eval(const ColRef*, int64_t tile_base, int64_t n_rows, int tid, int*) const {
     unsigned long long bits = 0;
+    constexpr int L = 4;  // independent 16-byte loads in flight per thread and round (8 costs 80 registers = 3 CTAs/SM: no single wave)
 #pragma unroll 1
-    for (int c = 0; c < I / 16; ++c) {
-      int4 v[4];
+    for (int c = 0; c < I / (4 * L); ++c) {
+      int4 v[L];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t row0 = tile_base + (int64_t(c * 4 + j) * FP_THREADS + tid) * 4;
+      for (int j = 0; j < L; ++j) {
+        const int64_t row0 = tile_base + (int64_t(c * L + j) * FP_THREADS + tid) * 4;
         if (row0 + 3 < n_rows) {
           v[j] = ldg_stream_v4(col + row0);
         } else {
@@ -109,12 +112,12 @@ struct PredI32 {
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t row0 = tile_base + (int64_t(c * 4 + j) * FP_THREADS + tid) * 4;
+      for (int j = 0; j < L; ++j) {
+        const int64_t row0 = tile_base + (int64_t(c * L + j) * FP_THREADS + tid) * 4;
         unsigned b = unsigned(test(v[j].x)) | (unsigned(test(v[j].y)) << 1) | (unsigned(test(v[j].z)) << 2) | (unsigned(test(v[j].w)) << 3);
         const int64_t left = n_rows - row0;  // mask rows past the end
         if (left < 4) b &= left <= 0 ? 0u : ((1u << left) - 1u);
-        bits |= (unsigned long long)b << (16 * c + 4 * j);
+        bits |= (unsigned long long)b << (4 * (c * L + j));
       }
     }
     return bits;
@@ -127,7 +130,7 @@ __device__ __forceinline__ void copy_value(void* dst, const void* src, int width
 }
 
 template <class PredFn>
-__global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid_constant__ PredFn pred, const __grid_constant__ FilterArgs a) {
+__global__ void __launch_bounds__(FP_THREADS, PredFn::MIN_CTAS) filter_compact_kernel(const __grid_constant__ PredFn pred, const __grid_constant__ FilterArgs a) {
   constexpr int E = PredFn::E;
   constexpr int I = PredFn::I;
   constexpr int TILE = FP_THREADS * I;
@@ -145,7 +148,8 @@ __global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid
   };
   unsigned long long t_begin = 0;
   if (a.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-  for (long long tile = cp_next_tile(sm, sc); tile >= 0; tile = cp_next_tile(sm, sc)) {
+  long long tile;
+  for (int it = 0; (tile = cp_next_tile(sm, sc, it)) >= 0; ++it) {
     const int64_t tile_base = tile * TILE;
     if (a.trace && tid == 0) a.trace[tile * 8 + 0] = t_begin;
     stamp(tile, 1);
@@ -156,23 +160,56 @@ __global__ void __launch_bounds__(FP_THREADS) filter_compact_kernel(const __grid
     stamp(tile, 3);
 
     // ---- write survivors in input order
+    // A thread may own many survivors (NEXMark's hot auction id: when it satisfies the predicate half of the rows
+    // of a stretch survive), and every pass-through value is a dependent ~1 us DRAM read: gather four survivors
+    // at a time so that their loads are in flight together.
     if (bits && sm.tile_total) {
       unsigned long long m = bits;
       while (m) {
-        const int k = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int64_t pos = cp_position<E, I>(sm, bits, k, lane_prefix);
-        const int64_t row = tile_base + cp_item_index<E>(k, tid);
-        if (a.sel_out) a.sel_out[pos] = uint32_t(row);
+        int64_t pos[4], row[4];
+        int nb = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          pos[q] = 0;
+          row[q] = -1;
+          if (m) {
+            const int k = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            pos[q] = cp_position<E, I>(sm, bits, k, lane_prefix);
+            row[q] = tile_base + cp_item_index<E>(k, tid);
+            nb = q + 1;
+          }
+        }
+        if (a.sel_out) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < nb) a.sel_out[pos[q]] = uint32_t(row[q]);
+        }
         for (int c = 0; c < a.n_out; ++c) {
           const OutCol& oc = a.outs[c];
           if (oc.kind == OUT_PASS) {
-            copy_value(oc.dst, a.cols[oc.src_col].data, oc.width, pos, row);
+            const void* src = a.cols[oc.src_col].data;
+            if (oc.width == 4) {
+              uint32_t v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = q < nb ? static_cast<const uint32_t*>(src)[row[q]] : 0u;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nb) static_cast<uint32_t*>(oc.dst)[pos[q]] = v[q];
+            } else {
+              uint64_t v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = q < nb ? static_cast<const uint64_t*>(src)[row[q]] : 0ull;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nb) static_cast<uint64_t*>(oc.dst)[pos[q]] = v[q];
+            }
           } else {
-            int64_t rows1[1] = {row};
-            Val acc[1];
-            eval_chain<1>(oc.chain, a.cols, rows1, acc, &err);
-            store_val(oc.dst, oc.out_dtype, pos, acc[0]);
+            Val acc[4];
+            eval_chain<4>(oc.chain, a.cols, row, acc, &err);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < nb) store_val(oc.dst, oc.out_dtype, pos[q], acc[q]);
           }
         }
       }

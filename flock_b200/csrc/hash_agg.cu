@@ -21,6 +21,7 @@
 //                 (agg_insert_rows_kernel); key equality is checked against the input columns.
 //   no keys       agg_global_kernel: register accumulators -> warp shuffle -> one atomic per warp.
 #include <algorithm>
+#include <cstdlib>
 
 #include "compact.cuh"
 #include "expr_program.h"
@@ -441,6 +442,173 @@ __global__ void __launch_bounds__(A32_THREADS) agg_local32_kernel(const __grid_c
 }
 
 // ================================================================================================
+// level 1, dense variant: a sliding DIRECT-ADDRESS histogram in shared memory
+// ================================================================================================
+// NEXMark ids are consecutive integers and a bid references one of the ~110 most recent auctions
+// (event.rs:354-371), so the keys of a CTA's contiguous row range fall into a narrow, slowly advancing window.
+// The CTA keeps counts[key - base] for a 16 Ki-key window: ONE native shared atomicAdd per row, no hashing, no
+// CAS, no probing (the hash kernel above spends ~129 instructions per row and ran at 0.94 ms on q5's 100 M
+// bids, profiles/r1_agg32_ncu.md; shared atomics sustain 3.2 Tops/s even with half of the lanes on one hot
+// key, profiles/r1_microbench.txt).  When a row falls outside the window the histogram is flushed as
+// (key, count) partials and re-based at the smallest key of the current step; rows below the base go to the
+// partial buffer one by one.  `slow_rows` counts those exceptions: if the data is not dense the caller re-runs
+// the hash kernel instead.
+constexpr int H32_THREADS = 256;
+constexpr int H32_WINDOW = 16384;             // 64 KB of u32 counters
+constexpr int H32_STEP = H32_THREADS * 16;    // rows per CTA iteration
+
+struct AggHist32Args {
+  int64_t n_rows;
+  const uint32_t* key_col;
+  int32_t has_count;
+  int32_t pad;
+  unsigned long long* part_keys;
+  unsigned long long* part_acc;
+  int64_t part_capacity;
+  unsigned long long* part_cursor;
+  unsigned long long* key_minmax;
+  unsigned long long* slow_rows;
+};
+
+__global__ void __launch_bounds__(H32_THREADS) agg_hist32_kernel(const __grid_constant__ AggHist32Args a) {
+  extern __shared__ __align__(16) unsigned h32_cnt[];  // [H32_WINDOW]
+  __shared__ unsigned s_warp[H32_THREADS / 32];
+  __shared__ unsigned long long s_base_pos;
+  __shared__ unsigned s_min;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int s = tid; s < H32_WINDOW; s += H32_THREADS) h32_cnt[s] = 0;
+
+  int64_t per_cta = (a.n_rows + gridDim.x - 1) / gridDim.x;
+  per_cta = (per_cta + H32_STEP - 1) / H32_STEP * H32_STEP;
+  const int64_t begin = int64_t(blockIdx.x) * per_cta;
+  const int64_t end = begin + per_cta < a.n_rows ? begin + per_cta : a.n_rows;
+  unsigned base = 0;     // CTA-uniform: key of counter 0
+  bool have_base = false;
+  unsigned kmin = ~0u, kmax = 0u;
+  unsigned long long slow = 0;
+  __syncthreads();
+
+  // writes the non-zero counters as partials and clears them
+  auto flush = [&]() {
+    constexpr int PER = H32_WINDOW / H32_THREADS;
+    unsigned cnt = 0;
+#pragma unroll 8
+    for (int j = 0; j < PER; ++j) cnt += h32_cnt[tid * PER + j] != 0;
+    unsigned incl = warp_inclusive_sum(cnt);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned warp_base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < H32_THREADS / 32; ++w) {
+      unsigned v = s_warp[w];
+      if (w < warp) warp_base += v;
+      total += v;
+    }
+    if (tid == 0) s_base_pos = total ? atomicAdd(a.part_cursor, (unsigned long long)total) : 0ull;
+    __syncthreads();
+    unsigned long long pos = s_base_pos + warp_base + (incl - cnt);
+#pragma unroll 8
+    for (int j = 0; j < PER; ++j) {
+      const int slot = tid * PER + j;
+      const unsigned c = h32_cnt[slot];
+      if (c) {
+        a.part_keys[pos] = (unsigned long long)(base + unsigned(slot));
+        if (a.has_count) a.part_acc[pos] = c;
+        h32_cnt[slot] = 0;
+        ++pos;
+      }
+    }
+    __syncthreads();
+  };
+
+  for (int64_t step = begin; step < end; step += H32_STEP) {
+    uint4 v[4];
+    unsigned valid = 0;  // bit (4 j + e): element present
+    unsigned lo = ~0u, hi = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r0 = step + (int64_t(j) * H32_THREADS + tid) * 4;
+      if (r0 + 3 < end) {
+        int4 t = ldg_stream_v4(a.key_col + r0);
+        v[j] = make_uint4(unsigned(t.x), unsigned(t.y), unsigned(t.z), unsigned(t.w));
+        valid |= 0xfu << (4 * j);
+      } else {
+        v[j] = make_uint4(0, 0, 0, 0);
+        if (r0 + 0 < end) { v[j].x = a.key_col[r0 + 0]; valid |= 1u << (4 * j); }
+        if (r0 + 1 < end) { v[j].y = a.key_col[r0 + 1]; valid |= 2u << (4 * j); }
+        if (r0 + 2 < end) { v[j].z = a.key_col[r0 + 2]; valid |= 4u << (4 * j); }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned ks[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if ((valid >> (4 * j + e)) & 1u) {
+          lo = ks[e] < lo ? ks[e] : lo;
+          hi = ks[e] > hi ? ks[e] : hi;
+        }
+    }
+    kmin = lo < kmin ? lo : kmin;
+    kmax = hi > kmax ? hi : kmax;
+    // does every key of this step fit the current window?  (one barrier per 4096 rows)
+    const bool fits = have_base && (valid == 0 || (lo >= base && hi - base < unsigned(H32_WINDOW)));
+    if (!__syncthreads_and(fits)) {
+      // re-base at the smallest key of the step (keys below a later base take the slow path)
+      unsigned m = lo;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        unsigned o = __shfl_xor_sync(FULL_MASK, m, d);
+        m = o < m ? o : m;
+      }
+      if (tid == 0) s_min = ~0u;
+      __syncthreads();
+      if (lane == 0) atomicMin(&s_min, m);
+      __syncthreads();
+      const unsigned new_base = s_min;
+      if (have_base) flush();  // uniform: have_base is CTA-uniform
+      base = new_base;
+      have_base = true;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned ks[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!((valid >> (4 * j + e)) & 1u)) continue;
+        const unsigned idx = ks[e] - base;
+        if (idx < unsigned(H32_WINDOW)) {
+          if (a.has_count) atomicAdd(&h32_cnt[idx], 1u);
+          else h32_cnt[idx] = 1u;
+        } else {
+          // outside the window even after re-basing (the step spans more than 16 Ki keys): one partial per row
+          unsigned long long pos = atomicAdd(a.part_cursor, 1ull);
+          a.part_keys[pos] = ks[e];
+          if (a.has_count) a.part_acc[pos] = 1;
+          ++slow;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (have_base) flush();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    unsigned o1 = __shfl_xor_sync(FULL_MASK, kmin, d), o2 = __shfl_xor_sync(FULL_MASK, kmax, d);
+    kmin = o1 < kmin ? o1 : kmin;
+    kmax = o2 > kmax ? o2 : kmax;
+    slow += __shfl_xor_sync(FULL_MASK, slow, d);
+  }
+  if (lane == 0) {
+    if (kmin <= kmax) {
+      atomicMin(a.key_minmax, (unsigned long long)kmin);
+      atomicMax(a.key_minmax + 1, (unsigned long long)kmax);
+    }
+    if (slow) atomicAdd(a.slow_rows, slow);
+  }
+}
+
+// ================================================================================================
 // level 2: global table (packed 64-bit keys)
 // ================================================================================================
 struct AggTable {
@@ -600,7 +768,8 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
   constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
   __shared__ CompactSmem<E, CP_ITEMS> sm;
   const int tid = threadIdx.x;
-  for (long long tile = cp_next_tile(sm, a.sc); tile >= 0; tile = cp_next_tile(sm, a.sc)) {
+  long long tile;
+  for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
     const unsigned long long tile_base = (unsigned long long)tile * CP_TILE;
     unsigned long long bits = 0;
 #pragma unroll
@@ -961,7 +1130,45 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       FG_CUDA(cudaMemsetAsync(la.key_minmax + 1, 0, 8, ctx->stream));  // max = 0
       FG_CUDA(cudaFuncSetAttribute(agg_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(local_smem)));
       const bool count32 = kp.n == 1 && kp.width[0] == 4 && (n_acc == 0 || (n_acc == 1 && accs[0].op == ACC_COUNT));
-      if (count32) {
+      bool done_l1 = false;
+      static const bool no_hist = getenv("FLOCKGPU_NO_HIST") != nullptr;
+      if (count32 && !no_hist) {
+        // optimistic dense pass; falls through to the hash kernel when too many rows miss the window
+        AggHist32Args h{};
+        h.n_rows = n;
+        h.key_col = static_cast<const uint32_t*>(in.cols[kp.col[0]].values());
+        h.has_count = n_acc;
+        h.part_keys = la.part_keys;
+        h.part_acc = la.part_acc;
+        h.part_capacity = n;
+        h.part_cursor = la.part_cursor;
+        h.key_minmax = la.key_minmax;
+        h.slow_rows = ctx->d_scalars + 9;
+        FG_CUDA(cudaMemsetAsync(h.slow_rows, 0, 8, ctx->stream));
+        constexpr size_t h_bytes = size_t(H32_WINDOW) * 4;
+        FG_CUDA(cudaFuncSetAttribute(agg_hist32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h_bytes)));
+        int per_sm = 1;
+        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_hist32_kernel, H32_THREADS, h_bytes));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + H32_STEP - 1) / H32_STEP)));
+        {
+          LaunchTimer lt(ctx, "agg_hist32_kernel");
+          agg_hist32_kernel<<<grid, H32_THREADS, h_bytes, ctx->stream>>>(h);
+        }
+        FG_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        unsigned long long slow = 0;
+        read_scalars(ctx, 9, 1, &slow);
+        if (slow * 8 <= (unsigned long long)n) {
+          done_l1 = true;
+        } else {
+          // not dense: start over with the hash kernel
+          FG_CUDA(cudaMemsetAsync(la.part_cursor, 0, 8, ctx->stream));
+          FG_CUDA(cudaMemsetAsync(la.key_minmax, 0xff, 8, ctx->stream));
+          FG_CUDA(cudaMemsetAsync(la.key_minmax + 1, 0, 8, ctx->stream));
+        }
+      }
+      if (done_l1) {
+      } else if (count32) {
         AggLocal32Args l32{};
         l32.n_rows = n;
         l32.key_col = static_cast<const uint32_t*>(in.cols[kp.col[0]].values());

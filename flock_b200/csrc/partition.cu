@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(CP_THREADS) partition_select_kernel(const __gr
   __shared__ CompactSmem<E, CP_ITEMS> sm;
   const int tid = threadIdx.x;
   const unsigned long long base = a.bases[a.part];
-  for (long long tile = cp_next_tile(sm, a.sc); tile >= 0; tile = cp_next_tile(sm, a.sc)) {
+  long long tile;
+  for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
     const int64_t tile_base = tile * CP_TILE;
     unsigned long long bits = 0;
 #pragma unroll
