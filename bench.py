@@ -192,7 +192,10 @@ def run_gpu(args) -> dict:
 
     # ---- e2e leg: host batches -> HBM -> plan -> host result, every step
     src = [fb.HostRelation(pinned)]      # exported once through the C Data Interface, like FFI structs held by the Rust shim
-    h2d = sum(b.num_rows for b in pinned) * 8      # projection pushdown: only auction + price (4 B each) cross PCIe
+    # page-locked, uniformly batched host columns stay in host memory: the filter reads `auction` in place over PCIe
+    # and fetches `price` only for the survivors (flockgpu_set_option "feed_zero_copy"; --e2e-copy forces the H2D copy)
+    ctx.set_option("feed_zero_copy", 0 if args.e2e_copy else 1)
+    h2d = sum(b.num_rows for b in pinned) * (8 if args.e2e_copy else 4) + (0 if args.e2e_copy else int(4 * float(np.mean(n_sel))))
     for _ in range(min(args.warmup, 3)):
         ec.feed_data_sources(src)
         res = ec.execute()
@@ -238,7 +241,9 @@ def run_gpu(args) -> dict:
                    "sharding": f"round-robin x{world}, no collective", "cache": f"inputs rotate over {RING} resident relations "
                    f"({RING} x {8 * args.bids / 1e6:.0f} MB > 126 MB L2)", "selectivity": mean_sel / args.bids},
         "e2e": {"value": world * args.bids * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "ms_per_step": e2e_ms / max(e2e_steps, 1)},
+                "steps": e2e_steps, "ms_per_step": e2e_ms / max(e2e_steps, 1),
+                "feed": "copy: auction + price columns DMA'd to HBM" if args.e2e_copy else
+                        "zero-copy: page-locked auction column read in place over PCIe, price fetched for survivors only"},
         "gpu_launches": int(launches), "host_enqueue_us_per_step": round(host_us, 2), "kernels": prof, "clocks": clocks, "roofline": roofline,
         "stream_events_per_sec": world * args.bids * (50 / 46) * args.steps / (dev_ms * 1e-3),
     }
@@ -316,6 +321,7 @@ def main():
     ap.add_argument("--bids", type=int, default=N_BIDS, help="bids per GPU per step (default: the BASELINE.json configuration)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the host-buffer leg (default: --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-copy", action="store_true", help="e2e leg: copy the fed columns to HBM instead of reading page-locked batches in place")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gpu" else args.warmup
     res = run_reference(args) if args.impl == "reference" else run_gpu(args)

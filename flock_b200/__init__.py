@@ -254,6 +254,9 @@ class Context:
         check(lib.flockgpu_timer_elapsed_ms(self.handle, slot, C.byref(ms)))
         return ms.value
 
+    def set_option(self, name: str, value: int) -> None:
+        check(lib.flockgpu_set_option(self.handle, name.encode(), int(value)))
+
     def profile_begin(self) -> None:
         check(lib.flockgpu_profile_begin(self.handle))
 

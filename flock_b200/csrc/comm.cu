@@ -109,7 +109,7 @@ TablePtr all_to_all(const CtxPtr& ctx, const std::vector<TablePtr>& parts) {
   Comm& cm = *ctx->comm;
   const int W = cm.world;
   FG_CHECK(int(parts.size()) == W, FLOCKGPU_ERR_INVALID, "all_to_all: %zu partitions for %d ranks", parts.size(), W);
-  for (const TablePtr& p : parts) p->resolve();
+  for (const TablePtr& p : parts) p->dense();
   const Table& proto = *parts[0];
   const size_t ncol = proto.cols.size();
   std::vector<int> utf8_cols;

@@ -334,8 +334,54 @@ static std::string copy_metadata(const char* md) {
   return std::string(md, p - md);
 }
 
+// Can this fixed-width column stay in host memory?  Needs page-locked sources (CUDA knows the pointer), uniform
+// power-of-two batch lengths (row -> chunk is a shift) and 16-byte aligned chunk bases (128-bit loads).
+static std::shared_ptr<HostChunks> try_host_chunks(const CtxPtr& ctx, const ArrowArray* const* batches, int n_batches, int p, int w) {
+  if (n_batches < 1) return nullptr;
+  const int64_t L = batches[0]->length;
+  if (L < 4096 || (L & (L - 1)) != 0) return nullptr;
+  auto hc = std::make_shared<HostChunks>();
+  hc->shift = 0;
+  while ((int64_t(1) << hc->shift) < L) ++hc->shift;
+  for (int b = 0; b < n_batches; ++b) {
+    const ArrowArray* a = batches[b]->children[p];
+    const int64_t len = batches[b]->length, off = batches[b]->offset + a->offset;
+    if (b + 1 < n_batches ? len != L : (len > L || len == 0)) return nullptr;
+    if (a->n_buffers < 2 || !a->buffers[1]) return nullptr;
+    const char* src = static_cast<const char*>(a->buffers[1]) + off * w;
+    if (reinterpret_cast<uintptr_t>(src) & 15) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+    hc->ptrs.push_back(attr.devicePointer);
+    hc->rows.push_back(len);
+  }
+  hc->table = alloc(ctx, hc->ptrs.size() * sizeof(void*));
+  FG_CUDA(cudaMemcpyAsync(hc->table->ptr, hc->ptrs.data(), hc->ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  return hc;
+}
+
+void Table::dense() const {
+  resolve();
+  for (Column& c : cols) {
+    if (!c.chunks) continue;
+    const int w = c.width();
+    c.data = alloc(ctx, size_t(c.length) * w);
+    int64_t row = 0;
+    for (size_t k = 0; k < c.chunks->ptrs.size(); ++k) {
+      FG_CUDA(cudaMemcpyAsync(static_cast<char*>(c.data->ptr) + row * w, c.chunks->ptrs[k], size_t(c.chunks->rows[k]) * w, cudaMemcpyHostToDevice,
+                              ctx->stream));
+      row += c.chunks->rows[k];
+    }
+    c.chunks.reset();
+  }
+}
+
 TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const ArrowArray* const* batches,
-                        int n_batches, const int* projection, int n_projection) {
+                        int n_batches, const int* projection, int n_projection, bool zero_copy) {
   FG_CHECK(schema && schema->format && !strcmp(schema->format, "+s"), FLOCKGPU_ERR_INVALID,
            "table_import: schema must be a struct (\"+s\"), got \"%s\"", schema && schema->format ? schema->format : "null");
   FG_CHECK(n_batches >= 0 && (n_batches == 0 || batches), FLOCKGPU_ERR_INVALID, "table_import: bad batch list");
@@ -382,7 +428,9 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
       FG_CHECK(!has_null, FLOCKGPU_ERR_UNSUPPORTED,
                "table_import: column \"%s\" contains nulls; the GPU path handles non-null columns only", col.name.c_str());
     }
-    if (dt != FLOCKGPU_UTF8) {
+    if (dt != FLOCKGPU_UTF8 && zero_copy && total > 0 && (col.chunks = try_host_chunks(ctx, batches, n_batches, p, dtype_width(dt)))) {
+      // stays in page-locked host memory; kernels read it over PCIe or Table::dense() copies it later
+    } else if (dt != FLOCKGPU_UTF8) {
       int w = dtype_width(dt);
       col.data = alloc(ctx, size_t(total) * w);
       int64_t row = 0;
@@ -560,7 +608,7 @@ __global__ void shift_offsets_kernel(const int32_t* __restrict__ src, int32_t* _
 void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t row_count, ArrowSchema* out_schema,
                   ArrowArray* out_array) {
   FG_CHECK(out_schema && out_array, FLOCKGPU_ERR_INVALID, "table_export: null output");
-  t.resolve();
+  t.dense();
   if (row_count < 0) row_count = t.num_rows - row_begin;
   FG_CHECK(row_begin >= 0 && row_begin + row_count <= t.num_rows, FLOCKGPU_ERR_INVALID,
            "table_export: rows [%lld, %lld) outside table of %lld rows", (long long)row_begin,
@@ -704,7 +752,7 @@ TablePtr empty_like(const CtxPtr& ctx, const Table& src) {
 TablePtr concat_tables(const CtxPtr& ctx, const std::vector<TablePtr>& tables) {
   FG_CHECK(!tables.empty(), FLOCKGPU_ERR_INVALID, "concat: no tables");
   if (tables.size() == 1) return tables[0];
-  for (const TablePtr& t : tables) t->resolve();
+  for (const TablePtr& t : tables) t->dense();
   const Table& first = *tables[0];
   int64_t total = 0;
   for (const TablePtr& t : tables) {
@@ -951,6 +999,16 @@ int64_t flockgpu_table_num_rows(const flockgpu_table* table) {
     n = table->table->num_rows;
   });
   return n;
+}
+
+int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value) {
+  return guarded([&] {
+    auto c = core_of(ctx);
+    FG_CHECK(name, FLOCKGPU_ERR_INVALID, "set_option: null name");
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    if (!strcmp(name, "feed_zero_copy")) c->feed_zero_copy = value != 0;
+    else fail(FLOCKGPU_ERR_INVALID, "set_option: unknown option \"%s\"", name);
+  });
 }
 
 int flockgpu_profile_begin(flockgpu_ctx* ctx) {

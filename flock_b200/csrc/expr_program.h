@@ -44,10 +44,11 @@ union Val {
 };
 
 struct ColRef {
-  const void* data;        // fixed width values / Utf8 bytes
+  const void* data;        // fixed width values / Utf8 bytes (NULL for a host-resident chunked column)
   const int32_t* offsets;  // Utf8 only
   int32_t dtype;
-  int32_t pad;
+  int32_t chunk_shift;     // chunked: rows per chunk = 1 << chunk_shift
+  const void* const* chunks;  // chunked: base pointer of every chunk (device-accessible host memory)
 };
 
 struct ChainStep {

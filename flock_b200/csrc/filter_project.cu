@@ -81,6 +81,13 @@ struct PredI32 {
   uint32_t d;
   int32_t cmp;
   int64_t rhs;
+  const void* const* chunks;  // host-resident column (zero-copy feed): chunk bases, else NULL
+  int32_t chunk_shift;
+  // address of rows [row0, row0 + 4): row0 is a multiple of 4 and chunk lengths are powers of two >= 4096
+  __device__ __forceinline__ const int32_t* at(int64_t row0) const {
+    if (!chunks) return col + row0;
+    return static_cast<const int32_t*>(chunks[row0 >> chunk_shift]) + (row0 & ((int64_t(1) << chunk_shift) - 1));
+  }
   __device__ __forceinline__ bool test(int32_t x) const {
     if (MODE == 0) return cmp_i64(cmp, int64_t(x), rhs);
     uint32_t ax = x < 0 ? 0u - uint32_t(x) : uint32_t(x);
@@ -103,12 +110,12 @@ struct PredI32 {
       for (int j = 0; j < L; ++j) {
         const int64_t row0 = tile_base + (int64_t(c * L + j) * FP_THREADS + tid) * 4;
         if (row0 + 3 < n_rows) {
-          v[j] = ldg_stream_v4(col + row0);
+          v[j] = ldg_stream_v4(at(row0));
         } else {
           v[j] = make_int4(0, 0, 0, 0);
-          if (row0 + 0 < n_rows) v[j].x = col[row0 + 0];
-          if (row0 + 1 < n_rows) v[j].y = col[row0 + 1];
-          if (row0 + 2 < n_rows) v[j].z = col[row0 + 2];
+          if (row0 + 0 < n_rows) v[j].x = at(row0)[0];
+          if (row0 + 1 < n_rows) v[j].y = at(row0)[1];
+          if (row0 + 2 < n_rows) v[j].z = at(row0)[2];
         }
       }
 #pragma unroll
@@ -188,8 +195,27 @@ __global__ void __launch_bounds__(FP_THREADS, PredFn::MIN_CTAS) filter_compact_k
         for (int c = 0; c < a.n_out; ++c) {
           const OutCol& oc = a.outs[c];
           if (oc.kind == OUT_PASS) {
-            const void* src = a.cols[oc.src_col].data;
-            if (oc.width == 4) {
+            const ColRef& sc_col = a.cols[oc.src_col];
+            const void* src = sc_col.data;
+            if (sc_col.chunks) {
+              // host-resident source: one PCIe read per survivor
+              const int64_t mask = (int64_t(1) << sc_col.chunk_shift) - 1;
+              uint64_t v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[q] = 0;
+                if (q < nb) {
+                  const char* base = static_cast<const char*>(sc_col.chunks[row[q] >> sc_col.chunk_shift]) + (row[q] & mask) * oc.width;
+                  v[q] = oc.width == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(base)) : *reinterpret_cast<const uint64_t*>(base);
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nb) {
+                  if (oc.width == 4) static_cast<uint32_t*>(oc.dst)[pos[q]] = uint32_t(v[q]);
+                  else static_cast<uint64_t*>(oc.dst)[pos[q]] = v[q];
+                }
+            } else if (oc.width == 4) {
               uint32_t v[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) v[q] = q < nb ? static_cast<const uint32_t*>(src)[row[q]] : 0u;
@@ -300,7 +326,8 @@ static void fill_colrefs(const Table& t, ColRef* refs) {
     refs[i].data = t.cols[i].values();
     refs[i].offsets = t.cols[i].offs();
     refs[i].dtype = t.cols[i].dtype;
-    refs[i].pad = 0;
+    refs[i].chunk_shift = t.cols[i].chunks ? t.cols[i].chunks->shift : 0;
+    refs[i].chunks = t.cols[i].chunks ? static_cast<const void* const*>(t.cols[i].chunks->table->ptr) : nullptr;
   }
 }
 
@@ -394,6 +421,7 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
 
   if (!predicate) {
     // ------------------------------------------------------------------ ProjectionExec only
+    in.dense();
     out->num_rows = in.num_rows;
     ProjectArgs pa{};
     pa.n_rows = in.num_rows;
@@ -463,6 +491,13 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   // -------------------------------------------------------------------- FilterExec (+ projection)
   CompiledPredicate cp = compile_predicate(*predicate, infos);
   check_err = cp.prog.has_div_by_col != 0;
+  // host-resident (zero-copy) columns can be consumed in place only by the vectorised predicate with plain
+  // pass-through fixed-width outputs; anything else scans the relation more than once and copies it to HBM first
+  if (in.has_host_columns()) {
+    bool in_place = cp.fast.kind != FAST_PRED_NONE;
+    for (const CompiledValue& v : vals) in_place &= v.passthrough && v.dtype != FLOCKGPU_UTF8;
+    if (!in_place) in.dense();
+  }
   if (in.num_rows == 0) {
     // nothing to scan: an empty table with the output schema
     out->num_rows = 0;
@@ -529,9 +564,12 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   }();
   auto launch_i32 = [&](auto mode_tag, const int32_t* col, uint64_t M, uint32_t d) {
     constexpr int MODE = decltype(mode_tag)::value;
-    if (items == 16) launch_filter(ctx, PredI32<MODE, 16>{col, M, d, cp.fast.cmp, cp.fast.rhs}, fa);
-    else if (items == 32) launch_filter(ctx, PredI32<MODE, 32>{col, M, d, cp.fast.cmp, cp.fast.rhs}, fa);
-    else launch_filter(ctx, PredI32<MODE, 64>{col, M, d, cp.fast.cmp, cp.fast.rhs}, fa);
+    const Column& pc = in.cols[cp.fast.col];
+    const void* const* chunks = pc.chunks ? static_cast<const void* const*>(pc.chunks->table->ptr) : nullptr;
+    const int32_t chunk_shift = pc.chunks ? pc.chunks->shift : 0;
+    if (items == 16) launch_filter(ctx, PredI32<MODE, 16>{col, M, d, cp.fast.cmp, cp.fast.rhs, chunks, chunk_shift}, fa);
+    else if (items == 32) launch_filter(ctx, PredI32<MODE, 32>{col, M, d, cp.fast.cmp, cp.fast.rhs, chunks, chunk_shift}, fa);
+    else launch_filter(ctx, PredI32<MODE, 64>{col, M, d, cp.fast.cmp, cp.fast.rhs, chunks, chunk_shift}, fa);
   };
   switch (cp.fast.kind) {
     case FAST_PRED_I32_MOD_CMP: {

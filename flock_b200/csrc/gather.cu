@@ -234,7 +234,7 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
 }
 
 TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx, int64_t n_idx) {
-  in.resolve();
+  in.dense();
   auto out = std::make_shared<Table>();
   out->ctx = ctx;
   out->metadata = in.metadata;

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(A32_THREADS) agg_local32_kernel(const __grid_c
 // ================================================================================================
 // NEXMark ids are consecutive integers and a bid references one of the ~110 most recent auctions
 // (event.rs:354-371), so the keys of a CTA's contiguous row range fall into a narrow, slowly advancing window.
-// The CTA keeps counts[key - base] for a 16 Ki-key window: ONE native shared atomicAdd per row, no hashing, no
+// The CTA keeps counts[key - base] for an 8 Ki-key window: ONE native shared atomicAdd per row, no hashing, no
 // CAS, no probing (the hash kernel above spends ~129 instructions per row and ran at 0.94 ms on q5's 100 M
 // bids, profiles/r1_agg32_ncu.md; shared atomics sustain 3.2 Tops/s even with half of the lanes on one hot
 // key, profiles/r1_microbench.txt).  When a row falls outside the window the histogram is flushed as
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(A32_THREADS) agg_local32_kernel(const __grid_c
 // partial buffer one by one.  `slow_rows` counts those exceptions: if the data is not dense the caller re-runs
 // the hash kernel instead.
 constexpr int H32_THREADS = 256;
-constexpr int H32_WINDOW = 16384;             // 64 KB of u32 counters
+constexpr int H32_WINDOW = 8192;              // 32 KB of u32 counters: 4 CTAs per SM (a CTA of q5 spans ~15 K auction ids: 2-3 re-bases)
 constexpr int H32_STEP = H32_THREADS * 16;    // rows per CTA iteration
 
 struct AggHist32Args {
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(H32_THREADS) agg_hist32_kernel(const __grid_co
           if (a.has_count) atomicAdd(&h32_cnt[idx], 1u);
           else h32_cnt[idx] = 1u;
         } else {
-          // outside the window even after re-basing (the step spans more than 16 Ki keys): one partial per row
+          // outside the window even after re-basing (the step spans more than 8 Ki keys): one partial per row
           unsigned long long pos = atomicAdd(a.part_cursor, 1ull);
           a.part_keys[pos] = ks[e];
           if (a.has_count) a.part_acc[pos] = 1;
@@ -966,7 +966,8 @@ void fill_cols(const Table& t, ColRef* refs) {
     refs[i].data = t.cols[i].values();
     refs[i].offsets = t.cols[i].offs();
     refs[i].dtype = t.cols[i].dtype;
-    refs[i].pad = 0;
+    refs[i].chunk_shift = 0;
+    refs[i].chunks = nullptr;
   }
 }
 
@@ -984,7 +985,7 @@ unsigned long long pow2_at_least(unsigned long long n) {
 
 TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs) {
   const Table& in = *in_ptr;
-  in.resolve();
+  in.dense();
   FG_CHECK(mode >= FLOCKGPU_AGG_PARTIAL && mode <= FLOCKGPU_AGG_SINGLE, FLOCKGPU_ERR_INVALID, "hash_aggregate: bad mode %d", mode);
   for (int g : group_cols) {
     FG_CHECK(g >= 0 && g < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_aggregate: group column %d out of range", g);

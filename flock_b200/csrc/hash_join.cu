@@ -205,7 +205,8 @@ static void fill_side(const Table& t, const std::vector<int>& keys, bool packed,
     s->cols[i].data = t.cols[i].values();
     s->cols[i].offsets = t.cols[i].offs();
     s->cols[i].dtype = t.cols[i].dtype;
-    s->cols[i].pad = 0;
+    s->cols[i].chunk_shift = 0;
+    s->cols[i].chunks = nullptr;
   }
   s->rk.n = int(keys.size());
   for (size_t i = 0; i < keys.size(); ++i) s->rk.col[i] = keys[i];
@@ -226,8 +227,8 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
                    const std::vector<int>& right_keys) {
   const Table& L = *left_ptr;
   const Table& R = *right_ptr;
-  L.resolve();
-  R.resolve();
+  L.dense();
+  R.dense();
   FG_CHECK(!left_keys.empty() && left_keys.size() == right_keys.size(), FLOCKGPU_ERR_INVALID, "hash_join: key lists must be non-empty and of equal length");
   FG_CHECK(left_keys.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_join: more than %d key columns", MAX_KEY_COLS);
   std::vector<int> widths;

@@ -640,7 +640,7 @@ static bool compare_schema(const std::vector<std::string>& a, const std::vector<
 }
 
 static TablePtr project_by_name(const CtxPtr& ctx, const TablePtr& t, const std::vector<std::string>& names) {
-  t->resolve();
+  t->dense();
   auto out = std::make_shared<fg::Table>();
   out->ctx = ctx;
   out->metadata = t->metadata;
@@ -730,7 +730,7 @@ void ExecutionContext::feed_data_sources(const ArrowSchema* const* schemas, cons
     if (hit != imported.end()) {
       leaf->fed = hit->second;
     } else {
-      leaf->fed = fg::import_batches(ctx, s.schema, s.batches, s.n, proj.data(), int(proj.size()));
+      leaf->fed = fg::import_batches(ctx, s.schema, s.batches, s.n, proj.data(), int(proj.size()), ctx->feed_zero_copy);
       imported[key] = leaf->fed;
     }
     sources.erase(sources.begin() + found);

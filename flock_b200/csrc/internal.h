@@ -119,6 +119,9 @@ struct CtxCore {
   };
   std::vector<ProfiledLaunch> profile;
 
+  // feed_data_sources keeps page-locked, uniformly batched fixed-width columns in host memory (flockgpu_set_option)
+  bool feed_zero_copy = false;
+
   // recycled CUDA events (creating one costs about a microsecond; a q2 step is one ~10 us kernel)
   std::vector<cudaEvent_t> sync_events;    // cudaEventDisableTiming
   std::vector<cudaEvent_t> timing_events;
@@ -182,13 +185,24 @@ const char* dtype_name(int dtype);
 int dtype_from_format(const char* format);  // -1 if unsupported
 std::string default_format(int dtype);
 
+// A fixed-width column that still lives in page-locked HOST memory, one chunk per fed record batch.  The filter
+// kernel reads such a column straight over PCIe (UVA), so a q2 invocation moves each input byte once and never
+// stages the relation in HBM; every other operator materialises it first (Table::dense()).
+struct HostChunks {
+  BufferPtr table;                // device array of chunk base pointers (device-accessible host addresses)
+  std::vector<const void*> ptrs;  // the same pointers on the host
+  std::vector<int64_t> rows;      // rows per chunk
+  int shift = 16;                 // rows per chunk = 1 << shift for every chunk but the last
+};
+
 struct Column {
   int dtype = FLOCKGPU_INT32;
   std::string name;
   std::string format;  // Arrow C format string ("i", "tsm:", "u", ...)
   bool nullable = false;
   int64_t length = 0;
-  BufferPtr data;      // fixed width: values; Utf8: value bytes
+  BufferPtr data;      // fixed width: values; Utf8: value bytes (NULL while `chunks` is set)
+  std::shared_ptr<HostChunks> chunks;  // host-resident form (zero-copy feed); see HostChunks
   BufferPtr offsets;   // Utf8 only: int32[length + 1]; offsets[0] may be > 0
   int64_t values_bytes = 0;  // Utf8: number of value bytes addressed by offsets
   // Only the one-row result of a global aggregate over empty input carries a NULL.
@@ -213,6 +227,13 @@ struct Table {
     num_rows = pending->wait();
     for (Column& c : cols) c.length = num_rows;
     pending.reset();
+  }
+  // resolve() + copy host-resident columns into HBM (every operator except the vectorised filter needs this)
+  void dense() const;
+  bool has_host_columns() const {
+    for (const Column& c : cols)
+      if (c.chunks) return true;
+    return false;
   }
 };
 using TablePtr = std::shared_ptr<const Table>;
@@ -250,7 +271,7 @@ struct ExprTok {
 using Expr = std::vector<ExprTok>;  // postfix
 
 TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const ArrowArray* const* batches,
-                        int n_batches, const int* projection, int n_projection);
+                        int n_batches, const int* projection, int n_projection, bool zero_copy = false);
 void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t row_count,
                   ArrowSchema* out_schema, ArrowArray* out_array);
 void export_schema(const Table& t, ArrowSchema* out_schema);

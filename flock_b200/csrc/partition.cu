@@ -97,7 +97,7 @@ __global__ void partition_advance_kernel(unsigned long long* bases, int part, co
 
 std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vector<int>& keys, int n_parts) {
   const Table& in = *in_ptr;
-  in.resolve();
+  in.dense();
   FG_CHECK(n_parts >= 1 && n_parts <= 255, FLOCKGPU_ERR_INVALID, "hash_partition: n_parts must be in [1, 255], got %d", n_parts);
   FG_CHECK(!keys.empty() && keys.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_INVALID, "hash_partition: 1..%d key columns", MAX_KEY_COLS);
   FG_CHECK(in.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d columns", MAX_IN_COLS);

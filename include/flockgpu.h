@@ -94,6 +94,13 @@ int flockgpu_timer_stop(flockgpu_ctx* ctx, int slot);              /* records th
 int flockgpu_timer_elapsed_ms(flockgpu_ctx* ctx, int slot, float* ms); /* syncs on the stop event  */
 /* Number of kernels this library has launched on the ctx since it was opened.                     */
 int64_t flockgpu_kernel_launches(flockgpu_ctx* ctx);
+/* Context options.  "feed_zero_copy" (0/1, default 0): flock_context_feed_data_sources leaves fixed-width columns
+ * whose buffers are page-locked (flockgpu_host_alloc / cudaHostRegister) and uniformly batched (every batch but the
+ * last has the same power-of-two row count >= 4096) in HOST memory; the vectorised filter then reads them in place
+ * over PCIe and other operators copy them to HBM on first use.  With the option on, fed batches must stay alive and
+ * unmodified until flock_context_clean_data_sources -- exactly what the reference does anyway: MemoryExec owns the fed
+ * RecordBatches until clean_data_sources (flock/src/runtime/context.rs:227-254).                                    */
+int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing: between _begin and _end every kernel this library launches on the ctx is
  * bracketed by its own pair of CUDA events on the ctx stream.  _end waits for the stream and writes a JSON
  * object {"<kernel>": {"launches": n, "ms": total}, ...} into out_json (bench.py's roofline numerator).  */

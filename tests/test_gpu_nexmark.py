@@ -114,6 +114,36 @@ def test_staged_execution_equals_single_plan(gpu_ctx, events_small):
     oracle.assert_tables_equal(single, oracle.execute_plan(plans.q3(), sources_for("q3", b)))
 
 
+def test_zero_copy_feed_of_pinned_batches(gpu_ctx):
+    """feed_zero_copy: page-locked, uniformly batched columns are read in place by the vectorised filter (q2) and
+    copied to HBM on first use by everything else (q5, q1); pageable or ragged batches silently take the copy path."""
+    bids = nexgen.split_batches(nexgen.bids(5 * 65536 + 1234, seed=17), 65536)
+    pinned = [gpu_ctx.pinned_copy(b) for b in bids]
+    gpu_ctx.set_option("feed_zero_copy", 1)
+    try:
+        for query in ("q2", "q5", "q1"):
+            for batches in (pinned, bids, [bids[0].slice(0, 1000)] + pinned[1:]):
+                src = [[batches]] * len(plans.SOURCES[query])
+                got = run_gpu(gpu_ctx, plans.QUERIES[query](), src)
+                want = oracle.execute_plan(plans.QUERIES[query](1), src)
+                oracle.assert_tables_equal(got, want, sort=query != "q2")
+        # a filter with a computed output column cannot run in place: it must densify and still be right
+        t = gpu_ctx.import_batches(pinned)
+        ec = fb.ExecutionContext(gpu_ctx, plans.projection_exec(
+            [(plans.column("auction", 0), "auction"), (plans.binary(plans.column("price", 1), "Plus", plans.literal("Int32", 1)), "p1")],
+            plans.filter_exec(plans.binary(plans.cast(plans.column("auction", 0), "Int64"), "Gt", plans.literal("Int64", 1500)),
+                              plans.memory_exec(nexgen.bid_schema(), [0, 2]))))
+        ec.feed_data_sources([fb.HostRelation(pinned)])
+        got = pa.Table.from_batches(ec.execute()[0])
+        ec.close()
+        full = pa.Table.from_batches(bids)
+        keep = full["auction"].to_numpy() > 1500
+        assert np.array_equal(got["auction"].to_numpy(), full["auction"].to_numpy()[keep])
+        assert np.array_equal(got["p1"].to_numpy(), full["price"].to_numpy()[keep] + 1)
+    finally:
+        gpu_ctx.set_option("feed_zero_copy", 0)
+
+
 def test_device_resident_feed(gpu_ctx, events_small):
     bids = gpu_ctx.import_batches(events_small["bid"])
     ec = fb.ExecutionContext(gpu_ctx, plans.q5())
