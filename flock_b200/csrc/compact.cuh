@@ -41,6 +41,7 @@ struct CompactScratch {
   unsigned* counts;                // per-tile survivor counts (single-wave mode)
   unsigned int* counters;          // [0] tickets issued, [1] tiles arrived -- both monotonic across launches
   unsigned long long* out_count;   // receives the total number of survivors
+  unsigned long long* host_count;  // optional second copy in page-locked host memory (saves the 8-byte D2H copy per launch)
   long long num_tiles;
   unsigned ticket_base;            // value of counters[0] when this launch starts
   unsigned arrived_base;           // value of counters[1] when this launch starts
@@ -124,7 +125,10 @@ __device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const Compa
   const unsigned long long excl = cp_block_sum(s, part);
   if (tid == 0) {
     s.excl = excl;
-    if (tile == sc.num_tiles - 1) *sc.out_count = excl + total;
+    if (tile == sc.num_tiles - 1) {
+      *sc.out_count = excl + total;
+      if (sc.host_count) *reinterpret_cast<volatile unsigned long long*>(sc.host_count) = excl + total;
+    }
   }
   __syncthreads();
 }
@@ -174,16 +178,25 @@ __device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const Co
   }
   if (tid == 0) {
     s.excl = excl;
-    if (tile == sc.num_tiles - 1) *sc.out_count = excl + total;
+    if (tile == sc.num_tiles - 1) {
+      *sc.out_count = excl + total;
+      if (sc.host_count) *reinterpret_cast<volatile unsigned long long*>(sc.host_count) = excl + total;
+    }
   }
   __syncthreads();
 }
 
 // Ranks the survivors of one tile (bit k of `bits` = item k survives).  On return (after the internal
 // barriers) cp_position() gives every survivor its output slot and s.tile_total the tile's survivor count.
-template <int E, int I>
+struct CpNoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// `before_wait` runs after the tile-local ranking and before the wait for the grid-wide prefix: work that does not
+// need output positions (prefetching the survivors' pass-through values) hides behind that wait.
+template <int E, int I, class Hook = CpNoHook>
 __device__ __forceinline__ void cp_rank_tile(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned long long bits,
-                                             unsigned (&lane_prefix)[I / E]) {
+                                             unsigned (&lane_prefix)[I / E], Hook before_wait = Hook{}) {
   constexpr int G = I / E;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = lanemask_lt();
@@ -223,6 +236,7 @@ __device__ __forceinline__ void cp_rank_tile(CompactSmem<E, I>& s, const Compact
     if (lane == 0) s.tile_total = total;
   }
   __syncthreads();
+  before_wait();
   if (sc.single_wave) cp_grid_prefix(s, sc, tile, s.tile_total);
   else cp_block_lookback(s, sc, tile, s.tile_total);
 }

@@ -234,7 +234,9 @@ cudaEvent_t CtxCore::get_event(bool timing) {
   return e;
 }
 
-std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned long long* d_count) {
+unsigned long long* PendingRows::host_slot() const { return ctx->h_scalars + 256 + slot; }
+
+std::shared_ptr<PendingRows> reserve_row_count(const CtxPtr& ctx) {
   const int slot = ctx->pending_next;
   ctx->pending_next = (ctx->pending_next + 1) % CtxCore::kPendingSlots;
   if (auto old = ctx->pending_owner[slot].lock()) old->wait();  // the pinned slot is about to be overwritten
@@ -242,10 +244,12 @@ std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned
   p->ctx = ctx;
   p->slot = slot;
   p->ev = ctx->get_event(false);
-  FG_CUDA(cudaMemcpyAsync(ctx->h_scalars + 256 + slot, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-  FG_CUDA(cudaEventRecord(p->ev, ctx->stream));
   ctx->pending_owner[slot] = p;
   return p;
+}
+
+void commit_row_count(const std::shared_ptr<PendingRows>& p) {
+  FG_CUDA(cudaEventRecord(p->ev, p->ctx->stream));
 }
 
 // ---- per-kernel profile ----------------------------------------------------------------------------

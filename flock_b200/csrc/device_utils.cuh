@@ -14,6 +14,10 @@ namespace fg {
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 // ---- streaming loads / stores (read-once data: do not pollute L1) -------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ int4 ldg_stream_v4(const void* p) {
   int4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"

@@ -31,6 +31,7 @@ struct FilterArgs {
   CompactScratch sc;                 // tickets / prefix scratch of this launch (compact.cuh)
   uint32_t* sel_out;                 // optional: indices of surviving rows
   unsigned long long* out_count;     // total surviving rows
+  unsigned long long* host_count;    // pinned host slot that also receives the total (NULL: none)
   int* err_flag;                     // set to 1 on divide-by-zero
   unsigned long long* trace;         // debug (FLOCKGPU_TRACE): 8 globaltimer stamps per tile, else NULL
   ColRef cols[MAX_IN_COLS];
@@ -163,7 +164,25 @@ __global__ void __launch_bounds__(FP_THREADS, PredFn::MIN_CTAS) filter_compact_k
     const unsigned long long bits = pred.eval(a.cols, tile_base, a.n_rows, tid, &err);
     stamp(tile, 2);
     unsigned lane_prefix[I / E];
-    cp_rank_tile<E, I>(sm, sc, tile, bits, lane_prefix);
+    // While the CTA waits for the grid-wide prefix, pull the survivors' pass-through values (one dependent ~1 us
+    // DRAM read each) into L2: the write phase below then finds them there.
+    auto prefetch_survivors = [&] {
+      if (!bits) return;
+      for (int c = 0; c < a.n_out; ++c) {
+        const OutCol& oc = a.outs[c];
+        if (oc.kind != OUT_PASS) continue;
+        const ColRef& src = a.cols[oc.src_col];
+        if (src.chunks) continue;  // host-resident: fetched once, when written
+        unsigned long long m = bits;
+#pragma unroll 1
+        for (int q = 0; q < 4 && m; ++q) {
+          const int k = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          prefetch_l2(static_cast<const char*>(src.data) + (tile_base + cp_item_index<E>(k, tid)) * oc.width);
+        }
+      }
+    };
+    cp_rank_tile<E, I>(sm, sc, tile, bits, lane_prefix, prefetch_survivors);
     stamp(tile, 3);
 
     // ---- write survivors in input order
@@ -358,6 +377,7 @@ static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args
   const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
   const int grid = persistent_grid(ctx, k, FP_THREADS, num_tiles);
   args.sc = prepare_compact(ctx, num_tiles, grid, args.out_count);
+  args.sc.host_count = args.host_count;
   BufferPtr trace_buf;
   static const char* trace_path = getenv("FLOCKGPU_TRACE");
   if (trace_path) {
@@ -555,6 +575,14 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
     fa.sel_out = sel->as<uint32_t>();
   }
   if (check_err) FG_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int), ctx->stream));
+  // fixed-width outputs only: the survivor count stays in flight.  The kernel stores it straight into a pinned host
+  // slot (no 8-byte D2H copy on the stream); the first consumer that needs the number waits for the event
+  // recorded behind the launch (Table::resolve).
+  std::shared_ptr<PendingRows> pending;
+  if (!check_err && utf8_outs.empty()) {
+    pending = reserve_row_count(ctx);
+    fa.host_count = pending->host_slot();
+  }
 
   // rows per thread per tile of the vectorised functors (FLOCKGPU_FILTER_ITEMS = 16 | 32 | 64 overrides, for tuning)
   static const int items = [] {
@@ -589,10 +617,9 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
     }
   }
 
-  if (!check_err && utf8_outs.empty()) {
-    // fixed-width outputs only: the survivor count stays in flight (one async 8-byte copy into a pinned
-    // slot); the first consumer that needs the number waits for it (Table::resolve)
-    out->pending = enqueue_row_count(ctx, fa.out_count);
+  if (pending) {
+    commit_row_count(pending);
+    out->pending = pending;
     out->num_rows = -1;
     for (Column& c : out->cols) c.length = -1;
     return out;

@@ -149,9 +149,13 @@ struct PendingRows {
   bool done = false;
   int64_t value = 0;
   int64_t wait();
+  unsigned long long* host_slot() const;  // pinned (device-accessible) slot the count lands in
   ~PendingRows();
 };
-std::shared_ptr<PendingRows> enqueue_row_count(const CtxPtr& ctx, const unsigned long long* d_count);
+// reserve a pinned host slot (the compaction kernel stores the count there itself: CompactScratch::host_count),
+// launch, then commit (records the event wait() blocks on)
+std::shared_ptr<PendingRows> reserve_row_count(const CtxPtr& ctx);
+void commit_row_count(const std::shared_ptr<PendingRows>& p);
 
 struct Buffer {
   CtxPtr ctx;

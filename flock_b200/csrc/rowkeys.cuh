@@ -28,11 +28,16 @@ struct RowKeys {
 };
 
 __device__ __forceinline__ unsigned long long pack_key(const KeyPack& k, const ColRef* cols, int64_t row) {
-  unsigned long long a;
-  if (k.width[0] == 4) a = static_cast<const uint32_t*>(cols[k.col[0]].data)[row];
-  else a = static_cast<const unsigned long long*>(cols[k.col[0]].data)[row];
-  if (k.n == 2) a = (a << 32) | static_cast<const uint32_t*>(cols[k.col[1]].data)[row];
-  return a;
+  // The two-column case is kept as two independent 32-bit loads combined at the end: ptxas 12.9 turned the
+  // earlier "a = (a << 32) | second" form into a load that overwrote `a` before its old value had been moved to
+  // the high half (tests/test_gpu_ops.py::test_hash_aggregate_single[*-group1] caught it).
+  if (k.n == 2) {
+    const uint32_t hi = __ldg(static_cast<const uint32_t*>(cols[k.col[0]].data) + row);
+    const uint32_t lo = __ldg(static_cast<const uint32_t*>(cols[k.col[1]].data) + row);
+    return (static_cast<unsigned long long>(hi) << 32) | lo;
+  }
+  if (k.width[0] == 4) return static_cast<const uint32_t*>(cols[k.col[0]].data)[row];
+  return static_cast<const unsigned long long*>(cols[k.col[0]].data)[row];
 }
 
 __device__ __forceinline__ unsigned long long hash_row(const RowKeys& k, const ColRef* cols, int64_t row) {

@@ -128,6 +128,68 @@ __global__ void gmem_atomics(unsigned long long* tab, size_t mask, int iters) {
   }
 }
 
+
+// (5) launch overhead and the skeleton of the single-wave filter: how much of a ~30 us kernel is not the kernel?
+struct BigParams {
+  unsigned long long words[470];  // ~3.7 KB, the size of FilterArgs
+};
+__global__ void empty_small(unsigned* sink) {
+  if (threadIdx.x == 1025) *sink = 1;
+}
+__global__ void empty_big(const __grid_constant__ BigParams p, unsigned* sink) {
+  if (threadIdx.x == 1025) *sink = unsigned(p.words[blockIdx.x % 470]);
+}
+// one 16 Ki-row tile per CTA: 16 x 16-byte loads per thread in four rounds, count multiples of 123, then
+// (BARRIER) arrival counter + prefix over the counts of all predecessors, as compact.cuh does it
+template <bool BARRIER>
+__global__ void __launch_bounds__(256, 5) skeleton(const int4* __restrict__ in, size_t n16, unsigned* counts, unsigned* arrived, unsigned target,
+                                                   unsigned long long* out) {
+  __shared__ unsigned long long wsum[8];
+  const int tid = threadIdx.x;
+  const size_t base = size_t(blockIdx.x) * 4096;
+  unsigned cnt = 0;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    int4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      size_t i = base + size_t(c * 4 + j) * 256 + tid;
+      v[j] = i < n16 ? ldg_stream(in + i) : make_int4(1, 1, 1, 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cnt += (v[j].x % 123 == 0) + (v[j].y % 123 == 0) + (v[j].z % 123 == 0) + (v[j].w % 123 == 0);
+  }
+  for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((tid & 31) == 0) wsum[tid >> 5] = cnt;
+  __syncthreads();
+  unsigned total = 0;
+  for (int w = 0; w < 8; ++w) total += unsigned(wsum[w]);
+  if (!BARRIER) {
+    if (tid == 0) counts[blockIdx.x] = total;
+    return;
+  }
+  if (tid == 0) {
+    counts[blockIdx.x] = total;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(arrived), "r"(1u) : "memory");
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrived) : "memory");
+    } while (int(seen - target) < 0);
+  }
+  __syncthreads();
+  unsigned long long part = 0;
+  for (unsigned i = tid; i < blockIdx.x; i += 256) part += __ldcg(counts + i);
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  __syncthreads();
+  if ((tid & 31) == 0) wsum[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long excl = 0;
+    for (int w = 0; w < 8; ++w) excl += wsum[w];
+    if (blockIdx.x == gridDim.x - 1) *out = excl + total;
+  }
+}
+
 template <class F>
 float time_ms(F&& f, int reps = 5) {
   cudaEvent_t a, b;
@@ -207,6 +269,66 @@ int main() {
     }
   }
   CK(cudaGetLastError());
+
+
+  {
+    // launch overhead (event-timed, best of 5, after an L2-evicting memset like the read tests)
+    auto timed = [&](auto&& launch) {
+      float best = 1e30f;
+      for (int r = 0; r < 7; ++r) {
+        cudaMemsetAsync(flush, r, size_t(512) << 20);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a);
+        launch();
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        best = ms < best ? ms : best;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+      }
+      return best;
+    };
+    BigParams bp{};
+    for (int grid : {148, 611, 740}) {
+      float t_small = timed([&] { empty_small<<<grid, 256>>>(sink); });
+      float t_big = timed([&] { empty_big<<<grid, 256>>>(bp, sink); });
+      void* args_small[] = {&sink};
+      float t_coop = timed([&] { cudaLaunchCooperativeKernel(reinterpret_cast<void*>(empty_small), dim3(grid), dim3(256), args_small, 0, nullptr); });
+      void* args_big[] = {&bp, &sink};
+      float t_coop_big = timed([&] { cudaLaunchCooperativeKernel(reinterpret_cast<void*>(empty_big), dim3(grid), dim3(256), args_big, 0, nullptr); });
+      printf("empty kernel grid=%3d x 256: plain %.2f us, 3.7KB params %.2f us, cooperative %.2f us, cooperative+3.7KB %.2f us\n", grid, t_small * 1e3,
+             t_big * 1e3, t_coop * 1e3, t_coop_big * 1e3);
+    }
+    unsigned* counts;
+    unsigned* arrived;
+    unsigned long long* total;
+    CK(cudaMalloc(&counts, 4096 * 4));
+    CK(cudaMalloc(&arrived, 64));
+    CK(cudaMalloc(&total, 64));
+    CK(cudaMemset(arrived, 0, 64));
+    const size_t n16 = size_t(10'000'000) / 4;  // 10 M int32 rows = 40 MB
+    const int grid = int((n16 + 4095) / 4096);
+    unsigned target = 0;
+    float t_nb = timed([&] { skeleton<false><<<grid, 256>>>(reinterpret_cast<const int4*>(buf), n16, counts, arrived, 0, total); });
+    float t_b = timed([&] {
+      target += unsigned(grid);
+      skeleton<true><<<grid, 256>>>(reinterpret_cast<const int4*>(buf), n16, counts, arrived, target, total);
+    });
+    float t_bc = timed([&] {
+      target += unsigned(grid);
+      const int4* in = reinterpret_cast<const int4*>(buf);
+      size_t n = n16;
+      void* a[] = {&in, &n, &counts, &arrived, &target, &total};
+      cudaLaunchCooperativeKernel(reinterpret_cast<void*>(skeleton<true>), dim3(grid), dim3(256), a, 0, nullptr);
+    });
+    printf("filter skeleton 10 M rows, grid %d x 256 (one wave): count only %.2f us, + arrival barrier and prefix %.2f us, cooperative %.2f us\n", grid,
+           t_nb * 1e3, t_b * 1e3, t_bc * 1e3);
+    CK(cudaGetLastError());
+  }
 
   const int iters = 4096;
   {
