@@ -69,19 +69,33 @@ __device__ __forceinline__ bool cmp_i64(int cmp, int64_t a, int64_t b) {
   }
 }
 
-// CAST(i32col AS Int64) [% m] CMP rhs, 128-bit loads.  MODE 0: plain compare; MODE 1: `% m` via
-// Lemire's fastmod (M = 2^64/m + 1: two multiplies instead of a software division); MODE 2: `% m = 0`
-// via the divisibility test n * M <= M - 1 (one multiply).
+// CAST(i32col AS Int64) [% m] CMP rhs over 128-bit loads, three arithmetic shapes:
+//   MODE 0  affine range test  keep = (uint32(x) * mul + add <= span) != neg      -- one IMAD + one compare per row.
+//           Covers every plain comparison (mul = 1, add = -lo, span = hi - lo for the interval [lo, hi] of
+//           accepted values, `neg` for the complement) AND `% m (=|!=) 0` for odd m: with inv = m^-1 mod 2^32,
+//           L = (2^31 - 1) / m, L2 = 2^31 / m, x is a multiple of m iff x * inv mod 2^32 lies in [0, L] (x >= 0)
+//           or in [2^32 - L2, 2^32) (x < 0), i.e. iff x * inv + L2 <= L + L2 (Granlund-Montgomery exact division
+//           test, Hacker's Delight 10-17, extended to signed dividends).
+//   MODE 1  general `% m CMP c` via Lemire's fastmod (M = 2^64 / m + 1: two multiplies instead of a division).
+//   MODE 2  `% m (=|!=) 0` for even m = 2^k q: rotr(|x| * q^-1, k) <= (2^32 - 1) / m.
+struct PredI32Consts {
+  // MODE 0 / 2
+  uint32_t mul, add, span, rot;
+  int32_t neg;
+  // MODE 1
+  int32_t cmp;
+  uint32_t d;
+  uint64_t M;
+  int64_t rhs;
+};
+
 template <int MODE, int ITEMS>
 struct PredI32 {
   static constexpr int E = 4;
   static constexpr int I = ITEMS;  // rows per thread per tile
   static constexpr int MIN_CTAS = 5;  // <= 51 registers: 740 resident CTAs, so 10 M rows (611 tiles) are one wave
   const int32_t* col;
-  uint64_t M;
-  uint32_t d;
-  int32_t cmp;
-  int64_t rhs;
+  PredI32Consts k;
   const void* const* chunks;  // host-resident column (zero-copy feed): chunk bases, else NULL
   int32_t chunk_shift;
   // address of rows [row0, row0 + 4): row0 is a multiple of 4 and chunk lengths are powers of two >= 4096
@@ -90,22 +104,48 @@ struct PredI32 {
     return static_cast<const int32_t*>(chunks[row0 >> chunk_shift]) + (row0 & ((int64_t(1) << chunk_shift) - 1));
   }
   __device__ __forceinline__ bool test(int32_t x) const {
-    if (MODE == 0) return cmp_i64(cmp, int64_t(x), rhs);
-    uint32_t ax = x < 0 ? 0u - uint32_t(x) : uint32_t(x);
-    uint64_t low = M * uint64_t(ax);
-    if (MODE == 2) return low <= M - 1;
-    int64_t r = int64_t(__umul64hi(low, uint64_t(d)));
+    if (MODE == 0) return (uint32_t(x) * k.mul + k.add <= k.span) != bool(k.neg);
+    const uint32_t ax = x < 0 ? 0u - uint32_t(x) : uint32_t(x);
+    if (MODE == 2) {
+      const uint32_t m = ax * k.mul;
+      return (__funnelshift_r(m, m, k.rot) <= k.span) != bool(k.neg);
+    }
+    const uint64_t low = k.M * uint64_t(ax);
+    int64_t r = int64_t(__umul64hi(low, uint64_t(k.d)));
     if (x < 0) r = -r;
-    return cmp_i64(cmp, r, rhs);
+    return cmp_i64(k.cmp, r, k.rhs);
   }
-  // Streams the thread's rows in chunks of four 16-byte loads: only the one-bit verdicts are kept (the values of
+  __device__ __forceinline__ unsigned test4(const int4& v) const {
+    return unsigned(test(v.x)) | (unsigned(test(v.y)) << 1) | (unsigned(test(v.z)) << 2) | (unsigned(test(v.w)) << 3);
+  }
+  // Streams the thread's rows in rounds of four 16-byte loads: only the one-bit verdicts are kept (the values of
   // the ~1 % survivors are re-read from L2 when they are written), so the kernel needs ~48 registers and five CTAs
   // stay resident per SM -- a 10 M-row relation (611 tiles of 16 Ki rows) is then a single wave.
   __device__ __forceinline__ unsigned long long eval(const ColRef*, int64_t tile_base, int64_t n_rows, int tid, int*) const {
-    unsigned long long bits = 0;
     constexpr int L = 4;  // independent 16-byte loads in flight per thread and round (8 costs 80 registers = 3 CTAs/SM: no single wave)
+    constexpr int ROUNDS = I / (4 * L);
+    if (!chunks && tile_base + int64_t(FP_THREADS) * I <= n_rows) {
+      // full tile of a device-resident column (every tile but the last): no bounds, no chunk lookup
+      const int4* p = reinterpret_cast<const int4*>(col + tile_base) + tid;
+      unsigned half[2] = {0u, 0u};  // verdicts of rounds {0, 1} and {2, 3}: 32-bit shifts only
+#pragma unroll
+      for (int h = 0; h < (ROUNDS + 1) / 2; ++h) {
 #pragma unroll 1
-    for (int c = 0; c < I / (4 * L); ++c) {
+        for (int c = 2 * h; c < ROUNDS && c < 2 * h + 2; ++c) {
+          int4 v[L];
+#pragma unroll
+          for (int j = 0; j < L; ++j) v[j] = ldg_stream_v4(p + (c * L + j) * FP_THREADS);
+          unsigned b16 = 0;
+#pragma unroll
+          for (int j = 0; j < L; ++j) b16 |= test4(v[j]) << (4 * j);
+          half[h] |= b16 << (16 * (c & 1));
+        }
+      }
+      return (unsigned long long)half[0] | ((unsigned long long)half[1] << 32);
+    }
+    unsigned long long bits = 0;
+#pragma unroll 1
+    for (int c = 0; c < ROUNDS; ++c) {
       int4 v[L];
 #pragma unroll
       for (int j = 0; j < L; ++j) {
@@ -122,7 +162,7 @@ struct PredI32 {
 #pragma unroll
       for (int j = 0; j < L; ++j) {
         const int64_t row0 = tile_base + (int64_t(c * L + j) * FP_THREADS + tid) * 4;
-        unsigned b = unsigned(test(v[j].x)) | (unsigned(test(v[j].y)) << 1) | (unsigned(test(v[j].z)) << 2) | (unsigned(test(v[j].w)) << 3);
+        unsigned b = test4(v[j]);
         const int64_t left = n_rows - row0;  // mask rows past the end
         if (left < 4) b &= left <= 0 ? 0u : ((1u << left) - 1u);
         bits |= (unsigned long long)b << (4 * (c * L + j));
@@ -131,6 +171,69 @@ struct PredI32 {
     return bits;
   }
 };
+
+// Host side: the constants of PredI32 for `CAST(col AS Int64) [% modulus] cmp rhs` (modulus = 0: no `%`).
+// Returns the MODE to launch.
+static int pred_i32_consts(int64_t modulus, int cmp, int64_t rhs, PredI32Consts* out) {
+  PredI32Consts k{};
+  k.cmp = cmp;
+  k.rhs = rhs;
+  if (modulus == 0) {
+    // accepted interval [lo, hi] of the positive form; NE is the complement of EQ
+    const int64_t MIN = INT32_MIN, MAX = INT32_MAX;
+    int64_t lo = MIN, hi = MAX;
+    bool neg = false;
+    switch (cmp) {
+      case FLOCKGPU_OP_EQ: lo = hi = rhs; break;
+      case FLOCKGPU_OP_NE: lo = hi = rhs; neg = true; break;
+      case FLOCKGPU_OP_LT: hi = rhs > MIN ? rhs - 1 : MIN - 1; break;
+      case FLOCKGPU_OP_LE: hi = rhs; break;
+      case FLOCKGPU_OP_GT: lo = rhs < MAX ? rhs + 1 : MAX + 1; break;
+      default: lo = rhs; break;  // GE
+    }
+    lo = std::max(lo, MIN);
+    hi = std::min(hi, MAX);
+    if (lo > hi) {  // nothing in the int32 domain: the complement of everything
+      lo = MIN;
+      hi = MAX;
+      neg = !neg;
+    }
+    k.mul = 1u;
+    k.add = 0u - uint32_t(int32_t(lo));
+    k.span = uint32_t(hi - lo);
+    k.neg = neg;
+    *out = k;
+    return 0;
+  }
+  const uint32_t d = uint32_t(modulus);
+  k.d = d;
+  k.M = ~uint64_t(0) / d + 1;
+  const bool divisibility = rhs == 0 && (cmp == FLOCKGPU_OP_EQ || cmp == FLOCKGPU_OP_NE);
+  if (!divisibility) {
+    *out = k;
+    return 1;
+  }
+  uint32_t rot = 0, q = d;
+  while (!(q & 1u)) {
+    q >>= 1;
+    ++rot;
+  }
+  uint32_t inv = q;  // Newton: doubles the number of correct low bits per step (3 -> 96)
+  for (int it = 0; it < 5; ++it) inv *= 2u - q * inv;
+  k.mul = inv;
+  k.neg = cmp == FLOCKGPU_OP_NE;
+  if (rot == 0) {
+    const uint32_t L = 0x7fffffffu / d, L2 = 0x80000000u / d;
+    k.add = L2;
+    k.span = L + L2;
+    *out = k;
+    return 0;
+  }
+  k.rot = rot;
+  k.span = 0xffffffffu / d;
+  *out = k;
+  return 2;
+}
 
 __device__ __forceinline__ void copy_value(void* dst, const void* src, int width, int64_t pos, int64_t row) {
   if (width == 4) static_cast<uint32_t*>(dst)[pos] = static_cast<const uint32_t*>(src)[row];
@@ -590,26 +693,29 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
     int v = e ? atoi(e) : 64;
     return (v == 16 || v == 32 || v == 64) ? v : 64;
   }();
-  auto launch_i32 = [&](auto mode_tag, const int32_t* col, uint64_t M, uint32_t d) {
-    constexpr int MODE = decltype(mode_tag)::value;
+  auto launch_i32 = [&](int64_t modulus) {
     const Column& pc = in.cols[cp.fast.col];
+    const int32_t* col = static_cast<const int32_t*>(pc.values());
     const void* const* chunks = pc.chunks ? static_cast<const void* const*>(pc.chunks->table->ptr) : nullptr;
     const int32_t chunk_shift = pc.chunks ? pc.chunks->shift : 0;
-    if (items == 16) launch_filter(ctx, PredI32<MODE, 16>{col, M, d, cp.fast.cmp, cp.fast.rhs, chunks, chunk_shift}, fa);
-    else if (items == 32) launch_filter(ctx, PredI32<MODE, 32>{col, M, d, cp.fast.cmp, cp.fast.rhs, chunks, chunk_shift}, fa);
-    else launch_filter(ctx, PredI32<MODE, 64>{col, M, d, cp.fast.cmp, cp.fast.rhs, chunks, chunk_shift}, fa);
+    PredI32Consts k;
+    const int mode = pred_i32_consts(modulus, cp.fast.cmp, cp.fast.rhs, &k);
+    auto go = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      if (items == 16) launch_filter(ctx, PredI32<MODE, 16>{col, k, chunks, chunk_shift}, fa);
+      else if (items == 32) launch_filter(ctx, PredI32<MODE, 32>{col, k, chunks, chunk_shift}, fa);
+      else launch_filter(ctx, PredI32<MODE, 64>{col, k, chunks, chunk_shift}, fa);
+    };
+    if (mode == 0) go(std::integral_constant<int, 0>{});
+    else if (mode == 1) go(std::integral_constant<int, 1>{});
+    else go(std::integral_constant<int, 2>{});
   };
   switch (cp.fast.kind) {
-    case FAST_PRED_I32_MOD_CMP: {
-      uint32_t d = uint32_t(cp.fast.modulus);
-      uint64_t M = ~uint64_t(0) / d + 1;
-      const int32_t* col = static_cast<const int32_t*>(in.cols[cp.fast.col].values());
-      if (cp.fast.cmp == FLOCKGPU_OP_EQ && cp.fast.rhs == 0) launch_i32(std::integral_constant<int, 2>{}, col, M, d);
-      else launch_i32(std::integral_constant<int, 1>{}, col, M, d);
+    case FAST_PRED_I32_MOD_CMP:
+      launch_i32(cp.fast.modulus);
       break;
-    }
     case FAST_PRED_I32_CMP:
-      launch_i32(std::integral_constant<int, 0>{}, static_cast<const int32_t*>(in.cols[cp.fast.col].values()), 0, 1);
+      launch_i32(0);
       break;
     default: {
       PredGeneric p{cp.prog};

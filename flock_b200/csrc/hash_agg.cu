@@ -455,7 +455,9 @@ __global__ void __launch_bounds__(A32_THREADS) agg_local32_kernel(const __grid_c
 // the hash kernel instead.
 constexpr int H32_THREADS = 256;
 constexpr int H32_WINDOW = 8192;              // 32 KB of u32 counters: 4 CTAs per SM (a CTA of q5 spans ~15 K auction ids: 2-3 re-bases)
-constexpr int H32_STEP = H32_THREADS * 16;    // rows per CTA iteration
+constexpr int H32_LOADS = 8;                  // 16-byte loads per thread and step: 128 B in flight per thread
+constexpr int H32_ROWS = H32_LOADS * 4;       // rows per thread and step
+constexpr int H32_STEP = H32_THREADS * H32_ROWS;  // rows per CTA iteration (8192)
 
 struct AggHist32Args {
   int64_t n_rows;
@@ -470,7 +472,10 @@ struct AggHist32Args {
   unsigned long long* slow_rows;
 };
 
-__global__ void __launch_bounds__(H32_THREADS) agg_hist32_kernel(const __grid_constant__ AggHist32Args a) {
+// Instruction budget of the common step (all 8192 rows inside the window): per row one subtract, a third of a
+// three-input OR (the window test: every offset < 2^13 iff the OR of the offsets is) and one shared atomic.
+// The key range (min / max) that decides the dense level-2 table is taken from the flushed counters, not per row.
+__global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid_constant__ AggHist32Args a) {
   extern __shared__ __align__(16) unsigned h32_cnt[];  // [H32_WINDOW]
   __shared__ unsigned s_warp[H32_THREADS / 32];
   __shared__ unsigned long long s_base_pos;
@@ -486,14 +491,28 @@ __global__ void __launch_bounds__(H32_THREADS) agg_hist32_kernel(const __grid_co
   bool have_base = false;
   unsigned kmin = ~0u, kmax = 0u;
   unsigned long long slow = 0;
+  const bool has_count = a.has_count != 0;
   __syncthreads();
 
   // writes the non-zero counters as partials and clears them
   auto flush = [&]() {
     constexpr int PER = H32_WINDOW / H32_THREADS;
     unsigned cnt = 0;
+    int first = PER, last = -1;
 #pragma unroll 8
-    for (int j = 0; j < PER; ++j) cnt += h32_cnt[tid * PER + j] != 0;
+    for (int j = 0; j < PER; ++j) {
+      const bool nz = h32_cnt[tid * PER + j] != 0;
+      cnt += nz;
+      if (nz) {
+        first = j < first ? j : first;
+        last = j;
+      }
+    }
+    if (cnt) {
+      const unsigned k0 = base + unsigned(tid * PER + first), k1 = base + unsigned(tid * PER + last);
+      kmin = k0 < kmin ? k0 : kmin;
+      kmax = k1 > kmax ? k1 : kmax;
+    }
     unsigned incl = warp_inclusive_sum(cnt);
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
@@ -513,7 +532,7 @@ __global__ void __launch_bounds__(H32_THREADS) agg_hist32_kernel(const __grid_co
       const unsigned c = h32_cnt[slot];
       if (c) {
         a.part_keys[pos] = (unsigned long long)(base + unsigned(slot));
-        if (a.has_count) a.part_acc[pos] = c;
+        if (has_count) a.part_acc[pos] = c;
         h32_cnt[slot] = 0;
         ++pos;
       }
@@ -521,74 +540,92 @@ __global__ void __launch_bounds__(H32_THREADS) agg_hist32_kernel(const __grid_co
     __syncthreads();
   };
 
-  for (int64_t step = begin; step < end; step += H32_STEP) {
-    uint4 v[4];
-    unsigned valid = 0;  // bit (4 j + e): element present
-    unsigned lo = ~0u, hi = 0u;
+  // one row at a time, any key: inside the window -> counter, outside -> its own partial
+  auto add_checked = [&](unsigned k) {
+    const unsigned idx = k - base;
+    if (idx < unsigned(H32_WINDOW)) {
+      if (has_count) atomicAdd(&h32_cnt[idx], 1u);
+      else h32_cnt[idx] = 1u;
+    } else {
+      // outside the window even after re-basing (the step spans more than 8 Ki keys)
+      unsigned long long pos = atomicAdd(a.part_cursor, 1ull);
+      a.part_keys[pos] = k;
+      if (has_count) a.part_acc[pos] = 1;
+      kmin = k < kmin ? k : kmin;
+      kmax = k > kmax ? k : kmax;
+      ++slow;
+    }
+  };
+
+  // re-base at the smallest key of the step (keys below a later base take the slow path)
+  auto rebase = [&](unsigned lo) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t r0 = step + (int64_t(j) * H32_THREADS + tid) * 4;
-      if (r0 + 3 < end) {
-        int4 t = ldg_stream_v4(a.key_col + r0);
-        v[j] = make_uint4(unsigned(t.x), unsigned(t.y), unsigned(t.z), unsigned(t.w));
-        valid |= 0xfu << (4 * j);
+    for (int d = 16; d > 0; d >>= 1) {
+      unsigned o = __shfl_xor_sync(FULL_MASK, lo, d);
+      lo = o < lo ? o : lo;
+    }
+    if (tid == 0) s_min = ~0u;
+    __syncthreads();
+    if (lane == 0) atomicMin(&s_min, lo);
+    __syncthreads();
+    const unsigned new_base = s_min;
+    if (have_base) flush();  // uniform: have_base is CTA-uniform
+    base = new_base;
+    have_base = true;
+  };
+
+  int64_t step = begin;
+  // ---- full steps: every thread owns H32_ROWS valid rows
+  for (; step + H32_STEP <= end; step += H32_STEP) {
+    uint4 v[H32_LOADS];
+#pragma unroll
+    for (int j = 0; j < H32_LOADS; ++j) {
+      int4 t = ldg_stream_v4(a.key_col + step + (int64_t(j) * H32_THREADS + tid) * 4);
+      v[j] = make_uint4(unsigned(t.x), unsigned(t.y), unsigned(t.z), unsigned(t.w));
+    }
+    unsigned ored = 0;
+#pragma unroll
+    for (int j = 0; j < H32_LOADS; ++j) ored |= (v[j].x - base) | (v[j].y - base) | (v[j].z - base) | (v[j].w - base);
+    if (__syncthreads_and(have_base && ored < unsigned(H32_WINDOW))) {
+      if (has_count) {
+#pragma unroll
+        for (int j = 0; j < H32_LOADS; ++j) {
+          atomicAdd(&h32_cnt[v[j].x - base], 1u);
+          atomicAdd(&h32_cnt[v[j].y - base], 1u);
+          atomicAdd(&h32_cnt[v[j].z - base], 1u);
+          atomicAdd(&h32_cnt[v[j].w - base], 1u);
+        }
       } else {
-        v[j] = make_uint4(0, 0, 0, 0);
-        if (r0 + 0 < end) { v[j].x = a.key_col[r0 + 0]; valid |= 1u << (4 * j); }
-        if (r0 + 1 < end) { v[j].y = a.key_col[r0 + 1]; valid |= 2u << (4 * j); }
-        if (r0 + 2 < end) { v[j].z = a.key_col[r0 + 2]; valid |= 4u << (4 * j); }
-      }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned ks[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if ((valid >> (4 * j + e)) & 1u) {
-          lo = ks[e] < lo ? ks[e] : lo;
-          hi = ks[e] > hi ? ks[e] : hi;
-        }
-    }
-    kmin = lo < kmin ? lo : kmin;
-    kmax = hi > kmax ? hi : kmax;
-    // does every key of this step fit the current window?  (one barrier per 4096 rows)
-    const bool fits = have_base && (valid == 0 || (lo >= base && hi - base < unsigned(H32_WINDOW)));
-    if (!__syncthreads_and(fits)) {
-      // re-base at the smallest key of the step (keys below a later base take the slow path)
-      unsigned m = lo;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        unsigned o = __shfl_xor_sync(FULL_MASK, m, d);
-        m = o < m ? o : m;
-      }
-      if (tid == 0) s_min = ~0u;
-      __syncthreads();
-      if (lane == 0) atomicMin(&s_min, m);
-      __syncthreads();
-      const unsigned new_base = s_min;
-      if (have_base) flush();  // uniform: have_base is CTA-uniform
-      base = new_base;
-      have_base = true;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned ks[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (!((valid >> (4 * j + e)) & 1u)) continue;
-        const unsigned idx = ks[e] - base;
-        if (idx < unsigned(H32_WINDOW)) {
-          if (a.has_count) atomicAdd(&h32_cnt[idx], 1u);
-          else h32_cnt[idx] = 1u;
-        } else {
-          // outside the window even after re-basing (the step spans more than 8 Ki keys): one partial per row
-          unsigned long long pos = atomicAdd(a.part_cursor, 1ull);
-          a.part_keys[pos] = ks[e];
-          if (a.has_count) a.part_acc[pos] = 1;
-          ++slow;
+        for (int j = 0; j < H32_LOADS; ++j) {
+          h32_cnt[v[j].x - base] = 1u;
+          h32_cnt[v[j].y - base] = 1u;
+          h32_cnt[v[j].z - base] = 1u;
+          h32_cnt[v[j].w - base] = 1u;
         }
       }
+    } else {
+      unsigned lo = ~0u;
+#pragma unroll
+      for (int j = 0; j < H32_LOADS; ++j) lo = min(min(lo, min(v[j].x, v[j].y)), min(v[j].z, v[j].w));
+      rebase(lo);
+#pragma unroll
+      for (int j = 0; j < H32_LOADS; ++j) {
+        add_checked(v[j].x);
+        add_checked(v[j].y);
+        add_checked(v[j].z);
+        add_checked(v[j].w);
+      }
     }
+  }
+  // ---- ragged tail of the CTA's range (at most one step): row by row
+  if (step < end) {
+    unsigned lo = ~0u;
+    for (int64_t r = step + tid; r < end; r += H32_THREADS) lo = min(lo, a.key_col[r]);
+    unsigned ok = 1;
+    for (int64_t r = step + tid; r < end; r += H32_THREADS) ok &= unsigned(a.key_col[r] - base < unsigned(H32_WINDOW));
+    if (!__syncthreads_and(have_base && ok)) rebase(lo);
+    for (int64_t r = step + tid; r < end; r += H32_THREADS) add_checked(a.key_col[r]);
   }
   __syncthreads();
   if (have_base) flush();

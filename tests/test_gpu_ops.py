@@ -100,6 +100,26 @@ def test_filter_matches_oracle(gpu_ctx, case, n):
     assert got.equals(want)                                   # stable: surviving rows keep their input order
 
 
+@pytest.mark.parametrize("m", [1, 2, 3, 96, 123, 1000, 1 << 20, 3 << 29, (1 << 31) - 1, -123])
+def test_divisibility_fast_path_all_moduli(gpu_ctx, m):
+    """`CAST(i32 AS Int64) % m = 0` runs the one-multiply divisibility test (PredI32 MODE 2): odd, even and
+    power-of-two moduli, negative dividends and INT_MIN; `!= 0` and `% m = c` take the Lemire path (MODE 1)."""
+    rng = np.random.default_rng(abs(m))
+    n = 200_003
+    x = rng.integers(-(1 << 31), 1 << 31, n).astype(np.int32)
+    am = abs(m)
+    x[::7] = (rng.integers(-((1 << 31) // am), ((1 << 31) - 1) // am + 1, len(x[::7])) * am).astype(np.int32)   # plenty of multiples
+    x[:4] = [0, -(1 << 31), (1 << 31) - 1, -1]
+    b = rb(v=pa.array(x), i=pa.array(np.arange(n, dtype=np.int64)))
+    t = gpu_ctx.import_batches([b])
+    rem = np.fmod(x.astype(np.int64), np.int64(m))            # sign follows the dividend, like Rust / Arrow
+    for pred, keep in ((col(0).cast("int64") % m == 0, rem == 0), (col(0).cast("int64") % m != 0, rem != 0),
+                       (col(0).cast("int64") % m == 1, rem == 1)):
+        got = gpu_ctx.filter_project(t, pred).to_batch()
+        assert np.array_equal(got["i"].to_numpy(), np.nonzero(keep)[0])
+        assert got.equals(oracle_filter(b, pred))
+
+
 def test_filter_with_projection_and_computed_columns(gpu_ctx):
     b = mixed_batch(50_000, seed=9)
     t = gpu_ctx.import_batches([b])
