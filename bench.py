@@ -202,18 +202,25 @@ def run_gpu(args) -> dict:
         ec.clean_data_sources()
     barrier(dist, local)
     sampler.active.set()
+    ctx.profile_begin()
     ctx.timer_start(1)
     t_wall = time.perf_counter()
     d2h = 0
     e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
+    t_feed = t_exec = 0.0
     for _ in range(e2e_steps):
+        t0 = time.perf_counter()
         ec.feed_data_sources(src)
+        t1 = time.perf_counter()
         res = ec.execute()
+        t_exec += time.perf_counter() - t1
+        t_feed += t1 - t0
         ec.clean_data_sources()
         d2h = sum(b.nbytes for b in res[0])
     ctx.timer_stop(1)
     ctx.synchronize()
     e2e_ms = max(ctx.timer_ms(1), (time.perf_counter() - t_wall) * 1e3)      # host-side work counts too
+    e2e_prof = ctx.profile_end()
     barrier(dist, local)
     sampler.active.clear()
     e2e_ms = dist_max(dist, local, e2e_ms)
@@ -242,6 +249,8 @@ def run_gpu(args) -> dict:
                    f"({RING} x {8 * args.bids / 1e6:.0f} MB > 126 MB L2)", "selectivity": mean_sel / args.bids},
         "e2e": {"value": world * args.bids * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_ms / max(e2e_steps, 1),
+                "host_ms_per_step": {"feed_data_sources": round(t_feed * 1e3 / max(e2e_steps, 1), 4), "execute+export": round(t_exec * 1e3 / max(e2e_steps, 1), 4)},
+                "kernels": e2e_prof,
                 "feed": "copy: auction + price columns DMA'd to HBM" if args.e2e_copy else
                         "zero-copy: page-locked auction column read in place over PCIe, price fetched for survivors only"},
         "gpu_launches": int(launches), "host_enqueue_us_per_step": round(host_us, 2), "kernels": prof, "clocks": clocks, "roofline": roofline,

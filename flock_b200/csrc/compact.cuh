@@ -38,7 +38,7 @@ constexpr unsigned long long EP_FLAG_MASK = 3ull << EP_VALUE_BITS;
 
 struct CompactScratch {
   unsigned long long* tile_state;  // epoch-tagged look-back words (many-wave mode)
-  unsigned* counts;                // per-tile survivor counts (single-wave mode)
+  unsigned long long* counts;      // per-tile survivor counts, epoch-tagged like the look-back words, dense (single-wave mode)
   unsigned int* counters;          // [0] tickets issued, [1] tiles arrived -- both monotonic across launches
   unsigned long long* out_count;   // receives the total number of survivors
   unsigned long long* host_count;  // optional second copy in page-locked host memory (saves the 8-byte D2H copy per launch)
@@ -107,21 +107,26 @@ __device__ __forceinline__ unsigned long long cp_block_sum(CompactSmem<E, I>& s,
   return tot;
 }
 
-// ---- single wave: counts + one arrival counter ------------------------------------------------------------
+// ---- single wave: every tile publishes ONE self-validating word, every tile reads all its predecessors ------------
+// All CTAs are resident (cooperative launch), so a tile can simply wait for each predecessor's count.  The count
+// and its "valid in this launch" tag (the 20-bit epoch) travel in the same 64-bit word, so the publish is one relaxed
+// store and the read one relaxed load: no fence, no arrival counter, no second round trip (the first version did
+// store + red.release + acquire-poll + reload and spent 4-5 us between the last load and the prefix; profiles/).
+// Thread i polls the words of tiles i, i + 256, ... -- dense, coalesced 2 KB reads of an L2-resident array.
 template <int E, int I>
 __device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned total) {
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    sc.counts[tile] = total;
-    red_release_add_u32(sc.counters + 1, 1u);  // release: the count is visible before the arrival
-    const unsigned target = sc.arrived_base + unsigned(sc.num_tiles);
-    while (int(ld_acquire_u32(sc.counters + 1) - target) < 0) {
-      if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
-    }
-  }
-  __syncthreads();  // thread 0's acquire + this barrier: every predecessor's count is visible to the CTA
+  const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
+  if (tid == 0) st_relaxed_u64(sc.counts + tile, tag | EP_PREFIX | (unsigned long long)total);
   unsigned long long part = 0;
-  for (long long i = tid; i < tile; i += CP_THREADS) part += __ldcg(sc.counts + i);
+  for (long long i = tid; i < tile; i += CP_THREADS) {
+    unsigned long long w = ld_relaxed_u64(sc.counts + i);
+    while ((w >> 44) != (tag >> 44)) {
+      if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
+      w = ld_relaxed_u64(sc.counts + i);
+    }
+    part += w & EP_VALUE_MASK;
+  }
   const unsigned long long excl = cp_block_sum(s, part);
   if (tid == 0) {
     s.excl = excl;

@@ -107,6 +107,11 @@ CtxCore::~CtxCore() {
   }
   for (cudaEvent_t e : sync_events) cudaEventDestroy(e);
   for (cudaEvent_t e : timing_events) cudaEventDestroy(e);
+  for (int i = 0; i < kCopyStreams; ++i) {
+    if (copy_streams[i]) cudaStreamDestroy(copy_streams[i]);
+    if (copy_join[i]) cudaEventDestroy(copy_join[i]);
+  }
+  if (copy_fork) cudaEventDestroy(copy_fork);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -172,14 +177,16 @@ CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, int grid,
     if (s.ep_state) FG_CUDA(cudaFree(s.ep_state));
     if (s.ep_counts) FG_CUDA(cudaFree(s.ep_counts));
     FG_CUDA(cudaMalloc(&s.ep_state, size_t(cap) * stride * sizeof(unsigned long long)));
-    FG_CUDA(cudaMalloc(&s.ep_counts, size_t(cap) * sizeof(unsigned)));
+    FG_CUDA(cudaMalloc(&s.ep_counts, size_t(cap) * sizeof(unsigned long long)));
     FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(cap) * stride * sizeof(unsigned long long), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, size_t(cap) * sizeof(unsigned long long), ctx->stream));
     s.ep_capacity = cap;
   }
   s.epoch = (s.epoch + 1) & 0xfffffu;
   if (s.epoch == 0) {
     // 2^20 launches later a stale word could carry the current epoch again: wipe them once per wrap
     FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(s.ep_capacity) * stride * sizeof(unsigned long long), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, size_t(s.ep_capacity) * sizeof(unsigned long long), ctx->stream));
     s.epoch = 1;
   }
   CompactScratch sc{};
@@ -340,6 +347,34 @@ static std::string copy_metadata(const char* md) {
 
 // Can this fixed-width column stay in host memory?  Needs page-locked sources (CUDA knows the pointer), uniform
 // power-of-two batch lengths (row -> chunk is a shift) and 16-byte aligned chunk bases (128-bit loads).
+// Deals host->device copies over the context's copy streams.  fork() orders them after everything already queued
+// on the main stream (the stream-ordered allocations of their destinations), join() makes the main stream wait for
+// all of them.
+struct CopyFan {
+  CtxCore* ctx;
+  int next = 0;
+  bool used[CtxCore::kCopyStreams] = {};
+  explicit CopyFan(const CtxPtr& c) : ctx(c.get()) {}
+  void fork() {
+    FG_CUDA(cudaEventRecord(ctx->copy_fork, ctx->stream));
+    for (int i = 0; i < CtxCore::kCopyStreams; ++i) FG_CUDA(cudaStreamWaitEvent(ctx->copy_streams[i], ctx->copy_fork, 0));
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    const int i = next;
+    next = (next + 1) % CtxCore::kCopyStreams;
+    used[i] = true;
+    FG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_streams[i]));
+  }
+  void join() {
+    for (int i = 0; i < CtxCore::kCopyStreams; ++i) {
+      if (!used[i]) continue;
+      FG_CUDA(cudaEventRecord(ctx->copy_join[i], ctx->copy_streams[i]));
+      FG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_join[i], 0));
+      used[i] = false;
+    }
+  }
+};
+
 static std::shared_ptr<HostChunks> try_host_chunks(const CtxPtr& ctx, const ArrowArray* const* batches, int n_batches, int p, int w) {
   if (n_batches < 1) return nullptr;
   const int64_t L = batches[0]->length;
@@ -374,12 +409,14 @@ void Table::dense() const {
     if (!c.chunks) continue;
     const int w = c.width();
     c.data = alloc(ctx, size_t(c.length) * w);
+    CopyFan fan(ctx);
+    fan.fork();
     int64_t row = 0;
     for (size_t k = 0; k < c.chunks->ptrs.size(); ++k) {
-      FG_CUDA(cudaMemcpyAsync(static_cast<char*>(c.data->ptr) + row * w, c.chunks->ptrs[k], size_t(c.chunks->rows[k]) * w, cudaMemcpyHostToDevice,
-                              ctx->stream));
+      fan.copy(static_cast<char*>(c.data->ptr) + row * w, c.chunks->ptrs[k], size_t(c.chunks->rows[k]) * w);
       row += c.chunks->rows[k];
     }
+    fan.join();
     c.chunks.reset();
   }
 }
@@ -395,6 +432,7 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
   } else {
     for (int i = 0; i < schema->n_children; ++i) proj.push_back(i);
   }
+  CopyFan fan(ctx);
   int64_t total = 0;
   for (int b = 0; b < n_batches; ++b) {
     FG_CHECK(batches[b] && batches[b]->n_children == schema->n_children, FLOCKGPU_ERR_INVALID,
@@ -437,17 +475,17 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
     } else if (dt != FLOCKGPU_UTF8) {
       int w = dtype_width(dt);
       col.data = alloc(ctx, size_t(total) * w);
+      fan.fork();
       int64_t row = 0;
       for (int b = 0; b < n_batches; ++b) {
         const ArrowArray* a = batches[b]->children[p];
         int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
         if (len == 0) continue;
         FG_CHECK(a->n_buffers >= 2 && a->buffers[1], FLOCKGPU_ERR_INVALID, "table_import: column \"%s\" has no data buffer", col.name.c_str());
-        FG_CUDA(cudaMemcpyAsync(static_cast<char*>(col.data->ptr) + row * w,
-                                static_cast<const char*>(a->buffers[1]) + off * w, size_t(len) * w,
-                                cudaMemcpyHostToDevice, ctx->stream));
+        fan.copy(static_cast<char*>(col.data->ptr) + row * w, static_cast<const char*>(a->buffers[1]) + off * w, size_t(len) * w);
         row += len;
       }
+      fan.join();
     } else {
       int64_t bytes = 0;
       for (int b = 0; b < n_batches; ++b) {
@@ -854,6 +892,11 @@ int flockgpu_open(int device, flockgpu_ctx** out) {
     FG_CUDA(cudaGetDeviceProperties(&prop, device));
     core->sm_count = prop.multiProcessorCount;
     FG_CUDA(cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < CtxCore::kCopyStreams; ++i) {
+      FG_CUDA(cudaStreamCreateWithFlags(&core->copy_streams[i], cudaStreamNonBlocking));
+      FG_CUDA(cudaEventCreateWithFlags(&core->copy_join[i], cudaEventDisableTiming));
+    }
+    FG_CUDA(cudaEventCreateWithFlags(&core->copy_fork, cudaEventDisableTiming));
     FG_CUDA(cudaDeviceGetDefaultMemPool(&core->pool, device));
     uint64_t threshold = UINT64_MAX;  // keep freed blocks in the pool: allocation is on the hot path
     FG_CUDA(cudaMemPoolSetAttribute(core->pool, cudaMemPoolAttrReleaseThreshold, &threshold));

@@ -455,9 +455,10 @@ __global__ void __launch_bounds__(A32_THREADS) agg_local32_kernel(const __grid_c
 // the hash kernel instead.
 constexpr int H32_THREADS = 256;
 constexpr int H32_WINDOW = 8192;              // 32 KB of u32 counters: 4 CTAs per SM (a CTA of q5 spans ~15 K auction ids: 2-3 re-bases)
-constexpr int H32_LOADS = 8;                  // 16-byte loads per thread and step: 128 B in flight per thread
+constexpr int H32_LOADS = 4;                  // 16-byte loads per thread and step; the NEXT step's loads are issued before this
+                                              // step's atomics (two register stages), so 64-128 B per thread are always in flight
 constexpr int H32_ROWS = H32_LOADS * 4;       // rows per thread and step
-constexpr int H32_STEP = H32_THREADS * H32_ROWS;  // rows per CTA iteration (8192)
+constexpr int H32_STEP = H32_THREADS * H32_ROWS;  // rows per CTA iteration (4096)
 
 struct AggHist32Args {
   int64_t n_rows;
@@ -494,27 +495,33 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
   const bool has_count = a.has_count != 0;
   __syncthreads();
 
-  // writes the non-zero counters as partials and clears them
+  // Writes the non-zero counters as partials and clears them.  Thread t owns counters (j * 256 + t) * 4 .. + 3
+  // (128-bit, conflict-free shared accesses; the first version let a thread walk 32 consecutive counters = a 32-way
+  // bank conflict on every access, 21 M conflict cycles per q5 launch); partial writes are compacted per warp and
+  // iteration with a ballot so that a warp writes consecutive entries.
   auto flush = [&]() {
-    constexpr int PER = H32_WINDOW / H32_THREADS;
+    constexpr int VEC = H32_WINDOW / (H32_THREADS * 4);  // uint4 per thread
+    const uint4* cnt4 = reinterpret_cast<const uint4*>(h32_cnt);
     unsigned cnt = 0;
-    int first = PER, last = -1;
-#pragma unroll 8
-    for (int j = 0; j < PER; ++j) {
-      const bool nz = h32_cnt[tid * PER + j] != 0;
+    unsigned smin = ~0u, smax = 0u;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const uint4 c = cnt4[j * H32_THREADS + tid];
+      const unsigned nz = unsigned(c.x != 0) + unsigned(c.y != 0) + unsigned(c.z != 0) + unsigned(c.w != 0);
       cnt += nz;
       if (nz) {
-        first = j < first ? j : first;
-        last = j;
+        const unsigned s0 = unsigned(j * H32_THREADS + tid) * 4u;
+        const unsigned first = c.x ? 0u : c.y ? 1u : c.z ? 2u : 3u, last = c.w ? 3u : c.z ? 2u : c.y ? 1u : 0u;
+        smin = min(smin, s0 + first);
+        smax = max(smax, s0 + last);
       }
     }
     if (cnt) {
-      const unsigned k0 = base + unsigned(tid * PER + first), k1 = base + unsigned(tid * PER + last);
-      kmin = k0 < kmin ? k0 : kmin;
-      kmax = k1 > kmax ? k1 : kmax;
+      kmin = min(kmin, base + smin);
+      kmax = max(kmax, base + smax);
     }
-    unsigned incl = warp_inclusive_sum(cnt);
-    if (lane == 31) s_warp[warp] = incl;
+    const unsigned warp_total = warp_sum(cnt);
+    if (lane == 0) s_warp[warp] = warp_total;
     __syncthreads();
     unsigned warp_base = 0, total = 0;
 #pragma unroll
@@ -525,17 +532,24 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
     }
     if (tid == 0) s_base_pos = total ? atomicAdd(a.part_cursor, (unsigned long long)total) : 0ull;
     __syncthreads();
-    unsigned long long pos = s_base_pos + warp_base + (incl - cnt);
-#pragma unroll 8
-    for (int j = 0; j < PER; ++j) {
-      const int slot = tid * PER + j;
-      const unsigned c = h32_cnt[slot];
-      if (c) {
-        a.part_keys[pos] = (unsigned long long)(base + unsigned(slot));
-        if (has_count) a.part_acc[pos] = c;
-        h32_cnt[slot] = 0;
-        ++pos;
+    unsigned long long pos = s_base_pos + warp_base;  // warp-uniform running position
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int v4 = j * H32_THREADS + tid;
+      const uint4 c = cnt4[v4];
+      const unsigned cs[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned b = __ballot_sync(FULL_MASK, cs[e] != 0);
+        if (cs[e]) {
+          const unsigned long long p = pos + __popc(b & lt);
+          a.part_keys[p] = (unsigned long long)(base + unsigned(v4) * 4u + unsigned(e));
+          if (has_count) a.part_acc[p] = cs[e];
+        }
+        pos += __popc(b);
       }
+      if (c.x | c.y | c.z | c.w) reinterpret_cast<uint4*>(h32_cnt)[v4] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
   };
@@ -575,14 +589,19 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
   };
 
   int64_t step = begin;
-  // ---- full steps: every thread owns H32_ROWS valid rows
-  for (; step + H32_STEP <= end; step += H32_STEP) {
-    uint4 v[H32_LOADS];
+  // ---- full steps: every thread owns H32_ROWS valid rows; two register stages
+  auto load_step = [&](uint4 (&v)[H32_LOADS], int64_t at) {
 #pragma unroll
     for (int j = 0; j < H32_LOADS; ++j) {
-      int4 t = ldg_stream_v4(a.key_col + step + (int64_t(j) * H32_THREADS + tid) * 4);
+      int4 t = ldg_stream_v4(a.key_col + at + (int64_t(j) * H32_THREADS + tid) * 4);
       v[j] = make_uint4(unsigned(t.x), unsigned(t.y), unsigned(t.z), unsigned(t.w));
     }
+  };
+  uint4 v[H32_LOADS], nxt[H32_LOADS];
+  if (step + H32_STEP <= end) load_step(v, step);
+  for (; step + H32_STEP <= end; step += H32_STEP) {
+    const bool more = step + 2 * int64_t(H32_STEP) <= end;
+    if (more) load_step(nxt, step + H32_STEP);  // in flight while this step waits at the barrier and counts
     unsigned ored = 0;
 #pragma unroll
     for (int j = 0; j < H32_LOADS; ++j) ored |= (v[j].x - base) | (v[j].y - base) | (v[j].z - base) | (v[j].w - base);
@@ -616,6 +635,10 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
         add_checked(v[j].z);
         add_checked(v[j].w);
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < H32_LOADS; ++j) v[j] = nxt[j];
     }
   }
   // ---- ragged tail of the CTA's range (at most one step): row by row
@@ -819,26 +842,65 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
     unsigned lane_prefix[CP_ITEMS / E];
     cp_rank_tile<E, CP_ITEMS>(sm, a.sc, tile, bits, lane_prefix);
     if (bits && sm.tile_total) {
+      // four survivors per round: their accumulator loads (dependent ~1 us reads when the table left L2) are in
+      // flight together instead of one after the other
       unsigned long long m = bits;
       while (m) {
-        const int k = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int64_t pos = cp_position<E, CP_ITEMS>(sm, bits, k, lane_prefix);
-        const unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
+        int64_t pos[4];
+        unsigned long long slot[4];
+        int nb = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          pos[q] = 0;
+          slot[q] = 0;
+          if (m) {
+            const int k = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            pos[q] = cp_position<E, CP_ITEMS>(sm, bits, k, lane_prefix);
+            slot[q] = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
+            nb = q + 1;
+          }
+        }
         if (a.keys || a.present) {
-          unsigned long long key = a.present ? a.dense_base + slot : (slot == a.n_slots - 1 ? EMPTY_KEY : a.keys[slot]);
-          if (a.n_key_out == 2) {
-            static_cast<uint32_t*>(a.key_dst[0])[pos] = uint32_t(key >> 32);
-            static_cast<uint32_t*>(a.key_dst[1])[pos] = uint32_t(key);
-          } else if (a.key_width[0] == 4) {
-            static_cast<uint32_t*>(a.key_dst[0])[pos] = uint32_t(key);
-          } else {
-            static_cast<unsigned long long*>(a.key_dst[0])[pos] = key;
+          unsigned long long key[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            key[q] = a.present ? a.dense_base + slot[q] : (slot[q] == a.n_slots - 1 || q >= nb ? EMPTY_KEY : a.keys[slot[q]]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q >= nb) continue;
+            if (a.n_key_out == 2) {
+              static_cast<uint32_t*>(a.key_dst[0])[pos[q]] = uint32_t(key[q] >> 32);
+              static_cast<uint32_t*>(a.key_dst[1])[pos[q]] = uint32_t(key[q]);
+            } else if (a.key_width[0] == 4) {
+              static_cast<uint32_t*>(a.key_dst[0])[pos[q]] = uint32_t(key[q]);
+            } else {
+              static_cast<unsigned long long*>(a.key_dst[0])[pos[q]] = key[q];
+            }
           }
         } else {
-          a.rep_rows[pos] = a.owner[slot];
+          unsigned r[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) r[q] = q < nb ? a.owner[slot[q]] : 0u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < nb) a.rep_rows[pos[q]] = r[q];
         }
-        emit_values(a.emit, a.n_emit, a.acc, a.n_slots, slot, pos);
+        for (int e = 0; e < a.n_emit; ++e) {
+          const EmitDesc& d = a.emit[e];
+          Val v[4], s2[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            v[q].u = q < nb ? a.acc[d.a0 * a.n_slots + slot[q]] : 0ull;
+            s2[q].u = (q < nb && d.kind == EMIT_AVG) ? a.acc[d.a1 * a.n_slots + slot[q]] : 0ull;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q >= nb) continue;
+            if (d.kind == EMIT_AVG) v[q].d = __ddiv_rn(s2[q].d, __ull2double_rn(v[q].u));
+            store_val(d.dst, d.out_dtype, pos[q], v[q]);
+          }
+        }
       }
     }
     __syncthreads();

@@ -75,7 +75,7 @@ struct ScanScratch {
   int64_t capacity = 0;
   // compact.cuh kernels (never reset between launches: monotonic counters + epoch-tagged words)
   unsigned long long* ep_state = nullptr;    // [ep_capacity * stride] {epoch:20, flag:2, value:42}
-  unsigned* ep_counts = nullptr;             // [ep_capacity] per-tile counts (single-wave mode)
+  unsigned long long* ep_counts = nullptr;   // [ep_capacity] dense epoch-tagged per-tile counts (single-wave mode)
   unsigned* ep_counters = nullptr;           // [0] tickets issued, [1] tiles arrived
   int64_t ep_capacity = 0;
   unsigned tickets_issued = 0, arrived = 0, epoch = 0;
@@ -84,6 +84,11 @@ struct ScanScratch {
 struct CtxCore {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // H2D fan-out (import_batches): one 256 KB copy per record batch and column leaves ~4 us of dead time between
+  // dependent copies on ONE stream (28 GB/s measured); dealt over several streams they overlap and fill the link.
+  static constexpr int kCopyStreams = 4;
+  cudaStream_t copy_streams[kCopyStreams] = {};
+  cudaEvent_t copy_fork = nullptr, copy_join[kCopyStreams] = {};
   cudaMemPool_t pool = nullptr;
   int sm_count = 148;
   std::recursive_mutex mu;
