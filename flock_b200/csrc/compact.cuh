@@ -39,12 +39,14 @@ constexpr unsigned long long EP_FLAG_MASK = 3ull << EP_VALUE_BITS;
 struct CompactScratch {
   unsigned long long* tile_state;  // epoch-tagged look-back words (many-wave mode)
   unsigned long long* counts;      // per-tile survivor counts, epoch-tagged like the look-back words, dense (single-wave mode)
-  unsigned int* counters;          // [0] tickets issued, [1] tiles arrived -- both monotonic across launches
+  unsigned long long* prefix;      // per-tile exclusive prefixes, epoch-tagged, written by the scanner CTA (single-wave mode)
+  int scanner;                     // single wave: 1 = one extra CTA (blockIdx.x == num_tiles) scans the counts for everybody
+  int grid;                        // CTAs to launch
+  unsigned int* counters;          // [0] tickets issued (many-wave mode), monotonic across launches
   unsigned long long* out_count;   // receives the total number of survivors
   unsigned long long* host_count;  // optional second copy in page-locked host memory (saves the 8-byte D2H copy per launch)
   long long num_tiles;
   unsigned ticket_base;            // value of counters[0] when this launch starts
-  unsigned arrived_base;           // value of counters[1] when this launch starts
   unsigned epoch;                  // 20-bit launch epoch of the look-back words
   int single_wave;
   int stride;                      // u64 words between look-back words of consecutive tiles (32 = one 256-byte L2 chunk each)
@@ -80,13 +82,18 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+template <int E, int I>
+__device__ __noinline__ void cp_scanner_cta(CompactSmem<E, I>& s, const CompactScratch& sc);
+
 // Fetches the next tile index for the CTA (or -1 when the work is exhausted); `iteration` counts the CTA's calls.
 // Many-wave mode: every CTA draws exactly one ticket past the end, so a launch consumes num_tiles + gridDim.x
 // tickets (the host advances its base by that).
 template <int E, int I>
 __device__ __forceinline__ long long cp_next_tile(CompactSmem<E, I>& s, const CompactScratch& sc, int iteration) {
   if (sc.single_wave) {
-    // one tile per CTA, all CTAs resident (cooperative launch, grid == num_tiles): the block index is the tile
+    // one tile per CTA, all CTAs resident (cooperative launch): the block index is the tile; with `scanner` the
+    // CTA behind the last tile has no tile and runs the scan instead
+    if (iteration == 0 && sc.scanner && (long long)blockIdx.x == sc.num_tiles) cp_scanner_cta(s, sc);
     return iteration == 0 && (long long)blockIdx.x < sc.num_tiles ? (long long)blockIdx.x : -1;
   }
   if (threadIdx.x == 0) s.tile = (long long)(atomicAdd(sc.counters, 1u) - sc.ticket_base);
@@ -107,17 +114,82 @@ __device__ __forceinline__ unsigned long long cp_block_sum(CompactSmem<E, I>& s,
   return tot;
 }
 
-// ---- single wave: every tile publishes ONE self-validating word, every tile reads all its predecessors ------------
-// All CTAs are resident (cooperative launch), so a tile can simply wait for each predecessor's count.  The count
-// and its "valid in this launch" tag (the 20-bit epoch) travel in the same 64-bit word, so the publish is one relaxed
-// store and the read one relaxed load: no fence, no arrival counter, no second round trip (the first version did
-// store + red.release + acquire-poll + reload and spent 4-5 us between the last load and the prefix; profiles/).
-// Thread i polls the words of tiles i, i + 256, ... -- dense, coalesced 2 KB reads of an L2-resident array.
+// ---- single wave ------------------------------------------------------------------------------------------------
+// All CTAs are resident (cooperative launch), so a tile may simply wait for data of other tiles.  Every word that
+// crosses CTAs is self-validating: {20-bit launch epoch, value} in 64 bits, one relaxed store to publish and one
+// relaxed load to read -- no fence, no arrival counter, nothing to reset between launches.
+//   few tiles (<= CP_DIRECT_TILES): every tile reads the counts of all its predecessors itself (one hop);
+//   more tiles: that would be T^2 / 2 polls of a few L2 lines (186 K loads for the 611 tiles of a 10 M-row
+//   relation: measured 4-7 us between the last load and the prefix, profiles/r1_filter_ncu.md), so ONE extra CTA --
+//   the scanner -- collects the T counts (<= 8 per thread), scans them and publishes T prefix words; a tile then
+//   polls exactly one word with one thread.
+constexpr int CP_DIRECT_TILES = 48;
+constexpr int CP_SCAN_PER_THREAD = 8;  // scanner capacity: 256 x 8 = 2048 tiles >= any single wave
+
 template <int E, int I>
-__device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned total) {
+__device__ __noinline__ void cp_scanner_cta(CompactSmem<E, I>& s, const CompactScratch& sc) {
   const int tid = threadIdx.x;
   const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
-  if (tid == 0) st_relaxed_u64(sc.counts + tile, tag | EP_PREFIX | (unsigned long long)total);
+  const long long T = sc.num_tiles;
+  const long long per = (T + CP_THREADS - 1) / CP_THREADS;  // contiguous tiles per thread
+  const long long first = tid * per;
+  unsigned long long v[CP_SCAN_PER_THREAD];
+  unsigned long long sum = 0;
+#pragma unroll
+  for (int k = 0; k < CP_SCAN_PER_THREAD; ++k) {
+    v[k] = 0;
+    const long long i = first + k;
+    if (k < per && i < T) {
+      unsigned long long w = ld_relaxed_u64(sc.counts + i);
+      while ((w >> 44) != (tag >> 44)) {
+        __nanosleep(40);
+        w = ld_relaxed_u64(sc.counts + i);
+      }
+      v[k] = w & EP_VALUE_MASK;
+    }
+    sum += v[k];
+  }
+  // block-wide exclusive scan of the per-thread sums (thread order == tile order)
+  const int lane = tid & 31, warp = tid >> 5;
+  const unsigned long long incl = warp_inclusive_sum(sum);
+  if (lane == 31) s.lb_sum[warp] = incl;
+  __syncthreads();
+  unsigned long long run = incl - sum, total = 0;
+#pragma unroll
+  for (int w = 0; w < CP_WARPS; ++w) {
+    const unsigned long long x = s.lb_sum[w];
+    if (w < warp) run += x;
+    total += x;
+  }
+#pragma unroll
+  for (int k = 0; k < CP_SCAN_PER_THREAD; ++k) {
+    const long long i = first + k;
+    if (k < per && i < T) st_relaxed_u64(sc.prefix + i, tag | EP_PREFIX | run);
+    run += v[k];
+  }
+  if (tid == 0) {
+    *sc.out_count = total;
+    if (sc.host_count) *reinterpret_cast<volatile unsigned long long*>(sc.host_count) = total;
+  }
+}
+
+template <int E, int I>
+__device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned long long total) {
+  const int tid = threadIdx.x;
+  const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
+  if (tid == 0) st_relaxed_u64(sc.counts + tile, tag | EP_PREFIX | total);
+  if (sc.scanner) {
+    if (tid == 0) {
+      unsigned long long w = ld_relaxed_u64(sc.prefix + tile);
+      while ((w >> 44) != (tag >> 44)) {
+        if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
+        w = ld_relaxed_u64(sc.prefix + tile);
+      }
+      s.excl = w & EP_VALUE_MASK;
+    }
+    __syncthreads();
+    return;
+  }
   unsigned long long part = 0;
   for (long long i = tid; i < tile; i += CP_THREADS) {
     unsigned long long w = ld_relaxed_u64(sc.counts + i);
@@ -140,7 +212,7 @@ __device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const Compa
 
 // ---- many waves: decoupled look-back, 256 predecessors per step, epoch-tagged words -------------------------
 template <int E, int I>
-__device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned total) {
+__device__ __forceinline__ void cp_block_lookback(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned long long total) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
   unsigned long long excl = 0;  // meaningful in thread 0 only
@@ -276,17 +348,18 @@ __device__ __forceinline__ void cp_rank_tile(CompactSmem<E, I>& s, const Compact
   else cp_block_lookback(s, sc, tile, s.tile_total);
 }
 
-// Host side (core.cu): sizes the scratch and fills a CompactScratch for ONE launch of `grid` CTAs over `num_tiles`
-// tiles; advances the context's ticket / arrival / epoch bookkeeping.  Call it right before the launch.
-CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, int grid, unsigned long long* out_count);
+// Host side (core.cu): sizes the scratch and fills a CompactScratch for ONE launch over `num_tiles` tiles by a kernel of
+// which `resident_ctas` fit on the device at once; chooses the mode and the grid (sc.grid); advances the context's
+// ticket / epoch bookkeeping.  Call it right before the launch.
+CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, long long resident_ctas, unsigned long long* out_count);
 
-// Launches a compaction kernel.  Single-wave launches wait on an arrival counter that only completes when EVERY CTA
-// of the grid is running, so they go through the cooperative-launch path: the driver then guarantees co-residency
-// (or fails the launch) instead of us assuming the GPU is otherwise idle.
+// Launches a compaction kernel with sc.grid CTAs.  Single-wave launches wait for data of other CTAs, which only
+// arrives when EVERY CTA of the grid is running, so they go through the cooperative-launch path: the driver then
+// guarantees co-residency (or fails the launch) instead of us assuming the GPU is otherwise idle.
 template <class Kernel, class... Args>
-inline void launch_compact(const CtxPtr& ctx, Kernel kernel, int grid, const CompactScratch& sc, Args&&... args) {
+inline void launch_compact(const CtxPtr& ctx, Kernel kernel, const CompactScratch& sc, Args&&... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(grid));
+  cfg.gridDim = dim3(unsigned(sc.grid));
   cfg.blockDim = dim3(CP_THREADS);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = ctx->stream;

@@ -89,11 +89,9 @@ CtxCore::~CtxCore() {
   if (stream) cudaStreamSynchronize(stream);
   for (auto& kv : pinned) cudaFreeHost(kv.first);
   pinned.clear();
-  if (scan.tile_state) cudaFree(scan.tile_state);
   if (scan.ep_state) cudaFree(scan.ep_state);
   if (scan.ep_counts) cudaFree(scan.ep_counts);
   if (scan.ep_counters) cudaFree(scan.ep_counters);
-  if (scan.counters) cudaFree(scan.counters);
   if (l2_flush) cudaFree(l2_flush);
   if (h_scalars) cudaFreeHost(h_scalars);
   if (d_scalars) cudaFree(d_scalars);
@@ -127,24 +125,6 @@ Buffer::~Buffer() {
 
 BufferPtr alloc(const CtxPtr& ctx, size_t bytes) { return std::make_shared<Buffer>(ctx, bytes); }
 
-void ensure_scan_scratch(const CtxPtr& ctx, int64_t tiles) {
-  ScanScratch& s = ctx->scan;
-  if (!s.counters) {
-    FG_CUDA(cudaMalloc(&s.counters, 64 * sizeof(unsigned int)));
-    FG_CUDA(cudaMemsetAsync(s.counters, 0, 64 * sizeof(unsigned int), ctx->stream));
-  }
-  tiles *= scan_stride();
-  if (tiles > s.capacity) {
-    int64_t cap = 1 << 16;
-    while (cap < tiles) cap <<= 1;
-    FG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (s.tile_state) FG_CUDA(cudaFree(s.tile_state));
-    FG_CUDA(cudaMalloc(&s.tile_state, cap * sizeof(unsigned long long)));
-    FG_CUDA(cudaMemsetAsync(s.tile_state, 0, cap * sizeof(unsigned long long), ctx->stream));
-    s.capacity = cap;
-  }
-}
-
 int scan_stride() {
   static const int v = [] {
     const char* e = getenv("FLOCKGPU_LB_STRIDE");
@@ -163,7 +143,7 @@ int scan_poll_sleep_ns() {
   return v;
 }
 
-CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, int grid, unsigned long long* out_count) {
+CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, long long resident_ctas, unsigned long long* out_count) {
   ScanScratch& s = ctx->scan;
   const int stride = scan_stride();
   if (!s.ep_counters) {
@@ -177,33 +157,37 @@ CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, int grid,
     if (s.ep_state) FG_CUDA(cudaFree(s.ep_state));
     if (s.ep_counts) FG_CUDA(cudaFree(s.ep_counts));
     FG_CUDA(cudaMalloc(&s.ep_state, size_t(cap) * stride * sizeof(unsigned long long)));
-    FG_CUDA(cudaMalloc(&s.ep_counts, size_t(cap) * sizeof(unsigned long long)));
+    FG_CUDA(cudaMalloc(&s.ep_counts, 2 * size_t(cap) * sizeof(unsigned long long)));  // counts | prefixes
     FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(cap) * stride * sizeof(unsigned long long), ctx->stream));
-    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, size_t(cap) * sizeof(unsigned long long), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, 2 * size_t(cap) * sizeof(unsigned long long), ctx->stream));
     s.ep_capacity = cap;
   }
   s.epoch = (s.epoch + 1) & 0xfffffu;
   if (s.epoch == 0) {
     // 2^20 launches later a stale word could carry the current epoch again: wipe them once per wrap
     FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(s.ep_capacity) * stride * sizeof(unsigned long long), ctx->stream));
-    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, size_t(s.ep_capacity) * sizeof(unsigned long long), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, 2 * size_t(s.ep_capacity) * sizeof(unsigned long long), ctx->stream));
     s.epoch = 1;
   }
   CompactScratch sc{};
   sc.tile_state = s.ep_state;
   sc.counts = s.ep_counts;
+  sc.prefix = s.ep_counts + s.ep_capacity;
   sc.counters = s.ep_counters;
   sc.out_count = out_count;
   sc.num_tiles = num_tiles;
   sc.ticket_base = s.tickets_issued;
-  sc.arrived_base = s.arrived;
   sc.epoch = s.epoch;
   static const bool force_lookback = getenv("FLOCKGPU_FORCE_LOOKBACK") != nullptr;
-  sc.single_wave = (num_tiles <= grid && !force_lookback) ? 1 : 0;
+  static const bool no_scanner = getenv("FLOCKGPU_NO_SCANNER") != nullptr;
+  if (resident_ctas < 1) resident_ctas = 1;
+  sc.single_wave = (num_tiles <= resident_ctas && !force_lookback) ? 1 : 0;
+  sc.scanner = (sc.single_wave && num_tiles > CP_DIRECT_TILES && num_tiles + 1 <= resident_ctas &&
+                num_tiles <= (long long)CP_THREADS * CP_SCAN_PER_THREAD && !no_scanner) ? 1 : 0;
+  sc.grid = int(std::max<long long>(1, sc.single_wave ? num_tiles + sc.scanner : std::min<long long>(resident_ctas, num_tiles)));
   sc.stride = stride;
   sc.poll_sleep_ns = scan_poll_sleep_ns();
-  if (sc.single_wave) s.arrived += unsigned(num_tiles);                  // one arrival per tile, no tickets
-  else s.tickets_issued += unsigned(num_tiles) + unsigned(grid);          // every CTA draws exactly one ticket past the end
+  if (!sc.single_wave) s.tickets_issued += unsigned(num_tiles) + unsigned(sc.grid);  // every CTA draws exactly one ticket past the end
   return sc;
 }
 
@@ -907,7 +891,6 @@ int flockgpu_open(int device, flockgpu_ctx** out) {
       FG_CUDA(cudaEventCreate(&core->timer_start[i]));
       FG_CUDA(cudaEventCreate(&core->timer_stop[i]));
     }
-    ensure_scan_scratch(core, 1);
     *out = new flockgpu_ctx{core};
   });
 }

@@ -61,15 +61,7 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
-// ---- decoupled look-back (single-pass chained scan) ----------------------------------------------
-// tile_state[t] packs {flag (2 bits), value (62 bits)} in ONE 64-bit word, so a relaxed 64-bit load
-// observes flag and value together and no fence is needed between them.
-constexpr unsigned long long LB_INVALID = 0ull;
-constexpr unsigned long long LB_PARTIAL = 1ull << 62;   // value = this tile's own aggregate
-constexpr unsigned long long LB_PREFIX = 2ull << 62;    // value = inclusive prefix up to this tile
-constexpr unsigned long long LB_FLAG_MASK = 3ull << 62;
-constexpr unsigned long long LB_VALUE_MASK = ~LB_FLAG_MASK;
-
+// ---- relaxed gpu-scope accesses used by the grid-wide prefix protocols (compact.cuh) --------------------
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -77,34 +69,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Called by ONE full warp of the CTA that owns tile `tile` (tile > 0) after it has published
-// (LB_PARTIAL | aggregate).  Returns the exclusive prefix (sum of aggregates of tiles < tile) in every
-// lane.  Tiles are handed out by an atomic ticket, so every predecessor has been started by a resident
-// CTA and the spin terminates.
-__device__ __forceinline__ unsigned long long lookback_exclusive_prefix(const unsigned long long* tile_state, long long tile) {
-  unsigned long long exclusive = 0;
-  long long base = tile - 1;  // lane L inspects tile base - L
-  while (true) {
-    long long t = base - (long long)lane_id();
-    unsigned long long s;
-    if (t >= 0) {
-      do {
-        s = ld_relaxed_u64(tile_state + t);
-      } while ((s & LB_FLAG_MASK) == LB_INVALID);
-    } else {
-      s = LB_PREFIX;  // virtual tile before the first one: inclusive prefix 0
-    }
-    unsigned has_prefix = __ballot_sync(FULL_MASK, (s & LB_FLAG_MASK) == LB_PREFIX);
-    // lanes nearer than the first PREFIX lane contribute their partials; that lane contributes its prefix
-    int first = has_prefix ? __ffs(has_prefix) - 1 : 32;
-    unsigned long long contrib = (int(lane_id()) <= first) ? (s & LB_VALUE_MASK) : 0ull;
-    exclusive += warp_sum(contrib);
-    if (has_prefix) break;
-    base -= 32;
-  }
-  return exclusive;
 }
 
 // ---- hashing --------------------------------------------------------------------------------------

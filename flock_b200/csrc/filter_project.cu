@@ -453,7 +453,8 @@ static void fill_colrefs(const Table& t, ColRef* refs) {
   }
 }
 
-static int persistent_grid(const CtxPtr& ctx, const void* kernel, int threads, int64_t work_items) {
+// CTAs of `kernel` that fit on the device at once
+static int resident_ctas(const CtxPtr& ctx, const void* kernel, int threads) {
   // the occupancy query costs microseconds per call; a q2 step is one ~10 us kernel, so cache it per kernel
   static std::mutex mu;
   static std::unordered_map<const void*, int> cache;
@@ -469,8 +470,7 @@ static int persistent_grid(const CtxPtr& ctx, const void* kernel, int threads, i
     std::lock_guard<std::mutex> g(mu);
     cache[kernel] = per_sm;
   }
-  int64_t g = int64_t(ctx->sm_count) * per_sm;
-  return int(std::max<int64_t>(1, std::min<int64_t>(g, work_items)));
+  return int(int64_t(ctx->sm_count) * per_sm);
 }
 
 template <class PredFn>
@@ -478,8 +478,8 @@ static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args
   constexpr int64_t TILE = int64_t(FP_THREADS) * PredFn::I;
   const int64_t num_tiles = (args.n_rows + TILE - 1) / TILE;
   const void* k = reinterpret_cast<const void*>(&filter_compact_kernel<PredFn>);
-  const int grid = persistent_grid(ctx, k, FP_THREADS, num_tiles);
-  args.sc = prepare_compact(ctx, num_tiles, grid, args.out_count);
+  args.sc = prepare_compact(ctx, num_tiles, resident_ctas(ctx, k, FP_THREADS), args.out_count);
+  const int grid = args.sc.grid;
   args.sc.host_count = args.host_count;
   BufferPtr trace_buf;
   static const char* trace_path = getenv("FLOCKGPU_TRACE");
@@ -490,7 +490,7 @@ static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args
   }
   {
     LaunchTimer lt(ctx, "filter_compact_kernel");
-    launch_compact(ctx, filter_compact_kernel<PredFn>, grid, args.sc, pred, args);
+    launch_compact(ctx, filter_compact_kernel<PredFn>, args.sc, pred, args);
   }
   FG_CUDA(cudaGetLastError());
   count_launch(ctx);

@@ -7,6 +7,7 @@
 //                 warp owns 32 consecutive OUTPUT rows, so output bytes are written densely in order.
 #include <algorithm>
 
+#include "compact.cuh"
 #include "device_utils.cuh"
 #include "internal.h"
 
@@ -40,23 +41,15 @@ struct GatherLenArgs {
   const uint32_t* idx;  // may be NULL: identity (plain offsets rebuild)
   int32_t* out_off;
   int64_t n;
-  int64_t num_tiles;
-  unsigned long long* tile_state;
-  unsigned int* counters;
-  unsigned long long* out_total;
+  CompactScratch sc;  // grid-wide exclusive prefix of the tiles' byte counts (compact.cuh); sc.out_count = total bytes
 };
 
 __global__ void __launch_bounds__(GA_THREADS) gather_lengths_scan_kernel(const __grid_constant__ GatherLenArgs a) {
+  __shared__ CompactSmem<1, 16> sm;
   __shared__ unsigned long long s_warp[GA_THREADS / 32];
-  __shared__ long long s_tile;
-  __shared__ unsigned long long s_excl;
-  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  while (true) {
-    if (tid == 0) s_tile = (long long)atomicAdd(a.counters, 1u);
-    __syncthreads();
-    const long long tile = s_tile;
-    if (tile >= a.num_tiles) break;
+  long long tile;
+  for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
     const int64_t i0 = tile * GL_TILE + int64_t(tid) * GL_ITEMS;
     unsigned len[GL_ITEMS];
     unsigned long long local = 0;
@@ -79,41 +72,16 @@ __global__ void __launch_bounds__(GA_THREADS) gather_lengths_scan_kernel(const _
       if (w < warp) warp_base += v;
       tile_total += v;
     }
-    if (warp == 0) {
-      unsigned long long excl = 0;
-      if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(a.tile_state, LB_PREFIX | tile_total);
-      } else {
-        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PARTIAL | tile_total);
-        excl = lookback_exclusive_prefix(a.tile_state, tile);
-        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PREFIX | (excl + tile_total));
-      }
-      if (lane == 0) {
-        s_excl = excl;
-        if (tile == a.num_tiles - 1) {
-          *a.out_total = excl + tile_total;
-          a.out_off[a.n] = int32_t(excl + tile_total);
-        }
-      }
-    }
-    __syncthreads();
-    unsigned long long run = s_excl + warp_base + (incl - local);
+    if (a.sc.single_wave) cp_grid_prefix(sm, a.sc, tile, tile_total);
+    else cp_block_lookback(sm, a.sc, tile, tile_total);
+    unsigned long long run = sm.excl + warp_base + (incl - local);
 #pragma unroll
     for (int k = 0; k < GL_ITEMS; ++k) {
       if (i0 + k < a.n) a.out_off[i0 + k] = int32_t(run);
       run += len[k];
     }
-    __syncthreads();
-  }
-  __threadfence();
-  if (tid == 0) s_last = (atomicAdd(a.counters + 1, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    for (int64_t i = tid; i < a.num_tiles; i += GA_THREADS) a.tile_state[i] = LB_INVALID;
-    if (tid == 0) {
-      a.counters[0] = 0;
-      a.counters[1] = 0;
-    }
+    if (tile == a.sc.num_tiles - 1 && tid == 0) a.out_off[a.n] = int32_t(sm.excl + tile_total);
+    __syncthreads();  // sm / s_warp are reused by the next tile
   }
 }
 
@@ -199,18 +167,14 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
   a.idx = d_idx;
   a.out_off = out.offsets->as<int32_t>();
   a.n = n;
-  a.num_tiles = (n + GL_TILE - 1) / GL_TILE;
-  ensure_scan_scratch(ctx, a.num_tiles);
-  a.tile_state = ctx->scan.tile_state;
-  a.counters = ctx->scan.counters;
-  a.out_total = ctx->d_scalars + 1;
+  const int64_t num_tiles = (n + GL_TILE - 1) / GL_TILE;
   {
     int per_sm = 1;
     FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_lengths_scan_kernel, GA_THREADS, 0));
-    int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), a.num_tiles)));
+    a.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + 1);
     {
       LaunchTimer lt(ctx, "gather_lengths_scan_kernel");
-      gather_lengths_scan_kernel<<<grid, GA_THREADS, 0, ctx->stream>>>(a);
+      launch_compact(ctx, gather_lengths_scan_kernel, a.sc, a);
     }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);

@@ -1411,11 +1411,10 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     const long long tiles = (long long)((n_slots + CP_THREADS * 16 - 1) / (CP_THREADS * 16));
     int per_sm = 1;
     FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_emit_kernel, CP_THREADS, 0));
-    int grid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), tiles)));
-    ea.sc = prepare_compact(ctx, tiles, grid, ctx->d_scalars + 3);
+    ea.sc = prepare_compact(ctx, tiles, (long long)ctx->sm_count * std::max(per_sm, 1), ctx->d_scalars + 3);
     {
       LaunchTimer lt(ctx, "agg_emit_kernel");
-      launch_compact(ctx, agg_emit_kernel, grid, ea.sc, ea);
+      launch_compact(ctx, agg_emit_kernel, ea.sc, ea);
     }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);

@@ -19,6 +19,7 @@
 // and gather.cu materialises the output columns (Utf8 included).
 #include <algorithm>
 
+#include "compact.cuh"
 #include "device_utils.cuh"
 #include "internal.h"
 #include "rowkeys.cuh"
@@ -96,24 +97,16 @@ struct JoinCountArgs {
   JoinSide build, probe;
   JoinTable table;
   unsigned* out_off;  // [probe rows + 1] exclusive pair offsets
-  int64_t num_tiles;
-  unsigned long long* tile_state;
-  unsigned int* counters;
-  unsigned long long* out_total;
+  CompactScratch sc;  // grid-wide exclusive prefix of the tiles' pair counts (compact.cuh); sc.out_count = total pairs
 };
 
 __global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __grid_constant__ JoinCountArgs a) {
+  __shared__ CompactSmem<1, 16> sm;
   __shared__ unsigned long long s_warp[JC_THREADS / 32];
-  __shared__ long long s_tile;
-  __shared__ unsigned long long s_excl;
-  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n = a.probe.n_rows;
-  while (true) {
-    if (tid == 0) s_tile = (long long)atomicAdd(a.counters, 1u);
-    __syncthreads();
-    const long long tile = s_tile;
-    if (tile >= a.num_tiles) break;
+  long long tile;
+  for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
     const int64_t i0 = tile * JC_TILE + int64_t(tid) * JC_ITEMS;
     unsigned cnt[JC_ITEMS];
     unsigned long long local = 0;
@@ -137,41 +130,18 @@ __global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __gri
       if (w < warp) warp_base += v;
       tile_total += v;
     }
-    if (warp == 0) {
-      unsigned long long excl = 0;
-      if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(a.tile_state, LB_PREFIX | tile_total);
-      } else {
-        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PARTIAL | tile_total);
-        excl = lookback_exclusive_prefix(a.tile_state, tile);
-        if (lane == 0) st_relaxed_u64(a.tile_state + tile, LB_PREFIX | (excl + tile_total));
-      }
-      if (lane == 0) {
-        s_excl = excl;
-        if (tile == a.num_tiles - 1) {
-          *a.out_total = excl + tile_total;
-          a.out_off[n] = unsigned(excl + tile_total);
-        }
-      }
-    }
-    __syncthreads();
-    unsigned long long run = s_excl + warp_base + (incl - local);
+    // exclusive prefix over the tiles: the whole CTA looks back (256 predecessors per step) or, when every tile is
+    // resident, reads its predecessors' self-validating count words
+    if (a.sc.single_wave) cp_grid_prefix(sm, a.sc, tile, tile_total);
+    else cp_block_lookback(sm, a.sc, tile, tile_total);
+    unsigned long long run = sm.excl + warp_base + (incl - local);
 #pragma unroll
     for (int k = 0; k < JC_ITEMS; ++k) {
       if (i0 + k < n) a.out_off[i0 + k] = unsigned(run);
       run += cnt[k];
     }
-    __syncthreads();
-  }
-  __threadfence();
-  if (tid == 0) s_last = (atomicAdd(a.counters + 1, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    for (int64_t i = tid; i < a.num_tiles; i += JC_THREADS) a.tile_state[i] = LB_INVALID;
-    if (tid == 0) {
-      a.counters[0] = 0;
-      a.counters[1] = 0;
-    }
+    if (tile == a.sc.num_tiles - 1 && tid == 0) a.out_off[n] = unsigned(sm.excl + tile_total);
+    __syncthreads();  // sm / s_warp are reused by the next tile
   }
 }
 
@@ -282,18 +252,14 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     ca.probe = ps;
     ca.table = tab;
     ca.out_off = off->as<unsigned>();
-    ca.num_tiles = (P.num_rows + JC_TILE - 1) / JC_TILE;
-    ensure_scan_scratch(ctx, ca.num_tiles);
-    ca.tile_state = ctx->scan.tile_state;
-    ca.counters = ctx->scan.counters;
-    ca.out_total = ctx->d_scalars + 4;
+    const int64_t num_tiles = (P.num_rows + JC_TILE - 1) / JC_TILE;
     {
       int per_sm = 1;
       FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_count_scan_kernel, JC_THREADS, 0));
-      int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), ca.num_tiles)));
+      ca.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + 4);
       {
         LaunchTimer lt(ctx, "join_count_scan_kernel");
-        join_count_scan_kernel<<<grid, JC_THREADS, 0, ctx->stream>>>(ca);
+        launch_compact(ctx, join_count_scan_kernel, ca.sc, ca);
       }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);

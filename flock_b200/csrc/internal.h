@@ -68,17 +68,14 @@ int guarded(F&& body) noexcept {
 // ------------------------------------------------------------------------------------------------
 struct Comm;  // comm.cc
 
-// Scratch for the single-pass (decoupled look-back) compaction/scan kernels; self-resetting.
+// Scratch of the single-pass compaction / scan kernels (compact.cuh).  Never reset between launches: tickets are a
+// monotonic counter whose base the host tracks, status words carry the launch epoch.
 struct ScanScratch {
-  unsigned long long* tile_state = nullptr;  // [capacity] packed {flag:2, value:62}
-  unsigned int* counters = nullptr;          // [0]=ticket, [1]=done, [2..] spare
-  int64_t capacity = 0;
-  // compact.cuh kernels (never reset between launches: monotonic counters + epoch-tagged words)
   unsigned long long* ep_state = nullptr;    // [ep_capacity * stride] {epoch:20, flag:2, value:42}
-  unsigned long long* ep_counts = nullptr;   // [ep_capacity] dense epoch-tagged per-tile counts (single-wave mode)
-  unsigned* ep_counters = nullptr;           // [0] tickets issued, [1] tiles arrived
+  unsigned long long* ep_counts = nullptr;   // [2 * ep_capacity] dense epoch-tagged per-tile counts, then prefixes (single-wave mode)
+  unsigned* ep_counters = nullptr;           // [0] tickets issued
   int64_t ep_capacity = 0;
-  unsigned tickets_issued = 0, arrived = 0, epoch = 0;
+  unsigned tickets_issued = 0, epoch = 0;
 };
 
 struct CtxCore {
@@ -179,7 +176,6 @@ using BufferPtr = std::shared_ptr<Buffer>;
 BufferPtr alloc(const CtxPtr& ctx, size_t bytes);  // bytes == 0 still yields a valid (tiny) buffer
 
 // Grows the look-back scratch to at least `tiles` entries (zero-initialised once).
-void ensure_scan_scratch(const CtxPtr& ctx, int64_t tiles);
 // Look-back tuning (FLOCKGPU_LB_STRIDE / FLOCKGPU_LB_SLEEP override): words between tile entries, poll back-off in ns.
 int scan_stride();
 int scan_poll_sleep_ns();

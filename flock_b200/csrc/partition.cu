@@ -158,13 +158,13 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   sa.idx = idx->as<uint32_t>();
   int per_sm = 1;
   FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_select_kernel, CP_THREADS, 0));
-  int sgrid = int(std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), tiles)));
+  const long long resident = (long long)ctx->sm_count * std::max(per_sm, 1);
   for (int p = 0; p < n_parts; ++p) {
     sa.part = p;
-    sa.sc = prepare_compact(ctx, tiles, sgrid, ctx->d_scalars + 5);
+    sa.sc = prepare_compact(ctx, tiles, resident, ctx->d_scalars + 5);
     {
       LaunchTimer lt(ctx, "partition_select_kernel");
-      launch_compact(ctx, partition_select_kernel, sgrid, sa.sc, sa);
+      launch_compact(ctx, partition_select_kernel, sa.sc, sa);
     }
     FG_CUDA(cudaGetLastError());
     {
