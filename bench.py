@@ -45,6 +45,12 @@ METRIC = "nexmark_q2_events_per_sec"
 UNIT = "events/s"
 
 
+# Libraries write to fd 1 behind Python's back (NCCL prints "NCCL version ..." there): keep the real stdout for the
+# JSON line(s) only and point fd 1 at stderr for everything else.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -335,7 +341,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "gpu" else args.warmup
     res = run_reference(args) if args.impl == "reference" else run_gpu(args)
     if res is not None:
-        print(json.dumps(res), flush=True)
+        print(json.dumps(res), file=_JSON_OUT, flush=True)
 
 
 if __name__ == "__main__":

@@ -39,14 +39,13 @@ constexpr unsigned long long EP_FLAG_MASK = 3ull << EP_VALUE_BITS;
 struct CompactScratch {
   unsigned long long* tile_state;  // epoch-tagged look-back words (many-wave mode)
   unsigned long long* counts;      // per-tile survivor counts, epoch-tagged like the look-back words, dense (single-wave mode)
-  unsigned long long* prefix;      // per-tile exclusive prefixes, epoch-tagged, written by the scanner CTA (single-wave mode)
-  int scanner;                     // single wave: 1 = one extra CTA (blockIdx.x == num_tiles) scans the counts for everybody
   int grid;                        // CTAs to launch
-  unsigned int* counters;          // [0] tickets issued (many-wave mode), monotonic across launches
+  unsigned int* counters;          // [0] tickets issued (many-wave mode), [1] tiles arrived (single-wave mode) -- monotonic across launches
   unsigned long long* out_count;   // receives the total number of survivors
   unsigned long long* host_count;  // optional second copy in page-locked host memory (saves the 8-byte D2H copy per launch)
   long long num_tiles;
   unsigned ticket_base;            // value of counters[0] when this launch starts
+  unsigned arrived_base;           // value of counters[1] when this launch starts
   unsigned epoch;                  // 20-bit launch epoch of the look-back words
   int single_wave;
   int stride;                      // u64 words between look-back words of consecutive tiles (32 = one 256-byte L2 chunk each)
@@ -73,27 +72,13 @@ struct CompactSmem {
   unsigned tile_total;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <int E, int I>
-__device__ __noinline__ void cp_scanner_cta(CompactSmem<E, I>& s, const CompactScratch& sc);
-
 // Fetches the next tile index for the CTA (or -1 when the work is exhausted); `iteration` counts the CTA's calls.
 // Many-wave mode: every CTA draws exactly one ticket past the end, so a launch consumes num_tiles + gridDim.x
 // tickets (the host advances its base by that).
 template <int E, int I>
 __device__ __forceinline__ long long cp_next_tile(CompactSmem<E, I>& s, const CompactScratch& sc, int iteration) {
   if (sc.single_wave) {
-    // one tile per CTA, all CTAs resident (cooperative launch): the block index is the tile; with `scanner` the
-    // CTA behind the last tile has no tile and runs the scan instead
-    if (iteration == 0 && sc.scanner && (long long)blockIdx.x == sc.num_tiles) cp_scanner_cta(s, sc);
+    // one tile per CTA, all CTAs resident (cooperative launch, grid == num_tiles): the block index is the tile
     return iteration == 0 && (long long)blockIdx.x < sc.num_tiles ? (long long)blockIdx.x : -1;
   }
   if (threadIdx.x == 0) s.tile = (long long)(atomicAdd(sc.counters, 1u) - sc.ticket_base);
@@ -115,88 +100,42 @@ __device__ __forceinline__ unsigned long long cp_block_sum(CompactSmem<E, I>& s,
 }
 
 // ---- single wave ------------------------------------------------------------------------------------------------
-// All CTAs are resident (cooperative launch), so a tile may simply wait for data of other tiles.  Every word that
-// crosses CTAs is self-validating: {20-bit launch epoch, value} in 64 bits, one relaxed store to publish and one
-// relaxed load to read -- no fence, no arrival counter, nothing to reset between launches.
-//   few tiles (<= CP_DIRECT_TILES): every tile reads the counts of all its predecessors itself (one hop);
-//   more tiles: that would be T^2 / 2 polls of a few L2 lines (186 K loads for the 611 tiles of a 10 M-row
-//   relation: measured 4-7 us between the last load and the prefix, profiles/r1_filter_ncu.md), so ONE extra CTA --
-//   the scanner -- collects the T counts (<= 8 per thread), scans them and publishes T prefix words; a tile then
-//   polls exactly one word with one thread.
-constexpr int CP_DIRECT_TILES = 48;
-constexpr int CP_SCAN_PER_THREAD = 8;  // scanner capacity: 256 x 8 = 2048 tiles >= any single wave
-
-template <int E, int I>
-__device__ __noinline__ void cp_scanner_cta(CompactSmem<E, I>& s, const CompactScratch& sc) {
-  const int tid = threadIdx.x;
-  const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
-  const long long T = sc.num_tiles;
-  const long long per = (T + CP_THREADS - 1) / CP_THREADS;  // contiguous tiles per thread
-  const long long first = tid * per;
-  unsigned long long v[CP_SCAN_PER_THREAD];
-  unsigned long long sum = 0;
-#pragma unroll
-  for (int k = 0; k < CP_SCAN_PER_THREAD; ++k) {
-    v[k] = 0;
-    const long long i = first + k;
-    if (k < per && i < T) {
-      unsigned long long w = ld_relaxed_u64(sc.counts + i);
-      while ((w >> 44) != (tag >> 44)) {
-        __nanosleep(40);
-        w = ld_relaxed_u64(sc.counts + i);
-      }
-      v[k] = w & EP_VALUE_MASK;
-    }
-    sum += v[k];
-  }
-  // block-wide exclusive scan of the per-thread sums (thread order == tile order)
-  const int lane = tid & 31, warp = tid >> 5;
-  const unsigned long long incl = warp_inclusive_sum(sum);
-  if (lane == 31) s.lb_sum[warp] = incl;
-  __syncthreads();
-  unsigned long long run = incl - sum, total = 0;
-#pragma unroll
-  for (int w = 0; w < CP_WARPS; ++w) {
-    const unsigned long long x = s.lb_sum[w];
-    if (w < warp) run += x;
-    total += x;
-  }
-#pragma unroll
-  for (int k = 0; k < CP_SCAN_PER_THREAD; ++k) {
-    const long long i = first + k;
-    if (k < per && i < T) st_relaxed_u64(sc.prefix + i, tag | EP_PREFIX | run);
-    run += v[k];
-  }
-  if (tid == 0) {
-    *sc.out_count = total;
-    if (sc.host_count) *reinterpret_cast<volatile unsigned long long*>(sc.host_count) = total;
-  }
+// All CTAs are resident (cooperative launch), so a tile may simply wait for the counts of its predecessors.
+//   publish   one relaxed store of a self-validating word {20-bit launch epoch, count} + one relaxed `red` on a
+//             monotonic arrival counter.  No fence: the arrival only says "now is a good time to read", the epoch
+//             tag in each word says whether that word is this launch's.
+//   wait      thread 0 polls the arrival counter -- one word, T pollers -- until every tile has arrived;
+//   read      the CTA reads its predecessors' words (thread i: tiles i, i + 256, ...: dense coalesced 2 KB reads of
+//             an L2-resident array) and re-polls the rare word whose store is not visible yet.
+// Measured alternatives on the 611 tiles of a 10 M-row relation (profiles/r1_filter_ncu.md): polling the count
+// words directly from the start (every thread spins on not-yet-valid words: +2 us), and a dedicated scanner CTA that
+// publishes per-tile prefix words (two more L2 hops: +2 us).  Nothing is reset between launches.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_relaxed_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <int E, int I>
 __device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned long long total) {
   const int tid = threadIdx.x;
   const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
-  if (tid == 0) st_relaxed_u64(sc.counts + tile, tag | EP_PREFIX | total);
-  if (sc.scanner) {
-    if (tid == 0) {
-      unsigned long long w = ld_relaxed_u64(sc.prefix + tile);
-      while ((w >> 44) != (tag >> 44)) {
-        if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
-        w = ld_relaxed_u64(sc.prefix + tile);
-      }
-      s.excl = w & EP_VALUE_MASK;
+  if (tid == 0) {
+    st_relaxed_u64(sc.counts + tile, tag | EP_PREFIX | total);
+    red_relaxed_add_u32(sc.counters + 1, 1u);
+    const unsigned target = sc.arrived_base + unsigned(sc.num_tiles);
+    while (int(ld_relaxed_u32(sc.counters + 1) - target) < 0) {
+      if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
     }
-    __syncthreads();
-    return;
   }
+  __syncthreads();
   unsigned long long part = 0;
   for (long long i = tid; i < tile; i += CP_THREADS) {
     unsigned long long w = ld_relaxed_u64(sc.counts + i);
-    while ((w >> 44) != (tag >> 44)) {
-      if (sc.poll_sleep_ns) __nanosleep(sc.poll_sleep_ns);
-      w = ld_relaxed_u64(sc.counts + i);
-    }
+    while ((w >> 44) != (tag >> 44)) w = ld_relaxed_u64(sc.counts + i);  // arrival seen before the count: rare
     part += w & EP_VALUE_MASK;
   }
   const unsigned long long excl = cp_block_sum(s, part);

@@ -157,37 +157,36 @@ CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, long long
     if (s.ep_state) FG_CUDA(cudaFree(s.ep_state));
     if (s.ep_counts) FG_CUDA(cudaFree(s.ep_counts));
     FG_CUDA(cudaMalloc(&s.ep_state, size_t(cap) * stride * sizeof(unsigned long long)));
-    FG_CUDA(cudaMalloc(&s.ep_counts, 2 * size_t(cap) * sizeof(unsigned long long)));  // counts | prefixes
+    FG_CUDA(cudaMalloc(&s.ep_counts, size_t(cap) * sizeof(unsigned long long)));
     FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(cap) * stride * sizeof(unsigned long long), ctx->stream));
-    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, 2 * size_t(cap) * sizeof(unsigned long long), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, size_t(cap) * sizeof(unsigned long long), ctx->stream));
     s.ep_capacity = cap;
   }
   s.epoch = (s.epoch + 1) & 0xfffffu;
   if (s.epoch == 0) {
     // 2^20 launches later a stale word could carry the current epoch again: wipe them once per wrap
     FG_CUDA(cudaMemsetAsync(s.ep_state, 0, size_t(s.ep_capacity) * stride * sizeof(unsigned long long), ctx->stream));
-    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, 2 * size_t(s.ep_capacity) * sizeof(unsigned long long), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(s.ep_counts, 0, size_t(s.ep_capacity) * sizeof(unsigned long long), ctx->stream));
     s.epoch = 1;
   }
   CompactScratch sc{};
   sc.tile_state = s.ep_state;
   sc.counts = s.ep_counts;
-  sc.prefix = s.ep_counts + s.ep_capacity;
   sc.counters = s.ep_counters;
   sc.out_count = out_count;
   sc.num_tiles = num_tiles;
   sc.ticket_base = s.tickets_issued;
+  sc.arrived_base = s.arrived;
   sc.epoch = s.epoch;
-  static const bool force_lookback = getenv("FLOCKGPU_FORCE_LOOKBACK") != nullptr;
-  static const bool no_scanner = getenv("FLOCKGPU_NO_SCANNER") != nullptr;
+  static const bool env_lookback = getenv("FLOCKGPU_FORCE_LOOKBACK") != nullptr;
+  const bool force_lookback = env_lookback || ctx->compact_mode == 1;
   if (resident_ctas < 1) resident_ctas = 1;
   sc.single_wave = (num_tiles <= resident_ctas && !force_lookback) ? 1 : 0;
-  sc.scanner = (sc.single_wave && num_tiles > CP_DIRECT_TILES && num_tiles + 1 <= resident_ctas &&
-                num_tiles <= (long long)CP_THREADS * CP_SCAN_PER_THREAD && !no_scanner) ? 1 : 0;
-  sc.grid = int(std::max<long long>(1, sc.single_wave ? num_tiles + sc.scanner : std::min<long long>(resident_ctas, num_tiles)));
+  sc.grid = int(std::max<long long>(1, std::min<long long>(resident_ctas, num_tiles)));
   sc.stride = stride;
   sc.poll_sleep_ns = scan_poll_sleep_ns();
-  if (!sc.single_wave) s.tickets_issued += unsigned(num_tiles) + unsigned(sc.grid);  // every CTA draws exactly one ticket past the end
+  if (sc.single_wave) s.arrived += unsigned(num_tiles);                      // one arrival per tile, no tickets
+  else s.tickets_issued += unsigned(num_tiles) + unsigned(sc.grid);          // every CTA draws exactly one ticket past the end
   return sc;
 }
 
@@ -1037,6 +1036,7 @@ int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value) {
     FG_CHECK(name, FLOCKGPU_ERR_INVALID, "set_option: null name");
     std::lock_guard<std::recursive_mutex> g(c->mu);
     if (!strcmp(name, "feed_zero_copy")) c->feed_zero_copy = value != 0;
+    else if (!strcmp(name, "compact_mode")) c->compact_mode = int(value);
     else fail(FLOCKGPU_ERR_INVALID, "set_option: unknown option \"%s\"", name);
   });
 }

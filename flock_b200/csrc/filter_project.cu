@@ -42,9 +42,12 @@ struct FilterArgs {
 // A functor evaluates this thread's FP_ITEMS rows of a tile and returns one bit per item.  E = rows a
 // thread loads contiguously (vector width); item k is row
 //   tile_base + ((k / E) * FP_THREADS + tid) * E + k % E.
-struct PredGeneric {
+// ROWS = rows per thread per tile: 16 for large inputs; 4 for small ones, where 4 Ki-row tiles would leave most SMs
+// idle and every thread would walk 16 rows' worth of dependent loads (NEXMark q3: 200 K persons = 49 tiles)
+template <int ROWS>
+struct PredGenericT {
   static constexpr int E = 1;
-  static constexpr int I = 16;
+  static constexpr int I = ROWS;
   static constexpr int MIN_CTAS = 1;
   Predicate p;
   __device__ __forceinline__ unsigned long long eval(const ColRef* cols, int64_t tile_base, int64_t n_rows, int tid, int* err) const {
@@ -688,11 +691,17 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   }
 
   // rows per thread per tile of the vectorised functors (FLOCKGPU_FILTER_ITEMS = 16 | 32 | 64 overrides, for tuning)
-  static const int items = [] {
+  // The smallest tile that still keeps the relation a single wave (<= ~700 tiles of 256 x items rows): small inputs
+  // spread over more SMs, 10 M-row relations use 64.
+  static const int items_env = [] {
     const char* e = getenv("FLOCKGPU_FILTER_ITEMS");
-    int v = e ? atoi(e) : 64;
-    return (v == 16 || v == 32 || v == 64) ? v : 64;
+    int v = e ? atoi(e) : 0;
+    return (v == 16 || v == 32 || v == 64) ? v : 0;
   }();
+  const int64_t single_wave_tiles = std::max<int64_t>(64, int64_t(ctx->sm_count) * 5 - 40);
+  const int items = items_env ? items_env
+                    : in.num_rows <= single_wave_tiles * FP_THREADS * 16 ? 16
+                    : in.num_rows <= single_wave_tiles * FP_THREADS * 32 ? 32 : 64;
   auto launch_i32 = [&](int64_t modulus) {
     const Column& pc = in.cols[cp.fast.col];
     const int32_t* col = static_cast<const int32_t*>(pc.values());
@@ -718,8 +727,8 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
       launch_i32(0);
       break;
     default: {
-      PredGeneric p{cp.prog};
-      launch_filter(ctx, p, fa);
+      if (in.num_rows >= int64_t(ctx->sm_count) * 4 * FP_THREADS * 16) launch_filter(ctx, PredGenericT<16>{cp.prog}, fa);
+      else launch_filter(ctx, PredGenericT<4>{cp.prog}, fa);
     }
   }
 

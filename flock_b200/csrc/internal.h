@@ -72,10 +72,10 @@ struct Comm;  // comm.cc
 // monotonic counter whose base the host tracks, status words carry the launch epoch.
 struct ScanScratch {
   unsigned long long* ep_state = nullptr;    // [ep_capacity * stride] {epoch:20, flag:2, value:42}
-  unsigned long long* ep_counts = nullptr;   // [2 * ep_capacity] dense epoch-tagged per-tile counts, then prefixes (single-wave mode)
-  unsigned* ep_counters = nullptr;           // [0] tickets issued
+  unsigned long long* ep_counts = nullptr;   // [ep_capacity] dense epoch-tagged per-tile counts (single-wave mode)
+  unsigned* ep_counters = nullptr;           // [0] tickets issued, [1] tiles arrived
   int64_t ep_capacity = 0;
-  unsigned tickets_issued = 0, epoch = 0;
+  unsigned tickets_issued = 0, arrived = 0, epoch = 0;
 };
 
 struct CtxCore {
@@ -123,6 +123,10 @@ struct CtxCore {
 
   // feed_data_sources keeps page-locked, uniformly batched fixed-width columns in host memory (flockgpu_set_option)
   bool feed_zero_copy = false;
+  // grid-wide prefix protocol of the compaction kernels: 0 = automatic (single wave when every tile is resident,
+  // decoupled look-back otherwise), 1 = always decoupled look-back (flockgpu_set_option "compact_mode"; the parity
+  // tests run both)
+  int compact_mode = 0;
 
   // recycled CUDA events (creating one costs about a microsecond; a q2 step is one ~10 us kernel)
   std::vector<cudaEvent_t> sync_events;    // cudaEventDisableTiming

@@ -99,7 +99,9 @@ int64_t flockgpu_kernel_launches(flockgpu_ctx* ctx);
  * last has the same power-of-two row count >= 4096) in HOST memory; the vectorised filter then reads them in place
  * over PCIe and other operators copy them to HBM on first use.  With the option on, fed batches must stay alive and
  * unmodified until flock_context_clean_data_sources -- exactly what the reference does anyway: MemoryExec owns the fed
- * RecordBatches until clean_data_sources (flock/src/runtime/context.rs:227-254).                                    */
+ * RecordBatches until clean_data_sources (flock/src/runtime/context.rs:227-254).
+ * "compact_mode" (0 automatic | 1 always decoupled look-back): which grid-wide prefix protocol the compaction /
+ * scan kernels use; results are identical, the parity tests run both.                                                */
 int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing: between _begin and _end every kernel this library launches on the ctx is
  * bracketed by its own pair of CUDA events on the ctx stream.  _end waits for the stream and writes a JSON

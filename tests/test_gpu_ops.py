@@ -264,3 +264,36 @@ def test_hash_partition(gpu_ctx, keys, n_parts):
             for key in zip(*[p.column(k).to_pylist() for k in keys]):
                 assert seen.setdefault(key, q) == q
         oracle.assert_tables_equal(pa.Table.from_batches(parts), pa.Table.from_batches([b]))
+
+
+# ---- the three grid-wide prefix protocols of compact.cuh give identical results ------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+def test_prefix_protocols_agree(gpu_ctx, mode):
+    """compact_mode 0 = automatic (single wave: arrival counter + self-validating count words; decoupled look-back
+    beyond one wave), 1 = decoupled look-back always."""
+    gpu_ctx.set_option("compact_mode", mode)
+    try:
+        for n in (5_000, 250_000, 1_500_000):
+            rng = np.random.default_rng(n)
+            b = rb(k=pa.array(rng.integers(0, 1 << 20, n).astype(np.int32)), v=pa.array(rng.integers(0, 1000, n)),
+                   s=pa.array([("w%d" % (x % 97)) * (x % 3) for x in rng.integers(0, 1 << 30, n)]))
+            t = gpu_ctx.import_batches([b])
+            # filter: vectorised functor (col 0) and generic interpreter with a Utf8 pass-through (selection vector + gather)
+            for pred in (col(0).cast("int64") % 7 == 0, (col(1) < 300) | (col(2) == "w5")):
+                got = gpu_ctx.filter_project(t, pred).to_batch()
+                assert got.equals(oracle_filter(b, pred))
+            # aggregate emit (hashed table) and join count scan
+            got = gpu_ctx.hash_aggregate(t, [0], [("count", -1, "n"), ("sum", 1, "s")], "single").to_arrow()
+            want = pa.Table.from_batches([oracle_agg(b, "Single", [0], [("count", -1, "n"), ("sum", 1, "s")])])
+            oracle.assert_tables_equal(got, want)
+            if n <= 250_000:
+                r = b.slice(0, n // 3)
+                got = gpu_ctx.hash_join(gpu_ctx.import_batches([r]), t, [0], [0]).to_arrow()
+                want = pa.Table.from_batches([oracle.hash_join(r, b, [0], [0])])
+                oracle.assert_tables_equal(got, want, check_names=False)
+            parts = gpu_ctx.hash_partition(t, [0], 3)
+            pid = sharding.partition_ids(b, [0], 3)
+            for q, p in enumerate(parts):
+                assert p.to_batch().equals(b.filter(pa.array(pid == q)))
+    finally:
+        gpu_ctx.set_option("compact_mode", 0)

@@ -37,6 +37,12 @@ EVENTS = {"q1": None, "q2": None, "q3": 10_000_000, "q5": None, "q8": 1_000_000_
 BIDS = {"q1": 65536, "q2": 10_000_000, "q5": 100_000_000}
 
 
+# Libraries write to fd 1 behind Python's back (NCCL prints "NCCL version ..." there): keep the real stdout for the
+# JSON line(s) only and point fd 1 at stderr for everything else.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -197,7 +203,7 @@ def main():
                 oracle.assert_tables_equal(res_tbl, want)
                 line["parity"] = "bit-exact vs oracle (sorted)"
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            print(json.dumps(line), file=_JSON_OUT, flush=True)
         ec.close()
         del resident, rel, out
 
