@@ -680,6 +680,7 @@ struct AggTable {
   // (q5: 6.5 M auctions x 9 B = 58 MB), where random 64-bit atomics run at 150-190 Gop/s instead of 25 (profiles/).
   unsigned char* present;    // [cap + 1] dense only
   unsigned long long dense_base;
+  unsigned long long stride; // slots between accumulator columns: cap + 1 rounded up to 4 (the emit kernel reads 4 slots per load)
 };
 
 __global__ void agg_init_kernel(AggTable t, int n_acc, unsigned long long ident0, unsigned long long ident1, unsigned long long ident2,
@@ -689,7 +690,7 @@ __global__ void agg_init_kernel(AggTable t, int n_acc, unsigned long long ident0
   const unsigned long long n = t.cap + 1;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
     if (t.keys) t.keys[i] = EMPTY_KEY;
-    for (int c = 0; c < n_acc; ++c) t.acc[c * n + i] = ident[c];
+    for (int c = 0; c < n_acc; ++c) t.acc[c * t.stride + i] = ident[c];
   }
 }
 
@@ -729,7 +730,7 @@ __device__ __forceinline__ unsigned long long table_find_or_insert(const AggTabl
 }
 
 __global__ void __launch_bounds__(256) agg_insert_kernel(const __grid_constant__ AggInsertArgs a) {
-  const unsigned long long stride_n = a.table.cap + 1;
+  const unsigned long long stride_n = a.table.stride;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < a.n; i += int64_t(gridDim.x) * blockDim.x) {
     const unsigned long long key = a.from_partials ? a.part_keys[i] : pack_key(a.keys, a.cols, i);
     const unsigned long long slot = table_find_or_insert(a.table, key);
@@ -794,11 +795,12 @@ __global__ void __launch_bounds__(256) agg_insert_rows_kernel(const __grid_const
 struct AggEmitArgs {
   CompactScratch sc;
   unsigned long long n_slots;       // slots to scan (cap + 1 packed, cap rows mode)
+  unsigned long long acc_stride;    // slots between accumulator columns (multiple of 4, >= n_slots)
   const unsigned long long* keys;   // packed hashed mode (NULL otherwise)
   const unsigned char* present;     // packed dense mode: key = dense_base + slot
   unsigned long long dense_base;
   const unsigned* owner;            // rows mode
-  const unsigned long long* acc;    // [n_acc][n_slots]
+  const unsigned long long* acc;    // [n_acc][acc_stride]
   int32_t n_emit;
   int32_t n_key_out;                // packed mode: 1 or 2 key columns
   int32_t key_width[2];
@@ -822,84 +824,106 @@ __device__ __forceinline__ void emit_values(const EmitDesc* emit, int n_emit, co
   }
 }
 
+// MODE 0: hashed packed keys, 1: dense (direct-address) table, 2: row-representative table.
+// A thread owns four groups of FOUR CONTIGUOUS slots: the occupancy test is one vector load per group (32 B of keys,
+// 4 present bytes or 16 B of owners), the ranking is the packed SWAR scan of compact.cuh, and a group's accumulators
+// are read with two 16-byte loads per column whatever its occupancy.  (The first version tested and emitted slot by
+// slot: 138 lane-instructions per slot and one dependent accumulator load per survivor, profiles/r1_q5_ncu.md.)
+template <int MODE>
 __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_constant__ AggEmitArgs a) {
-  constexpr int E = 1;
+  constexpr int E = 4;
   constexpr int CP_ITEMS = 16;
+  constexpr int G = CP_ITEMS / E;
   constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
   __shared__ CompactSmem<E, CP_ITEMS> sm;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
   long long tile;
   for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
     const unsigned long long tile_base = (unsigned long long)tile * CP_TILE;
     unsigned long long bits = 0;
 #pragma unroll
-    for (int k = 0; k < CP_ITEMS; ++k) {
-      unsigned long long slot = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
-      bool occ = false;
-      if (slot < a.n_slots) occ = a.keys ? a.keys[slot] != EMPTY_KEY : a.present ? a.present[slot] != 0 : a.owner[slot] != EMPTY_OWNER;
-      bits |= (unsigned long long)occ << k;
+    for (int g = 0; g < G; ++g) {
+      const unsigned long long slot0 = tile_base + ((unsigned long long)g * CP_THREADS + tid) * E;
+      unsigned nib = 0;
+      if (slot0 < a.n_slots) {
+        if (MODE == 0) {
+          const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(a.keys + slot0);
+          const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(a.keys + slot0 + 2);
+          nib = unsigned(k01.x != EMPTY_KEY) | (unsigned(k01.y != EMPTY_KEY) << 1) | (unsigned(k23.x != EMPTY_KEY) << 2) | (unsigned(k23.y != EMPTY_KEY) << 3);
+        } else if (MODE == 1) {
+          const unsigned p4 = *reinterpret_cast<const unsigned*>(a.present + slot0);
+          nib = unsigned((p4 & 0xffu) != 0) | (unsigned((p4 & 0xff00u) != 0) << 1) | (unsigned((p4 & 0xff0000u) != 0) << 2) | (unsigned((p4 >> 24) != 0) << 3);
+        } else {
+          const uint4 o = *reinterpret_cast<const uint4*>(a.owner + slot0);
+          nib = unsigned(o.x != EMPTY_OWNER) | (unsigned(o.y != EMPTY_OWNER) << 1) | (unsigned(o.z != EMPTY_OWNER) << 2) | (unsigned(o.w != EMPTY_OWNER) << 3);
+        }
+        const unsigned long long left = a.n_slots - slot0;  // the padding slots behind the table are not part of it
+        if (left < 4) nib &= (1u << left) - 1u;
+      }
+      bits |= (unsigned long long)nib << (g * E);
     }
-    unsigned lane_prefix[CP_ITEMS / E];
+    unsigned lane_prefix[G];
     cp_rank_tile<E, CP_ITEMS>(sm, a.sc, tile, bits, lane_prefix);
     if (bits && sm.tile_total) {
-      // four survivors per round: their accumulator loads (dependent ~1 us reads when the table left L2) are in
-      // flight together instead of one after the other
-      unsigned long long m = bits;
-      while (m) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const unsigned nib = unsigned(bits >> (g * E)) & 0xfu;
+        if (!nib) continue;
+        const unsigned long long slot0 = tile_base + ((unsigned long long)g * CP_THREADS + tid) * E;
+        const int64_t pos0 = int64_t(sm.excl) + sm.group_warp[g][warp] + lane_prefix[g];
+        // output position of element e of the group: pos0 + number of survivors below it
         int64_t pos[4];
-        unsigned long long slot[4];
-        int nb = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          pos[q] = 0;
-          slot[q] = 0;
-          if (m) {
-            const int k = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            pos[q] = cp_position<E, CP_ITEMS>(sm, bits, k, lane_prefix);
-            slot[q] = tile_base + (unsigned long long)cp_item_index<E>(k, tid);
-            nb = q + 1;
-          }
-        }
-        if (a.keys || a.present) {
+        for (int e = 0; e < 4; ++e) pos[e] = pos0 + __popc(nib & ((1u << e) - 1u));
+        if (MODE == 2) {
+          const uint4 o = *reinterpret_cast<const uint4*>(a.owner + slot0);
+          const unsigned r[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if ((nib >> e) & 1u) a.rep_rows[pos[e]] = r[e];
+        } else {
           unsigned long long key[4];
+          if (MODE == 0) {
+            const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(a.keys + slot0);
+            const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(a.keys + slot0 + 2);
+            key[0] = k01.x; key[1] = k01.y; key[2] = k23.x; key[3] = k23.y;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            key[q] = a.present ? a.dense_base + slot[q] : (slot[q] == a.n_slots - 1 || q >= nb ? EMPTY_KEY : a.keys[slot[q]]);
+            for (int e = 0; e < 4; ++e)
+              if (slot0 + e == a.n_slots - 1) key[e] = EMPTY_KEY;  // the reserved slot of the key that equals EMPTY_KEY
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q >= nb) continue;
+            for (int e = 0; e < 4; ++e) key[e] = a.dense_base + slot0 + e;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!((nib >> e) & 1u)) continue;
             if (a.n_key_out == 2) {
-              static_cast<uint32_t*>(a.key_dst[0])[pos[q]] = uint32_t(key[q] >> 32);
-              static_cast<uint32_t*>(a.key_dst[1])[pos[q]] = uint32_t(key[q]);
+              static_cast<uint32_t*>(a.key_dst[0])[pos[e]] = uint32_t(key[e] >> 32);
+              static_cast<uint32_t*>(a.key_dst[1])[pos[e]] = uint32_t(key[e]);
             } else if (a.key_width[0] == 4) {
-              static_cast<uint32_t*>(a.key_dst[0])[pos[q]] = uint32_t(key[q]);
+              static_cast<uint32_t*>(a.key_dst[0])[pos[e]] = uint32_t(key[e]);
             } else {
-              static_cast<unsigned long long*>(a.key_dst[0])[pos[q]] = key[q];
+              static_cast<unsigned long long*>(a.key_dst[0])[pos[e]] = key[e];
             }
           }
-        } else {
-          unsigned r[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) r[q] = q < nb ? a.owner[slot[q]] : 0u;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q < nb) a.rep_rows[pos[q]] = r[q];
         }
-        for (int e = 0; e < a.n_emit; ++e) {
-          const EmitDesc& d = a.emit[e];
-          Val v[4], s2[4];
+        for (int c = 0; c < a.n_emit; ++c) {
+          const EmitDesc& d = a.emit[c];
+          const unsigned long long* p0 = a.acc + d.a0 * a.acc_stride + slot0;
+          const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(p0), v23 = *reinterpret_cast<const ulonglong2*>(p0 + 2);
+          Val v[4];
+          v[0].u = v01.x; v[1].u = v01.y; v[2].u = v23.x; v[3].u = v23.y;
+          if (d.kind == EMIT_AVG) {
+            const unsigned long long* p1 = a.acc + d.a1 * a.acc_stride + slot0;
+            const ulonglong2 s01 = *reinterpret_cast<const ulonglong2*>(p1), s23 = *reinterpret_cast<const ulonglong2*>(p1 + 2);
+            Val sv[4];
+            sv[0].u = s01.x; sv[1].u = s01.y; sv[2].u = s23.x; sv[3].u = s23.y;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            v[q].u = q < nb ? a.acc[d.a0 * a.n_slots + slot[q]] : 0ull;
-            s2[q].u = (q < nb && d.kind == EMIT_AVG) ? a.acc[d.a1 * a.n_slots + slot[q]] : 0ull;
+            for (int e = 0; e < 4; ++e) v[e].d = __ddiv_rn(sv[e].d, __ull2double_rn(v[e].u));
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q >= nb) continue;
-            if (d.kind == EMIT_AVG) v[q].d = __ddiv_rn(s2[q].d, __ull2double_rn(v[q].u));
-            store_val(d.dst, d.out_dtype, pos[q], v[q]);
-          }
+          for (int e = 0; e < 4; ++e)
+            if ((nib >> e) & 1u) store_val(d.dst, d.out_dtype, pos[e], v[e]);
         }
       }
     }
@@ -1196,7 +1220,8 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
 
   AggEmitArgs ea{};
   BufferPtr tkeys, tacc, towner, rep_rows, keep_alive;
-  unsigned long long n_slots = 0;
+  unsigned long long n_slots = 0, acc_stride = 0;
+  int emit_mode = 0;  // 0 hashed packed keys, 1 dense, 2 row representatives
 
   if (packed) {
     KeyPack kp{};
@@ -1316,16 +1341,17 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     }
     const unsigned long long cap = dense ? key_max - key_min + 1 : pow2_at_least(2ull * (unsigned long long)n_entries);
     n_slots = cap + 1;
+    acc_stride = (n_slots + 3) & ~3ull;  // the emit kernel reads whole groups of four slots
     BufferPtr tpresent;
     if (dense) {
-      tpresent = alloc(ctx, size_t(n_slots));
-      FG_CUDA(cudaMemsetAsync(tpresent->ptr, 0, size_t(n_slots), ctx->stream));
+      tpresent = alloc(ctx, size_t(acc_stride));
+      FG_CUDA(cudaMemsetAsync(tpresent->ptr, 0, size_t(acc_stride), ctx->stream));
     } else {
-      tkeys = alloc(ctx, size_t(n_slots) * 8);
+      tkeys = alloc(ctx, size_t(acc_stride) * 8);
     }
-    tacc = alloc(ctx, size_t(n_slots) * 8 * std::max(n_acc, 1));
+    tacc = alloc(ctx, size_t(acc_stride) * 8 * std::max(n_acc, 1));
     AggTable tab{dense ? nullptr : tkeys->as<unsigned long long>(), tacc->as<unsigned long long>(), cap,
-                 dense ? tpresent->as<unsigned char>() : nullptr, key_min};
+                 dense ? tpresent->as<unsigned char>() : nullptr, key_min, acc_stride};
     {
       LaunchTimer lt(ctx, "agg_init_kernel");
       agg_init_kernel<<<grid_for(ctx, int64_t(n_slots), 256, 8), 256, 0, ctx->stream>>>(tab, n_acc, ident[0], ident[1], ident[2], ident[3], ident[4],
@@ -1352,6 +1378,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
     }
+    emit_mode = dense ? 1 : 0;
     ea.keys = tab.keys;
     ea.present = tab.present;
     ea.dense_base = tab.dense_base;
@@ -1362,8 +1389,10 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     ea.key_width[1] = kp.width[1];
   } else {
     FG_CHECK(group_cols.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: more than %d group columns", MAX_KEY_COLS);
-    const unsigned long long cap = pow2_at_least(2ull * (unsigned long long)n);
+    const unsigned long long cap = std::max<unsigned long long>(4, pow2_at_least(2ull * (unsigned long long)n));
     n_slots = cap;
+    acc_stride = cap;
+    emit_mode = 2;
     towner = alloc(ctx, size_t(cap) * 4);
     tacc = alloc(ctx, size_t(cap) * 8 * std::max(n_acc, 1));
     {
@@ -1410,15 +1439,19 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   for (const OutPlan& p : outs) val_cols.push_back(make_out_col(p, max_groups));
   fill_emit(ea.emit, &ea.n_emit, val_cols);
   ea.n_slots = n_slots;
+  ea.acc_stride = acc_stride;
   {
     const long long tiles = (long long)((n_slots + CP_THREADS * 16 - 1) / (CP_THREADS * 16));
-    int per_sm = 1;
-    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_emit_kernel, CP_THREADS, 0));
-    ea.sc = prepare_compact(ctx, tiles, (long long)ctx->sm_count * std::max(per_sm, 1), ctx->d_scalars + 3);
-    {
+    auto launch = [&](auto kernel) {
+      int per_sm = 1;
+      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CP_THREADS, 0));
+      ea.sc = prepare_compact(ctx, tiles, (long long)ctx->sm_count * std::max(per_sm, 1), ctx->d_scalars + 3);
       LaunchTimer lt(ctx, "agg_emit_kernel");
-      launch_compact(ctx, agg_emit_kernel, ea.sc, ea);
-    }
+      launch_compact(ctx, kernel, ea.sc, ea);
+    };
+    if (emit_mode == 0) launch(agg_emit_kernel<0>);
+    else if (emit_mode == 1) launch(agg_emit_kernel<1>);
+    else launch(agg_emit_kernel<2>);
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
   }
