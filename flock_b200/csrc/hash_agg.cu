@@ -894,17 +894,21 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) key[e] = a.dense_base + slot0 + e;
           }
+          if (a.n_key_out == 2) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (!((nib >> e) & 1u)) continue;
-            if (a.n_key_out == 2) {
-              static_cast<uint32_t*>(a.key_dst[0])[pos[e]] = uint32_t(key[e] >> 32);
-              static_cast<uint32_t*>(a.key_dst[1])[pos[e]] = uint32_t(key[e]);
-            } else if (a.key_width[0] == 4) {
-              static_cast<uint32_t*>(a.key_dst[0])[pos[e]] = uint32_t(key[e]);
-            } else {
-              static_cast<unsigned long long*>(a.key_dst[0])[pos[e]] = key[e];
-            }
+            for (int e = 0; e < 4; ++e)
+              if ((nib >> e) & 1u) {
+                static_cast<uint32_t*>(a.key_dst[0])[pos[e]] = uint32_t(key[e] >> 32);
+                static_cast<uint32_t*>(a.key_dst[1])[pos[e]] = uint32_t(key[e]);
+              }
+          } else if (a.key_width[0] == 4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if ((nib >> e) & 1u) static_cast<uint32_t*>(a.key_dst[0])[pos[e]] = uint32_t(key[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if ((nib >> e) & 1u) static_cast<unsigned long long*>(a.key_dst[0])[pos[e]] = key[e];
           }
         }
         for (int c = 0; c < a.n_emit; ++c) {
@@ -921,9 +925,16 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e].d = __ddiv_rn(sv[e].d, __ull2double_rn(v[e].u));
           }
+          // one uniform width branch per column instead of a type switch per element
+          if (d.out_dtype == FLOCKGPU_INT32 || d.out_dtype == FLOCKGPU_UINT32) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if ((nib >> e) & 1u) store_val(d.dst, d.out_dtype, pos[e], v[e]);
+            for (int e = 0; e < 4; ++e)
+              if ((nib >> e) & 1u) static_cast<uint32_t*>(d.dst)[pos[e]] = uint32_t(v[e].u);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if ((nib >> e) & 1u) static_cast<unsigned long long*>(d.dst)[pos[e]] = v[e].u;
+          }
         }
       }
     }

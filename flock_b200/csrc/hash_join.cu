@@ -32,6 +32,7 @@ struct JoinSide {
   int64_t n_rows;
   int32_t packed;
   int32_t pad;
+  const void* key0;  // the key column when the join has ONE fixed-width key (kernels instantiated with KW = 4 / 8)
   KeyPack pack;
   RowKeys rk;
   ColRef cols[MAX_IN_COLS];
@@ -45,7 +46,19 @@ struct JoinTable {
   unsigned long long cap;  // power of two
 };
 
+// KW = 4 / 8: one fixed-width key column, read straight from JoinSide::key0 (every NEXMark join); KW = 0: the general
+// form (two packed columns, or row comparison for Utf8 / wide keys).  The general form cost ~140 lane-instructions per
+// probe row on q5 (dynamic indexing of the column table in parameter space, width and mode branches).
+template <int KW>
 __device__ __forceinline__ unsigned long long side_hash(const JoinSide& s, int64_t row, unsigned long long* key) {
+  if (KW == 4) {
+    *key = static_cast<const uint32_t*>(s.key0)[row];
+    return fmix64(*key);
+  }
+  if (KW == 8) {
+    *key = static_cast<const unsigned long long*>(s.key0)[row];
+    return fmix64(*key);
+  }
   if (s.packed) {
     *key = pack_key(s.pack, s.cols, row);
     return fmix64(*key);
@@ -55,21 +68,25 @@ __device__ __forceinline__ unsigned long long side_hash(const JoinSide& s, int64
 }
 
 // Does build row `r` carry the key (`key` / row `row` of side `other`)?
+template <int KW>
 __device__ __forceinline__ bool build_row_matches(const JoinSide& build, unsigned r, const JoinSide& other, int64_t row, unsigned long long key) {
+  if (KW == 4) return static_cast<const uint32_t*>(build.key0)[r] == uint32_t(key);
+  if (KW == 8) return static_cast<const unsigned long long*>(build.key0)[r] == key;
   return build.packed ? pack_key(build.pack, build.cols, int64_t(r)) == key : rows_equal(build.rk, build.cols, int64_t(r), other.rk, other.cols, row);
 }
 
+template <int KW>
 __global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__ JoinSide build, const JoinTable t) {
   for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < build.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
     unsigned long long key;
-    unsigned long long slot = side_hash(build, row, &key) & (t.cap - 1);
+    unsigned long long slot = side_hash<KW>(build, row, &key) & (t.cap - 1);
     while (true) {
       unsigned r = t.rep[slot];
       if (r == JOIN_EMPTY) {
         r = atomicCAS(&t.rep[slot], JOIN_EMPTY, unsigned(row));
         if (r == JOIN_EMPTY) break;  // claimed: this row represents the key
       }
-      if (build_row_matches(build, r, build, row, key)) break;
+      if (build_row_matches<KW>(build, r, build, row, key)) break;
       slot = (slot + 1) & (t.cap - 1);
     }
     t.next[row] = atomicExch(&t.head[slot], unsigned(row));
@@ -78,13 +95,14 @@ __global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__
 }
 
 // Slot of the key of probe row `row`, or ~0 when no build row has it.
+template <int KW>
 __device__ __forceinline__ unsigned long long find_slot(const JoinSide& build, const JoinSide& probe, const JoinTable& t, int64_t row) {
   unsigned long long key;
-  unsigned long long slot = side_hash(probe, row, &key) & (t.cap - 1);
+  unsigned long long slot = side_hash<KW>(probe, row, &key) & (t.cap - 1);
   while (true) {
     const unsigned r = t.rep[slot];
     if (r == JOIN_EMPTY) return ~0ull;
-    if (build_row_matches(build, r, probe, row, key)) return slot;
+    if (build_row_matches<KW>(build, r, probe, row, key)) return slot;
     slot = (slot + 1) & (t.cap - 1);
   }
 }
@@ -100,6 +118,7 @@ struct JoinCountArgs {
   CompactScratch sc;  // grid-wide exclusive prefix of the tiles' pair counts (compact.cuh); sc.out_count = total pairs
 };
 
+template <int KW>
 __global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __grid_constant__ JoinCountArgs a) {
   __shared__ CompactSmem<1, 16> sm;
   __shared__ unsigned long long s_warp[JC_THREADS / 32];
@@ -114,7 +133,7 @@ __global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __gri
     for (int k = 0; k < JC_ITEMS; ++k) {
       unsigned c = 0;
       if (i0 + k < n) {
-        const unsigned long long slot = find_slot(a.build, a.probe, a.table, i0 + k);
+        const unsigned long long slot = find_slot<KW>(a.build, a.probe, a.table, i0 + k);
         if (slot != ~0ull) c = a.table.cnt[slot];
       }
       cnt[k] = c;
@@ -153,11 +172,12 @@ struct JoinEmitArgs {
   unsigned* probe_idx;
 };
 
+template <int KW>
 __global__ void __launch_bounds__(256) join_emit_kernel(const __grid_constant__ JoinEmitArgs a) {
   for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.probe.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
     unsigned pos = a.off[row];
     if (a.off[row + 1] == pos) continue;
-    const unsigned long long slot = find_slot(a.build, a.probe, a.table, row);
+    const unsigned long long slot = find_slot<KW>(a.build, a.probe, a.table, row);
     for (unsigned r = a.table.head[slot]; r != JOIN_EMPTY; r = a.table.next[r]) {
       a.build_idx[pos] = r;
       a.probe_idx[pos] = unsigned(row);
@@ -231,6 +251,17 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     JoinSide bs{}, ps{};
     fill_side(B, swap_sides ? right_keys : left_keys, packed, &bs);
     fill_side(P, swap_sides ? left_keys : right_keys, packed, &ps);
+    // kernel flavour: one fixed-width key column (4 / 8 bytes) or the general form
+    const int kw = (packed && widths.size() == 1) ? widths[0] : 0;
+    if (kw) {
+      bs.key0 = B.cols[(swap_sides ? right_keys : left_keys)[0]].values();
+      ps.key0 = P.cols[(swap_sides ? left_keys : right_keys)[0]].values();
+    }
+    auto by_width = [&](auto&& f) {
+      if (kw == 4) f(std::integral_constant<int, 4>{});
+      else if (kw == 8) f(std::integral_constant<int, 8>{});
+      else f(std::integral_constant<int, 0>{});
+    };
     unsigned long long cap = 1024;
     while (cap < 2ull * (unsigned long long)B.num_rows) cap <<= 1;
     // rep | head | cnt in one allocation (cap words each), then next[build rows]
@@ -241,7 +272,7 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     JoinTable tab{w, w + cap, w + 2 * cap, w + 3 * cap, cap};
     {
       LaunchTimer lt(ctx, "join_build_kernel");
-      join_build_kernel<<<grid_for(ctx, B.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab);
+      by_width([&](auto w) { join_build_kernel<decltype(w)::value><<<grid_for(ctx, B.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab); });
     }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
@@ -253,17 +284,16 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     ca.table = tab;
     ca.out_off = off->as<unsigned>();
     const int64_t num_tiles = (P.num_rows + JC_TILE - 1) / JC_TILE;
-    {
+    by_width([&](auto w) {
+      auto kernel = join_count_scan_kernel<decltype(w)::value>;
       int per_sm = 1;
-      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, join_count_scan_kernel, JC_THREADS, 0));
+      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, JC_THREADS, 0));
       ca.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + 4);
-      {
-        LaunchTimer lt(ctx, "join_count_scan_kernel");
-        launch_compact(ctx, join_count_scan_kernel, ca.sc, ca);
-      }
-      FG_CUDA(cudaGetLastError());
-      count_launch(ctx);
-    }
+      LaunchTimer lt(ctx, "join_count_scan_kernel");
+      launch_compact(ctx, kernel, ca.sc, ca);
+    });
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
     unsigned long long total = 0;
     read_scalars(ctx, 4, 1, &total);
     FG_CHECK(total < (1ull << 32) - 1, FLOCKGPU_ERR_UNSUPPORTED, "hash_join: %llu output rows exceed 2^32-2", total);
@@ -280,7 +310,7 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       ea.probe_idx = probe_idx->as<unsigned>();
       {
         LaunchTimer lt(ctx, "join_emit_kernel");
-        join_emit_kernel<<<grid_for(ctx, P.num_rows, 256, 8), 256, 0, ctx->stream>>>(ea);
+        by_width([&](auto w) { join_emit_kernel<decltype(w)::value><<<grid_for(ctx, P.num_rows, 256, 8), 256, 0, ctx->stream>>>(ea); });
       }
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);

@@ -189,7 +189,45 @@ def q8(n: int = TARGET_PARTITIONS) -> dict:
     return projection_exec([(column("p_id", 0), "p_id"), (column("name", 1), "name")], coalesce_batches_exec(join))
 
 
-QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q5": q5, "q8": q8}
+def q4(n: int = TARGET_PARTITIONS) -> dict:
+    """benchmarks/src/nexmark/query/q4.sql, types q4_plan.fmt:
+       SELECT category, AVG(final) FROM (SELECT MAX(price) AS final, category FROM auction JOIN bid ON a_id = auction
+       WHERE b_date_time BETWEEN a_date_time AND expires GROUP BY a_id, category) GROUP BY category.
+    Physical shape as DataFusion 6 builds it: Hash-repartitioned Partitioned join, Filter (BETWEEN = two comparisons),
+    two two-phase aggregates."""
+    a_scan = repartition_rr(memory_exec(AUCTION, [0, 5, 6, 8]), n)     # a_id, a_date_time, expires, category
+    b_scan = repartition_rr(memory_exec(BID, [0, 2, 3]), n)            # auction, price, b_date_time
+    lsh = coalesce_batches_exec(repartition_hash(a_scan, [column("a_id", 0)], n))
+    rsh = coalesce_batches_exec(repartition_hash(b_scan, [column("auction", 0)], n))
+    join = coalesce_batches_exec(hash_join_exec(lsh, rsh, [(column("a_id", 0), column("auction", 0))]))
+    # a_id 0, a_date_time 1, expires 2, category 3, auction 4, price 5, b_date_time 6
+    between = binary(binary(column("b_date_time", 6), "GtEq", column("a_date_time", 1)), "And",
+                     binary(column("b_date_time", 6), "LtEq", column("expires", 2)))
+    filt = coalesce_batches_exec(filter_exec(between, join))
+    mx = aggregate_expr("max", "MAX(bid.price)", column("price", 5), "Int32")
+    inner = two_phase_aggregate([("a_id", 0), ("category", 3)], [mx], filt, n)           # a_id, category, MAX(bid.price)
+    q = projection_exec([(column("MAX(bid.price)", 2), "final"), (column("category", 1), "category")], inner)
+    avg = aggregate_expr("avg", "AVG(Q.final)", column("final", 0), "Float64")
+    outer = two_phase_aggregate([("category", 1)], [avg], q, n)
+    return projection_exec([(column("category", 0), "category"), (column("AVG(Q.final)", 1), "AVG(Q.final)")], outer)
+
+
+def q7(n: int = TARGET_PARTITIONS) -> dict:
+    """benchmarks/src/nexmark/query/q7.sql, types q7_plan.fmt:
+       SELECT auction, price, bidder, b_date_time FROM bid JOIN (SELECT MAX(price) AS maxprice FROM bid) ON price = maxprice."""
+    bid = repartition_rr(memory_exec(BID, [0, 1, 2, 3]), n)
+    mx = aggregate_expr("max", "MAX(bid.price)", column("price", 2), "Int32")
+    b1 = projection_exec([(column("MAX(bid.price)", 0), "maxprice")],
+                         two_phase_aggregate([], [mx], repartition_rr(memory_exec(BID, [0, 1, 2, 3]), n), n))
+    lsh = coalesce_batches_exec(repartition_hash(bid, [column("price", 2)], n))
+    rsh = coalesce_batches_exec(repartition_hash(b1, [column("maxprice", 0)], n))
+    join = hash_join_exec(lsh, rsh, [(column("price", 2), column("maxprice", 0))])
+    return projection_exec([(column("auction", 0), "auction"), (column("price", 2), "price"), (column("bidder", 1), "bidder"),
+                            (column("b_date_time", 3), "b_date_time")], coalesce_batches_exec(join))
+
+
+QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q4": q4, "q5": q5, "q7": q7, "q8": q8}
 # relations each query feeds, in feed order (flock/src/datasource/nexmark/nexmark.rs:181-203); q5 scans bid
 # twice, and feed_data_sources hands one source to one leaf (context.rs:293-303), so bid is fed twice.
-SOURCES = {"q1": ["bid"], "q2": ["bid"], "q3": ["auction", "person"], "q5": ["bid", "bid"], "q8": ["person", "auction"]}
+SOURCES = {"q1": ["bid"], "q2": ["bid"], "q3": ["auction", "person"], "q4": ["auction", "bid"], "q5": ["bid", "bid"],
+           "q7": ["bid", "bid"], "q8": ["person", "auction"]}

@@ -60,4 +60,37 @@ def q8(person, auction) -> pa.Table:
     return p.filter(pc.is_in(p["p_id"], value_set=sellers)).select(["p_id", "name"])
 
 
-QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q5": q5, "q8": q8}
+def q4(auction, bid) -> pa.Table:
+    """SELECT category, AVG(final) FROM (SELECT MAX(price) final, category FROM auction JOIN bid ON a_id = auction
+       WHERE b_date_time BETWEEN a_date_time AND expires GROUP BY a_id, category) GROUP BY category  -- numpy, from the SQL"""
+    a = _table(auction)
+    b = _table(bid)
+    a_id = a["a_id"].to_numpy()
+    order = np.argsort(a_id, kind="stable")
+    keys = a_id[order]
+    auc = b["auction"].to_numpy()
+    lo = np.searchsorted(keys, auc, "left")
+    hi = np.searchsorted(keys, auc, "right")
+    reps = hi - lo                                                     # matches per bid (a_id is unique in NEXMark, but stay general)
+    bi = np.repeat(np.arange(len(auc)), reps)
+    ai = order[np.concatenate([np.arange(l, h) for l, h in zip(lo[reps > 0], hi[reps > 0])])] if reps.sum() else np.zeros(0, np.int64)
+    ts = b["b_date_time"].cast(pa.int64()).to_numpy()[bi]
+    keep = (ts >= a["a_date_time"].cast(pa.int64()).to_numpy()[ai]) & (ts <= a["expires"].cast(pa.int64()).to_numpy()[ai])
+    ai, bi = ai[keep], bi[keep]
+    inner = pa.table({"a_id": a_id[ai], "category": a["category"].to_numpy()[ai], "price": b["price"].to_numpy()[bi]})
+    inner = inner.group_by(["a_id", "category"]).aggregate([("price", "max")])
+    cat = inner["category"].to_numpy()
+    final = inner["price_max"].to_numpy().astype(np.float64)
+    cats = np.unique(cat)
+    avg = np.array([final[cat == c].sum() / np.float64((cat == c).sum()) for c in cats], np.float64)   # exact integer sums < 2^53
+    return pa.table({"category": pa.array(cats, pa.int32()), "AVG(Q.final)": pa.array(avg, pa.float64())})
+
+
+def q7(bid) -> pa.Table:
+    """SELECT auction, price, bidder, b_date_time FROM bid JOIN (SELECT MAX(price) maxprice FROM bid) ON price = maxprice"""
+    t = _table(bid)
+    mx = pc.max(t["price"])
+    return t.filter(pc.equal(t["price"], mx)).select(["auction", "price", "bidder", "b_date_time"])
+
+
+QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q4": q4, "q5": q5, "q7": q7, "q8": q8}

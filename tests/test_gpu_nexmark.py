@@ -29,7 +29,7 @@ def run_gpu(ctx, plan, sources):
     return pa.Table.from_batches(out[0])
 
 
-@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q5", "q8"])
+@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q4", "q5", "q7", "q8"])
 def test_nexmark_matches_oracle(gpu_ctx, query, events_small):
     got = run_gpu(gpu_ctx, plans.QUERIES[query](), sources_for(query, events_small))
     want = oracle.execute_plan(plans.QUERIES[query](), sources_for(query, events_small))
@@ -41,7 +41,7 @@ def test_nexmark_matches_oracle(gpu_ctx, query, events_small):
         oracle.assert_tables_equal(got, one, sort=False)
 
 
-@pytest.mark.parametrize("query", ["q2", "q3", "q5", "q8"])
+@pytest.mark.parametrize("query", ["q2", "q3", "q4", "q5", "q7", "q8"])
 def test_nexmark_seed7_full_batches(gpu_ctx, query, events_seed7):
     got = run_gpu(gpu_ctx, plans.QUERIES[query](), sources_for(query, events_seed7))
     oracle.assert_tables_equal(got, oracle.execute_plan(plans.QUERIES[query](), sources_for(query, events_seed7)))

@@ -44,7 +44,7 @@ def test_version_and_no_cpu_fallback():
         ctx.close()
 
 
-@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q5", "q8"])
+@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q4", "q5", "q7", "q8"])
 def test_unmarshal_nexmark_plans(query):
     ec = fb.ExecutionContext(None, plans.QUERIES[query]())
     assert ec.num_plans == 1 and not ec.is_shuffling()
@@ -61,6 +61,11 @@ def test_unmarshal_nexmark_plans(query):
         assert s.count("RepartitionExec: partitioning=Hash") == 2 and s.count("FilterExec") == 2
     if query == "q5":
         assert s.count("HashAggregateExec: mode=Partial") == 3 and s.count("MemoryExec") == 2
+    if query == "q4":
+        assert "FilterExec: b_date_time@6 >= a_date_time@1 AND b_date_time@6 <= expires@2" in s       # BETWEEN, q4.sql
+        assert "gby=[a_id@0 as a_id, category@3 as category], aggr=[MAX(bid.price)]" in s and "aggr=[AVG(Q.final)]" in s
+    if query == "q7":
+        assert "HashJoinExec: mode=Partitioned, join_type=Inner, on=[(price, maxprice)]" in s and "mode=Final, gby=[]" in s
 
 
 def test_shuffle_stage_and_marshalled_context():
