@@ -213,16 +213,21 @@ def run_gpu(args) -> dict:
     t_wall = time.perf_counter()
     d2h = 0
     e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
-    t_feed = t_exec = 0.0
+    t_feed = t_exec = t_clean = 0.0
+    step_ms = []
     for _ in range(e2e_steps):
         t0 = time.perf_counter()
         ec.feed_data_sources(src)
         t1 = time.perf_counter()
         res = ec.execute()
-        t_exec += time.perf_counter() - t1
-        t_feed += t1 - t0
+        t2 = time.perf_counter()
         ec.clean_data_sources()
+        t3 = time.perf_counter()
         d2h = sum(b.nbytes for b in res[0])
+        t_feed += t1 - t0
+        t_exec += t2 - t1
+        t_clean += t3 - t2
+        step_ms.append((time.perf_counter() - t0) * 1e3)
     ctx.timer_stop(1)
     ctx.synchronize()
     e2e_ms = max(ctx.timer_ms(1), (time.perf_counter() - t_wall) * 1e3)      # host-side work counts too
@@ -255,7 +260,10 @@ def run_gpu(args) -> dict:
                    f"({RING} x {8 * args.bids / 1e6:.0f} MB > 126 MB L2)", "selectivity": mean_sel / args.bids},
         "e2e": {"value": world * args.bids * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_ms / max(e2e_steps, 1),
-                "host_ms_per_step": {"feed_data_sources": round(t_feed * 1e3 / max(e2e_steps, 1), 4), "execute+export": round(t_exec * 1e3 / max(e2e_steps, 1), 4)},
+                "host_ms_per_step": {"feed_data_sources": round(t_feed * 1e3 / max(e2e_steps, 1), 4), "execute+export": round(t_exec * 1e3 / max(e2e_steps, 1), 4),
+                                     "clean_data_sources": round(t_clean * 1e3 / max(e2e_steps, 1), 4),
+                                     "step_median": round(statistics.median(step_ms), 4) if step_ms else None,
+                                     "step_max": round(max(step_ms), 4) if step_ms else None},
                 "kernels": e2e_prof,
                 "feed": "copy: auction + price columns DMA'd to HBM" if args.e2e_copy else
                         "zero-copy: page-locked auction column read in place over PCIe, price fetched for survivors only"},

@@ -282,8 +282,8 @@ struct AggLocal32Args {
   const uint32_t* key_col;
   int32_t has_count;
   int32_t pad;
-  unsigned long long* part_keys;
-  unsigned long long* part_acc;  // [1][part_capacity] (unused without COUNT)
+  uint32_t* part_keys;  // 32-bit partials: 8 B per (key, count) instead of 16 -- q5's 4.9 M partials + the 58 MB level-2 table
+  uint32_t* part_acc;   // then fit the L2 together ([part_capacity], unused without COUNT)
   int64_t part_capacity;
   unsigned long long* part_cursor;
   unsigned long long* key_minmax;
@@ -465,8 +465,8 @@ struct AggHist32Args {
   const uint32_t* key_col;
   int32_t has_count;
   int32_t pad;
-  unsigned long long* part_keys;
-  unsigned long long* part_acc;
+  uint32_t* part_keys;  // 32-bit partials (see AggLocal32Args)
+  uint32_t* part_acc;
   int64_t part_capacity;
   unsigned long long* part_cursor;
   unsigned long long* key_minmax;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
         const unsigned b = __ballot_sync(FULL_MASK, cs[e] != 0);
         if (cs[e]) {
           const unsigned long long p = pos + __popc(b & lt);
-          a.part_keys[p] = (unsigned long long)(base + unsigned(v4) * 4u + unsigned(e));
+          a.part_keys[p] = base + unsigned(v4) * 4u + unsigned(e);
           if (has_count) a.part_acc[p] = cs[e];
         }
         pos += __popc(b);
@@ -704,6 +704,8 @@ struct AggInsertArgs {
   const unsigned long long* part_keys;
   const unsigned long long* part_acc;
   int64_t part_capacity;
+  int32_t part32;  // from_partials: keys / single accumulator are uint32_t arrays (the 4-byte-key level-1 kernels)
+  int32_t pad2;
   AggTable table;
 };
 
@@ -732,13 +734,15 @@ __device__ __forceinline__ unsigned long long table_find_or_insert(const AggTabl
 __global__ void __launch_bounds__(256) agg_insert_kernel(const __grid_constant__ AggInsertArgs a) {
   const unsigned long long stride_n = a.table.stride;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < a.n; i += int64_t(gridDim.x) * blockDim.x) {
-    const unsigned long long key = a.from_partials ? a.part_keys[i] : pack_key(a.keys, a.cols, i);
+    const unsigned long long key = !a.from_partials ? pack_key(a.keys, a.cols, i)
+                                   : a.part32       ? (unsigned long long)reinterpret_cast<const uint32_t*>(a.part_keys)[i]
+                                                    : a.part_keys[i];
     const unsigned long long slot = table_find_or_insert(a.table, key);
     for (int c = 0; c < a.n_acc; ++c) {
       Val v;
       int op;
       if (a.from_partials) {
-        v.u = a.part_acc[int64_t(c) * a.part_capacity + i];
+        v.u = a.part32 ? (unsigned long long)reinterpret_cast<const uint32_t*>(a.part_acc)[i] : a.part_acc[int64_t(c) * a.part_capacity + i];
         op = acc_merge_op(a.acc[c].op);
       } else {
         v = load_acc_input(a.acc[c], a.cols, i);
@@ -958,7 +962,21 @@ __global__ void __launch_bounds__(256) agg_global_kernel(const __grid_constant__
   Val local[MAX_ACC];
 #pragma unroll
   for (int c = 0; c < MAX_ACC; ++c) local[c].u = c < a.n_acc ? acc_identity(a.acc[c].op) : 0ull;
-  for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+  // four rows per thread and iteration: their loads are independent and in flight together
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  for (; row + 3 * stride < a.n_rows; row += 4 * stride) {
+#pragma unroll
+    for (int c = 0; c < MAX_ACC; ++c) {
+      if (c >= a.n_acc) continue;
+      Val v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = load_acc_input(a.acc[c], a.cols, row + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) local[c] = acc_combine(a.acc[c].op, local[c], v[u]);
+    }
+  }
+  for (; row < a.n_rows; row += stride) {
 #pragma unroll
     for (int c = 0; c < MAX_ACC; ++c)
       if (c < a.n_acc) local[c] = acc_combine(a.acc[c].op, local[c], load_acc_input(a.acc[c], a.cols, row));
@@ -1245,6 +1263,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     BufferPtr pkeys, pacc;
     int64_t n_entries = n;
     bool from_partials = false;
+    bool part32 = false;  // the partial buffers hold uint32 keys / counts (4-byte-key level-1 kernels)
     unsigned long long key_min = 1, key_max = 0;
     const size_t local_smem = size_t(AL_SLOTS) * 8 * (1 + n_acc);
     // Final* inputs are partial states: every key occurs at most once per producer, so a CTA-local pre-aggregation
@@ -1269,6 +1288,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       FG_CUDA(cudaMemsetAsync(la.key_minmax + 1, 0, 8, ctx->stream));  // max = 0
       FG_CUDA(cudaFuncSetAttribute(agg_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(local_smem)));
       const bool count32 = kp.n == 1 && kp.width[0] == 4 && (n_acc == 0 || (n_acc == 1 && accs[0].op == ACC_COUNT));
+      part32 = count32;
       bool done_l1 = false;
       static const bool no_hist = getenv("FLOCKGPU_NO_HIST") != nullptr;
       if (count32 && !no_hist) {
@@ -1277,8 +1297,8 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
         h.n_rows = n;
         h.key_col = static_cast<const uint32_t*>(in.cols[kp.col[0]].values());
         h.has_count = n_acc;
-        h.part_keys = la.part_keys;
-        h.part_acc = la.part_acc;
+        h.part_keys = reinterpret_cast<uint32_t*>(la.part_keys);
+        h.part_acc = reinterpret_cast<uint32_t*>(la.part_acc);
         h.part_capacity = n;
         h.part_cursor = la.part_cursor;
         h.key_minmax = la.key_minmax;
@@ -1312,8 +1332,8 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
         l32.n_rows = n;
         l32.key_col = static_cast<const uint32_t*>(in.cols[kp.col[0]].values());
         l32.has_count = n_acc;
-        l32.part_keys = la.part_keys;
-        l32.part_acc = la.part_acc;
+        l32.part_keys = reinterpret_cast<uint32_t*>(la.part_keys);
+        l32.part_acc = reinterpret_cast<uint32_t*>(la.part_acc);
         l32.part_capacity = n;
         l32.part_cursor = la.part_cursor;
         l32.key_minmax = la.key_minmax;
@@ -1377,6 +1397,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     ia.from_partials = from_partials ? 1 : 0;
     for (int c = 0; c < n_acc; ++c) ia.acc[c] = accs[c];
     fill_cols(in, ia.cols);
+    ia.part32 = part32 ? 1 : 0;
     ia.part_keys = pkeys ? pkeys->as<unsigned long long>() : nullptr;
     ia.part_acc = pacc ? pacc->as<unsigned long long>() : nullptr;
     ia.part_capacity = n;

@@ -164,6 +164,68 @@ __global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __gri
   }
 }
 
+// ---- build side of ONE row (NEXMark q5 / q7 join a relation with a global aggregate): no table, no chains -- the
+// probe is an equality filter.  One stable compaction pass writes the matching probe rows; every pair's build row is 0.
+struct JoinOneArgs {
+  CompactScratch sc;
+  const void* probe_key;
+  const void* build_key;  // device pointer to the single build key
+  int64_t n_rows;
+  unsigned* probe_idx;
+};
+
+template <int KW>
+__global__ void __launch_bounds__(CP_THREADS) join_one_kernel(const __grid_constant__ JoinOneArgs a) {
+  constexpr int E = 4, I = 16, G = I / E;
+  constexpr int TILE = CP_THREADS * I;
+  __shared__ CompactSmem<E, I> sm;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned long long want = KW == 4 ? (unsigned long long)*static_cast<const uint32_t*>(a.build_key) : *static_cast<const unsigned long long*>(a.build_key);
+  long long tile;
+  for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
+    const int64_t tile_base = tile * TILE;
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int64_t r0 = tile_base + (int64_t(g) * CP_THREADS + tid) * E;
+      unsigned nib = 0;
+      if (r0 + 3 < a.n_rows) {
+        if (KW == 4) {
+          const uint4 k = *reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(a.probe_key) + r0);
+          nib = unsigned(k.x == uint32_t(want)) | (unsigned(k.y == uint32_t(want)) << 1) | (unsigned(k.z == uint32_t(want)) << 2) | (unsigned(k.w == uint32_t(want)) << 3);
+        } else {
+          const unsigned long long* p = static_cast<const unsigned long long*>(a.probe_key) + r0;
+          const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(p), k23 = *reinterpret_cast<const ulonglong2*>(p + 2);
+          nib = unsigned(k01.x == want) | (unsigned(k01.y == want) << 1) | (unsigned(k23.x == want) << 2) | (unsigned(k23.y == want) << 3);
+        }
+      } else {
+        for (int e = 0; e < E; ++e) {
+          if (r0 + e >= a.n_rows) break;
+          const unsigned long long k = KW == 4 ? (unsigned long long)static_cast<const uint32_t*>(a.probe_key)[r0 + e]
+                                               : static_cast<const unsigned long long*>(a.probe_key)[r0 + e];
+          nib |= unsigned(k == want) << e;
+        }
+      }
+      bits |= (unsigned long long)nib << (g * E);
+    }
+    unsigned lane_prefix[G];
+    cp_rank_tile<E, I>(sm, a.sc, tile, bits, lane_prefix);
+    if (bits && sm.tile_total) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const unsigned nib = unsigned(bits >> (g * E)) & 0xfu;
+        if (!nib) continue;
+        const int64_t r0 = tile_base + (int64_t(g) * CP_THREADS + tid) * E;
+        const int64_t pos0 = int64_t(sm.excl) + sm.group_warp[g][warp] + lane_prefix[g];
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if ((nib >> e) & 1u) a.probe_idx[pos0 + __popc(nib & ((1u << e) - 1u))] = unsigned(r0 + e);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 struct JoinEmitArgs {
   JoinSide build, probe;
   JoinTable table;
@@ -262,6 +324,35 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       else if (kw == 8) f(std::integral_constant<int, 8>{});
       else f(std::integral_constant<int, 0>{});
     };
+    if (kw && B.num_rows == 1) {
+      // one build row: equality filter over the probe side (see join_one_kernel)
+      probe_idx = alloc(ctx, size_t(P.num_rows) * 4);
+      JoinOneArgs oa{};
+      oa.probe_key = ps.key0;
+      oa.build_key = bs.key0;
+      oa.n_rows = P.num_rows;
+      oa.probe_idx = probe_idx->as<unsigned>();
+      const int64_t num_tiles = (P.num_rows + CP_THREADS * 16 - 1) / (CP_THREADS * 16);
+      by_width([&](auto w) {
+        constexpr int KW = decltype(w)::value == 8 ? 8 : 4;
+        auto kernel = join_one_kernel<KW>;
+        int per_sm = 1;
+        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CP_THREADS, 0));
+        oa.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + 4);
+        LaunchTimer lt(ctx, "join_one_kernel");
+        launch_compact(ctx, kernel, oa.sc, oa);
+      });
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+      unsigned long long total = 0;
+      read_scalars(ctx, 4, 1, &total);
+      FG_CHECK(total <= (unsigned long long)P.num_rows, FLOCKGPU_ERR_CUDA, "hash_join: corrupt match count");
+      n_pairs = int64_t(total);
+      if (n_pairs > 0) {
+        build_idx = alloc(ctx, size_t(n_pairs) * 4);
+        FG_CUDA(cudaMemsetAsync(build_idx->ptr, 0, size_t(n_pairs) * 4, ctx->stream));
+      }
+    } else {
     unsigned long long cap = 1024;
     while (cap < 2ull * (unsigned long long)B.num_rows) cap <<= 1;
     // rep | head | cnt in one allocation (cap words each), then next[build rows]
@@ -315,6 +406,7 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       FG_CUDA(cudaGetLastError());
       count_launch(ctx);
     }
+    }  // general build / probe
   }
   out->num_rows = n_pairs;
   if (n_pairs == 0) {

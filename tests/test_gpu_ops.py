@@ -247,6 +247,28 @@ def test_hash_join_edge_cases(gpu_ctx):
         gpu_ctx.hash_join(gpu_ctx.import_batches([l]), gpu_ctx.import_batches([r]), [0], [1])   # Int32 vs Int64 keys
 
 
+@pytest.mark.parametrize("key_type", [pa.int32(), pa.int64(), pa.uint64()])
+@pytest.mark.parametrize("one_row_side", ["left", "right"])
+def test_hash_join_against_a_single_row(gpu_ctx, key_type, one_row_side):
+    """NEXMark q5 / q7 shape: a relation joined with a one-row global aggregate -- an equality filter on the GPU.
+    Output columns stay left ++ right, matching probe rows keep their order."""
+    n = 70_003
+    rng = np.random.default_rng(11)
+    k = rng.integers(0, 50, n)
+    big = rb(k=pa.array(k, key_type), v=pa.array(np.arange(n, dtype=np.int64)), s=pa.array(["r%d" % (x % 13) for x in range(n)]))
+    for wanted in (7, 1000):                                              # present many times / absent
+        one = rb(m=pa.array([wanted], key_type), tag=pa.array(["only"]))
+        l, r = (one, big) if one_row_side == "left" else (big, one)
+        lk, rk = [0], [0]
+        got = gpu_ctx.hash_join(gpu_ctx.import_batches([l]), gpu_ctx.import_batches([r]), lk, rk).to_arrow()
+        want = pa.Table.from_batches([oracle.hash_join(l, r, lk, rk)])
+        assert got.num_rows == int((k == wanted).sum()) == want.num_rows
+        assert got.schema.names == l.schema.names + r.schema.names
+        oracle.assert_tables_equal(got, want, check_names=False)
+        if got.num_rows:
+            assert got["v"].to_pylist() == np.nonzero(k == wanted)[0].tolist()      # probe order preserved
+
+
 # ---- RepartitionExec: Hash -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("keys", [[0], [5], [6, 0], [1]])
 @pytest.mark.parametrize("n_parts", [2, 8])
