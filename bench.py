@@ -243,11 +243,20 @@ def run_gpu(args) -> dict:
     mean_sel = float(np.mean(n_sel)) if n_sel else 0.0
     alg_bytes = 4.0 * args.bids + 12.0 * mean_sel          # read auction 4 B x N; per survivor read price 4 B, write 8 B
     roofline = None
+    traffic = None
+    tp = ROOT / "profiles" / "r1_filter_dram_traffic.json"      # dram__bytes_{read,write}.sum of one ncu --set full capture of this kernel
+    if tp.exists() and args.bids == N_BIDS:
+        try:
+            tj = json.loads(tp.read_text())
+            traffic = int(tj["dram_bytes_read_per_launch"]) + int(tj["dram_bytes_write_per_launch"])
+        except Exception:
+            traffic = None
     if k and k["launches"]:
         k_ms = k["ms"] / k["launches"]
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": None, "kernel": "filter_compact_kernel", "kernel_ms": round(k_ms, 5), "launches_timed": k["launches"],
+                    "traffic": traffic, "traffic_source": "profiles/r1_filter_dram_traffic.json (ncu --set full, one launch)" if traffic else None,
+                    "kernel": "filter_compact_kernel", "kernel_ms": round(k_ms, 5), "launches_timed": k["launches"],
                     "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src}
 
     result = {

@@ -8,7 +8,8 @@
 //
 //   partition_ids_kernel     pid[row] = high 32 hash bits scaled to [0, n)  (tables use the LOW bits)
 //   partition_select_kernel  one stable single-pass compaction per partition (compact.cuh) appending
-//                            the row indices of partition p behind those of partitions < p
+//                            the row indices of partition p behind those of partitions < p (the pass's
+//                            last tile writes where the next partition starts)
 //   gather.cu                materialises each partition's columns from its slice of the index vector
 #include <algorithm>
 
@@ -79,6 +80,8 @@ __global__ void __launch_bounds__(CP_THREADS) partition_select_kernel(const __gr
     }
     unsigned lane_prefix[CP_ITEMS / E];
     cp_rank_tile<E, CP_ITEMS>(sm, a.sc, tile, bits, lane_prefix);
+    // the last tile knows the partition's size: the next pass starts behind it (no separate "advance" launch)
+    if (tile == a.sc.num_tiles - 1 && tid == 0) a.bases[a.part + 1] = base + sm.excl + sm.tile_total;
     if (bits && sm.tile_total) {
       unsigned long long m = bits;
       while (m) {
@@ -89,10 +92,6 @@ __global__ void __launch_bounds__(CP_THREADS) partition_select_kernel(const __gr
     }
     __syncthreads();
   }
-}
-
-__global__ void partition_advance_kernel(unsigned long long* bases, int part, const unsigned long long* count) {
-  bases[part + 1] = bases[part] + *count;
 }
 
 std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vector<int>& keys, int n_parts) {
@@ -167,12 +166,7 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
       launch_compact(ctx, partition_select_kernel, sa.sc, sa);
     }
     FG_CUDA(cudaGetLastError());
-    {
-      LaunchTimer lt(ctx, "partition_advance_kernel");
-      partition_advance_kernel<<<1, 1, 0, ctx->stream>>>(bases, p, ctx->d_scalars + 5);
-    }
-    FG_CUDA(cudaGetLastError());
-    count_launch(ctx, 2);
+    count_launch(ctx);
   }
   std::vector<unsigned long long> hb(n_parts + 1);
   read_scalars(ctx, 16, n_parts + 1, hb.data());
