@@ -54,13 +54,31 @@ def peak_gbs():
 
 def make_inputs(q: str, scale: float, seed: int, rank: int, world: int) -> dict:
     """relation name -> list of 64 Ki-row batches this rank scans."""
+    cols = {"person": ["p_id", "name", "city", "state"] if q == "q3" else ["p_id", "name"],
+            "auction": ["a_id", "seller", "category"] if q == "q3" else ["seller"]}
+    if world > 1 and not os.environ.get("NEXMARK_ROUND_ROBIN"):
+        # every rank generates ONLY its own contiguous slice of the stream (as if it hosted that slice of the source):
+        # a 1 B-event q8 run must not build 20 M persons + 60 M auctions eight times on one host
+        def own(total):
+            share = (total + world - 1) // world
+            first = min(rank * share, total)
+            return first, min(share, total - first)
+
+        def pieces(total, fn, extra):
+            first, n = own(total)
+            parts = [fn(min(4_000_000, n - o), seed, first + o, *extra) for o in range(0, n, 4_000_000)] or [fn(0, seed, first, *extra)]
+            tbl = pa.Table.from_batches(parts).combine_chunks()
+            return nexgen.split_batches(tbl.to_batches()[0] if tbl.num_rows else parts[0], BATCH)
+
+        if q in BIDS:
+            return {"bid": pieces(max(int(BIDS[q] * scale), 1), nexgen.bids, ())}
+        n_p, n_a, _ = nexgen.relation_counts(int(EVENTS[q] * scale))
+        return {"person": pieces(n_p, nexgen.persons, (cols["person"],)), "auction": pieces(n_a, nexgen.auctions, (cols["auction"],))}
     if q in BIDS:
         n = max(int(BIDS[q] * scale), 1)
         rel = {"bid": nexgen.split_batches(nexgen.bids(n, seed=seed), BATCH)}
     else:
         n_ev = int(EVENTS[q] * scale)
-        cols = {"person": ["p_id", "name", "city", "state"] if q == "q3" else ["p_id", "name"],
-                "auction": ["a_id", "seller", "category"] if q == "q3" else ["seller"]}
         rel = nexgen.generate(n_ev, seed=seed, batch_rows=BATCH, relations=("person", "auction"), columns=cols)
     return {k: sharding.round_robin(v, rank, world) or [v[0].slice(0, 0)] for k, v in rel.items()}
 
