@@ -833,10 +833,13 @@ __device__ __forceinline__ void emit_values(const EmitDesc* emit, int n_emit, co
 // 4 present bytes or 16 B of owners), the ranking is the packed SWAR scan of compact.cuh, and a group's accumulators
 // are read with two 16-byte loads per column whatever its occupancy.  (The first version tested and emitted slot by
 // slot: 138 lane-instructions per slot and one dependent accumulator load per survivor, profiles/r1_q5_ncu.md.)
-template <int MODE>
+// slots per thread and tile: 64 = 16 Ki-slot tiles, so that q5's 6.5 M-slot table is 397 tiles = ONE wave (the cheaper
+// single-wave prefix) instead of 1587 tiles in three waves of decoupled look-back
+// (ITEMS = 64, large tables); small tables keep 4 Ki-slot tiles (ITEMS = 16) so that they spread over the SMs.
+template <int MODE, int EMIT_ITEMS>
 __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_constant__ AggEmitArgs a) {
   constexpr int E = 4;
-  constexpr int CP_ITEMS = 16;
+  constexpr int CP_ITEMS = EMIT_ITEMS;
   constexpr int G = CP_ITEMS / E;
   constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
   __shared__ CompactSmem<E, CP_ITEMS> sm;
@@ -1473,7 +1476,9 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   ea.n_slots = n_slots;
   ea.acc_stride = acc_stride;
   {
-    const long long tiles = (long long)((n_slots + CP_THREADS * 16 - 1) / (CP_THREADS * 16));
+    const bool big = n_slots > (unsigned long long)ctx->sm_count * 4 * CP_THREADS * 16;
+    const int items = big ? 64 : 16;
+    const long long tiles = (long long)((n_slots + CP_THREADS * items - 1) / (CP_THREADS * items));
     auto launch = [&](auto kernel) {
       int per_sm = 1;
       FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CP_THREADS, 0));
@@ -1481,9 +1486,9 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       LaunchTimer lt(ctx, "agg_emit_kernel");
       launch_compact(ctx, kernel, ea.sc, ea);
     };
-    if (emit_mode == 0) launch(agg_emit_kernel<0>);
-    else if (emit_mode == 1) launch(agg_emit_kernel<1>);
-    else launch(agg_emit_kernel<2>);
+    if (emit_mode == 0) big ? launch(agg_emit_kernel<0, 64>) : launch(agg_emit_kernel<0, 16>);
+    else if (emit_mode == 1) big ? launch(agg_emit_kernel<1, 64>) : launch(agg_emit_kernel<1, 16>);
+    else big ? launch(agg_emit_kernel<2, 64>) : launch(agg_emit_kernel<2, 16>);
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
   }

@@ -220,6 +220,31 @@ def test_aggregate_key_edge_cases(gpu_ctx):
     assert sorted(zip(got["k"].to_pylist(), got["n"].to_pylist())) == [(-1, 399_600), (7, 400)]
 
 
+@pytest.mark.parametrize("shape", ["hashed_i64", "dense_i32", "rows_utf8"])
+def test_hash_aggregate_large_tables(gpu_ctx, shape):
+    """Level-2 tables beyond 2.4 M slots take the 16 Ki-slot emit tiles (agg_emit_kernel<*, 64>): hashed packed keys,
+    the direct-address table behind the shared-memory histogram, and the row-representative table."""
+    rng = np.random.default_rng(5)
+    if shape == "hashed_i64":
+        n = 3_000_000
+        b = rb(k=pa.array(rng.integers(0, 1 << 22, n) * 1_000_003), v=pa.array(rng.integers(0, 100, n)))
+        aggs = [("count", -1, "n"), ("sum", 1, "s"), ("max", 1, "m")]
+    elif shape == "dense_i32":
+        n = 6_000_000
+        b = rb(k=pa.array((np.arange(n) // 2 + rng.integers(0, 50, n)).astype(np.int32) + 1000))
+        aggs = [("count", -1, "n")]
+    else:
+        n = 1_300_000
+        ids = rng.permutation(n)
+        b = rb(k=pa.array(["p%07d" % i for i in ids]), v=pa.array(rng.integers(0, 100, n)))
+        aggs = [("count", -1, "n"), ("min", 1, "lo")]
+    t = gpu_ctx.import_batches(nexgen.split_batches(b, 65536))
+    got = gpu_ctx.hash_aggregate(t, [0], aggs, "single").to_arrow()
+    want = pa.Table.from_batches([oracle_agg(b, "Single", [0], aggs)])
+    assert got.num_rows > 1_000_000
+    oracle.assert_tables_equal(got, want)
+
+
 # ---- HashJoinExec -----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("keys", [([0], [0]), ([5], [5]), ([6, 0], [6, 0]), ([6, 5], [6, 5]), ([1], [1])])
 def test_hash_join_matches_oracle(gpu_ctx, keys):
