@@ -1,22 +1,24 @@
-// compact.cuh -- the single-pass stable compaction skeleton shared by FilterExec (filter_project.cu),
-// the hash-table emitter (hash_agg.cu) and the partition selector (partition.cu).
+// compact.cuh -- the single-pass stable compaction / scan skeleton shared by FilterExec (filter_project.cu), the
+// hash-table emitter (hash_agg.cu), the partition selector (partition.cu), the join's pair-count scan and
+// one-row-build probe (hash_join.cu) and the Utf8 length scan (gather.cu).
 //
-// A persistent CTA takes tiles of CP_THREADS x I items from an atomic ticket.  For each tile it gets one
-// bit per item ("survives"), ranks the survivors in item order with warp ballots, obtains the tile's
-// global output offset and hands every survivor its output position.  Two ways to get that offset:
+// A CTA processes tiles of CP_THREADS x I items.  For each tile it gets one bit per item ("survives"), ranks the
+// survivors in item order (packed SWAR scan for four-item groups, ballots otherwise), obtains the tile's global
+// output offset and hands every survivor its output position.  Two ways to get that offset:
 //
-//   single wave   (tiles <= resident CTAs; NEXMark q2's 10 M rows = 611 tiles): every tile needs the counts of
-//                 ALL its predecessors and they all finish counting at about the same time, so a chained
-//                 look-back degenerates into everybody polling everybody (measured: 43 % of the stall samples,
-//                 profiles/r1_filter_ncu.md).  Instead each CTA stores its count, bumps ONE arrival counter
-//                 (release), ONE thread per CTA polls that counter (acquire) until all tiles have arrived, then
-//                 the CTA sums its predecessors' counts with one strided read.
-//   many waves    decoupled look-back with the whole CTA (thread i inspects predecessor i): earlier waves have
-//                 long published their inclusive prefixes, so one 256-wide window almost always suffices.
+//   single wave   (tiles <= resident CTAs; NEXMark q2's 10 M rows = 611 tiles; cooperative launch, tile = blockIdx.x):
+//                 every tile needs the counts of ALL its predecessors and they all finish counting at about the same
+//                 time, so a chained look-back degenerates into everybody polling everybody (measured: 43 % of the
+//                 stall samples, profiles/r1_filter_ncu.md).  Instead each CTA publishes one self-validating word
+//                 {launch epoch, count}, bumps ONE arrival counter, ONE thread per CTA polls that counter until all
+//                 tiles have arrived, then the CTA sums its predecessors' words with one strided read.
+//   many waves    persistent CTAs draw tiles from an atomic ticket; decoupled look-back with the whole CTA (thread i
+//                 inspects predecessor i): earlier waves have long published their inclusive prefixes, so one 256-wide
+//                 window almost always suffices.
 //
-// Nothing is reset between launches: tickets and arrivals are monotonic counters (the host passes the base
-// value of the launch), look-back words carry a 20-bit launch epoch and a stale epoch reads as "invalid".
-// That removes the end-of-kernel fence + atomic + reset loop (~2 us of a ~30 us kernel).
+// Nothing is reset between launches: tickets and arrivals are monotonic counters (the host passes the base value of
+// the launch), status words carry a 20-bit launch epoch and a stale epoch reads as "invalid".  That removes the
+// end-of-kernel fence + atomic + reset loop (~2 us of a ~30 us kernel).
 #pragma once
 
 #include <utility>

@@ -3,7 +3,7 @@
 // playground/src/distributed_plan/shuffle_writer.rs:129-146), and the Utf8 half of `filter`.
 //
 //   fixed width : out[i] = in[idx[i]]
-//   Utf8        : lengths -> exclusive scan (single pass, decoupled look-back) -> byte copy where each
+//   Utf8        : lengths -> exclusive scan (single pass, the grid-wide prefix of compact.cuh) -> byte copy where each
 //                 warp owns 32 consecutive OUTPUT rows, so output bytes are written densely in order.
 #include <algorithm>
 

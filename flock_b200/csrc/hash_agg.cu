@@ -8,15 +8,17 @@
 //
 // GPU design
 //   packed keys   up to two fixed-width group columns (<= 8 bytes together) become one 64-bit key.
-//     level 1     agg_local_kernel: every CTA owns a contiguous row range and pre-aggregates it in a
-//                 SHARED-MEMORY hash table (NEXMark keys are local in time: a 64 Ki-row bid batch
-//                 touches ~4 300 auctions, half of the rows one "hot" id), flushing (key, state)
-//                 partials to HBM when the table is 3/4 full.  This is the reference's Partial stage,
-//                 with the CTA in the role of the partition.
-//     level 2     agg_insert_kernel: partials (or raw rows when the input is small) are merged into a
-//                 global open-addressing table with 64-bit CAS + atomics; its size is known from the
-//                 partial count, not from the row count.
-//     emit        agg_emit_kernel: stable single-pass compaction of the occupied slots (compact.cuh).
+//     level 1     (raw rows, large inputs) every CTA owns a contiguous row range and pre-aggregates it in SHARED
+//                 MEMORY -- the reference's Partial stage with the CTA in the role of the partition:
+//                   agg_hist32_kernel   one 4-byte key + COUNT / DISTINCT: sliding direct-address histogram (NEXMark
+//                                       ids are consecutive and local in time), 32-bit (key, count) partials;
+//                   agg_local32_kernel  its hash-table fallback when the keys are not dense;
+//                   agg_local_kernel    any packed key / accumulators: 64 KB hash table, 64-bit CAS + shared atomics.
+//     level 2     agg_insert_kernel: partials (or raw rows when the input is small, or partial STATES in the Final*
+//                 modes) are merged into a global table -- direct-address when one key column fills its range,
+//                 open addressing with 64-bit CAS otherwise; its size comes from the partial count.
+//     emit        agg_emit_kernel: stable single-pass compaction of the occupied slots (compact.cuh), four
+//                 contiguous slots per vector load.
 //   row keys      Utf8 or wide group keys: the table stores the index of a representative input row
 //                 (agg_insert_rows_kernel); key equality is checked against the input columns.
 //   no keys       agg_global_kernel: register accumulators -> warp shuffle -> one atomic per warp.
@@ -829,13 +831,13 @@ __device__ __forceinline__ void emit_values(const EmitDesc* emit, int n_emit, co
 }
 
 // MODE 0: hashed packed keys, 1: dense (direct-address) table, 2: row-representative table.
-// A thread owns four groups of FOUR CONTIGUOUS slots: the occupancy test is one vector load per group (32 B of keys,
+// A thread owns groups of FOUR CONTIGUOUS slots: the occupancy test is one vector load per group (32 B of keys,
 // 4 present bytes or 16 B of owners), the ranking is the packed SWAR scan of compact.cuh, and a group's accumulators
 // are read with two 16-byte loads per column whatever its occupancy.  (The first version tested and emitted slot by
 // slot: 138 lane-instructions per slot and one dependent accumulator load per survivor, profiles/r1_q5_ncu.md.)
-// slots per thread and tile: 64 = 16 Ki-slot tiles, so that q5's 6.5 M-slot table is 397 tiles = ONE wave (the cheaper
-// single-wave prefix) instead of 1587 tiles in three waves of decoupled look-back
-// (ITEMS = 64, large tables); small tables keep 4 Ki-slot tiles (ITEMS = 16) so that they spread over the SMs.
+// EMIT_ITEMS = slots per thread and tile: 64 for large tables (16 Ki-slot tiles: q5's 6.5 M-slot table is 397 tiles =
+// ONE wave with the cheap single-wave prefix instead of 1587 tiles in three waves of look-back), 16 for small
+// tables so that they still spread over the SMs.
 template <int MODE, int EMIT_ITEMS>
 __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_constant__ AggEmitArgs a) {
   constexpr int E = 4;

@@ -13,10 +13,13 @@
 // values; q3's hot sellers) therefore cost one probe step, not one per duplicate.  The SMALLER input is
 // the build side (the reference always builds on the left; which side is hashed is not observable).
 //   join_build_kernel        claim / find the key's slot, push the row on its list
-//   join_count_scan_kernel   per probe row: number of matches -> exclusive offsets (decoupled
-//                            look-back, single pass) and the total pair count
+//   join_count_scan_kernel   per probe row: number of matches -> exclusive offsets (the grid-wide prefix
+//                            protocol of compact.cuh, single pass) and the total pair count
 //   join_emit_kernel         second walk (table lines are L2-hot) writes the (build, probe) index pairs
-// and gather.cu materialises the output columns (Utf8 included).
+//   join_one_kernel          build side of ONE row (q5 / q7 join with a global aggregate): a stable equality
+//                            compaction over the probe side, no table
+// and gather.cu materialises the output columns (Utf8 included).  The kernels are instantiated per key shape:
+// one 4-byte key, one 8-byte key, or the general form (two packed columns / row comparison for Utf8 keys).
 #include <algorithm>
 
 #include "compact.cuh"

@@ -179,8 +179,8 @@ struct Buffer {
 using BufferPtr = std::shared_ptr<Buffer>;
 BufferPtr alloc(const CtxPtr& ctx, size_t bytes);  // bytes == 0 still yields a valid (tiny) buffer
 
-// Grows the look-back scratch to at least `tiles` entries (zero-initialised once).
-// Look-back tuning (FLOCKGPU_LB_STRIDE / FLOCKGPU_LB_SLEEP override): words between tile entries, poll back-off in ns.
+// Grid-prefix tuning (FLOCKGPU_LB_STRIDE / FLOCKGPU_LB_SLEEP override): 64-bit words between the look-back words of
+// consecutive tiles (32 = one 256-byte L2 chunk each), back-off of a polling thread in ns.
 int scan_stride();
 int scan_poll_sleep_ns();
 // Copies `n` u64 scalars from d_scalars[first..] to the host and waits.
