@@ -312,11 +312,17 @@ inline void launch_compact(const CtxPtr& ctx, Kernel kernel, const CompactScratc
   FG_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
+// Rank of survivor item k among the survivors of its tile (0 .. tile_total - 1) / its global output position.
 template <int E, int I>
-__device__ __forceinline__ long long cp_position(const CompactSmem<E, I>& s, unsigned long long bits, int k, const unsigned (&lane_prefix)[I / E]) {
+__device__ __forceinline__ unsigned cp_local_position(const CompactSmem<E, I>& s, unsigned long long bits, int k, const unsigned (&lane_prefix)[I / E]) {
   const int g = k / E, e = k % E;
   const unsigned within = __popcll(bits & (((1ull << e) - 1ull) << (g * E)));
-  return (long long)s.excl + s.group_warp[g][threadIdx.x >> 5] + lane_prefix[g] + within;
+  return s.group_warp[g][threadIdx.x >> 5] + lane_prefix[g] + within;
+}
+
+template <int E, int I>
+__device__ __forceinline__ long long cp_position(const CompactSmem<E, I>& s, unsigned long long bits, int k, const unsigned (&lane_prefix)[I / E]) {
+  return (long long)s.excl + cp_local_position<E, I>(s, bits, k, lane_prefix);
 }
 
 }  // namespace fg
