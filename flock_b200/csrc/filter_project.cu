@@ -6,13 +6,12 @@
 //   ProjectionExec: per-batch expression evaluation; plain Column exprs are zero-copy
 //
 // filter_compact_kernel: ONE launch for the whole relation (all 64 Ki-row batches: a 1.3 MB batch is
-// 0.2 us of HBM traffic, far below launch latency, so per-batch launches cannot work).  CTAs take tiles of
-// 256 x {4, 16, 32, 64} rows (sized so that the relation is one wave of resident CTAs whenever possible),
-// evaluate the predicate (PredI32: one multiply-add + compare per row for the NEXMark shapes; the generic term
-// interpreter otherwise), rank the survivors (compact.cuh), obtain the tile's global output offset from the
-// grid-wide prefix protocol (each input byte is read once, no second pass), and write the surviving rows of every
-// fixed-width output column in input order.  Utf8 outputs leave through the selection vector and gather.cu.
-// Host-resident (page-locked, zero-copy fed) predicate columns are read in place over PCIe.
+// 0.2 us of HBM traffic, far below launch latency, so per-batch launches cannot work).  Persistent
+// CTAs take 4096-row tiles from an atomic ticket, evaluate the predicate (a hand-specialised functor
+// for the NEXMark shapes, the generic term interpreter otherwise), rank the survivors with warp
+// ballots, obtain the tile's global output offset by decoupled look-back (each input byte is read
+// once, no second pass), and write the surviving rows of every fixed-width output column in input
+// order.  Utf8 outputs leave through the selection vector and gather.cu.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -24,12 +23,11 @@
 namespace fg {
 
 constexpr int FP_THREADS = CP_THREADS;
-constexpr int FP_LIST_CAP = 2048;  // survivors of a tile that take the balanced write path (4 KB of shared memory)
 
 struct FilterArgs {
   int64_t n_rows;
   int32_t n_out;
-  int32_t balanced;                  // 1: survivors of a tile are written through the shared list (FLOCKGPU_NO_BALANCED=1 disables, for A/B runs)
+  int32_t pad;
   CompactScratch sc;                 // tickets / prefix scratch of this launch (compact.cuh)
   uint32_t* sel_out;                 // optional: indices of surviving rows
   unsigned long long* out_count;     // total surviving rows
@@ -251,8 +249,6 @@ __global__ void __launch_bounds__(FP_THREADS, PredFn::MIN_CTAS) filter_compact_k
   constexpr int I = PredFn::I;
   constexpr int TILE = FP_THREADS * I;
   __shared__ CompactSmem<E, I> sm;
-  __shared__ unsigned short s_list[FP_LIST_CAP];  // tile-local item indices of the survivors, in output order
-  static_assert(TILE <= 65536, "tile-local item indices are 16-bit");
   const int tid = threadIdx.x;
   const CompactScratch& sc = a.sc;
   int err = 0;
@@ -296,91 +292,10 @@ __global__ void __launch_bounds__(FP_THREADS, PredFn::MIN_CTAS) filter_compact_k
     stamp(tile, 3);
 
     // ---- write survivors in input order
-    // Up to four survivors per call: every pass-through value is a dependent ~1 us read (DRAM, or L2 after the
-    // prefetch above), so the loads of a round are issued together.
-    auto write_rows = [&](const int64_t (&pos)[4], const int64_t (&row)[4], int nb) {
-      if (a.sel_out) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q < nb) a.sel_out[pos[q]] = uint32_t(row[q]);
-      }
-      for (int c = 0; c < a.n_out; ++c) {
-        const OutCol& oc = a.outs[c];
-        if (oc.kind == OUT_PASS) {
-          const ColRef& sc_col = a.cols[oc.src_col];
-          const void* src = sc_col.data;
-          if (sc_col.chunks) {
-            // host-resident source: one PCIe read per survivor
-            const int64_t mask = (int64_t(1) << sc_col.chunk_shift) - 1;
-            uint64_t v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              v[q] = 0;
-              if (q < nb) {
-                const char* base = static_cast<const char*>(sc_col.chunks[row[q] >> sc_col.chunk_shift]) + (row[q] & mask) * oc.width;
-                v[q] = oc.width == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(base)) : *reinterpret_cast<const uint64_t*>(base);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (q < nb) {
-                if (oc.width == 4) static_cast<uint32_t*>(oc.dst)[pos[q]] = uint32_t(v[q]);
-                else static_cast<uint64_t*>(oc.dst)[pos[q]] = v[q];
-              }
-          } else if (oc.width == 4) {
-            uint32_t v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = q < nb ? static_cast<const uint32_t*>(src)[row[q]] : 0u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (q < nb) static_cast<uint32_t*>(oc.dst)[pos[q]] = v[q];
-          } else {
-            uint64_t v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = q < nb ? static_cast<const uint64_t*>(src)[row[q]] : 0ull;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (q < nb) static_cast<uint64_t*>(oc.dst)[pos[q]] = v[q];
-          }
-        } else {
-          Val acc[4];
-          eval_chain<4>(oc.chain, a.cols, row, acc, &err);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q < nb) store_val(oc.dst, oc.out_dtype, pos[q], acc[q]);
-        }
-      }
-    };
-    const unsigned total = sm.tile_total;  // CTA-uniform
-    if (total && total <= FP_LIST_CAP && a.balanced) {
-      // Balanced write: survivors are unevenly spread over the threads (NEXMark's hot auction id: when it satisfies
-      // the predicate, half of the rows of a stretch survive and one thread may own dozens), and the kernel ends with
-      // its slowest thread.  The tile-local item indices go through a small shared list in output order; then thread
-      // t writes entries t, t + 256, ...: every thread does ceil(total / 256) rounds and a warp's stores are dense.
-      unsigned long long m = bits;
-      while (m) {
-        const int k = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        s_list[cp_local_position<E, I>(sm, bits, k, lane_prefix)] = (unsigned short)cp_item_index<E>(k, tid);
-      }
-      __syncthreads();
-      for (unsigned i0 = 0; i0 < total; i0 += 4 * FP_THREADS) {
-        int64_t pos[4], row[4];
-        int nb = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const unsigned i = i0 + q * FP_THREADS + tid;
-          pos[q] = 0;
-          row[q] = -1;
-          if (i < total) {
-            pos[q] = int64_t(sm.excl) + i;
-            row[q] = tile_base + s_list[i];
-            nb = q + 1;
-          }
-        }
-        if (nb) write_rows(pos, row, nb);
-      }
-    } else if (bits && total) {
+    // A thread may own many survivors (NEXMark's hot auction id: when it satisfies the predicate half of the rows
+    // of a stretch survive), and every pass-through value is a dependent ~1 us DRAM read: gather four survivors
+    // at a time so that their loads are in flight together.
+    if (bits && sm.tile_total) {
       unsigned long long m = bits;
       while (m) {
         int64_t pos[4], row[4];
@@ -397,7 +312,57 @@ __global__ void __launch_bounds__(FP_THREADS, PredFn::MIN_CTAS) filter_compact_k
             nb = q + 1;
           }
         }
-        write_rows(pos, row, nb);
+        if (a.sel_out) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < nb) a.sel_out[pos[q]] = uint32_t(row[q]);
+        }
+        for (int c = 0; c < a.n_out; ++c) {
+          const OutCol& oc = a.outs[c];
+          if (oc.kind == OUT_PASS) {
+            const ColRef& sc_col = a.cols[oc.src_col];
+            const void* src = sc_col.data;
+            if (sc_col.chunks) {
+              // host-resident source: one PCIe read per survivor
+              const int64_t mask = (int64_t(1) << sc_col.chunk_shift) - 1;
+              uint64_t v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[q] = 0;
+                if (q < nb) {
+                  const char* base = static_cast<const char*>(sc_col.chunks[row[q] >> sc_col.chunk_shift]) + (row[q] & mask) * oc.width;
+                  v[q] = oc.width == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(base)) : *reinterpret_cast<const uint64_t*>(base);
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nb) {
+                  if (oc.width == 4) static_cast<uint32_t*>(oc.dst)[pos[q]] = uint32_t(v[q]);
+                  else static_cast<uint64_t*>(oc.dst)[pos[q]] = v[q];
+                }
+            } else if (oc.width == 4) {
+              uint32_t v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = q < nb ? static_cast<const uint32_t*>(src)[row[q]] : 0u;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nb) static_cast<uint32_t*>(oc.dst)[pos[q]] = v[q];
+            } else {
+              uint64_t v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = q < nb ? static_cast<const uint64_t*>(src)[row[q]] : 0ull;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < nb) static_cast<uint64_t*>(oc.dst)[pos[q]] = v[q];
+            }
+          } else {
+            Val acc[4];
+            eval_chain<4>(oc.chain, a.cols, row, acc, &err);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < nb) store_val(oc.dst, oc.out_dtype, pos[q], acc[q]);
+          }
+        }
       }
     }
     __syncthreads();  // sm is reused by the next tile
@@ -679,8 +644,6 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   }
 
   FilterArgs fa{};
-  static const bool no_balanced = getenv("FLOCKGPU_NO_BALANCED") != nullptr;
-  fa.balanced = no_balanced ? 0 : 1;
   fa.n_rows = in.num_rows;
   fa.out_count = ctx->d_scalars + 0;
   fa.err_flag = err_flag;
