@@ -6,12 +6,13 @@
 //   ProjectionExec: per-batch expression evaluation; plain Column exprs are zero-copy
 //
 // filter_compact_kernel: ONE launch for the whole relation (all 64 Ki-row batches: a 1.3 MB batch is
-// 0.2 us of HBM traffic, far below launch latency, so per-batch launches cannot work).  Persistent
-// CTAs take 4096-row tiles from an atomic ticket, evaluate the predicate (a hand-specialised functor
-// for the NEXMark shapes, the generic term interpreter otherwise), rank the survivors with warp
-// ballots, obtain the tile's global output offset by decoupled look-back (each input byte is read
-// once, no second pass), and write the surviving rows of every fixed-width output column in input
-// order.  Utf8 outputs leave through the selection vector and gather.cu.
+// 0.2 us of HBM traffic, far below launch latency, so per-batch launches cannot work).  CTAs take tiles of
+// 256 x {4, 16, 32, 64} rows (sized so that the relation is one wave of resident CTAs whenever possible),
+// evaluate the predicate (PredI32: one multiply-add + compare per row for the NEXMark shapes; the generic term
+// interpreter otherwise), rank the survivors (compact.cuh), obtain the tile's global output offset from the
+// grid-wide prefix protocol (each input byte is read once, no second pass), and write the surviving rows of every
+// fixed-width output column in input order.  Utf8 outputs leave through the selection vector and gather.cu.
+// Host-resident (page-locked, zero-copy fed) predicate columns are read in place over PCIe.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
