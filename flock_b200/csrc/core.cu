@@ -202,7 +202,7 @@ int64_t PendingRows::wait() {
   if (!done) {
     cudaSetDevice(ctx->device);
     FG_CUDA(cudaEventSynchronize(ev));
-    value = int64_t(ctx->h_scalars[256 + slot]);
+    value = int64_t(ctx->h_scalars[CtxCore::kScalars + slot]);
     done = true;
   }
   return value;
@@ -224,7 +224,7 @@ cudaEvent_t CtxCore::get_event(bool timing) {
   return e;
 }
 
-unsigned long long* PendingRows::host_slot() const { return ctx->h_scalars + 256 + slot; }
+unsigned long long* PendingRows::host_slot() const { return ctx->h_scalars + CtxCore::kScalars + slot; }
 
 std::shared_ptr<PendingRows> reserve_row_count(const CtxPtr& ctx) {
   const int slot = ctx->pending_next;
@@ -883,9 +883,9 @@ int flockgpu_open(int device, flockgpu_ctx** out) {
     FG_CUDA(cudaDeviceGetDefaultMemPool(&core->pool, device));
     uint64_t threshold = UINT64_MAX;  // keep freed blocks in the pool: allocation is on the hot path
     FG_CUDA(cudaMemPoolSetAttribute(core->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    FG_CUDA(cudaHostAlloc(&core->h_scalars, 512 * sizeof(unsigned long long), cudaHostAllocDefault));
-    FG_CUDA(cudaMalloc(&core->d_scalars, 512 * sizeof(unsigned long long)));
-    FG_CUDA(cudaMemset(core->d_scalars, 0, 512 * sizeof(unsigned long long)));
+    FG_CUDA(cudaHostAlloc(&core->h_scalars, (CtxCore::kScalars + CtxCore::kPendingSlots) * sizeof(unsigned long long), cudaHostAllocDefault));
+    FG_CUDA(cudaMalloc(&core->d_scalars, CtxCore::kScalars * sizeof(unsigned long long)));
+    FG_CUDA(cudaMemset(core->d_scalars, 0, CtxCore::kScalars * sizeof(unsigned long long)));
     for (int i = 0; i < 16; ++i) {
       FG_CUDA(cudaEventCreate(&core->timer_start[i]));
       FG_CUDA(cudaEventCreate(&core->timer_stop[i]));

@@ -747,10 +747,14 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   FG_CHECK(n_sel >= 0 && n_sel <= in.num_rows, FLOCKGPU_ERR_CUDA, "filter: corrupt survivor count %lld", (long long)n_sel);
   out->num_rows = n_sel;
   for (Column& c : out->cols) c.length = n_sel;
-  for (int i : utf8_outs) {
-    Column g = gather_column(ctx, in.cols[vals[i].src_col], fa.sel_out, n_sel);
-    g.name = out->cols[i].name;
-    out->cols[i] = std::move(g);
+  if (!utf8_outs.empty()) {
+    std::vector<const Column*> src;
+    for (int i : utf8_outs) src.push_back(&in.cols[vals[i].src_col]);
+    std::vector<Column> g = gather_columns(ctx, src, fa.sel_out, n_sel);  // one host round trip for all byte totals
+    for (size_t u = 0; u < utf8_outs.size(); ++u) {
+      g[u].name = out->cols[utf8_outs[u]].name;
+      out->cols[utf8_outs[u]] = std::move(g[u]);
+    }
   }
   return out;
 }

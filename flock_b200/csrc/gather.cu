@@ -32,6 +32,39 @@ __global__ void __launch_bounds__(GA_THREADS) gather_fixed_kernel(const T* __res
   for (; i < n; i += stride) out[i] = in[idx[i]];
 }
 
+// All fixed-width columns of one take() in ONE launch: the index is read once per row, the gathers of a row's columns
+// are independent and in flight together (q3's join output: 4 launches -> 1).
+constexpr int GM_MAX_COLS = 16;
+constexpr int kGatherTotalsSlot = 384;  // d_scalars[384 .. 447]: byte totals of the Utf8 columns of one take()
+struct GatherMultiArgs {
+  const uint32_t* idx;
+  int64_t n;
+  int32_t n_cols;
+  int32_t pad;
+  const void* src[GM_MAX_COLS];
+  void* dst[GM_MAX_COLS];
+  int32_t width[GM_MAX_COLS];
+};
+
+__global__ void __launch_bounds__(GA_THREADS) gather_fixed_multi_kernel(const __grid_constant__ GatherMultiArgs a) {
+  const int64_t stride = int64_t(gridDim.x) * GA_THREADS;
+  for (int64_t i = int64_t(blockIdx.x) * GA_THREADS + threadIdx.x; i < a.n; i += 2 * stride) {
+    const int64_t j = i + stride;
+    const uint32_t r0 = a.idx[i], r1 = j < a.n ? a.idx[j] : 0u;
+    for (int c = 0; c < a.n_cols; ++c) {
+      if (a.width[c] == 4) {
+        const uint32_t v0 = static_cast<const uint32_t*>(a.src[c])[r0], v1 = j < a.n ? static_cast<const uint32_t*>(a.src[c])[r1] : 0u;
+        static_cast<uint32_t*>(a.dst[c])[i] = v0;
+        if (j < a.n) static_cast<uint32_t*>(a.dst[c])[j] = v1;
+      } else {
+        const uint64_t v0 = static_cast<const uint64_t*>(a.src[c])[r0], v1 = j < a.n ? static_cast<const uint64_t*>(a.src[c])[r1] : 0ull;
+        static_cast<uint64_t*>(a.dst[c])[i] = v0;
+        if (j < a.n) static_cast<uint64_t*>(a.dst[c])[j] = v1;
+      }
+    }
+  }
+}
+
 // ---- Utf8 pass 1: out_off[i] = sum_{j<i} len(idx[j]); out_off[n] = total ---------------------------
 constexpr int GL_ITEMS = 8;
 constexpr int GL_TILE = GA_THREADS * GL_ITEMS;
@@ -230,16 +263,105 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
   return out;
 }
 
+// take() of several columns through one index vector: one launch for all fixed-width columns; the Utf8 columns' length
+// scans are launched back to back and their byte totals read with ONE host round trip (each used to cost its own).
+std::vector<Column> gather_columns(const CtxPtr& ctx, const std::vector<const Column*>& in, const uint32_t* d_idx, int64_t n) {
+  std::vector<Column> out(in.size());
+  std::vector<size_t> fixed, utf8;
+  for (size_t k = 0; k < in.size(); ++k) {
+    const Column& c = *in[k];
+    FG_CHECK(!c.all_null, FLOCKGPU_ERR_UNSUPPORTED, "gather: NULL column \"%s\"", c.name.c_str());
+    Column& o = out[k];
+    o.dtype = c.dtype;
+    o.name = c.name;
+    o.format = c.format;
+    o.nullable = c.nullable;
+    o.length = n;
+    (c.dtype == FLOCKGPU_UTF8 ? utf8 : fixed).push_back(k);
+  }
+  for (size_t first = 0; first < fixed.size(); first += GM_MAX_COLS) {
+    GatherMultiArgs a{};
+    a.idx = d_idx;
+    a.n = n;
+    a.n_cols = int(std::min<size_t>(GM_MAX_COLS, fixed.size() - first));
+    for (int c = 0; c < a.n_cols; ++c) {
+      const Column& src = *in[fixed[first + c]];
+      Column& o = out[fixed[first + c]];
+      o.data = alloc(ctx, size_t(n) * src.width());
+      a.src[c] = src.values();
+      a.dst[c] = o.data->ptr;
+      a.width[c] = src.width();
+    }
+    if (n > 0) {
+      {
+        LaunchTimer lt(ctx, "gather_fixed_multi_kernel");
+        gather_fixed_multi_kernel<<<stream_grid(ctx, n, GA_THREADS * 2), GA_THREADS, 0, ctx->stream>>>(a);
+      }
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    }
+  }
+  if (utf8.empty()) return out;
+  FG_CHECK(utf8.size() <= 64, FLOCKGPU_ERR_UNSUPPORTED, "gather: more than 64 Utf8 columns");
+  for (size_t u = 0; u < utf8.size(); ++u) {
+    Column& o = out[utf8[u]];
+    o.offsets = alloc(ctx, size_t(n + 1) * 4);
+    if (n == 0) {
+      FG_CUDA(cudaMemsetAsync(o.offsets->ptr, 0, 4, ctx->stream));
+      o.data = alloc(ctx, 0);
+      o.values_bytes = 0;
+      continue;
+    }
+    GatherLenArgs a{};
+    a.in_off = in[utf8[u]]->offs();
+    a.idx = d_idx;
+    a.out_off = o.offsets->as<int32_t>();
+    a.n = n;
+    const int64_t num_tiles = (n + GL_TILE - 1) / GL_TILE;
+    int per_sm = 1;
+    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_lengths_scan_kernel, GA_THREADS, 0));
+    a.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + kGatherTotalsSlot + u);
+    {
+      LaunchTimer lt(ctx, "gather_lengths_scan_kernel");
+      launch_compact(ctx, gather_lengths_scan_kernel, a.sc, a);
+    }
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
+  if (n == 0) return out;
+  std::vector<unsigned long long> totals(utf8.size());
+  read_scalars(ctx, kGatherTotalsSlot, int(utf8.size()), totals.data());
+  for (size_t u = 0; u < utf8.size(); ++u) {
+    const Column& src = *in[utf8[u]];
+    Column& o = out[utf8[u]];
+    FG_CHECK(totals[u] < (1ull << 31), FLOCKGPU_ERR_UNSUPPORTED, "gather: Utf8 result column \"%s\" exceeds 2^31-1 bytes", src.name.c_str());
+    o.values_bytes = int64_t(totals[u]);
+    o.data = alloc(ctx, size_t(totals[u]));
+    if (totals[u] > 0) {
+      {
+        LaunchTimer lt(ctx, "gather_utf8_copy_kernel");
+        gather_utf8_copy_kernel<<<stream_grid(ctx, (n + 31) / 32, GA_THREADS / 32), GA_THREADS, 0, ctx->stream>>>(
+            static_cast<const uint8_t*>(src.values()), src.offs(), d_idx, o.offsets->as<int32_t>(), o.data->as<uint8_t>(), n);
+      }
+      FG_CUDA(cudaGetLastError());
+      count_launch(ctx);
+    }
+  }
+  return out;
+}
+
 TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx, int64_t n_idx) {
   in.dense();
   auto out = std::make_shared<Table>();
   out->ctx = ctx;
   out->metadata = in.metadata;
   out->num_rows = n_idx;
+  std::vector<const Column*> src;
   for (int c : cols) {
     FG_CHECK(c >= 0 && c < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "gather: column %d out of range", c);
-    out->cols.push_back(gather_column(ctx, in.cols[c], d_idx, n_idx));
+    src.push_back(&in.cols[c]);
   }
+  out->cols = gather_columns(ctx, src, d_idx, n_idx);
   return out;
 }
 

@@ -1504,7 +1504,9 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       out->cols.push_back(std::move(c));
     }
   } else {
-    for (int g : group_cols) out->cols.push_back(gather_column(ctx, in.cols[g], rep_rows->as<uint32_t>(), int64_t(n_groups)));
+    std::vector<const Column*> src;
+    for (int g : group_cols) src.push_back(&in.cols[g]);
+    for (Column& c : gather_columns(ctx, src, rep_rows->as<uint32_t>(), int64_t(n_groups))) out->cols.push_back(std::move(c));
   }
   for (Column& c : val_cols) {
     c.length = int64_t(n_groups);

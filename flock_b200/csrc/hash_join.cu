@@ -421,8 +421,11 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
   // output schema is always left ++ right, whichever side was hashed
   const uint32_t* l_idx = (swap_sides ? probe_idx : build_idx)->as<uint32_t>();
   const uint32_t* r_idx = (swap_sides ? build_idx : probe_idx)->as<uint32_t>();
-  for (const Column& c : L.cols) out->cols.push_back(gather_column(ctx, c, l_idx, n_pairs));
-  for (const Column& c : R.cols) out->cols.push_back(gather_column(ctx, c, r_idx, n_pairs));
+  std::vector<const Column*> lsrc, rsrc;
+  for (const Column& c : L.cols) lsrc.push_back(&c);
+  for (const Column& c : R.cols) rsrc.push_back(&c);
+  for (Column& c : gather_columns(ctx, lsrc, l_idx, n_pairs)) out->cols.push_back(std::move(c));
+  for (Column& c : gather_columns(ctx, rsrc, r_idx, n_pairs)) out->cols.push_back(std::move(c));
   return out;
 }
 

@@ -91,8 +91,11 @@ struct CtxCore {
   std::recursive_mutex mu;
 
   // small pinned buffer for device->host scalar read-backs and device scalars
-  unsigned long long* h_scalars = nullptr;  // pinned, 512 x u64
-  unsigned long long* d_scalars = nullptr;  // device, 512 x u64
+  // d_scalars[0, kScalars): counters / totals written by kernels; read_scalars() mirrors a range into h_scalars at the
+  // same indices.  h_scalars[kScalars, kScalars + kPendingSlots): the pinned row-count slots of PendingRows.
+  static constexpr int kScalars = 512;
+  unsigned long long* h_scalars = nullptr;  // pinned, kScalars + kPendingSlots x u64
+  unsigned long long* d_scalars = nullptr;  // device, kScalars x u64
 
   ScanScratch scan;
   void* l2_flush = nullptr;
@@ -108,7 +111,7 @@ struct CtxCore {
 
   std::shared_ptr<Comm> comm;  // comm.cc (shared_ptr: Comm is incomplete here)
 
-  // row counts still in flight (see PendingRows): pinned slots h_scalars[256 + i]
+  // row counts still in flight (see PendingRows): pinned slots h_scalars[kScalars + i]
   static constexpr int kPendingSlots = 256;
   std::weak_ptr<struct PendingRows> pending_owner[kPendingSlots];
   int pending_next = 0;
@@ -306,6 +309,7 @@ TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>&
                      int64_t n_idx);
 // Gathers single columns (used by filter for Utf8 pass-through and by join).
 Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx, int64_t n_idx);
+std::vector<Column> gather_columns(const CtxPtr& ctx, const std::vector<const Column*>& in, const uint32_t* d_idx, int64_t n);
 
 TablePtr all_to_all(const CtxPtr& ctx, const std::vector<TablePtr>& parts);
 void comm_unique_id(uint8_t* out);

@@ -145,7 +145,7 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   count_launch(ctx);
 
   // bases live in d_scalars[16 .. 16 + n_parts]; the per-pass survivor count in d_scalars[5]
-  FG_CHECK(16 + n_parts + 1 <= 512, FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: too many partitions");
+  FG_CHECK(16 + n_parts + 1 <= 384, FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: too many partitions");  // d_scalars[384 ..] belongs to gather.cu
   unsigned long long* bases = ctx->d_scalars + 16;
   FG_CUDA(cudaMemsetAsync(bases, 0, sizeof(unsigned long long) * (n_parts + 1), ctx->stream));
   BufferPtr idx = alloc(ctx, size_t(n) * 4);

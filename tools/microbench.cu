@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #define CK(x)                                                                      \
@@ -209,7 +210,8 @@ float time_ms(F&& f, int reps = 5) {
   return best;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const bool only_pcie = argc > 1 && !strcmp(argv[1], "pcie");
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -222,6 +224,55 @@ int main() {
   CK(cudaMemset(buf, 1, big));
   char* flush;
   CK(cudaMalloc(&flush, size_t(512) << 20));
+
+  {
+    // (6) zero-copy reads of page-locked HOST memory over PCIe: SM loads (the filter's zero-copy feed) vs TMA bulk
+    // copies into shared memory vs one cudaMemcpyAsync of the same 40 MB
+    const size_t hbytes = size_t(40) << 20;
+    char* hbuf;
+    CK(cudaHostAlloc(&hbuf, hbytes, cudaHostAllocDefault));
+    memset(hbuf, 1, hbytes);
+    auto timed1 = [&](auto&& launch) {
+      float best = 1e30f;
+      for (int r = 0; r < 4; ++r) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a);
+        launch();
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        best = ms < best ? ms : best;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+      }
+      return best;
+    };
+    for (int cta_per_sm : {2, 4, 8}) {
+      float t4 = timed1([&] { read_ldg<4><<<sms * cta_per_sm, 256>>>(reinterpret_cast<const int4*>(hbuf), hbytes / 16, sink); });
+      float t8 = timed1([&] { read_ldg<8><<<sms * cta_per_sm, 256>>>(reinterpret_cast<const int4*>(hbuf), hbytes / 16, sink); });
+      printf("pcie read_ldg 40MB pinned host ctas/sm=%d: unroll4 %.3f ms %.1f GB/s, unroll8 %.3f ms %.1f GB/s\n", cta_per_sm, t4, hbytes / t4 / 1e6, t8, hbytes / t8 / 1e6);
+    }
+    {
+      constexpr int STAGES = 4, CHUNK = 16384;
+      CK(cudaFuncSetAttribute(read_tma<STAGES, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * CHUNK));
+      for (int cta_per_sm : {1, 2, 3}) {
+        float t = timed1([&] { read_tma<STAGES, CHUNK><<<sms * cta_per_sm, 256, STAGES * CHUNK>>>(hbuf, hbytes, sink); });
+        printf("pcie read_tma 4x16KB 40MB pinned host ctas/sm=%d: %.3f ms %.1f GB/s\n", cta_per_sm, t, hbytes / t / 1e6);
+      }
+    }
+    float tc = timed1([&] { cudaMemcpyAsync(buf, hbuf, hbytes, cudaMemcpyHostToDevice); });
+    printf("pcie cudaMemcpyAsync 40MB pinned host -> HBM (one call): %.3f ms %.1f GB/s\n", tc, hbytes / tc / 1e6);
+    float tc153 = timed1([&] {
+      for (int b = 0; b < 153; ++b) cudaMemcpyAsync(buf + size_t(b) * 262144, hbuf + size_t(b) * 262144, 262144, cudaMemcpyHostToDevice);
+    });
+    printf("pcie 153 x cudaMemcpyAsync of 256 KB (the per-batch feed): %.3f ms %.1f GB/s\n", tc153, 153 * 262144.0 / tc153 / 1e6);
+    CK(cudaGetLastError());
+    cudaFreeHost(hbuf);
+    if (only_pcie) return 0;
+  }
 
   for (size_t bytes : {size_t(40) << 20, size_t(400) << 20, big}) {
     for (int cta_per_sm : {2, 4, 8}) {
