@@ -89,6 +89,9 @@ CtxCore::~CtxCore() {
   if (stream) cudaStreamSynchronize(stream);
   for (auto& kv : pinned) cudaFreeHost(kv.first);
   pinned.clear();
+  for (PinSlab& sl : pin_slabs)
+    if (sl.base) cudaFreeHost(sl.base);
+  pin_slabs.clear();
   if (scan.ep_state) cudaFree(scan.ep_state);
   if (scan.ep_counts) cudaFree(scan.ep_counts);
   if (scan.ep_counters) cudaFree(scan.ep_counters);
@@ -874,6 +877,10 @@ int flockgpu_open(int device, flockgpu_ctx** out) {
     cudaDeviceProp prop;
     FG_CUDA(cudaGetDeviceProperties(&prop, device));
     core->sm_count = prop.multiProcessorCount;
+    // the single-wave prefix needs co-resident CTAs (cooperative launch); without it every compaction uses look-back
+    int coop = 0;
+    FG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) core->compact_mode = 1;
     FG_CUDA(cudaStreamCreateWithFlags(&core->stream, cudaStreamNonBlocking));
     for (int i = 0; i < CtxCore::kCopyStreams; ++i) {
       FG_CUDA(cudaStreamCreateWithFlags(&core->copy_streams[i], cudaStreamNonBlocking));
@@ -943,10 +950,38 @@ int flockgpu_host_alloc(flockgpu_ctx* ctx, int64_t bytes, void** out) {
   return guarded([&] {
     auto c = core_of(ctx);
     FG_CHECK(out && bytes >= 0, FLOCKGPU_ERR_INVALID, "host_alloc: bad arguments");
-    void* p = nullptr;
-    FG_CUDA(cudaHostAlloc(&p, size_t(bytes ? bytes : 8), cudaHostAllocDefault));
+    const size_t need = (size_t(bytes ? bytes : 8) + 255) & ~size_t(255);  // Arrow wants 64-byte alignment; kernels read 16-byte vectors
     std::lock_guard<std::mutex> g(c->pin_mu);
-    c->pinned.emplace(p, size_t(bytes));
+    size_t slab = c->pin_slabs.size();
+    for (size_t i = c->pin_slabs.size(); i-- > 0;) {  // newest first: consecutive allocations stay contiguous
+      CtxCore::PinSlab& sl = c->pin_slabs[i];
+      if (sl.base && sl.size - sl.used >= need) {
+        slab = i;
+        break;
+      }
+    }
+    if (slab == c->pin_slabs.size()) {
+      CtxCore::PinSlab sl;
+      sl.size = std::max(need, CtxCore::kPinSlabBytes);
+      FG_CUDA(cudaSetDevice(c->device));
+      void* p = nullptr;
+      FG_CUDA(cudaHostAlloc(&p, sl.size, cudaHostAllocDefault));
+      sl.base = static_cast<char*>(p);
+      // reuse the table entry of a released slab if there is one
+      slab = c->pin_slabs.size();
+      for (size_t i = 0; i < c->pin_slabs.size(); ++i)
+        if (!c->pin_slabs[i].base) {
+          slab = i;
+          break;
+        }
+      if (slab == c->pin_slabs.size()) c->pin_slabs.push_back(sl);
+      else c->pin_slabs[slab] = sl;
+    }
+    CtxCore::PinSlab& sl = c->pin_slabs[slab];
+    void* p = sl.base + sl.used;
+    sl.used += need;
+    ++sl.live;
+    c->pin_owner.emplace(p, slab);
     *out = p;
   });
 }
@@ -955,10 +990,21 @@ int flockgpu_host_free(flockgpu_ctx* ctx, void* ptr) {
   return guarded([&] {
     auto c = core_of(ctx);
     std::lock_guard<std::mutex> g(c->pin_mu);
-    auto it = c->pinned.find(ptr);
-    FG_CHECK(it != c->pinned.end(), FLOCKGPU_ERR_INVALID, "host_free: pointer was not allocated by host_alloc");
-    c->pinned.erase(it);
-    FG_CUDA(cudaFreeHost(ptr));
+    auto it = c->pin_owner.find(ptr);
+    FG_CHECK(it != c->pin_owner.end(), FLOCKGPU_ERR_INVALID, "host_free: pointer was not allocated by host_alloc");
+    CtxCore::PinSlab& sl = c->pin_slabs[it->second];
+    c->pin_owner.erase(it);
+    if (--sl.live == 0) {
+      // the slab is empty again: keep one standard slab for reuse, give everything else back
+      size_t idle = 0;
+      for (const CtxCore::PinSlab& o : c->pin_slabs) idle += (o.base && o.live == 0 && &o != &sl) ? 1 : 0;
+      if (sl.size > CtxCore::kPinSlabBytes || idle >= 1) {
+        FG_CUDA(cudaFreeHost(sl.base));
+        sl = CtxCore::PinSlab{};
+      } else {
+        sl.used = 0;
+      }
+    }
   });
 }
 

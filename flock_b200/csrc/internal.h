@@ -108,6 +108,18 @@ struct CtxCore {
   // pinned host blocks handed out by flockgpu_host_alloc and by table export
   std::mutex pin_mu;
   std::unordered_map<void*, size_t> pinned;
+  // flockgpu_host_alloc sub-allocates from page-locked SLABS: record batches allocated one after the other end up
+  // contiguous in one large registration (few, large GPU mappings) instead of thousands of 256 KB registrations --
+  // the in-place PCIe read of such batches measured 40.6 GB/s over 153 separate allocations against 51.1 GB/s over
+  // one 40 MB allocation (profiles/r1_microbench_pcie_run17.txt).
+  struct PinSlab {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    int64_t live = 0;
+  };
+  static constexpr size_t kPinSlabBytes = size_t(64) << 20;
+  std::vector<PinSlab> pin_slabs;
+  std::unordered_map<void*, size_t> pin_owner;  // allocation -> slab index
 
   std::shared_ptr<Comm> comm;  // comm.cc (shared_ptr: Comm is incomplete here)
 

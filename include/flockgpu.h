@@ -109,7 +109,10 @@ int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value);
 int flockgpu_profile_begin(flockgpu_ctx* ctx);
 int flockgpu_profile_end(flockgpu_ctx* ctx, char* out_json, int32_t capacity);
 /* Pinned host memory (page-locked) for staging Arrow buffers: bench.py's e2e leg and the Rust shim
- * allocate record-batch buffers here so that host<->device copies are true DMA.                    */
+ * allocate record-batch buffers here so that host<->device copies are true DMA and the zero-copy feed can read them
+ * in place.  Blocks are 256-byte aligned and carved out of 64 MB page-locked slabs in allocation order (buffers
+ * allocated one after the other are contiguous: few large GPU mappings instead of one per buffer); a slab's space
+ * returns when all of its blocks have been freed -- the lifetime pattern of record batches.            */
 int flockgpu_host_alloc(flockgpu_ctx* ctx, int64_t bytes, void** out);
 int flockgpu_host_free(flockgpu_ctx* ctx, void* ptr);
 /* Overwrites a scratch buffer larger than L2 (126 MB) so that the next timed launch starts cold.   */
