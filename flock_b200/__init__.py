@@ -398,6 +398,18 @@ def selftest_eval_predicate(batch: pa.RecordBatch, predicate: E):
     return mask[:batch.num_rows].astype(bool), fast.value
 
 
+def selftest_pred_i32(x, modulus: int, cmp: int, rhs: int):
+    """CPU-only: `CAST(x AS Int64) [% modulus] cmp rhs` (modulus 0 = no `%`) with the constants and the per-row test of the
+    vectorised filter kernel (csrc/pred_i32.h).  Returns (bool mask, arithmetic mode 0 / 1 / 2)."""
+    import numpy as np
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    keep = np.zeros(max(len(x), 1), np.uint8)
+    mode = C.c_int32()
+    check(lib.flockgpu_selftest_pred_i32(modulus, cmp, rhs, x.ctypes.data_as(C.POINTER(C.c_int32)), len(x),
+                                         keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(mode)))
+    return keep[:len(x)].astype(bool), mode.value
+
+
 def selftest_eval_value(batch: pa.RecordBatch, expr: E):
     """CPU-only check of value-expression lowering: returns (numpy values or None if pass-through, dtype code)."""
     import numpy as np

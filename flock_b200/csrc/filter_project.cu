@@ -20,6 +20,7 @@
 #include "compact.cuh"
 #include "expr_compile.h"
 #include "internal.h"
+#include "pred_i32.h"
 
 namespace fg {
 
@@ -62,36 +63,6 @@ struct PredGenericT {
   }
 };
 
-__device__ __forceinline__ bool cmp_i64(int cmp, int64_t a, int64_t b) {
-  switch (cmp) {
-    case FLOCKGPU_OP_EQ: return a == b;
-    case FLOCKGPU_OP_NE: return a != b;
-    case FLOCKGPU_OP_LT: return a < b;
-    case FLOCKGPU_OP_LE: return a <= b;
-    case FLOCKGPU_OP_GT: return a > b;
-    default: return a >= b;
-  }
-}
-
-// CAST(i32col AS Int64) [% m] CMP rhs over 128-bit loads, three arithmetic shapes:
-//   MODE 0  affine range test  keep = (uint32(x) * mul + add <= span) != neg      -- one IMAD + one compare per row.
-//           Covers every plain comparison (mul = 1, add = -lo, span = hi - lo for the interval [lo, hi] of
-//           accepted values, `neg` for the complement) AND `% m (=|!=) 0` for odd m: with inv = m^-1 mod 2^32,
-//           L = (2^31 - 1) / m, L2 = 2^31 / m, x is a multiple of m iff x * inv mod 2^32 lies in [0, L] (x >= 0)
-//           or in [2^32 - L2, 2^32) (x < 0), i.e. iff x * inv + L2 <= L + L2 (Granlund-Montgomery exact division
-//           test, Hacker's Delight 10-17, extended to signed dividends).
-//   MODE 1  general `% m CMP c` via Lemire's fastmod (M = 2^64 / m + 1: two multiplies instead of a division).
-//   MODE 2  `% m (=|!=) 0` for even m = 2^k q: rotr(|x| * q^-1, k) <= (2^32 - 1) / m.
-struct PredI32Consts {
-  // MODE 0 / 2
-  uint32_t mul, add, span, rot;
-  int32_t neg;
-  // MODE 1
-  int32_t cmp;
-  uint32_t d;
-  uint64_t M;
-  int64_t rhs;
-};
 
 template <int MODE, int ITEMS>
 struct PredI32 {
@@ -107,18 +78,7 @@ struct PredI32 {
     if (!chunks) return col + row0;
     return static_cast<const int32_t*>(chunks[row0 >> chunk_shift]) + (row0 & ((int64_t(1) << chunk_shift) - 1));
   }
-  __device__ __forceinline__ bool test(int32_t x) const {
-    if (MODE == 0) return (uint32_t(x) * k.mul + k.add <= k.span) != bool(k.neg);
-    const uint32_t ax = x < 0 ? 0u - uint32_t(x) : uint32_t(x);
-    if (MODE == 2) {
-      const uint32_t m = ax * k.mul;
-      return (__funnelshift_r(m, m, k.rot) <= k.span) != bool(k.neg);
-    }
-    const uint64_t low = k.M * uint64_t(ax);
-    int64_t r = int64_t(__umul64hi(low, uint64_t(k.d)));
-    if (x < 0) r = -r;
-    return cmp_i64(k.cmp, r, k.rhs);
-  }
+  __device__ __forceinline__ bool test(int32_t x) const { return pred_i32_test<MODE>(k, x); }
   __device__ __forceinline__ unsigned test4(const int4& v) const {
     return unsigned(test(v.x)) | (unsigned(test(v.y)) << 1) | (unsigned(test(v.z)) << 2) | (unsigned(test(v.w)) << 3);
   }
@@ -175,69 +135,6 @@ struct PredI32 {
     return bits;
   }
 };
-
-// Host side: the constants of PredI32 for `CAST(col AS Int64) [% modulus] cmp rhs` (modulus = 0: no `%`).
-// Returns the MODE to launch.
-static int pred_i32_consts(int64_t modulus, int cmp, int64_t rhs, PredI32Consts* out) {
-  PredI32Consts k{};
-  k.cmp = cmp;
-  k.rhs = rhs;
-  if (modulus == 0) {
-    // accepted interval [lo, hi] of the positive form; NE is the complement of EQ
-    const int64_t MIN = INT32_MIN, MAX = INT32_MAX;
-    int64_t lo = MIN, hi = MAX;
-    bool neg = false;
-    switch (cmp) {
-      case FLOCKGPU_OP_EQ: lo = hi = rhs; break;
-      case FLOCKGPU_OP_NE: lo = hi = rhs; neg = true; break;
-      case FLOCKGPU_OP_LT: hi = rhs > MIN ? rhs - 1 : MIN - 1; break;
-      case FLOCKGPU_OP_LE: hi = rhs; break;
-      case FLOCKGPU_OP_GT: lo = rhs < MAX ? rhs + 1 : MAX + 1; break;
-      default: lo = rhs; break;  // GE
-    }
-    lo = std::max(lo, MIN);
-    hi = std::min(hi, MAX);
-    if (lo > hi) {  // nothing in the int32 domain: the complement of everything
-      lo = MIN;
-      hi = MAX;
-      neg = !neg;
-    }
-    k.mul = 1u;
-    k.add = 0u - uint32_t(int32_t(lo));
-    k.span = uint32_t(hi - lo);
-    k.neg = neg;
-    *out = k;
-    return 0;
-  }
-  const uint32_t d = uint32_t(modulus);
-  k.d = d;
-  k.M = ~uint64_t(0) / d + 1;
-  const bool divisibility = rhs == 0 && (cmp == FLOCKGPU_OP_EQ || cmp == FLOCKGPU_OP_NE);
-  if (!divisibility) {
-    *out = k;
-    return 1;
-  }
-  uint32_t rot = 0, q = d;
-  while (!(q & 1u)) {
-    q >>= 1;
-    ++rot;
-  }
-  uint32_t inv = q;  // Newton: doubles the number of correct low bits per step (3 -> 96)
-  for (int it = 0; it < 5; ++it) inv *= 2u - q * inv;
-  k.mul = inv;
-  k.neg = cmp == FLOCKGPU_OP_NE;
-  if (rot == 0) {
-    const uint32_t L = 0x7fffffffu / d, L2 = 0x80000000u / d;
-    k.add = L2;
-    k.span = L + L2;
-    *out = k;
-    return 0;
-  }
-  k.rot = rot;
-  k.span = 0xffffffffu / d;
-  *out = k;
-  return 2;
-}
 
 __device__ __forceinline__ void copy_value(void* dst, const void* src, int width, int64_t pos, int64_t row) {
   if (width == 4) static_cast<uint32_t*>(dst)[pos] = static_cast<const uint32_t*>(src)[row];

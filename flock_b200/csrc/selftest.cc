@@ -6,6 +6,7 @@
 // path: no operator, plan node or Python wrapper calls them, and they handle one expression, not plans.
 #include "expr_compile.h"
 #include "internal.h"
+#include "pred_i32.h"
 
 using namespace fg;
 
@@ -86,3 +87,18 @@ int flockgpu_selftest_eval_value(const struct ArrowSchema* schema, const struct 
 }
 
 }  // extern "C"
+
+// The vectorised predicate `CAST(x AS Int64) [% modulus] cmp rhs` (modulus = 0: no `%`) exactly as the filter kernel
+// evaluates it: same constants (pred_i32_consts), same per-row test (pred_i32_test), on the host.  out_mode receives the
+// arithmetic shape chosen (0 affine range test, 1 Lemire fastmod, 2 rotate test for even moduli).
+int flockgpu_selftest_pred_i32(int64_t modulus, int32_t cmp, int64_t rhs, const int32_t* x, int64_t n, uint8_t* out_keep, int32_t* out_mode) {
+  return guarded([&] {
+    FG_CHECK(x && out_keep && n >= 0 && modulus >= 0 && modulus < (int64_t(1) << 31), FLOCKGPU_ERR_INVALID, "selftest_pred_i32: bad arguments");
+    PredI32Consts k;
+    const int mode = pred_i32_consts(modulus, cmp, rhs, &k);
+    if (out_mode) *out_mode = mode;
+    for (int64_t i = 0; i < n; ++i)
+      out_keep[i] = mode == 0 ? pred_i32_test<0>(k, x[i]) : mode == 1 ? pred_i32_test<1>(k, x[i]) : pred_i32_test<2>(k, x[i]);
+  });
+}
+

@@ -300,6 +300,9 @@ int flockgpu_selftest_eval_predicate(const struct ArrowSchema* schema, const str
 int flockgpu_selftest_eval_value(const struct ArrowSchema* schema, const struct ArrowArray* batch,
                                  const flockgpu_expr* expr, void* out, int32_t* out_dtype,
                                  int32_t* out_passthrough);
+/* CPU-only: the arithmetic of the vectorised filter predicate CAST(x AS Int64) [% modulus] cmp rhs (modulus 0 = no `%`),
+ * with the constants and the per-row test the GPU kernel uses (flock_b200/csrc/pred_i32.h).  out_keep[i] in {0, 1}. */
+int flockgpu_selftest_pred_i32(int64_t modulus, int32_t cmp, int64_t rhs, const int32_t* x, int64_t n, uint8_t* out_keep, int32_t* out_mode);
 
 #ifdef __cplusplus
 }

@@ -206,3 +206,32 @@ def test_nexgen_invariants():
     a = pa.Table.from_batches(ev["auction"])
     assert set(a["category"].to_pylist()) <= set(range(10, 15))
     assert all(1000 <= s < 1000 + 200 + 10 for s in a["seller"].to_pylist())
+
+
+# ---- the arithmetic of the vectorised filter predicate (csrc/pred_i32.h), exactly as the GPU kernel runs it ---------------
+@pytest.mark.parametrize("modulus", [0, 1, 2, 3, 6, 96, 123, 1000, 1 << 20, 3 << 29, (1 << 31) - 1])
+def test_pred_i32_arithmetic_matches_truncated_remainder(modulus):
+    """`CAST(x AS Int64) % m cmp c` with Rust / Arrow semantics (sign follows the dividend) for every comparison, boundary
+    literals, negative dividends and INT_MIN -- through the same constants and per-row test the kernel uses."""
+    import operator
+    rng = np.random.default_rng(modulus + 1)
+    n = 200_000
+    x = rng.integers(-(1 << 31), 1 << 31, n).astype(np.int64)
+    if modulus:
+        x[::5] = rng.integers(-((1 << 31) // modulus), ((1 << 31) - 1) // modulus + 1, len(x[::5])) * modulus   # plenty of multiples
+    x[:6] = [0, -(1 << 31), (1 << 31) - 1, -1, 1, -(1 << 31) + 1]
+    lhs = np.fmod(x, modulus) if modulus else x
+    ops = {fb.OP_EQ: operator.eq, fb.OP_NE: operator.ne, fb.OP_LT: operator.lt, fb.OP_LE: operator.le, fb.OP_GT: operator.gt, fb.OP_GE: operator.ge}
+    literals = [0, 1, -1, 10, -7] + ([] if modulus else [-(1 << 31), (1 << 31) - 1, -(1 << 31) - 1, 1 << 31, 1 << 40, -(1 << 40)])
+    modes = set()
+    for cmp, fn in ops.items():
+        for rhs in literals:
+            keep, mode = fb.selftest_pred_i32(x, modulus, cmp, rhs)
+            modes.add(mode)
+            assert np.array_equal(keep, fn(lhs, rhs)), (modulus, cmp, rhs, mode)
+    if modulus == 0:
+        assert modes == {0}                      # every plain comparison is one affine range test
+    elif modulus % 2:
+        assert modes == {0, 1}                   # odd m: `% m (=|!=) 0` is the affine test, everything else Lemire
+    else:
+        assert modes == {1, 2}                   # even m: rotate test for divisibility
