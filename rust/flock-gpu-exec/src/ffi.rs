@@ -3,7 +3,7 @@
 //! `struct ArrowSchema`).
 #![allow(non_camel_case_types)]
 use datafusion::arrow::ffi::{FFI_ArrowArray, FFI_ArrowSchema};
-use std::os::raw::{c_char, c_int};
+use std::os::raw::{c_char, c_int, c_void};
 
 #[repr(C)]
 pub struct flockgpu_ctx {
@@ -25,6 +25,11 @@ extern "C" {
     pub fn flockgpu_open(device: c_int, out: *mut *mut flockgpu_ctx) -> c_int;
     pub fn flockgpu_close(ctx: *mut flockgpu_ctx) -> c_int;
     pub fn flockgpu_last_error() -> *const c_char;
+    /// "feed_zero_copy" (0/1): page-locked, uniformly batched fixed-width columns stay in host memory and are read in place.
+    pub fn flockgpu_set_option(ctx: *mut flockgpu_ctx, name: *const c_char, value: i64) -> c_int;
+    /// Page-locked host memory for record-batch buffers (256-byte aligned, carved out of 64 MB slabs).
+    pub fn flockgpu_host_alloc(ctx: *mut flockgpu_ctx, bytes: i64, out: *mut *mut c_void) -> c_int;
+    pub fn flockgpu_host_free(ctx: *mut flockgpu_ctx, ptr: *mut c_void) -> c_int;
 
     pub fn flockgpu_table_export(
         ctx: *mut flockgpu_ctx,
