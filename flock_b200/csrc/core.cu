@@ -389,54 +389,20 @@ static std::shared_ptr<HostChunks> try_host_chunks(const CtxPtr& ctx, const Arro
   return hc;
 }
 
-// Host-resident chunked column -> one contiguous HBM column, by the SMs: 16-byte loads straight from the page-locked
-// batches (51 GB/s measured for such reads) instead of one cudaMemcpyAsync per 256 KB batch (30 GB/s,
-// profiles/r1_microbench_pcie_run17.txt).  Every chunk but the last holds 1 << shift rows and starts 16-byte aligned.
-__global__ void __launch_bounds__(256) chunks_to_dense_kernel(const void* const* __restrict__ chunks, int shift, int64_t n_vec, int vec_per_chunk_shift,
-                                                              int4* __restrict__ dst) {
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  const int64_t mask = (int64_t(1) << vec_per_chunk_shift) - 1;
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n_vec; i += 4 * stride) {
-    int4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t j = i + u * stride;
-      v[u] = ldg_stream_v4(static_cast<const int4*>(chunks[j >> vec_per_chunk_shift]) + (j & mask));
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) dst[i + u * stride] = v[u];
-  }
-  for (; i < n_vec; i += stride) dst[i] = ldg_stream_v4(static_cast<const int4*>(chunks[i >> vec_per_chunk_shift]) + (i & mask));
-}
-
 void Table::dense() const {
   resolve();
   for (Column& c : cols) {
     if (!c.chunks) continue;
     const int w = c.width();
     c.data = alloc(ctx, size_t(c.length) * w);
-    // whole 16-byte vectors by kernel (the buffer is padded, and so is every Arrow / slab buffer it reads from: a tail
-    // of < 16 bytes goes through one small memcpy instead of an over-read of host memory)
-    const int64_t bytes = c.length * w;
-    const int64_t n_vec = bytes / 16;
-    const int vshift = c.chunks->shift + (w == 8 ? 3 : 2) - 4;  // 16-byte vectors per full chunk = rows * w / 16
-    if (n_vec > 0) {
-      const int grid = int(std::max<int64_t>(1, std::min<int64_t>((n_vec + 1023) / 1024, int64_t(ctx->sm_count) * 8)));
-      {
-        LaunchTimer lt(ctx, "chunks_to_dense_kernel");
-        chunks_to_dense_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const void* const*>(c.chunks->table->ptr), c.chunks->shift, n_vec, vshift,
-                                                              static_cast<int4*>(c.data->ptr));
-      }
-      FG_CUDA(cudaGetLastError());
-      count_launch(ctx);
+    CopyFan fan(ctx);
+    fan.fork();
+    int64_t row = 0;
+    for (size_t k = 0; k < c.chunks->ptrs.size(); ++k) {
+      fan.copy(static_cast<char*>(c.data->ptr) + row * w, c.chunks->ptrs[k], size_t(c.chunks->rows[k]) * w);
+      row += c.chunks->rows[k];
     }
-    if (bytes > n_vec * 16) {
-      const int64_t done_rows = n_vec * 16 / w, chunk_rows = int64_t(1) << c.chunks->shift;
-      const size_t k = size_t(done_rows / chunk_rows);
-      FG_CUDA(cudaMemcpyAsync(static_cast<char*>(c.data->ptr) + n_vec * 16, static_cast<const char*>(c.chunks->ptrs[k]) + (done_rows % chunk_rows) * w,
-                              size_t(bytes - n_vec * 16), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    fan.join();
     c.chunks.reset();
   }
 }

@@ -181,11 +181,7 @@ def main():
 
         e2e_ms = None
         if not args.no_e2e:
-            # the reference-facing call sequence with page-locked host batches (flockgpu_host_alloc) and the zero-copy feed:
-            # fixed-width columns are read / materialised by kernels straight from host memory, Utf8 columns are copied
-            pinned = {r: [ctx.pinned_copy(b) for b in rel[r]] for r in dict.fromkeys(order)}
-            src = [[pinned[r]] for r in order]
-            ctx.set_option("feed_zero_copy", 1)
+            src = [[rel[r]] for r in order]
             ec.feed_data_sources(src); ec.execute(); ec.clean_data_sources()
             ts = []
             for _ in range(max(3, args.reps // 4)):
@@ -195,8 +191,6 @@ def main():
                 ec.clean_data_sources()
                 ts.append(dmax((time.perf_counter() - t) * 1e3))
             e2e_ms = statistics.median(ts)
-            ctx.set_option("feed_zero_copy", 0)
-            del src, pinned
 
         res_tbl = out.to_arrow()
         extra = {}
