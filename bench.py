@@ -262,7 +262,7 @@ def run_gpu(args) -> dict:
     result = {
         "metric": METRIC, "value": world * args.bids * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32 keys / int64 predicate arithmetic", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": "nexmark_q2_10M_bids" if args.bids == N_BIDS else f"nexmark_q2_{args.bids}_bids", "query": "q2",
                    "bids_per_gpu": args.bids, "batch_rows": BATCH_ROWS, "batches_per_step": n_batches,
                    "sharding": f"round-robin x{world}, no collective", "cache": f"inputs rotate over {RING} resident relations "
@@ -335,7 +335,7 @@ def run_reference(args) -> dict | None:
     value = args.bids * args.steps / dt
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32 keys / int64 predicate arithmetic", "data": "synthetic",
+            "dtype": "int32", "data": "synthetic",
             "config": {"workload": "nexmark_q2_10M_bids" if args.bids == N_BIDS else f"nexmark_q2_{args.bids}_bids", "query": "q2",
                        "bids_per_gpu": args.bids, "batch_rows": BATCH_ROWS, "batches_per_step": len(batches)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
