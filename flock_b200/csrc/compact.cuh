@@ -290,8 +290,8 @@ __device__ __forceinline__ void cp_rank_tile(CompactSmem<E, I>& s, const Compact
 }
 
 // Host side (core.cu): sizes the scratch and fills a CompactScratch for ONE launch over `num_tiles` tiles by a kernel of
-// which `resident_ctas` fit on the device at once; chooses the mode and the grid (sc.grid); advances the context's
-// ticket / epoch bookkeeping.  Call it right before the launch.
+// which `resident_ctas` fit on the device at once; chooses the mode and the grid (sc.grid) and draws a launch epoch.
+// Call it right before launch_compact(), which advances the ticket / arrival bookkeeping once the launch is accepted.
 CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, long long resident_ctas, unsigned long long* out_count);
 
 // Launches a compaction kernel with sc.grid CTAs.  Single-wave launches wait for data of other CTAs, which only
@@ -310,6 +310,11 @@ inline void launch_compact(const CtxPtr& ctx, Kernel kernel, const CompactScratc
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   FG_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  // Only a launch that was accepted consumes arrivals / tickets: if anything fails between prepare_compact() and here,
+  // the host's view of the monotonic device counters stays exact (a mismatch would make the next launch wait forever).
+  ScanScratch& s = ctx->scan;
+  if (sc.single_wave) s.arrived += unsigned(sc.num_tiles);                      // one arrival per tile, no tickets
+  else s.tickets_issued += unsigned(sc.num_tiles) + unsigned(sc.grid);          // every CTA draws exactly one ticket past the end
 }
 
 // Rank of survivor item k among the survivors of its tile (0 .. tile_total - 1) / its global output position.

@@ -188,8 +188,7 @@ CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, long long
   sc.grid = int(std::max<long long>(1, std::min<long long>(resident_ctas, num_tiles)));
   sc.stride = stride;
   sc.poll_sleep_ns = scan_poll_sleep_ns();
-  if (sc.single_wave) s.arrived += unsigned(num_tiles);                      // one arrival per tile, no tickets
-  else s.tickets_issued += unsigned(num_tiles) + unsigned(sc.grid);          // every CTA draws exactly one ticket past the end
+  // the arrival / ticket bases advance in launch_compact(), after the launch has been accepted
   return sc;
 }
 
