@@ -280,7 +280,11 @@ def run_gpu(args) -> dict:
         "stream_events_per_sec": world * args.bids * (50 / 46) * args.steps / (dev_ms * 1e-3),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(relations[0], args.bids)
+        try:
+            result["cpu_baseline"] = cpu_baseline(args.bids)
+        except Exception as e:                      # the GPU numbers above must still be reported
+            log(f"cpu_baseline failed: {e}")
+            result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e}"[:300]}
     ec.close()
     ctx.close()
     if dist is not None:
@@ -288,60 +292,86 @@ def run_gpu(args) -> dict:
     return result if rank == 0 else None
 
 
-def cpu_baseline(batches, n_bids: int, reps: int = 3) -> dict:
-    """The oracle port of the reference's CPU path (oracle/: DataFusion-6 restatement, target_partitions = host cores)
-    on the same q2 input, whole workload per repetition."""
+# ---- the reference's CPU path (oracle port) -----------------------------------------------------------------------
+# DataFusion runs one task per partition on a multi-threaded runtime.  The oracle is driven from Python, where a thread
+# pool serialises on the interpreter lock (measured: 60 ms per 10 M-bid step on 128 host threads, 150 ms on 8), so the
+# timed CPU arm runs the SAME plan JSON with one worker PROCESS per partition: worker p executes the plan over the
+# round-robin share of batches the plan's RepartitionExec(RoundRobinBatch(n)) would hand partition p, and the parent
+# concatenates the partitions' results like `collect` does.
+_REF_BATCHES = None
+_REF_EX = None
+
+
+def _ref_partition(task):
+    """Worker: partition `p` of `n` -- feed, execute, clean; returns the result as an Arrow IPC stream."""
+    global _REF_EX
+    p, n = task
     import oracle
     from flock_b200 import plans
-    cores = os.cpu_count() or 1
-    plan = plans.q2(cores)
-    ex = oracle.PlanExecutor(plan, threads=cores)
-    best = None
-    for _ in range(reps + 1):                       # first repetition = warm-up (arch/source.rs:44-49 discards none; we do)
-        ex.feed_data_sources([[list(batches)]])
-        t = time.perf_counter()
-        out = ex.execute()
-        dt = time.perf_counter() - t
-        ex.clean_data_sources()
-        best = dt if best is None else min(best, dt)
-    return {"value": n_bids / best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"all {n_bids} bids ({len(batches)} batches), best of {reps} after 1 warm-up, {best * 1e3:.1f} ms",
-            "rows_out": sum(b.num_rows for b in out[0])}
+    if _REF_EX is None:
+        _REF_EX = oracle.PlanExecutor(plans.q2(1), threads=1)
+    share = _REF_BATCHES[p::n] or [_REF_BATCHES[0].slice(0, 0)]
+    _REF_EX.feed_data_sources([[share]])
+    out = _REF_EX.execute()[0]
+    _REF_EX.clean_data_sources()
+    sink = pa.BufferOutputStream()
+    with pa.ipc.new_stream(sink, out[0].schema) as w:
+        for b in out:
+            w.write_batch(b)
+    return sink.getvalue().to_pybytes()
 
 
 def run_reference(args) -> dict | None:
     """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust original cannot be
-    built here) on the host cores.  Under torchrun only rank 0 works."""
+    built here) on all host cores.  Under torchrun only rank 0 works."""
+    global _REF_BATCHES
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    import oracle
-    from flock_b200 import nexgen, plans
+    import multiprocessing as mp
+    import oracle      # builds / loads liboracle.so before the workers are forked
+    from flock_b200 import nexgen
+    oracle.lib()
     cores = os.cpu_count() or 1
-    batches = nexgen.split_batches(nexgen.bids(args.bids, seed=42), BATCH_ROWS)
-    ex = oracle.PlanExecutor(plans.q2(cores), threads=cores)
-
-    def step():
-        ex.feed_data_sources([[batches]])
-        out = ex.execute()
-        ex.clean_data_sources()
-        return out
-    for _ in range(args.warmup):
-        step()
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        out = step()
-    dt = time.perf_counter() - t
+    _REF_BATCHES = nexgen.split_batches(nexgen.bids(args.bids, seed=42), BATCH_ROWS)
+    n_parts = min(cores, len(_REF_BATCHES))
+    with mp.get_context("fork").Pool(n_parts) as pool:      # forked AFTER the input exists: workers share it copy-on-write
+        def step():
+            parts = pool.map(_ref_partition, [(p, n_parts) for p in range(n_parts)], chunksize=1)
+            return sum(pa.ipc.open_stream(x).read_all().num_rows for x in parts)
+        for _ in range(max(args.warmup, 1)):
+            step()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            rows_out = step()
+        dt = time.perf_counter() - t
     value = args.bids * args.steps / dt
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": "nexmark_q2_10M_bids" if args.bids == N_BIDS else f"nexmark_q2_{args.bids}_bids", "query": "q2",
-                       "bids_per_gpu": args.bids, "batch_rows": BATCH_ROWS, "batches_per_step": len(batches)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"all {args.bids} bids per step, {args.steps} steps, target_partitions = {cores}"},
+                       "bids_per_gpu": args.bids, "batch_rows": BATCH_ROWS, "batches_per_step": len(_REF_BATCHES)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_parts, "kind": "port",
+                             "sample": f"all {args.bids} bids per step, {args.steps} steps, one worker process per partition, target_partitions = {n_parts}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "rows_out": sum(b.num_rows for b in out[0])}
+            "gpu_launches": 0, "rows_out": rows_out}
+
+
+def cpu_baseline(n_bids: int, steps: int = 5) -> dict:
+    """The CPU arm timed beside the GPU run: `bench.py --impl reference` in a child process (no CUDA context to fork
+    around), a bounded sample of the same workload."""
+    import subprocess
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", str(steps), "--warmup", "1", "--bids", str(n_bids)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    line = next((l for l in r.stdout.splitlines() if l.startswith("{")), None)
+    if r.returncode != 0 or line is None:
+        raise RuntimeError(f"reference arm failed (rc={r.returncode}): {r.stderr[-400:]}")
+    d = json.loads(line)
+    cb = d["cpu_baseline"]
+    cb["sample"] += f"; {d['ms_per_step']:.1f} ms per step"
+    cb["rows_out"] = d.get("rows_out")
+    return cb
 
 
 def main():
