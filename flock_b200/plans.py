@@ -102,6 +102,25 @@ def hash_join_exec(left: dict, right: dict, on: list[tuple[dict, dict]], mode: s
             "on": [[{"name": l["name"], "index": l["index"]}, {"name": r["name"], "index": r["index"]}] for l, r in on]}
 
 
+def sort_exec(exprs: list[tuple[dict, bool, bool]], input: dict) -> dict:
+    """flock/src/tests/data/plan/join.json: {"expr": [{"expr": column, "options": {"descending", "nulls_first"}}]}."""
+    return {"execution_plan": "sort_exec", "input": input,
+            "expr": [{"expr": e, "options": {"descending": desc, "nulls_first": nf}} for e, desc, nf in exprs]}
+
+
+def global_limit_exec(input: dict, limit: int) -> dict:
+    return {"execution_plan": "global_limit_exec", "input": input, "limit": limit}
+
+
+def row_number_window(name: str, partition_by: list[dict], order_by: list[tuple[dict, bool, bool]], input: dict) -> dict:
+    """WindowAggExec with one ROW_NUMBER() (the only window function NEXMark q6 uses).  No fixture of the reference
+    serialises this node; the layout follows DataFusion 6's WindowAggExec { input, window_expr } and its
+    BuiltInWindowExpr { fun, name, partition_by, order_by } fields."""
+    return {"execution_plan": "window_agg_exec", "input": input,
+            "window_expr": [{"window_expr": "built_in_window_expr", "fun": "RowNumber", "name": name, "partition_by": partition_by,
+                             "order_by": [{"expr": e, "options": {"descending": desc, "nulls_first": nf}} for e, desc, nf in order_by]}]}
+
+
 def two_phase_aggregate(group: list[tuple[str, int]], aggrs: list[dict], input: dict, n: int = TARGET_PARTITIONS) -> dict:
     """Partial -> RepartitionExec(Hash[group]) -> CoalesceBatches -> FinalPartitioned (stage.rs:597-601);
     without group columns: Partial -> CoalescePartitions -> Final (stage.rs:535-537)."""
@@ -226,8 +245,43 @@ def q7(n: int = TARGET_PARTITIONS) -> dict:
                             (column("b_date_time", 3), "b_date_time")], coalesce_batches_exec(join))
 
 
-QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q4": q4, "q5": q5, "q7": q7, "q8": q8}
+def q6(n: int = TARGET_PARTITIONS) -> dict:
+    """benchmarks/src/nexmark/query/q6.sql, types q6_plan.fmt: average selling price of each seller's last ten closed
+    auctions.  Needs SortExec + WindowAggExec(ROW_NUMBER): restated in the ORACLE only so far (SURVEY section 8f rank 3);
+    the GPU plan layer rejects these nodes with FLOCKGPU_ERR_UNSUPPORTED."""
+    a_scan = repartition_rr(memory_exec(AUCTION, [0, 5, 6, 7]), n)     # a_id, a_date_time, expires, seller
+    b_scan = repartition_rr(memory_exec(BID, [0, 2, 3]), n)            # auction, price, b_date_time
+    lsh = coalesce_batches_exec(repartition_hash(a_scan, [column("a_id", 0)], n))
+    rsh = coalesce_batches_exec(repartition_hash(b_scan, [column("auction", 0)], n))
+    join = coalesce_batches_exec(hash_join_exec(lsh, rsh, [(column("a_id", 0), column("auction", 0))]))
+    # a_id 0, a_date_time 1, expires 2, seller 3, auction 4, price 5, b_date_time 6
+    between = binary(binary(column("b_date_time", 6), "GtEq", column("a_date_time", 1)), "And",
+                     binary(column("b_date_time", 6), "LtEq", column("expires", 2)))
+    filt = coalesce_partitions_exec(coalesce_batches_exec(filter_exec(between, join)))
+    w1_name = "ROW_NUMBER() PARTITION BY [#auction.a_id] ORDER BY [#bid.price DESC NULLS FIRST]"
+    w1 = row_number_window(w1_name, [column("a_id", 0)], [(column("price", 5), True, True)],
+                           sort_exec([(column("a_id", 0), False, False), (column("price", 5), True, True)], filt))
+    # window column first: rn 0, a_id 1, a_date_time 2, expires 3, seller 4, auction 5, price 6, b_date_time 7
+    winners = coalesce_batches_exec(filter_exec(binary(column(w1_name, 0), "Eq", literal("UInt64", 1)), w1))
+    q = projection_exec([(column("seller", 4), "seller"), (column("a_id", 1), "a_id"), (column("price", 6), "price"),
+                         (column("b_date_time", 7), "b_date_time"), (column(w1_name, 0), "price_rank")], winners)
+    q_sorted = sort_exec([(column("a_id", 1), False, False), (column("price", 2), True, True)], q)       # ORDER BY a_id, price DESC of subquery Q
+    q2 = projection_exec([(column("seller", 0), "seller"), (column("price", 2), "price"), (column("b_date_time", 3), "b_date_time"),
+                          (column("price_rank", 4), "price_rank")], q_sorted)
+    w2_name = "ROW_NUMBER() PARTITION BY [#Q.seller] ORDER BY [#Q.b_date_time DESC NULLS FIRST]"
+    w2 = row_number_window(w2_name, [column("seller", 0)], [(column("b_date_time", 2), True, True)],
+                           sort_exec([(column("seller", 0), False, False), (column("b_date_time", 2), True, True)], q2))
+    # rn 0, seller 1, price 2, b_date_time 3, price_rank 4
+    last10 = coalesce_batches_exec(filter_exec(binary(column(w2_name, 0), "LtEq", literal("UInt64", 10)), w2))
+    r = projection_exec([(column("seller", 1), "seller"), (column("price", 2), "price"), (column(w2_name, 0), "time_rank")], last10)
+    avg = aggregate_expr("avg", "AVG(R.price)", column("price", 1), "Float64")
+    outer = two_phase_aggregate([("seller", 0)], [avg], repartition_rr(r, n), n)
+    return projection_exec([(column("seller", 0), "seller"), (column("AVG(R.price)", 1), "AVG(R.price)")], outer)
+
+
+QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q8": q8}
+GPU_QUERIES = [q for q in QUERIES if q != "q6"]      # q6 needs SortExec / WindowAggExec: oracle only so far
 # relations each query feeds, in feed order (flock/src/datasource/nexmark/nexmark.rs:181-203); q5 scans bid
 # twice, and feed_data_sources hands one source to one leaf (context.rs:293-303), so bid is fed twice.
 SOURCES = {"q1": ["bid"], "q2": ["bid"], "q3": ["auction", "person"], "q4": ["auction", "bid"], "q5": ["bid", "bid"],
-           "q7": ["bid", "bid"], "q8": ["person", "auction"]}
+           "q6": ["auction", "bid"], "q7": ["bid", "bid"], "q8": ["person", "auction"]}

@@ -271,6 +271,59 @@ def _minmax_kind(t: pa.DataType, is_min: bool) -> int:
     return A_MIN_I if is_min else A_MAX_I
 
 
+def _sortable(arr: pa.Array) -> np.ndarray:
+    """Dense rank of every value in the column's ascending order (Utf8: byte order, like Arrow) as int64: negating it
+    gives the descending order without overflow for any type."""
+    if pa.types.is_string(arr.type):
+        vals = np.array([v.encode("utf-8") for v in arr.to_pylist()], dtype=object)
+    elif pa.types.is_timestamp(arr.type):
+        vals = arr.cast(pa.int64()).to_numpy(zero_copy_only=False)
+    else:
+        vals = arr.to_numpy(zero_copy_only=False)
+    _, inv = np.unique(vals, return_inverse=True)
+    return inv.astype(np.int64)
+
+
+def sort_batch(batch: pa.RecordBatch, sort_exprs: list[dict]) -> pa.RecordBatch:
+    """Lexicographic sort by [{expr: column, options: {descending, nulls_first}}]; ties by the other columns ascending."""
+    if batch.num_rows == 0:
+        return batch
+    names = batch.schema.names
+    used, keys = [], []
+    for se in sort_exprs:
+        i = _resolve(names, se["expr"])
+        used.append(i)
+        k = _sortable(batch.column(i))
+        keys.append(-k if se.get("options", {}).get("descending", False) else k)
+    for i in range(batch.num_columns):                     # deterministic tie-break
+        if i not in used:
+            keys.append(_sortable(batch.column(i)))
+    order = np.lexsort(tuple(reversed(keys)))              # np.lexsort: LAST key is primary
+    return batch.take(pa.array(order))
+
+
+def window_batch(batch: pa.RecordBatch, window_exprs: list[dict]) -> pa.RecordBatch:
+    """ROW_NUMBER() OVER (PARTITION BY p.. ORDER BY o..) on an input already sorted by (p.., o..)."""
+    names = batch.schema.names
+    n = batch.num_rows
+    cols, fields = [], []
+    for w in window_exprs:
+        if w.get("fun") != "RowNumber":
+            raise OracleError(f"oracle: window function {w.get('fun')} is not restated")
+        part = [_resolve(names, e) for e in w.get("partition_by", [])]
+        start = np.ones(n, bool)
+        if n:
+            start[1:] = False
+            for i in part:
+                k = _sortable(batch.column(i))
+                start[1:] |= k[1:] != k[:-1]
+        idx = np.arange(n, dtype=np.int64)
+        first = np.maximum.accumulate(np.where(start, idx, 0))
+        cols.append(pa.array((idx - first + 1).astype(np.uint64)))
+        fields.append(pa.field(w["name"], pa.uint64(), True))
+    return pa.RecordBatch.from_arrays(cols + list(batch.columns), schema=pa.schema(fields + list(batch.schema), metadata=batch.schema.metadata))
+
+
 def hash_aggregate(batch: pa.RecordBatch, mode: str, group: list[tuple[int, str]], aggrs: list[dict]) -> pa.RecordBatch:
     """One partition of HashAggregateExec.  aggrs: [{func, col (or first state col), name}]."""
     final = mode in ("Final", "FinalPartitioned")
@@ -537,6 +590,24 @@ class PlanExecutor:
                     out.append(hash_join(build, rb, lk, rk))
                 return out
             return self._map(run, list(zip(lparts, rparts)))
+        if tag == "sort_exec":
+            # SortExec (DataFusion 6): sorts each input partition by the expr list (planners put a CoalescePartitions /
+            # MergeExec below it).  Rows with equal sort keys have NO defined order in the reference (arrow
+            # lexsort_to_indices is not stable); the oracle breaks ties by the remaining columns, ascending, so that
+            # two independent implementations can agree -- one valid instance of the reference's behaviour.
+            return [[sort_batch(_concat([b for b in src if b.num_rows], src[0].schema), p["expr"])] if src else [] for src in self._exec(p["input"])]
+        if tag == "global_limit_exec":
+            src = [b for part in self._exec(p["input"]) for b in part]
+            if not src:
+                return [[]]
+            whole = _concat(src, src[0].schema)
+            return [[whole.slice(0, p["limit"])]]
+        if tag == "window_agg_exec":
+            # WindowAggExec with ROW_NUMBER() OVER (PARTITION BY .. ORDER BY ..): the input arrives sorted by
+            # (partition keys, order keys) -- the planner's SortExec below -- and the window columns are emitted FIRST,
+            # then the input columns (q6_plan.fmt).  Row order is the input order.
+            return [[window_batch(_concat([b for b in src if b.num_rows], src[0].schema), p["window_expr"])] if src else []
+                    for src in self._exec(p["input"])]
         raise OracleError(f"oracle: execution plan node {tag} is not restated")
 
     def execute_partitioned(self) -> list[Partitions]:

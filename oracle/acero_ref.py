@@ -93,4 +93,44 @@ def q7(bid) -> pa.Table:
     return t.filter(pc.equal(t["price"], mx)).select(["auction", "price", "bidder", "b_date_time"])
 
 
-QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q4": q4, "q5": q5, "q7": q7, "q8": q8}
+def q6(auction, bid) -> pa.Table:
+    """SELECT seller, AVG(price) FROM (last ten winning bids per seller, by closing-bid time) -- q6.sql, from the SQL text.
+    Ties (the reference leaves them undefined) are broken like oracle.sort_batch: by the remaining columns, ascending --
+    i.e. among equal maximum prices of an auction the earliest bid wins, among equal bid times of a seller the lower price
+    ranks first."""
+    a = _table(auction)
+    b = _table(bid)
+    a_id = a["a_id"].to_numpy()
+    order = np.argsort(a_id, kind="stable")
+    keys = a_id[order]
+    auc = b["auction"].to_numpy()
+    pos = np.searchsorted(keys, auc, "left")
+    hit = (pos < len(keys)) & (keys[np.minimum(pos, len(keys) - 1)] == auc)      # a_id is unique in NEXMark
+    bi = np.nonzero(hit)[0]
+    ai = order[pos[hit]]
+    ts = b["b_date_time"].cast(pa.int64()).to_numpy()[bi]
+    keep = (ts >= a["a_date_time"].cast(pa.int64()).to_numpy()[ai]) & (ts <= a["expires"].cast(pa.int64()).to_numpy()[ai])
+    ai, bi, ts = ai[keep], bi[keep], ts[keep]
+    price = b["price"].to_numpy()[bi].astype(np.int64)
+    aid = a_id[ai]
+    o = np.lexsort((ts, -price, aid))                                           # a_id, price DESC, then earliest bid
+    first = np.ones(len(o), bool)
+    first[1:] = aid[o][1:] != aid[o][:-1]
+    w = o[first]                                                                # the winning bid of every auction
+    seller = a["seller"].to_numpy()[ai][w]
+    wprice, wts = price[w], ts[w]
+    o2 = np.lexsort((wprice, -wts, seller))                                     # seller, b_date_time DESC, then lower price
+    s2 = seller[o2]
+    start = np.ones(len(o2), bool)
+    start[1:] = s2[1:] != s2[:-1]
+    idx = np.arange(len(o2))
+    rank = idx - np.maximum.accumulate(np.where(start, idx, 0)) + 1
+    last10 = rank <= 10
+    s3, p3 = s2[last10], wprice[o2][last10]
+    sellers, inv = np.unique(s3, return_inverse=True)
+    sums = np.bincount(inv, weights=p3.astype(np.float64))
+    cnts = np.bincount(inv)
+    return pa.table({"seller": pa.array(sellers, pa.int32()), "AVG(R.price)": pa.array(sums / cnts.astype(np.float64), pa.float64())})
+
+
+QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q8": q8}

@@ -1,4 +1,4 @@
-"""Writes tests/golden/nexmark_golden.json: expected NEXMark q1/q2/q3/q4/q5/q7/q8 outputs on a small seeded input.
+"""Writes tests/golden/nexmark_golden.json: expected NEXMark q1-q8 outputs (q6: oracle only so far) on a small seeded input.
 
 The vectors are produced by the CPU oracle (oracle/) AFTER it has been cross-checked, in this script,
 against the independent Arrow C++ implementation (oracle/acero_ref.py); the reference itself cannot run
@@ -23,7 +23,7 @@ N_EVENTS, SEED, BATCH_ROWS = 50_000, 1234, 4096
 def main():
     ev = nexgen.generate(N_EVENTS, seed=SEED, batch_rows=BATCH_ROWS)
     out = {"n_events": N_EVENTS, "seed": SEED, "batch_rows": BATCH_ROWS, "queries": {}}
-    for q in ["q1", "q2", "q3", "q4", "q5", "q7", "q8"]:
+    for q in ["q1", "q2", "q3", "q4", "q5", "q6", "q7", "q8"]:
         sources = [[ev[r]] for r in plans.SOURCES[q]]
         got = oracle.execute_plan(plans.QUERIES[q](), sources)
         rels = [ev[r] for r in dict.fromkeys(plans.SOURCES[q])]

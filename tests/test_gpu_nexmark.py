@@ -51,6 +51,8 @@ def test_golden_vectors(gpu_ctx):
     g = json.loads(goldens.GOLDEN.read_text())
     ev = nexgen.generate(g["n_events"], seed=g["seed"], batch_rows=g["batch_rows"])
     for query, want in g["queries"].items():
+        if query not in plans.GPU_QUERIES:          # q6 (SortExec / WindowAggExec) is restated in the oracle only so far
+            continue
         got = oracle.canonical(run_gpu(gpu_ctx, plans.QUERIES[query](), sources_for(query, ev)))
         assert got.num_rows == want["num_rows"] and got.schema.names == want["columns"], query
         assert goldens._digest(got) == want["digest"], query

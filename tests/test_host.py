@@ -68,6 +68,15 @@ def test_unmarshal_nexmark_plans(query):
         assert "HashJoinExec: mode=Partitioned, join_type=Inner, on=[(price, maxprice)]" in s and "mode=Final, gby=[]" in s
 
 
+def test_q6_is_rejected_not_emulated():
+    """q6 needs SortExec + WindowAggExec, which only the oracle restates so far: the GPU plan layer must refuse the plan
+    (the Rust shim then keeps the CPU nodes) instead of falling back to anything."""
+    with pytest.raises(fb.FlockGpuError) as info:
+        fb.ExecutionContext(None, plans.q6())
+    assert info.value.code == _ffi.ERR_UNSUPPORTED
+    assert "sort_exec" in info.value.message or "window_agg_exec" in info.value.message
+
+
 def test_shuffle_stage_and_marshalled_context():
     a, p = plans.q3_stage0()
     ec = fb.ExecutionContext(None, [a, p])

@@ -123,7 +123,7 @@ def test_partition_count_invariants():
 
 
 # ---- (b) two independent implementations agree -------------------------------------------------------------
-@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q4", "q5", "q7", "q8"])
+@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q4", "q5", "q6", "q7", "q8"])
 @pytest.mark.parametrize("n_parts", [1, 8])
 def test_oracle_matches_acero(query, n_parts, events_small):
     got = oracle.execute_plan(plans.QUERIES[query](n_parts), sources_for(query, events_small))
@@ -134,7 +134,7 @@ def test_oracle_matches_acero(query, n_parts, events_small):
 
 
 def test_oracle_matches_acero_seed7(events_seed7):
-    for query in ["q2", "q3", "q4", "q5", "q7", "q8"]:
+    for query in ["q2", "q3", "q4", "q5", "q6", "q7", "q8"]:
         got = oracle.execute_plan(plans.QUERIES[query](), sources_for(query, events_seed7))
         rels = [events_seed7[r] for r in dict.fromkeys(plans.SOURCES[query])]
         oracle.assert_tables_equal(got, acero_ref.QUERIES[query](*rels))
