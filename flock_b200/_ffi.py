@@ -1,7 +1,8 @@
 """ctypes binding of libflockgpu.so (include/flockgpu.h) -- the same C ABI the Rust shim binds.
 
-The library is loaded eagerly and loudly: if the shared object is missing there is NO fallback
-(importing flock_b200 raises).  Opening a context without a CUDA device raises FlockGpuError too.
+Loud, no fallback: importing flock_b200 raises when the shared object is missing; the object itself is mapped (and
+every declared symbol resolved) on first use, so that pure-Python helpers (plans, nexgen) can be imported by the CPU
+reference arm without mapping the product library.  Opening a context without a CUDA device raises FlockGpuError too.
 """
 from __future__ import annotations
 
@@ -60,15 +61,43 @@ class AggSpec(C.Structure):
     _fields_ = [("func", C.c_int32), ("col", C.c_int32), ("name", C.c_char_p)]
 
 
-def _load() -> C.CDLL:
+def _require_library() -> None:
     if not LIB_PATH.exists():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(flock_b200 has no CPU fallback)")
-    return C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
 
 
-lib = _load()
+_require_library()      # importing the package without the shared object fails here, loudly
+
+
+class _Library:
+    """The shared object, mapped on FIRST USE: `bench.py --impl reference` imports flock_b200.plans / .nexgen (plan JSON
+    and input generators, pure Python) and must not map the product library into the CPU arm's process."""
+
+    def __init__(self):
+        self._cdll = None
+
+    def _load(self) -> C.CDLL:
+        if self._cdll is None:
+            _require_library()
+            cdll = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(cdll, name)          # AttributeError here = the .so does not export a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            self._cdll = cdll
+        return self._cdll
+
+    @property
+    def loaded(self) -> bool:
+        return self._cdll is not None
+
+    def __getattr__(self, name):
+        return getattr(self._load(), name)
+
+
+lib = _Library()
 
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
@@ -123,11 +152,6 @@ PROTOTYPES = {
     "flockgpu_selftest_eval_value": (C.c_int, [C.POINTER(ArrowSchema), C.POINTER(ArrowArray), C.POINTER(Expr), _P, _I32P, _I32P]),
     "flockgpu_selftest_pred_i32": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _I32P, C.c_int64, C.POINTER(C.c_uint8), _I32P]),
 }
-
-for _name, (_res, _args) in PROTOTYPES.items():
-    _fn = getattr(lib, _name)          # AttributeError here = the .so does not export a declared symbol
-    _fn.restype = _res
-    _fn.argtypes = _args
 
 
 def check(rc: int) -> None:

@@ -4,6 +4,8 @@
 // ExecutionContext::feed_data_sources (flock/src/runtime/context.rs:257-325) for the way in, and the
 // Vec<RecordBatch> returned by `collect` (context.rs:172-191) for the way out.
 #include <algorithm>
+#include <map>
+#include <tuple>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -190,6 +192,29 @@ CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, long long
   sc.poll_sleep_ns = scan_poll_sleep_ns();
   // the arrival / ticket bases advance in launch_compact(), after the launch has been accepted
   return sc;
+}
+
+int resident_ctas(const CtxPtr& ctx, const void* kernel, int threads, size_t smem) {
+  struct Key {
+    int device;
+    const void* kernel;
+    size_t smem;
+    bool operator<(const Key& o) const { return std::tie(device, kernel, smem) < std::tie(o.device, o.kernel, o.smem); }
+  };
+  static std::mutex mu;
+  static std::map<Key, int> cache;
+  const Key key{ctx->device, kernel, smem};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return int(int64_t(ctx->sm_count) * it->second);
+  }
+  int per_sm = 0;
+  FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  std::lock_guard<std::mutex> g(mu);
+  cache[key] = per_sm;
+  return int(int64_t(ctx->sm_count) * per_sm);
 }
 
 void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out) {

@@ -191,7 +191,12 @@ FG_HD void eval_chain(const Chain& c, const ColRef* cols, const int64_t (&rows)[
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < R; ++j) acc[j] = apply_step(st.op, acc[j], st.lit, err);
+      for (int j = 0; j < R; ++j) {
+        // padded rows carry acc = 0: a reversed literal step (`lit / (col*k)`, `lit % (col*k)`) would raise a
+        // spurious divide-by-zero on them
+        if (rows[j] < 0) continue;
+        acc[j] = apply_step(st.op, acc[j], st.lit, err);
+      }
     }
   }
 }

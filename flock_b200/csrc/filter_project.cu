@@ -354,26 +354,6 @@ static void fill_colrefs(const Table& t, ColRef* refs) {
   }
 }
 
-// CTAs of `kernel` that fit on the device at once
-static int resident_ctas(const CtxPtr& ctx, const void* kernel, int threads) {
-  // the occupancy query costs microseconds per call; a q2 step is one ~10 us kernel, so cache it per kernel
-  static std::mutex mu;
-  static std::unordered_map<const void*, int> cache;
-  int per_sm = 0;
-  {
-    std::lock_guard<std::mutex> g(mu);
-    auto it = cache.find(kernel);
-    if (it != cache.end()) per_sm = it->second;
-  }
-  if (per_sm == 0) {
-    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
-    if (per_sm < 1) per_sm = 1;
-    std::lock_guard<std::mutex> g(mu);
-    cache[kernel] = per_sm;
-  }
-  return int(int64_t(ctx->sm_count) * per_sm);
-}
-
 template <class PredFn>
 static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args) {
   constexpr int64_t TILE = int64_t(FP_THREADS) * PredFn::I;

@@ -235,9 +235,7 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
   a.n = n;
   const int64_t num_tiles = (n + GL_TILE - 1) / GL_TILE;
   {
-    int per_sm = 1;
-    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_lengths_scan_kernel, GA_THREADS, 0));
-    a.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + 1);
+    a.sc = prepare_compact(ctx, num_tiles, resident_ctas(ctx, reinterpret_cast<const void*>(gather_lengths_scan_kernel), GA_THREADS), ctx->d_scalars + 1);
     {
       LaunchTimer lt(ctx, "gather_lengths_scan_kernel");
       launch_compact(ctx, gather_lengths_scan_kernel, a.sc, a);
@@ -318,9 +316,7 @@ std::vector<Column> gather_columns(const CtxPtr& ctx, const std::vector<const Co
     a.out_off = o.offsets->as<int32_t>();
     a.n = n;
     const int64_t num_tiles = (n + GL_TILE - 1) / GL_TILE;
-    int per_sm = 1;
-    FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_lengths_scan_kernel, GA_THREADS, 0));
-    a.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + kGatherTotalsSlot + u);
+    a.sc = prepare_compact(ctx, num_tiles, resident_ctas(ctx, reinterpret_cast<const void*>(gather_lengths_scan_kernel), GA_THREADS), ctx->d_scalars + kGatherTotalsSlot + u);
     {
       LaunchTimer lt(ctx, "gather_lengths_scan_kernel");
       launch_compact(ctx, gather_lengths_scan_kernel, a.sc, a);

@@ -249,8 +249,12 @@ __global__ void __launch_bounds__(AL_THREADS) agg_local_kernel(const __grid_cons
       }
       for (int c = 0; c < a.n_acc; ++c) acc_apply(&s_acc[c * AL_SLOTS + slot], a.acc[c].op, load_acc_input(a.acc[c], a.cols, row[u]));
     }
+    // the decision must be CTA-uniform: s_occ is bumped again by fast warps in the next step, so every thread
+    // reads it between two barriers
     __syncthreads();
-    if (s_occ > AL_SLOTS * 3 / 4 - STEP) local_flush(a, s_keys, s_acc, s_warp, &s_base, &s_occ);
+    const bool do_flush = s_occ > AL_SLOTS * 3 / 4 - STEP;
+    __syncthreads();
+    if (do_flush) local_flush(a, s_keys, s_acc, s_warp, &s_base, &s_occ);
   }
   local_flush(a, s_keys, s_acc, s_warp, &s_base, &s_occ);
 #pragma unroll
@@ -428,7 +432,9 @@ __global__ void __launch_bounds__(A32_THREADS) agg_local32_kernel(const __grid_c
       }
     }
     __syncthreads();
-    if (s_occ > A32_SLOTS * 3 / 4 - A32_STEP) flush();
+    const bool do_flush = s_occ > A32_SLOTS * 3 / 4 - A32_STEP;  // CTA-uniform: read between two barriers
+    __syncthreads();
+    if (do_flush) flush();
   }
   flush();
 #pragma unroll
@@ -1311,9 +1317,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
         FG_CUDA(cudaMemsetAsync(h.slow_rows, 0, 8, ctx->stream));
         constexpr size_t h_bytes = size_t(H32_WINDOW) * 4;
         FG_CUDA(cudaFuncSetAttribute(agg_hist32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h_bytes)));
-        int per_sm = 1;
-        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_hist32_kernel, H32_THREADS, h_bytes));
-        int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + H32_STEP - 1) / H32_STEP)));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(agg_hist32_kernel), H32_THREADS, h_bytes), (n + H32_STEP - 1) / H32_STEP)));
         {
           LaunchTimer lt(ctx, "agg_hist32_kernel");
           agg_hist32_kernel<<<grid, H32_THREADS, h_bytes, ctx->stream>>>(h);
@@ -1344,17 +1348,13 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
         l32.key_minmax = la.key_minmax;
         constexpr size_t a32_bytes = size_t(A32_SLOTS) * 8;
         FG_CUDA(cudaFuncSetAttribute(agg_local32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(a32_bytes)));
-        int per_sm = 1;
-        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_local32_kernel, A32_THREADS, a32_bytes));
-        int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + A32_STEP - 1) / A32_STEP)));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(agg_local32_kernel), A32_THREADS, a32_bytes), (n + A32_STEP - 1) / A32_STEP)));
         {
           LaunchTimer lt(ctx, "agg_local32_kernel");
           agg_local32_kernel<<<grid, A32_THREADS, a32_bytes, ctx->stream>>>(l32);
         }
       } else {
-        int per_sm = 1;
-        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_local_kernel, AL_THREADS, local_smem));
-        int grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * std::max(per_sm, 1), (n + AL_THREADS * AL_UNROLL - 1) / (AL_THREADS * AL_UNROLL))));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(agg_local_kernel), AL_THREADS, local_smem), (n + AL_THREADS * AL_UNROLL - 1) / (AL_THREADS * AL_UNROLL))));
         LaunchTimer lt(ctx, "agg_local_kernel");
         agg_local_kernel<<<grid, AL_THREADS, local_smem, ctx->stream>>>(la);
       }
@@ -1482,9 +1482,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     const int items = big ? 64 : 16;
     const long long tiles = (long long)((n_slots + CP_THREADS * items - 1) / (CP_THREADS * items));
     auto launch = [&](auto kernel) {
-      int per_sm = 1;
-      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CP_THREADS, 0));
-      ea.sc = prepare_compact(ctx, tiles, (long long)ctx->sm_count * std::max(per_sm, 1), ctx->d_scalars + 3);
+      ea.sc = prepare_compact(ctx, tiles, resident_ctas(ctx, reinterpret_cast<const void*>(kernel), CP_THREADS), ctx->d_scalars + 3);
       LaunchTimer lt(ctx, "agg_emit_kernel");
       launch_compact(ctx, kernel, ea.sc, ea);
     };

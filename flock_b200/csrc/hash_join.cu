@@ -339,9 +339,7 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       by_width([&](auto w) {
         constexpr int KW = decltype(w)::value == 8 ? 8 : 4;
         auto kernel = join_one_kernel<KW>;
-        int per_sm = 1;
-        FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CP_THREADS, 0));
-        oa.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + 4);
+        oa.sc = prepare_compact(ctx, num_tiles, resident_ctas(ctx, reinterpret_cast<const void*>(kernel), CP_THREADS), ctx->d_scalars + 4);
         LaunchTimer lt(ctx, "join_one_kernel");
         launch_compact(ctx, kernel, oa.sc, oa);
       });
@@ -380,9 +378,7 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     const int64_t num_tiles = (P.num_rows + JC_TILE - 1) / JC_TILE;
     by_width([&](auto w) {
       auto kernel = join_count_scan_kernel<decltype(w)::value>;
-      int per_sm = 1;
-      FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, JC_THREADS, 0));
-      ca.sc = prepare_compact(ctx, num_tiles, int64_t(ctx->sm_count) * std::max(per_sm, 1), ctx->d_scalars + 4);
+      ca.sc = prepare_compact(ctx, num_tiles, resident_ctas(ctx, reinterpret_cast<const void*>(kernel), JC_THREADS), ctx->d_scalars + 4);
       LaunchTimer lt(ctx, "join_count_scan_kernel");
       launch_compact(ctx, kernel, ca.sc, ca);
     });

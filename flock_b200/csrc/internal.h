@@ -198,6 +198,10 @@ BufferPtr alloc(const CtxPtr& ctx, size_t bytes);  // bytes == 0 still yields a 
 // consecutive tiles (32 = one 256-byte L2 chunk each), back-off of a polling thread in ns.
 int scan_stride();
 int scan_poll_sleep_ns();
+// CTAs of `kernel` (block size `threads`, `smem` dynamic shared bytes) that fit on the context's device at once.  The
+// occupancy query costs microseconds per call and most kernels here run ~10 us, so the answer is cached per
+// (device, kernel, smem): processes that drive unlike GPUs get the right value for each.
+int resident_ctas(const CtxPtr& ctx, const void* kernel, int threads, size_t smem = 0);
 // Copies `n` u64 scalars from d_scalars[first..] to the host and waits.
 void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out);
 
