@@ -8,29 +8,11 @@
 // NCCL is bound with dlopen/dlsym so that libflockgpu.so carries no link-time NCCL dependency: inside
 // a torch process the already-loaded (torch-bundled) libnccl.so.2 is reused, stand-alone the system
 // library is loaded.
-#include <dlfcn.h>
-#include <nccl.h>
-
 #include <algorithm>
 
-#include "internal.h"
+#include "comm.h"
 
 namespace fg {
-
-namespace {
-
-struct NcclApi {
-  void* handle = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
 
 NcclApi& nccl() {
   static NcclApi api;
@@ -59,23 +41,11 @@ NcclApi& nccl() {
   return api;
 }
 
-#define FG_NCCL(expr)                                                                                              \
-  do {                                                                                                             \
-    ncclResult_t _r = (expr);                                                                                      \
-    if (_r != ncclSuccess)                                                                                         \
-      ::fg::fail(FLOCKGPU_ERR_NCCL, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                                  \
-                 nccl().GetErrorString ? nccl().GetErrorString(_r) : "nccl error");                                \
-  } while (0)
-
-}  // namespace
-
-struct Comm {
-  ncclComm_t comm = nullptr;
-  int rank = 0, world = 1;
-  ~Comm() {
-    if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
-  }
-};
+Comm::~Comm() {
+  cudaSetDevice(device);
+  peer_windows_destroy(*this);
+  if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
+}
 
 void comm_unique_id(uint8_t* out) {
   static_assert(sizeof(ncclUniqueId) <= FLOCKGPU_UNIQUE_ID_BYTES, "ncclUniqueId does not fit the ABI buffer");
@@ -92,8 +62,10 @@ void comm_init(const CtxPtr& ctx, const uint8_t* idbytes, int rank, int world) {
   auto c = std::make_shared<Comm>();
   c->rank = rank;
   c->world = world;
+  c->device = ctx->device;
   FG_NCCL(nccl().CommInitRank(&c->comm, world, id, rank));
   ctx->comm = c;
+  peer_windows_init(ctx, *c);  // NVLink peer windows for the exchange; on failure the NCCL all-to-all below stays in charge
 }
 
 int comm_world(const CtxPtr& ctx) { return ctx->comm ? ctx->comm->world : 1; }
@@ -259,22 +231,6 @@ int flockgpu_all_to_all(flockgpu_ctx* ctx, flockgpu_table* const* parts, int32_t
       ps.push_back(parts[i]->table);
     }
     *out = wrap_table(all_to_all(c, ps));
-  });
-}
-
-int flockgpu_hash_exchange(flockgpu_ctx* ctx, const flockgpu_table* in, const int32_t* key_cols, int32_t n_keys, flockgpu_table** out) {
-  return guarded([&] {
-    auto c = core_of(ctx);
-    FG_CHECK(out && in && in->table && key_cols && n_keys > 0, FLOCKGPU_ERR_INVALID, "hash_exchange: bad arguments");
-    std::lock_guard<std::recursive_mutex> g(c->mu);
-    FG_CUDA(cudaSetDevice(c->device));
-    std::vector<int> keys(key_cols, key_cols + n_keys);
-    int world = c->comm ? c->comm->world : 1;
-    if (world == 1) {
-      *out = wrap_table(in->table);
-      return;
-    }
-    *out = wrap_table(all_to_all(c, hash_partition(c, in->table, keys, world)));
   });
 }
 

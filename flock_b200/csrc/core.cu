@@ -125,7 +125,7 @@ Buffer::Buffer(CtxPtr c, size_t n) : ctx(std::move(c)), bytes(n) {
 }
 
 Buffer::~Buffer() {
-  if (ptr) cudaFreeAsync(ptr, ctx->stream);
+  if (ptr && !parent) cudaFreeAsync(ptr, ctx->stream);
 }
 
 BufferPtr alloc(const CtxPtr& ctx, size_t bytes) { return std::make_shared<Buffer>(ctx, bytes); }
@@ -1107,6 +1107,7 @@ int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value) {
     std::lock_guard<std::recursive_mutex> g(c->mu);
     if (!strcmp(name, "feed_zero_copy")) c->feed_zero_copy = value != 0;
     else if (!strcmp(name, "compact_mode")) c->compact_mode = int(value);
+    else if (!strcmp(name, "exchange_window_mb")) c->exchange_window_mb = value;
     else fail(FLOCKGPU_ERR_INVALID, "set_option: unknown option \"%s\"", name);
   });
 }

@@ -419,6 +419,19 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   auto out = std::make_shared<Table>();
   out->ctx = ctx;
   out->metadata = in.metadata;
+  // rows stay on their rank: the routing property of an exchanged input survives when its columns pass through by name
+  if (!in.partitioned_on.empty()) {
+    bool kept = true;
+    for (const std::string& p : in.partitioned_on) {
+      bool found = false;
+      for (size_t i = 0; i < vals.size(); ++i) found |= vals[i].passthrough && in.cols[vals[i].src_col].name == p && out_name(i) == p;
+      kept &= found;
+    }
+    if (kept) {
+      out->partitioned_on = in.partitioned_on;
+      out->partition_world = in.partition_world;
+    }
+  }
 
   int* err_flag = reinterpret_cast<int*>(ctx->d_scalars + 8);
   bool check_err = false;

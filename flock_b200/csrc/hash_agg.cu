@@ -1147,9 +1147,16 @@ unsigned long long pow2_at_least(unsigned long long n) {
 }  // namespace
 
 TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs) {
-  const Table& in = *in_ptr;
-  in.dense();
+  in_ptr->dense();
   FG_CHECK(mode >= FLOCKGPU_AGG_PARTIAL && mode <= FLOCKGPU_AGG_SINGLE, FLOCKGPU_ERR_INVALID, "hash_aggregate: bad mode %d", mode);
+  // A NULL state column (the state row of an aggregate over no input) merges as "absent": Final over such a row is
+  // Final over no row (the reference skips NULL states; COUNT's state is 0 there, the identity).
+  if ((mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED) && group_cols.empty()) {
+    bool null_state = false;
+    for (const Column& c : in_ptr->cols) null_state |= c.all_null;
+    if (null_state) return hash_aggregate(ctx, empty_like(ctx, *in_ptr), mode, group_cols, aggs);
+  }
+  const Table& in = *in_ptr;
   for (int g : group_cols) {
     FG_CHECK(g >= 0 && g < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_aggregate: group column %d out of range", g);
     FG_CHECK(!in.cols[g].all_null, FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: NULL group column");
@@ -1212,11 +1219,18 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
     }
     FG_CUDA(cudaGetLastError());
     count_launch(ctx);
-    // aggregates other than COUNT over zero rows are NULL
-    bool from_states = mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED;
-    if (n == 0 && !from_states)
-      for (size_t i = 0; i < cols.size(); ++i)
-        if (accs[outs[i].a0].op != ACC_COUNT || outs[i].kind == EMIT_AVG) cols[i].all_null = true;
+    // aggregates other than COUNT over zero rows are NULL; the same holds for a Final merge
+    // that received no state row at all (every producer's partition was empty): COUNT merges to 0, the rest is NULL
+    if (n == 0) {
+      size_t o = 0;
+      for (const AggSpec& s : aggs) {
+        const size_t width = (s.func == FLOCKGPU_AGG_AVG && mode == FLOCKGPU_AGG_PARTIAL) ? 2 : 1;
+        for (size_t k = 0; k < width; ++k, ++o) {
+          const bool is_count_state = s.func == FLOCKGPU_AGG_COUNT || (s.func == FLOCKGPU_AGG_AVG && mode == FLOCKGPU_AGG_PARTIAL && k == 0);
+          if (!is_count_state) cols[o].all_null = true;
+        }
+      }
+    }
     out->cols = std::move(cols);
     // keep `state` alive until the kernels have run: stream-ordered free does that
     return out;
@@ -1509,6 +1523,19 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   for (Column& c : val_cols) {
     c.length = int64_t(n_groups);
     out->cols.push_back(std::move(c));
+  }
+  // groups stay on the rank their rows were routed to: the routing property survives when its columns are group columns
+  if (!in.partitioned_on.empty()) {
+    bool kept = true;
+    for (const std::string& p : in.partitioned_on) {
+      bool found = false;
+      for (int g : group_cols) found |= in.cols[g].name == p;
+      kept &= found;
+    }
+    if (kept) {
+      out->partitioned_on = in.partitioned_on;
+      out->partition_world = in.partition_world;
+    }
   }
   return out;
 }

@@ -295,10 +295,15 @@ TablePtr CoalescePartitionsExec::execute(const ExecEnv& env) {
   TablePtr in = input->execute(env);
   if (env.world == 1) return in;
   // "merge every partition into one": with one partition per GPU that is a gather to rank 0 (the other ranks
-  // continue with an empty relation), done with the same all-to-all primitive as the hash shuffle
-  std::vector<TablePtr> parts;
-  for (int r = 0; r < env.world; ++r) parts.push_back(r == 0 ? in : fg::empty_like(env.ctx, *in));
-  return fg::all_to_all(env.ctx, parts);
+  // continue with an empty relation), done by the exchange with a constant destination.
+  // A rank whose partition holds the state row of an aggregate over NO input carries NULL states (SUM / MIN / MAX /
+  // AVG over zero rows): a NULL state merges as "absent" in the reference, so the row stays
+  // home (its COUNT state is 0, the identity of the merge).
+  in->resolve();
+  bool null_state = false;
+  for (const fg::Column& c : in->cols) null_state |= c.all_null;
+  if (null_state) in = fg::empty_like(env.ctx, *in);
+  return fg::hash_exchange(env.ctx, in, {}, 0);
 }
 
 std::string RepartitionExec::fmt_as() const {
@@ -320,8 +325,18 @@ std::vector<int> RepartitionExec::key_columns(const fg::Table& in) const {
 TablePtr RepartitionExec::execute(const ExecEnv& env) {
   TablePtr in = input->execute(env);
   if (hash && env.world > 1) {
-    // the inter-function shuffle of the reference (actor.rs:425-543) as one NVLink all-to-all
-    return fg::all_to_all(env.ctx, fg::hash_partition(env.ctx, in, key_columns(*in), env.world));
+    // the inter-function shuffle of the reference (actor.rs:425-543): the partition kernel pushes every row into its
+    // receiver's window over NVLink (exchange.cu).  An input that an earlier exchange already routed on the same
+    // columns is in place: DataFusion 6 plans Hash([p_id, name]) for q8's aggregate and Hash([p_id]) for its join,
+    // two shuffles where one suffices (routing hashes the fixed-width key columns, here p_id both times).
+    in->resolve();
+    const std::vector<int> keys = key_columns(*in);
+    if (in->partition_world == env.world && !in->partitioned_on.empty()) {
+      std::vector<std::string> want;
+      for (int k : fg::routing_columns(*in, keys)) want.push_back(in->cols[k].name);
+      if (want == in->partitioned_on) return in;
+    }
+    return fg::hash_exchange(env.ctx, in, keys);
   }
   return in;  // single device partition: nothing to move
 }
@@ -359,7 +374,11 @@ static TablePtr rename_columns(const ExecEnv& env, const TablePtr& t, const std:
   t->resolve();
   auto r = std::make_shared<fg::Table>(*t);
   for (size_t i = 0; i < names.size() && i < r->cols.size(); ++i)
-    if (!names[i].empty()) r->cols[i].name = names[i];
+    if (!names[i].empty() && r->cols[i].name != names[i]) {
+      for (std::string& p : r->partitioned_on)  // same values under a new name: the rows are still where they were routed
+        if (p == r->cols[i].name) p = names[i];
+      r->cols[i].name = names[i];
+    }
   (void)env;
   return r;
 }

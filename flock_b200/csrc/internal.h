@@ -142,6 +142,8 @@ struct CtxCore {
   // decoupled look-back otherwise), 1 = always decoupled look-back (flockgpu_set_option "compact_mode"; the parity
   // tests run both)
   int compact_mode = 0;
+  // size of this rank's NVLink receive window (exchange.cu), fixed when the communicator is attached
+  int64_t exchange_window_mb = 4096;
 
   // recycled CUDA events (creating one costs about a microsecond; a q2 step is one ~10 us kernel)
   std::vector<cudaEvent_t> sync_events;    // cudaEventDisableTiming
@@ -182,7 +184,11 @@ struct Buffer {
   CtxPtr ctx;
   void* ptr = nullptr;
   size_t bytes = 0;
+  // A VIEW (a slice of another allocation: one partition of a partition-ordered relation, a column inside a
+  // peer-exchange window) keeps its owner alive through `parent` and frees nothing itself.
+  std::shared_ptr<const void> parent;
   Buffer(CtxPtr c, size_t n);
+  Buffer(CtxPtr c, void* p, size_t n, std::shared_ptr<const void> owner) : ctx(std::move(c)), ptr(p), bytes(n), parent(std::move(owner)) {}
   ~Buffer();
   Buffer(const Buffer&) = delete;
   Buffer& operator=(const Buffer&) = delete;
@@ -193,6 +199,10 @@ struct Buffer {
 };
 using BufferPtr = std::shared_ptr<Buffer>;
 BufferPtr alloc(const CtxPtr& ctx, size_t bytes);  // bytes == 0 still yields a valid (tiny) buffer
+// `bytes` bytes of `b` starting at byte `off`; the caller keeps `off` 16-byte aligned when vector loads will read it
+inline BufferPtr view_of(const BufferPtr& b, size_t off, size_t bytes) {
+  return std::make_shared<Buffer>(b->ctx, static_cast<char*>(b->ptr) + off, bytes, std::static_pointer_cast<const void>(b));
+}
 
 // Grid-prefix tuning (FLOCKGPU_LB_STRIDE / FLOCKGPU_LB_SLEEP override): 64-bit words between the look-back words of
 // consecutive tiles (32 = one 256-byte L2 chunk each), back-off of a polling thread in ns.
@@ -249,6 +259,12 @@ struct Table {
   mutable int64_t num_rows = 0;
   mutable std::shared_ptr<PendingRows> pending;
   std::string metadata;  // raw Arrow schema metadata block (may be empty)
+  // Set on the output of a multi-GPU hash exchange: the NAMES of the columns whose values routed the rows (the
+  // routing function of partition.cu over exactly these columns, `partition_world` ranks).  Operators that keep those
+  // columns under the same names hand the property on; a later RepartitionExec(Hash) over the same routing columns
+  // finds its input already in place and moves nothing (q8 plans Hash([p_id, name]) and then Hash([p_id])).
+  std::vector<std::string> partitioned_on;
+  int partition_world = 0;
   int64_t nbytes() const;
   void resolve() const {
     if (!pending) return;
@@ -320,6 +336,14 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left, const TablePtr& righ
                    const std::vector<int>& left_keys, const std::vector<int>& right_keys);
 std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in, const std::vector<int>& keys,
                                      int n_parts);
+// The columns of `keys` that actually route a row: the fixed-width ones when there are any (hashing `p_id` routes
+// (p_id, name) groups just as well as hashing the name bytes too, and lets a later Hash([p_id]) stay in place).
+std::vector<int> routing_columns(const Table& in, const std::vector<int>& keys);
+// RepartitionExec(Hash(keys, world)) + the inter-GPU shuffle in one step (exchange.cu): rows travel straight from the
+// partition kernel into the receivers' windows over NVLink peer memory; `dest` >= 0 sends every row to that rank
+// instead (CoalescePartitionsExec).  Falls back to hash_partition + the NCCL all-to-all when peer windows are
+// unavailable.
+TablePtr hash_exchange(const CtxPtr& ctx, const TablePtr& in, const std::vector<int>& keys, int dest = -1);
 // Row gather: out.col[c][i] = in.col[c][idx[i]] for every column (fixed width and Utf8).
 TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx,
                      int64_t n_idx);

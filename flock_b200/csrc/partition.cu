@@ -1,4 +1,4 @@
-// partition.cu -- K2: RepartitionExec: partitioning = Hash([keys], n).
+// partition.cu -- K2: RepartitionExec: partitioning = Hash([keys], n) as ONE multi-way pass (see partition.h).
 //
 // Reference operator (DataFusion fork; used at flock/src/distributed_plan/planner.rs:153, :160, :223,
 // :234; standalone helper flock/src/transmute.rs:77-109; the call shape is spelled out in
@@ -6,105 +6,518 @@
 // partition = hash % n -> per-partition index lists -> arrow `take` of every column.  Rows keep their
 // input order inside a partition.
 //
-//   partition_ids_kernel     pid[row] = high 32 hash bits scaled to [0, n)  (tables use the LOW bits)
-//   partition_select_kernel  one stable single-pass compaction per partition (compact.cuh) appending
-//                            the row indices of partition p behind those of partitions < p (the pass's
-//                            last tile writes where the next partition starts)
-//   gather.cu                materialises each partition's columns from its slice of the index vector
+// Here: count -> scan -> place -> scatter, four launches whatever n is; the n output tables are VIEWS of one
+// partition-ordered set of buffers (every partition starts on a 16-byte boundary so that vector loads keep working).
+#include "partition.h"
+
 #include <algorithm>
 
-#include "compact.cuh"
-#include "internal.h"
-#include "rowkeys.cuh"
+#include "device_utils.cuh"
 
 namespace fg {
-
-struct PartIdArgs {
-  int64_t n_rows;
-  int32_t packed;
-  int32_t n_parts;
-  KeyPack pack;
-  RowKeys rk;
-  ColRef cols[MAX_IN_COLS];
-  uint8_t* pid;
-};
 
 __host__ __device__ __forceinline__ uint32_t partition_of(uint64_t hash, uint32_t n_parts) {
   return uint32_t(((hash >> 32) * uint64_t(n_parts)) >> 32);
 }
 
-__global__ void __launch_bounds__(256) partition_ids_kernel(const __grid_constant__ PartIdArgs a) {
-  for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
-    unsigned long long h = a.packed ? fmix64(pack_key(a.pack, a.cols, row)) : hash_row(a.rk, a.cols, row);
-    a.pid[row] = uint8_t(partition_of(h, uint32_t(a.n_parts)));
+// ================================================================================================
+// step 1: destinations + per-CTA histograms
+// ================================================================================================
+struct PartCountArgs {
+  int64_t n_rows, chunk;
+  int32_t n_parts, packed, dest_rank, n_utf8, grid, pad;
+  KeyPack pack;
+  RowKeys rk;
+  ColRef cols[MAX_IN_COLS];
+  const int32_t* uoff[PT_MAX_UTF8];
+  uint8_t* pid;
+  uint32_t* hist;  // [(1 + n_utf8)][grid][n_parts]
+};
+
+__global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __grid_constant__ PartCountArgs a) {
+  extern __shared__ __align__(16) unsigned pc_smem[];
+  const int P = a.n_parts;
+  unsigned* h_rows = pc_smem;                  // [PT_WARPS][P] private to a warp: plain updates by one leader lane per value
+  unsigned* h_bytes = pc_smem + PT_WARPS * P;  // [n_utf8][P] shared atomics
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < (PT_WARPS + a.n_utf8) * P; i += PT_THREADS) pc_smem[i] = 0;
+  __syncthreads();
+  const int64_t begin = int64_t(blockIdx.x) * a.chunk;
+  const int64_t end = begin + a.chunk < a.n_rows ? begin + a.chunk : a.n_rows;
+  const unsigned lt = lanemask_lt();
+  unsigned* mine = h_rows + warp * P;
+  for (int64_t base = begin; base < end; base += PT_THREADS) {
+    const int64_t row = base + tid;
+    const bool valid = row < end;
+    unsigned pid = 0;
+    if (valid) {
+      if (a.dest_rank >= 0) {
+        pid = unsigned(a.dest_rank);
+      } else {
+        const unsigned long long h = a.packed ? fmix64(pack_key(a.pack, a.cols, row)) : hash_row(a.rk, a.cols, row);
+        pid = partition_of(h, uint32_t(P));
+      }
+      a.pid[row] = uint8_t(pid);
+      for (int u = 0; u < a.n_utf8; ++u) atomicAdd(&h_bytes[u * P + pid], unsigned(a.uoff[u][row + 1] - a.uoff[u][row]));
+    }
+    const unsigned vmask = __ballot_sync(FULL_MASK, valid);
+    unsigned m = 0, before = 0;
+    if (valid) {
+      m = __match_any_sync(vmask, pid);
+      before = mine[pid];
+    }
+    __syncwarp();
+    if (valid && lane == __ffs(m) - 1) mine[pid] = before + __popc(m);
+    __syncwarp();
+    (void)lt;
+  }
+  __syncthreads();
+  for (int p = tid; p < P; p += PT_THREADS) {
+    unsigned rows = 0;
+#pragma unroll
+    for (int w = 0; w < PT_WARPS; ++w) rows += h_rows[w * P + p];
+    a.hist[(int64_t(0) * a.grid + blockIdx.x) * P + p] = rows;
+    for (int u = 0; u < a.n_utf8; ++u) a.hist[(int64_t(1 + u) * a.grid + blockIdx.x) * P + p] = h_bytes[u * P + p];
   }
 }
 
-struct PartSelectArgs {
-  CompactScratch sc;
+// ================================================================================================
+// step 2: per destination (and per kind: rows, bytes of Utf8 column u) exclusive scan over the CTAs
+// ================================================================================================
+__global__ void __launch_bounds__(1024) partition_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cta_pos,
+                                                              unsigned long long* __restrict__ totals, int grid, int n_parts, int n_items) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int item = warp; item < n_items; item += 32) {
+    const int k = item / n_parts, p = item % n_parts;
+    unsigned long long run = 0;
+    for (int c0 = 0; c0 < grid; c0 += 32) {
+      const int c = c0 + lane;
+      const unsigned v = c < grid ? hist[(int64_t(k) * grid + c) * n_parts + p] : 0u;
+      const unsigned incl = warp_inclusive_sum(v);
+      if (c < grid) cta_pos[(int64_t(k) * grid + c) * n_parts + p] = unsigned(run) + incl - v;
+      run += __shfl_sync(FULL_MASK, incl, 31);
+    }
+    if (lane == 0) totals[item] = run;
+  }
+}
+
+// ================================================================================================
+// step 4: stable scatter through shared memory
+// ================================================================================================
+struct PartScatterArgs {
+  int64_t n_rows, chunk;
+  int32_t n_parts, n_fixed, n_utf8, grid;
   const uint8_t* pid;
-  int64_t n_rows;
-  int32_t part;
-  int32_t pad;
-  unsigned long long* bases;  // bases[p] = first index slot of partition p; the kernel writes bases[p + 1]
-  uint32_t* idx;
+  const void* fsrc[MAX_IN_COLS];
+  int32_t fwidth[MAX_IN_COLS];
+  const int32_t* uoff[PT_MAX_UTF8];
+  const uint8_t* udata[PT_MAX_UTF8];
+  const uint32_t* cta_pos;
+  const PartDest* dest;
+  const unsigned* abort_flag;
 };
 
-__global__ void __launch_bounds__(CP_THREADS) partition_select_kernel(const __grid_constant__ PartSelectArgs a) {
-  constexpr int E = 4;
-  constexpr int CP_ITEMS = 16;
-  constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
-  __shared__ CompactSmem<E, CP_ITEMS> sm;
-  const int tid = threadIdx.x;
-  const unsigned long long base = a.bases[a.part];
-  long long tile;
-  for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
-    const int64_t tile_base = tile * CP_TILE;
-    unsigned long long bits = 0;
+// dynamic shared memory layout of the scatter kernel (P destinations, U Utf8 columns)
+struct ScatterSmem {
+  size_t wcnt, woff, seg, tot, run, runb, segb, sege, row, pid, wscan, dest, stage, total;
+  __host__ __device__ ScatterSmem(int P, int U, bool dest_in_smem) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+      size_t at = o;
+      o = (o + bytes + 15) & ~size_t(15);
+      return at;
+    };
+    wcnt = take(size_t(PT_WARPS) * P * 2);
+    woff = take(size_t(PT_WARPS) * P * 2);
+    seg = take(size_t(P + 1) * 2);
+    tot = take(size_t(P) * 2);
+    run = take(size_t(P) * 4);
+    runb = take(size_t(U ? U : 1) * P * 4);
+    segb = take(size_t(P) * 4);
+    sege = take(size_t(P) * 4);
+    row = take(size_t(PT_TILE) * 2);
+    pid = take(size_t(PT_TILE));
+    wscan = take(size_t(PT_WARPS + 1) * 4);
+    dest = take(dest_in_smem ? size_t(P) * sizeof(PartDest) : 0);
+    stage = take(U ? size_t(PT_STAGE_BYTES) : 0);
+    total = o;
+  }
+};
+constexpr int PT_DEST_SMEM_PARTS = 16;  // up to this many destinations the PartDest table is copied to shared memory
+
+__global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __grid_constant__ PartScatterArgs a) {
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  if (a.abort_flag && *reinterpret_cast<const volatile unsigned*>(a.abort_flag)) return;
+  const int P = a.n_parts, U = a.n_utf8;
+  const bool dest_in_smem = P <= PT_DEST_SMEM_PARTS;
+  const ScatterSmem L(P, U, dest_in_smem);
+  unsigned short* s_wcnt = reinterpret_cast<unsigned short*>(ps_smem + L.wcnt);
+  unsigned short* s_woff = reinterpret_cast<unsigned short*>(ps_smem + L.woff);
+  unsigned short* s_seg = reinterpret_cast<unsigned short*>(ps_smem + L.seg);
+  unsigned short* s_tot = reinterpret_cast<unsigned short*>(ps_smem + L.tot);
+  unsigned* s_run = reinterpret_cast<unsigned*>(ps_smem + L.run);
+  unsigned* s_runb = reinterpret_cast<unsigned*>(ps_smem + L.runb);
+  unsigned* s_segb = reinterpret_cast<unsigned*>(ps_smem + L.segb);
+  unsigned* s_sege = reinterpret_cast<unsigned*>(ps_smem + L.sege);
+  unsigned short* s_row = reinterpret_cast<unsigned short*>(ps_smem + L.row);
+  unsigned char* s_pid = ps_smem + L.pid;
+  unsigned* s_wscan = reinterpret_cast<unsigned*>(ps_smem + L.wscan);
+  unsigned char* s_stage = ps_smem + L.stage;
+  const PartDest* dest = a.dest;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t begin = int64_t(blockIdx.x) * a.chunk;
+  const int64_t end = begin + a.chunk < a.n_rows ? begin + a.chunk : a.n_rows;
+  if (begin >= end) return;
+  if (dest_in_smem) {
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(ps_smem + L.dest);
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(a.dest);
+    for (int i = tid; i < int(P * sizeof(PartDest) / 8); i += PT_THREADS) d[i] = s[i];
+    dest = reinterpret_cast<const PartDest*>(ps_smem + L.dest);
+  }
+  for (int p = tid; p < P; p += PT_THREADS) {
+    s_run[p] = a.cta_pos[(int64_t(0) * a.grid + blockIdx.x) * P + p];
+    for (int u = 0; u < U; ++u) s_runb[u * P + p] = a.cta_pos[(int64_t(1 + u) * a.grid + blockIdx.x) * P + p];
+  }
+  const unsigned lt = lanemask_lt();
+  unsigned short* my_wcnt = s_wcnt + warp * P;
+
+  for (int64_t tile0 = begin; tile0 < end; tile0 += PT_TILE) {
+    const int rows = int(end - tile0 < PT_TILE ? end - tile0 : PT_TILE);
+    for (int p = lane; p < P; p += 32) my_wcnt[p] = 0;
+    __syncthreads();  // also: s_run / dest are initialised, the previous tile's readers of s_row / s_pid are done
+    // ---- rank of every row among the rows of its warp with the same destination (rows in input order)
+    unsigned char mypid[8];
+    unsigned short myrank[8];
 #pragma unroll
-    for (int g = 0; g < CP_ITEMS / E; ++g) {
-      const int64_t r0 = tile_base + (int64_t(g) * CP_THREADS + tid) * E;
-      uint32_t w = 0xffffffffu;
-      if (r0 + 3 < a.n_rows) {
-        w = *reinterpret_cast<const uint32_t*>(a.pid + r0);
-      } else {
-        for (int e = 0; e < 4; ++e)
-          if (r0 + e < a.n_rows) w = (w & ~(0xffu << (8 * e))) | (uint32_t(a.pid[r0 + e]) << (8 * e));
-          else w = (w & ~(0xffu << (8 * e))) | (0xffu << (8 * e));
+    for (int j = 0; j < 8; ++j) {
+      const int local = warp * 256 + j * 32 + lane;
+      const bool valid = local < rows;
+      unsigned pid = 0, m = 0, before = 0;
+      if (valid) pid = a.pid[tile0 + local];
+      const unsigned vmask = __ballot_sync(FULL_MASK, valid);
+      if (valid) {
+        m = __match_any_sync(vmask, pid);
+        before = my_wcnt[pid];
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        bool in_range = r0 + e < a.n_rows;
-        bits |= (unsigned long long)(in_range && ((w >> (8 * e)) & 0xffu) == uint32_t(a.part)) << (g * E + e);
-      }
+      __syncwarp();
+      if (valid && lane == __ffs(m) - 1) my_wcnt[pid] = (unsigned short)(before + __popc(m));
+      __syncwarp();
+      mypid[j] = (unsigned char)pid;
+      myrank[j] = (unsigned short)(before + __popc(m & lt));
     }
-    unsigned lane_prefix[CP_ITEMS / E];
-    cp_rank_tile<E, CP_ITEMS>(sm, a.sc, tile, bits, lane_prefix);
-    // the last tile knows the partition's size: the next pass starts behind it (no separate "advance" launch)
-    if (tile == a.sc.num_tiles - 1 && tid == 0) a.bases[a.part + 1] = base + sm.excl + sm.tile_total;
-    if (bits && sm.tile_total) {
-      unsigned long long m = bits;
-      while (m) {
-        const int k = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        a.idx[base + (unsigned long long)cp_position<E, CP_ITEMS>(sm, bits, k, lane_prefix)] = uint32_t(tile_base + cp_item_index<E>(k, tid));
+    __syncthreads();
+    // ---- per destination: offsets of the warps, the tile's total
+    for (int p = tid; p < P; p += PT_THREADS) {
+      unsigned run = 0;
+#pragma unroll
+      for (int w = 0; w < PT_WARPS; ++w) {
+        s_woff[w * P + p] = (unsigned short)run;
+        run += s_wcnt[w * P + p];
+      }
+      s_tot[p] = (unsigned short)run;
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the totals over the destinations: where each segment starts in the tile
+      unsigned run = 0;
+      for (int p0 = 0; p0 < P; p0 += 32) {
+        const int p = p0 + lane;
+        const unsigned v = p < P ? s_tot[p] : 0u;
+        const unsigned incl = warp_inclusive_sum(v);
+        if (p < P) s_seg[p] = (unsigned short)(run + incl - v);
+        run += __shfl_sync(FULL_MASK, incl, 31);
+      }
+      if (lane == 0) s_seg[P] = (unsigned short)run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int local = warp * 256 + j * 32 + lane;
+      if (local < rows) {
+        const unsigned p = mypid[j];
+        const unsigned s = unsigned(s_seg[p]) + s_woff[warp * P + p] + myrank[j];
+        s_row[s] = (unsigned short)local;
+        s_pid[s] = (unsigned char)p;
       }
     }
     __syncthreads();
+    // ---- fixed-width columns: consecutive threads write consecutive rows of one destination
+    for (int s = tid; s < rows; s += PT_THREADS) {
+      const unsigned p = s_pid[s];
+      const int64_t pos = int64_t(s_run[p]) + (s - int(s_seg[p]));
+      const int64_t row = tile0 + s_row[s];
+      for (int f = 0; f < a.n_fixed; ++f) {
+        if (a.fwidth[f] == 4) static_cast<uint32_t*>(dest[p].val[f])[pos] = static_cast<const uint32_t*>(a.fsrc[f])[row];
+        else static_cast<unsigned long long*>(dest[p].val[f])[pos] = static_cast<const unsigned long long*>(a.fsrc[f])[row];
+      }
+    }
+    // ---- Utf8 columns: a thread owns 8 consecutive slots of the ordered tile
+    for (int u = 0; u < U; ++u) {
+      for (int p = tid; p < P; p += PT_THREADS) {
+        s_segb[p] = 0;
+        s_sege[p] = 0;
+      }
+      int len[8], src[8];
+      unsigned local_sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int s = tid * 8 + k;
+        len[k] = 0;
+        src[k] = 0;
+        if (s < rows) {
+          const int64_t row = tile0 + s_row[s];
+          src[k] = a.uoff[u][row];
+          len[k] = a.uoff[u][row + 1] - src[k];
+        }
+        local_sum += unsigned(len[k]);
+      }
+      const unsigned incl = warp_inclusive_sum(local_sum);
+      if (lane == 31) s_wscan[warp] = incl;
+      __syncthreads();  // s_segb / s_sege zeroed, warp sums published
+      unsigned warp_base = 0, tile_bytes = 0;
+#pragma unroll
+      for (int w = 0; w < PT_WARPS; ++w) {
+        const unsigned v = s_wscan[w];
+        if (w < warp) warp_base += v;
+        tile_bytes += v;
+      }
+      unsigned bytepos[8];
+      unsigned run = warp_base + incl - local_sum;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        bytepos[k] = run;
+        run += unsigned(len[k]);
+        const int s = tid * 8 + k;
+        if (s < rows) {
+          const unsigned p = s_pid[s];
+          if (s == int(s_seg[p])) s_segb[p] = bytepos[k];
+          if (s == int(s_seg[p]) + int(s_tot[p]) - 1) s_sege[p] = bytepos[k] + unsigned(len[k]);
+        }
+      }
+      __syncthreads();
+      const bool staged = tile_bytes <= unsigned(PT_STAGE_BYTES);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int s = tid * 8 + k;
+        if (s >= rows) continue;
+        const unsigned p = s_pid[s];
+        const int64_t pos = int64_t(s_run[p]) + (s - int(s_seg[p]));
+        const unsigned rel = s_runb[u * P + p] + (bytepos[k] - s_segb[p]);
+        dest[p].off[u][pos] = int32_t(dest[p].byte_origin[u] + (long long)rel);
+        const uint8_t* from = a.udata[u] + src[k];
+        if (staged) {
+          unsigned char* to = s_stage + bytepos[k];
+          for (int b = 0; b < len[k]; ++b) to[b] = from[b];
+        } else {  // a tile of long strings: straight to the destination
+          uint8_t* to = dest[p].bytes[u] + rel;
+          for (int b = 0; b < len[k]; ++b) to[b] = from[b];
+        }
+      }
+      __syncthreads();
+      if (staged) {
+        // a warp per destination segment: the lanes write consecutive bytes (full sectors on the wire)
+        for (int p = warp; p < P; p += PT_WARPS) {
+          const unsigned b0 = s_segb[p], b1 = s_sege[p];
+          uint8_t* to = dest[p].bytes[u] + s_runb[u * P + p];
+          // head up to a 4-byte boundary of the destination, aligned words, tail
+          unsigned head = unsigned(-(long long)reinterpret_cast<uintptr_t>(to)) & 3u;
+          if (head > b1 - b0) head = b1 - b0;
+          if (lane < head) to[lane] = s_stage[b0 + lane];
+          const unsigned words = (b1 - b0 - head) >> 2;
+          for (unsigned w = lane; w < words; w += 32) {
+            const unsigned char* sp = s_stage + b0 + head + 4 * w;
+            const unsigned v = unsigned(sp[0]) | (unsigned(sp[1]) << 8) | (unsigned(sp[2]) << 16) | (unsigned(sp[3]) << 24);
+            *reinterpret_cast<unsigned*>(to + head + 4 * w) = v;
+          }
+          const unsigned done = head + 4 * words;
+          if (lane < (b1 - b0) - done) to[done + lane] = s_stage[b0 + done + lane];
+        }
+      }
+      __syncthreads();
+      for (int p = tid; p < P; p += PT_THREADS) s_runb[u * P + p] += s_sege[p] - s_segb[p];
+    }
+    __syncthreads();
+    for (int p = tid; p < P; p += PT_THREADS) s_run[p] += s_tot[p];
+  }
+}
+
+// ================================================================================================
+// host: steps 1, 2 and 4
+// ================================================================================================
+std::vector<int> routing_columns(const Table& in, const std::vector<int>& keys) {
+  std::vector<int> fixed;
+  for (int k : keys)
+    if (in.cols[k].dtype != FLOCKGPU_UTF8) fixed.push_back(k);
+  return fixed.empty() ? keys : fixed;
+}
+
+static void fill_colrefs(const Table& in, ColRef* refs) {
+  for (size_t i = 0; i < in.cols.size(); ++i) {
+    refs[i].data = in.cols[i].values();
+    refs[i].offsets = in.cols[i].offs();
+    refs[i].dtype = in.cols[i].dtype;
+    refs[i].chunk_shift = 0;
+    refs[i].chunks = nullptr;
+  }
+}
+
+PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vector<int>& routing_cols, int n_parts, int dest_rank) {
+  FG_CHECK(n_parts >= 1 && n_parts <= PT_MAX_PARTS, FLOCKGPU_ERR_INVALID, "hash_partition: n_parts must be in [1, %d], got %d", PT_MAX_PARTS, n_parts);
+  FG_CHECK(in.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d columns", MAX_IN_COLS);
+  FG_CHECK(dest_rank >= 0 || (!routing_cols.empty() && routing_cols.size() <= size_t(MAX_KEY_COLS)), FLOCKGPU_ERR_INVALID, "hash_partition: 1..%d key columns",
+           MAX_KEY_COLS);
+  PartPass ps;
+  ps.n_rows = in.num_rows;
+  ps.n_parts = n_parts;
+  for (size_t i = 0; i < in.cols.size(); ++i) {
+    FG_CHECK(!in.cols[i].all_null, FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: NULL column \"%s\"", in.cols[i].name.c_str());
+    if (in.cols[i].dtype == FLOCKGPU_UTF8) ps.utf8_cols.push_back(int(i));
+    else {
+      FG_CHECK(in.cols[i].width() == 4 || in.cols[i].width() == 8, FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: column width %d", in.cols[i].width());
+      ps.fixed_cols.push_back(int(i));
+    }
+  }
+  FG_CHECK(ps.utf8_cols.size() <= size_t(PT_MAX_UTF8), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d Utf8 columns", PT_MAX_UTF8);
+  const int U = int(ps.utf8_cols.size());
+  // geometry: as many CTAs as stay resident, each owning a contiguous, tile-aligned range of rows
+  const ScatterSmem L(n_parts, U, n_parts <= PT_DEST_SMEM_PARTS);
+  FG_CUDA(cudaFuncSetAttribute(partition_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.total)));
+  const int64_t resident = resident_ctas(ctx, reinterpret_cast<const void*>(partition_scatter_kernel), PT_THREADS, L.total);
+  const int64_t tiles = std::max<int64_t>(1, (ps.n_rows + PT_TILE - 1) / PT_TILE);
+  const int64_t tiles_per_cta = (tiles + resident - 1) / resident;
+  ps.chunk = tiles_per_cta * PT_TILE;
+  ps.grid = int((tiles + tiles_per_cta - 1) / tiles_per_cta);
+  const size_t cells = size_t(1 + U) * ps.grid * n_parts;
+  ps.pid = alloc(ctx, size_t(ps.n_rows) + 16);
+  ps.hist = alloc(ctx, cells * 4);
+  ps.cta_pos = alloc(ctx, cells * 4);
+  ps.totals = alloc(ctx, size_t(1 + U) * n_parts * 8);
+  ps.dest = alloc(ctx, size_t(n_parts) * sizeof(PartDest));
+
+  PartCountArgs ca{};
+  ca.n_rows = ps.n_rows;
+  ca.chunk = ps.chunk;
+  ca.n_parts = n_parts;
+  ca.dest_rank = dest_rank;
+  ca.n_utf8 = U;
+  ca.grid = ps.grid;
+  fill_colrefs(in, ca.cols);
+  if (dest_rank < 0) {
+    std::vector<int> widths;
+    for (int k : routing_cols) {
+      FG_CHECK(k >= 0 && k < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_partition: key column %d out of range", k);
+      widths.push_back(in.cols[k].width());
+    }
+    ca.packed = keys_packable(widths.data(), int(widths.size())) ? 1 : 0;
+    ca.rk.n = int(routing_cols.size());
+    for (size_t i = 0; i < routing_cols.size(); ++i) ca.rk.col[i] = routing_cols[i];
+    if (ca.packed) {
+      ca.pack.n = int(routing_cols.size());
+      for (size_t i = 0; i < routing_cols.size(); ++i) {
+        ca.pack.col[i] = routing_cols[i];
+        ca.pack.width[i] = widths[i];
+      }
+    }
+  }
+  for (int u = 0; u < U; ++u) ca.uoff[u] = in.cols[ps.utf8_cols[u]].offs();
+  ca.pid = ps.pid->as<uint8_t>();
+  ca.hist = ps.hist->as<uint32_t>();
+  const size_t count_smem = size_t(PT_WARPS + U) * n_parts * 4;
+  {
+    LaunchTimer lt(ctx, "partition_count_kernel");
+    partition_count_kernel<<<ps.grid, PT_THREADS, count_smem, ctx->stream>>>(ca);
+  }
+  FG_CUDA(cudaGetLastError());
+  {
+    LaunchTimer lt(ctx, "partition_scan_kernel");
+    partition_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ps.hist->as<uint32_t>(), ps.cta_pos->as<uint32_t>(), ps.totals->as<unsigned long long>(), ps.grid,
+                                                       n_parts, (1 + U) * n_parts);
+  }
+  FG_CUDA(cudaGetLastError());
+  count_launch(ctx, 2);
+  return ps;
+}
+
+void partition_scatter(const CtxPtr& ctx, const Table& in, const PartPass& ps, const unsigned* abort_flag) {
+  const int U = int(ps.utf8_cols.size());
+  PartScatterArgs sa{};
+  sa.n_rows = ps.n_rows;
+  sa.chunk = ps.chunk;
+  sa.n_parts = ps.n_parts;
+  sa.n_fixed = int(ps.fixed_cols.size());
+  sa.n_utf8 = U;
+  sa.grid = ps.grid;
+  sa.pid = ps.pid->as<uint8_t>();
+  for (size_t f = 0; f < ps.fixed_cols.size(); ++f) {
+    sa.fsrc[f] = in.cols[ps.fixed_cols[f]].values();
+    sa.fwidth[f] = in.cols[ps.fixed_cols[f]].width();
+  }
+  for (int u = 0; u < U; ++u) {
+    sa.uoff[u] = in.cols[ps.utf8_cols[u]].offs();
+    sa.udata[u] = static_cast<const uint8_t*>(in.cols[ps.utf8_cols[u]].values());
+  }
+  sa.cta_pos = ps.cta_pos->as<uint32_t>();
+  sa.dest = ps.dest->as<PartDest>();
+  sa.abort_flag = abort_flag;
+  const ScatterSmem L(ps.n_parts, U, ps.n_parts <= PT_DEST_SMEM_PARTS);
+  if (ps.n_rows > 0) {
+    {
+      LaunchTimer lt(ctx, "partition_scatter_kernel");
+      partition_scatter_kernel<<<ps.grid, PT_THREADS, L.total, ctx->stream>>>(sa);
+    }
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
+}
+
+// ================================================================================================
+// one GPU: the partitions one behind the other in local buffers, handed out as views
+// ================================================================================================
+// Partition p starts at row base[p] of every output column: base[0] = 0, base[p + 1] = align4(base[p] + rows[p] + 1).
+// The alignment keeps 16-byte vector loads working on a view; the spare row keeps the terminal offsets entry of a
+// Utf8 partition apart from the first entry of the next one.
+__host__ __device__ __forceinline__ unsigned long long next_partition_base(unsigned long long base, unsigned long long rows) {
+  return (base + rows + 1 + 3) & ~3ull;
+}
+
+struct PlaceLocalArgs {
+  int32_t n_parts, n_fixed, n_utf8, pad;
+  const unsigned long long* totals;  // [(1 + n_utf8)][n_parts]
+  void* fdst[MAX_IN_COLS];
+  int32_t fwidth[MAX_IN_COLS];
+  int32_t* uoff_dst[PT_MAX_UTF8];
+  uint8_t* ubytes_dst[PT_MAX_UTF8];
+  PartDest* dest;
+};
+
+__global__ void partition_place_local_kernel(const __grid_constant__ PlaceLocalArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long base = 0;
+  unsigned long long byte_base[PT_MAX_UTF8] = {};
+  for (int p = 0; p < a.n_parts; ++p) {
+    const unsigned long long rows = a.totals[p];
+    PartDest d{};
+    for (int f = 0; f < a.n_fixed; ++f) d.val[f] = static_cast<char*>(a.fdst[f]) + base * a.fwidth[f];
+    for (int u = 0; u < a.n_utf8; ++u) {
+      const unsigned long long bytes = a.totals[(1 + u) * a.n_parts + p];
+      d.off[u] = a.uoff_dst[u] + base;
+      d.bytes[u] = a.ubytes_dst[u] + byte_base[u];
+      d.byte_origin[u] = 0;  // a partition's offsets are relative to its own view of the value bytes
+      a.uoff_dst[u][base + rows] = int32_t(bytes);  // terminal entry (also the only entry of an empty partition)
+      byte_base[u] += bytes;
+    }
+    a.dest[p] = d;
+    base = next_partition_base(base, rows);
   }
 }
 
 std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vector<int>& keys, int n_parts) {
   const Table& in = *in_ptr;
   in.dense();
-  FG_CHECK(n_parts >= 1 && n_parts <= 255, FLOCKGPU_ERR_INVALID, "hash_partition: n_parts must be in [1, 255], got %d", n_parts);
+  FG_CHECK(n_parts >= 1 && n_parts <= PT_MAX_PARTS, FLOCKGPU_ERR_INVALID, "hash_partition: n_parts must be in [1, %d], got %d", PT_MAX_PARTS, n_parts);
   FG_CHECK(!keys.empty() && keys.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_INVALID, "hash_partition: 1..%d key columns", MAX_KEY_COLS);
-  FG_CHECK(in.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d columns", MAX_IN_COLS);
-  std::vector<int> widths;
   for (int k : keys) {
     FG_CHECK(k >= 0 && k < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_partition: key column %d out of range", k);
     FG_CHECK(!in.cols[k].all_null, FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: NULL key column");
-    widths.push_back(in.cols[k].width());
   }
   std::vector<TablePtr> out;
   if (n_parts == 1) {
@@ -116,68 +529,79 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
     return out;
   }
   const int64_t n = in.num_rows;
-  BufferPtr pid = alloc(ctx, size_t(n) + 16);
-  PartIdArgs ia{};
-  ia.n_rows = n;
-  ia.packed = keys_packable(widths.data(), int(widths.size())) ? 1 : 0;
-  ia.n_parts = n_parts;
-  for (size_t i = 0; i < in.cols.size(); ++i) {
-    ia.cols[i].data = in.cols[i].values();
-    ia.cols[i].offsets = in.cols[i].offs();
-    ia.cols[i].dtype = in.cols[i].dtype;
+  PartPass ps = partition_count_scan(ctx, in, routing_columns(in, keys), n_parts);
+  const int U = int(ps.utf8_cols.size());
+  // ---- output buffers: every column once, partitions one behind the other (5 spare rows per partition at most)
+  const size_t cap_rows = size_t(n) + 5 * size_t(n_parts) + 4;
+  std::vector<BufferPtr> fbuf(ps.fixed_cols.size()), obuf(U), bbuf(U);
+  PlaceLocalArgs pa{};
+  pa.n_parts = n_parts;
+  pa.n_fixed = int(ps.fixed_cols.size());
+  pa.n_utf8 = U;
+  pa.totals = ps.totals->as<unsigned long long>();
+  for (size_t f = 0; f < ps.fixed_cols.size(); ++f) {
+    const int w = in.cols[ps.fixed_cols[f]].width();
+    fbuf[f] = alloc(ctx, cap_rows * w);
+    pa.fdst[f] = fbuf[f]->ptr;
+    pa.fwidth[f] = w;
   }
-  ia.rk.n = int(keys.size());
-  for (size_t i = 0; i < keys.size(); ++i) ia.rk.col[i] = keys[i];
-  if (ia.packed) {
-    ia.pack.n = int(keys.size());
-    for (size_t i = 0; i < keys.size(); ++i) {
-      ia.pack.col[i] = keys[i];
-      ia.pack.width[i] = widths[i];
-    }
+  for (int u = 0; u < U; ++u) {
+    obuf[u] = alloc(ctx, cap_rows * 4);
+    bbuf[u] = alloc(ctx, size_t(in.cols[ps.utf8_cols[u]].values_bytes));
+    pa.uoff_dst[u] = obuf[u]->as<int32_t>();
+    pa.ubytes_dst[u] = bbuf[u]->as<uint8_t>();
   }
-  ia.pid = pid->as<uint8_t>();
-  int grid = int(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, int64_t(ctx->sm_count) * 8)));
+  pa.dest = ps.dest->as<PartDest>();
   {
-    LaunchTimer lt(ctx, "partition_ids_kernel");
-    partition_ids_kernel<<<grid, 256, 0, ctx->stream>>>(ia);
+    LaunchTimer lt(ctx, "partition_place_local_kernel");
+    partition_place_local_kernel<<<1, 32, 0, ctx->stream>>>(pa);
   }
   FG_CUDA(cudaGetLastError());
   count_launch(ctx);
-
-  // bases live in d_scalars[16 .. 16 + n_parts]; the per-pass survivor count in d_scalars[5]
-  FG_CHECK(16 + n_parts + 1 <= 384, FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: too many partitions");  // d_scalars[384 ..] belongs to gather.cu
-  unsigned long long* bases = ctx->d_scalars + 16;
-  FG_CUDA(cudaMemsetAsync(bases, 0, sizeof(unsigned long long) * (n_parts + 1), ctx->stream));
-  BufferPtr idx = alloc(ctx, size_t(n) * 4);
-  PartSelectArgs sa{};
-  const long long tiles = (n + CP_THREADS * 16 - 1) / (CP_THREADS * 16);
-  sa.pid = pid->as<uint8_t>();
-  sa.n_rows = n;
-  sa.bases = bases;
-  sa.idx = idx->as<uint32_t>();
-  int per_sm = 1;
-  FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_select_kernel, CP_THREADS, 0));
-  const long long resident = (long long)ctx->sm_count * std::max(per_sm, 1);
+  partition_scatter(ctx, in, ps, nullptr);
+  // ---- the partition sizes are the one thing the host needs: views are cut from them
+  std::vector<unsigned long long> tot(size_t(1 + U) * n_parts);
+  FG_CUDA(cudaMemcpyAsync(tot.data(), ps.totals->ptr, tot.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FG_CUDA(cudaStreamSynchronize(ctx->stream));
+  unsigned long long sum = 0;
+  for (int p = 0; p < n_parts; ++p) sum += tot[p];
+  FG_CHECK(int64_t(sum) == n, FLOCKGPU_ERR_CUDA, "hash_partition: partition sizes sum to %llu, expected %lld", sum, (long long)n);
+  unsigned long long base = 0;
+  std::vector<unsigned long long> byte_base(U, 0);
   for (int p = 0; p < n_parts; ++p) {
-    sa.part = p;
-    sa.sc = prepare_compact(ctx, tiles, resident, ctx->d_scalars + 5);
-    {
-      LaunchTimer lt(ctx, "partition_select_kernel");
-      launch_compact(ctx, partition_select_kernel, sa.sc, sa);
+    const int64_t rows = int64_t(tot[p]);
+    auto t = std::make_shared<Table>();
+    t->ctx = ctx;
+    t->metadata = in.metadata;
+    t->num_rows = rows;
+    t->cols.resize(in.cols.size());
+    for (size_t f = 0; f < ps.fixed_cols.size(); ++f) {
+      const Column& src = in.cols[ps.fixed_cols[f]];
+      Column& c = t->cols[ps.fixed_cols[f]];
+      c.dtype = src.dtype;
+      c.name = src.name;
+      c.format = src.format;
+      c.nullable = src.nullable;
+      c.length = rows;
+      c.data = view_of(fbuf[f], size_t(base) * src.width(), size_t(rows) * src.width());
     }
-    FG_CUDA(cudaGetLastError());
-    count_launch(ctx);
+    for (int u = 0; u < U; ++u) {
+      const Column& src = in.cols[ps.utf8_cols[u]];
+      Column& c = t->cols[ps.utf8_cols[u]];
+      const unsigned long long bytes = tot[size_t(1 + u) * n_parts + p];
+      c.dtype = src.dtype;
+      c.name = src.name;
+      c.format = src.format;
+      c.nullable = src.nullable;
+      c.length = rows;
+      c.offsets = view_of(obuf[u], size_t(base) * 4, size_t(rows + 1) * 4);
+      c.data = view_of(bbuf[u], size_t(byte_base[u]), size_t(bytes));
+      c.values_bytes = int64_t(bytes);
+      byte_base[u] += bytes;
+    }
+    out.push_back(std::move(t));
+    base = next_partition_base(base, tot[p]);
   }
-  std::vector<unsigned long long> hb(n_parts + 1);
-  read_scalars(ctx, 16, n_parts + 1, hb.data());
-  FG_CHECK(int64_t(hb[n_parts]) == n, FLOCKGPU_ERR_CUDA, "hash_partition: partition sizes sum to %llu, expected %lld", hb[n_parts], (long long)n);
-  std::vector<int> all_cols;
-  for (size_t i = 0; i < in.cols.size(); ++i) all_cols.push_back(int(i));
-  for (int p = 0; p < n_parts; ++p) {
-    int64_t cnt = int64_t(hb[p + 1] - hb[p]);
-    out.push_back(gather_rows(ctx, in, all_cols, idx->as<uint32_t>() + hb[p], cnt));
-  }
-  // `idx` must outlive the gathers: they are stream-ordered before its (stream-ordered) free
   return out;
 }
 

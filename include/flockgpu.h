@@ -101,7 +101,9 @@ int64_t flockgpu_kernel_launches(flockgpu_ctx* ctx);
  * unmodified until flock_context_clean_data_sources -- exactly what the reference does anyway: MemoryExec owns the fed
  * RecordBatches until clean_data_sources (flock/src/runtime/context.rs:227-254).
  * "compact_mode" (0 automatic | 1 always decoupled look-back): which grid-wide prefix protocol the compaction /
- * scan kernels use; results are identical, the parity tests run both.                                                */
+ * scan kernels use; results are identical, the parity tests run both.
+ * "exchange_window_mb" (default 4096): size of the receive window the multi-GPU exchange stores rows into over NVLink
+ * peer memory; read by flockgpu_comm_init, so set it first.                                                           */
 int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing: between _begin and _end every kernel this library launches on the ctx is
  * bracketed by its own pair of CUDA events on the ctx stream.  _end waits for the stream and writes a JSON
@@ -252,7 +254,9 @@ int flockgpu_comm_rank(flockgpu_ctx* ctx, int32_t* rank, int32_t* world_size);
 /* parts[r] goes to rank r; `out` = concatenation (in rank order) of what every rank sent to us.    */
 int flockgpu_all_to_all(flockgpu_ctx* ctx, flockgpu_table* const* parts, int32_t n_parts,
                         flockgpu_table** out);
-/* RepartitionExec(Hash(keys, world_size)) fused with the exchange.                                 */
+/* RepartitionExec(Hash(keys, world_size)) fused with the exchange: the partition kernel stores every row straight
+ * into the receiving rank's window over NVLink peer memory (CUDA IPC; no NCCL call on the data path).  The result
+ * holds, in source-rank order, the rows every rank routed here; inside one source the input order is kept.           */
 int flockgpu_hash_exchange(flockgpu_ctx* ctx, const flockgpu_table* in, const int32_t* key_cols,
                            int32_t n_keys, flockgpu_table** out);
 

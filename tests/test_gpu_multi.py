@@ -1,7 +1,9 @@
-"""Multi-GPU parity (`-m gpu`, needs >= 2 devices; skipped on a 1-GPU box): two processes, one GPU each,
-an NCCL communicator attached through the C ABI (flockgpu_comm_init).  Checks the all-to-all itself and the
-distributed execution of the reference's plans (every RepartitionExec(Hash) becomes an NVLink all-to-all):
-the union of the ranks' results must equal the CPU oracle's single-process result."""
+"""Multi-GPU parity (`-m gpu`, needs >= 2 devices; skipped on a 1-GPU box): two processes, one GPU each, a communicator
+attached through the C ABI (flockgpu_comm_init).  Checks the exchange itself -- once over NVLink peer windows (the
+product path: the partition kernel stores into the receiver's HBM) and once over the NCCL fallback -- and the
+distributed execution of the reference's plans (every RepartitionExec(Hash) becomes an exchange): the union of the
+ranks' results must equal the CPU oracle's single-process result.  bench.py --gpus N repeats the q8 check on the
+driver's multi-GPU box (its JSON line carries `parity_check`)."""
 import io
 import os
 import socket
@@ -28,11 +30,14 @@ def _ipc(t: pa.Table) -> bytes:
     return sink.getvalue()
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     import torch.distributed as dist
     import flock_b200 as fb
     from flock_b200 import nexgen, plans, sharding
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if mode == "nccl":
+        os.environ["FLOCKGPU_EXCHANGE"] = "nccl"        # read by flockgpu_comm_init: peer windows off
+    os.environ["FLOCKGPU_WINDOW_MB"] = "256"
     dist.init_process_group("gloo", rank=rank, world_size=world)          # control plane only: ships the NCCL id
     ctx = fb.Context(rank)
     ids = [fb.Context.comm_unique_id() if rank == 0 else None]
@@ -46,7 +51,9 @@ def _worker(rank, world, port, out_dir):
     b = pa.RecordBatch.from_arrays([pa.array(rng.integers(0, 1 << 30, n).astype(np.int32)), pa.array([words[k] for k in rng.integers(0, 5, n)]),
                                     pa.array(np.full(n, rank, np.int64))], names=["k", "s", "src"])
     t = ctx.import_batches([b])
-    got = ctx.hash_exchange(t, [0]).to_arrow()
+    dist.barrier()                                   # a rank that is late by more than the exchange time-out fails the others
+    held = ctx.hash_exchange(t, [0])                 # stays alive: its columns are views into the receive window
+    got = held.to_arrow()
     pid = sharding.partition_ids(b, [0], world)
     mine = b.filter(pa.array(pid == rank))
     assert got.filter(pa.compute.equal(got["src"], rank)).to_batches()[0].equals(mine) if mine.num_rows else True   # own rows, input order kept
@@ -54,11 +61,42 @@ def _worker(rank, world, port, out_dir):
     counts = [None] * world
     dist.all_gather_object(counts, (b.num_rows, got.num_rows))
     assert sum(c[0] for c in counts) == sum(c[1] for c in counts)                                                   # nothing lost
+    # a second exchange while the first result is still alive lands behind it in the window and leaves it intact;
+    # routing on (k, s) uses the fixed-width column alone, so the result is the same relation
+    again = ctx.hash_exchange(t, [0, 1]).to_arrow()
+    assert again.equals(got) and held.to_arrow().equals(got)
+    # the operators run on a received relation like on any other
+    agg = ctx.hash_aggregate(held, [2], [("count", -1, "n")], "single").to_arrow()
+    per_src = {s: got.filter(pa.compute.equal(got["src"], s)).num_rows for s in range(world)}
+    assert dict(zip(agg["src"].to_pylist(), agg["n"].to_pylist())) == {s: n for s, n in per_src.items() if n}
+    del held
+
+    # ---- a global aggregate with one EMPTY shard: rank 1 scans no bids; MAX must come out of rank 0's state alone, and
+    # with every shard empty the merged MAX is NULL while COUNT is 0
+    bids = nexgen.split_batches(nexgen.bids(50_000, seed=9), 8192)
+    mx = plans.aggregate_expr("max", "MAX(bid.price)", plans.column("price", 2), "Int32")
+    cnt = plans.aggregate_expr("count", "COUNT(UInt8(1))", plans.literal("UInt8", 1), "UInt64")
+    plan = plans.two_phase_aggregate([], [mx, cnt], plans.repartition_rr(plans.memory_exec(nexgen.bid_schema(), [0, 1, 2, 3])))
+    for shard, want in ((bids if rank == 0 else [bids[0].slice(0, 0)], "value"), ([bids[0].slice(0, 0)], "null")):
+        ec = fb.ExecutionContext(ctx, plan)
+        dist.barrier()
+        ec.feed_data_sources([[shard]])
+        out = pa.Table.from_batches(ec.execute()[0])
+        ec.close()
+        if rank == 0:
+            price = np.concatenate([x["price"].to_numpy() for x in bids])
+            if want == "value":
+                assert out.num_rows == 1 and out.column(0).to_pylist() == [int(price.max())] and out.column(1).to_pylist() == [price.size]
+            else:
+                assert out.num_rows == 1 and out.column(0).to_pylist() == [None] and out.column(1).to_pylist() == [0]
+        else:
+            assert out.num_rows == 0
 
     # ---- distributed plans
     ev = nexgen.generate(400_000, seed=21, batch_rows=4096)
     for q in ("q8", "q5", "q3"):
         ec = fb.ExecutionContext(ctx, plans.QUERIES[q]())
+        dist.barrier()
         ec.feed_data_sources([[sharding.round_robin(ev[r], rank, world)] for r in plans.SOURCES[q]])
         out = pa.Table.from_batches(ec.execute()[0])
         ec.close()
@@ -77,12 +115,13 @@ def _free_port():
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
 @pytest.mark.timeout(900)
-def test_two_gpu_exchange_and_plans(tmp_path):
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_two_gpu_exchange_and_plans(tmp_path, mode):
     import torch.multiprocessing as mp
     import oracle
     from flock_b200 import nexgen, plans
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     ev = nexgen.generate(400_000, seed=21, batch_rows=4096)
     for q in ("q8", "q5", "q3"):
         parts = [pa.ipc.open_stream((tmp_path / f"{q}_rank{r}.arrow").read_bytes()).read_all() for r in range(world)]

@@ -313,6 +313,54 @@ def test_hash_partition(gpu_ctx, keys, n_parts):
         oracle.assert_tables_equal(pa.Table.from_batches(parts), pa.Table.from_batches([b]))
 
 
+@pytest.mark.parametrize("n_parts", [3, 33, 255])
+def test_hash_partition_many_ways(gpu_ctx, n_parts):
+    """One multi-way pass whatever n is; a fixed-width key column next to a Utf8 one routes alone (partition.cu:
+    routing_columns), so the numpy model over [i32] must reproduce membership and order for keys [i32, s]."""
+    b = mixed_batch(300_007, seed=n_parts)
+    parts = [p.to_batch() for p in gpu_ctx.hash_partition(gpu_ctx.import_batches([b]), [0, 5], n_parts)]
+    pid = sharding.partition_ids(b, [0], n_parts)
+    assert len(parts) == n_parts
+    for q, p in enumerate(parts):
+        assert p.equals(b.filter(pa.array(pid == q))), q
+    # views of one partition-ordered buffer set are ordinary tables: they filter, aggregate and concatenate
+    tabs = gpu_ctx.hash_partition(gpu_ctx.import_batches([b]), [6], 4)
+    back = gpu_ctx.concat(tabs).to_arrow()
+    oracle.assert_tables_equal(back, pa.Table.from_batches([b]))
+    pid6 = sharding.partition_ids(b, [6], 4)
+    for q, t in enumerate(tabs):
+        got = gpu_ctx.filter_project(t, col(0).cast("int64") % 7 == 0).to_batch()
+        assert got.equals(oracle_filter(b.filter(pa.array(pid6 == q)), col(0).cast("int64") % 7 == 0))
+
+
+def test_hash_partition_long_strings_and_empty_partitions(gpu_ctx):
+    """Tiles whose strings exceed the 40 KB shared staging take the direct byte path; destinations nobody routes to
+    come back as empty relations with the right schema."""
+    rng = np.random.default_rng(5)
+    n = 20_000
+    lens = rng.integers(0, 600, n)
+    s = pa.array(["".join(chr(97 + (i + j) % 26) for j in range(l)) if l < 40 else ("q%d" % i) * (l // 4) for i, l in enumerate(lens)])
+    b = rb(k=pa.array(np.full(n, 7, np.int32)), s=s, v=pa.array(np.arange(n, dtype=np.int64)))
+    parts = [p.to_batch() for p in gpu_ctx.hash_partition(gpu_ctx.import_batches([b]), [0], 5)]
+    home = int(sharding.partition_ids(b.slice(0, 1), [0], 5)[0])
+    for q, p in enumerate(parts):
+        assert p.schema.names == ["k", "s", "v"]
+        assert p.equals(b) if q == home else p.num_rows == 0
+
+
+def test_reversed_literal_division_on_a_ragged_tile(gpu_ctx):
+    """lit / (col * k) and lit % (col * k): the padded rows of a tile must not raise a divide-by-zero (they carry 0)."""
+    b = rb(x=pa.array([3, 5, -2], pa.int64()))
+    t = gpu_ctx.import_batches([b])
+    got = gpu_ctx.filter_project(t, None, [lit(10) / (col(0) * 2), lit(7) % (col(0) * 3)], ["d", "m"]).to_batch()
+    assert got["d"].to_pylist() == [1, 1, -2] and got["m"].to_pylist() == [7, 7, 1]
+    kept = gpu_ctx.filter_project(t, (lit(10) / (col(0) * 2)) == 1).to_batch()
+    assert kept["x"].to_pylist() == [3, 5]
+    with pytest.raises(fb.FlockGpuError) as info:
+        gpu_ctx.filter_project(gpu_ctx.import_batches([rb(x=pa.array([3, 0, 1], pa.int64()))]), None, [lit(10) / (col(0) * 2)], ["d"]).to_batch()
+    assert info.value.code == -5
+
+
 # ---- the three grid-wide prefix protocols of compact.cuh give identical results ------------------------------------
 @pytest.mark.parametrize("mode", [0, 1])
 def test_prefix_protocols_agree(gpu_ctx, mode):
