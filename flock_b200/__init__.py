@@ -269,6 +269,10 @@ class Context:
     def kernel_launches(self) -> int:
         return lib.flockgpu_kernel_launches(self.handle)
 
+    def bytes_moved(self) -> tuple[int, int]:
+        """(host -> device, device -> host) bytes this context has moved over the host link so far."""
+        return lib.flockgpu_bytes_moved(self.handle, 0), lib.flockgpu_bytes_moved(self.handle, 1)
+
     def host_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         check(lib.flockgpu_host_alloc(self.handle, nbytes, C.byref(p)))

@@ -299,6 +299,7 @@ CompactScratch prepare_compact(const CtxPtr& ctx, long long num_tiles, long long
 // guarantees co-residency (or fails the launch) instead of us assuming the GPU is otherwise idle.
 template <class Kernel, class... Args>
 inline void launch_compact(const CtxPtr& ctx, Kernel kernel, const CompactScratch& sc, Args&&... args) {
+  HostSpan span("launch_compact");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(sc.grid));
   cfg.blockDim = dim3(CP_THREADS);

@@ -5,7 +5,10 @@
 // Vec<RecordBatch> returned by `collect` (context.rs:172-191) for the way out.
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <tuple>
+#include <thread>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -89,6 +92,7 @@ std::string default_format(int dtype) {
 CtxCore::~CtxCore() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
+  drop_cached_blocks();
   for (auto& kv : pinned) cudaFreeHost(kv.first);
   pinned.clear();
   for (PinSlab& sl : pin_slabs)
@@ -118,14 +122,89 @@ CtxCore::~CtxCore() {
   if (stream) cudaStreamDestroy(stream);
 }
 
+static const bool g_host_trace = getenv("FLOCKGPU_HOST_TRACE") != nullptr;
+static std::mutex g_trace_mu;
+static std::map<std::string, std::pair<long long, long long>> g_trace;  // name -> (calls, ns)
+static long long now_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+HostSpan::HostSpan(const char* n) : name(n), t0(g_host_trace ? now_ns() : 0) {}
+HostSpan::~HostSpan() {
+  if (!g_host_trace) return;
+  const long long dt = now_ns() - t0;
+  std::lock_guard<std::mutex> g(g_trace_mu);
+  auto& e = g_trace[name];
+  e.first += 1;
+  e.second += dt;
+}
+void host_trace_dump(bool reset) {
+  if (!g_host_trace) return;
+  std::lock_guard<std::mutex> g(g_trace_mu);
+  for (auto& kv : g_trace)
+    fprintf(stderr, "[flockgpu host] %-28s calls %8lld  total %10.3f ms  mean %9.3f us\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e-6,
+            kv.second.first ? kv.second.second * 1e-3 / kv.second.first : 0.0);
+  if (reset) g_trace.clear();
+}
+
+// size classes: eight per power of two (at most 12.5 % slack), 512 bytes at least
+static size_t round_block(size_t n) {
+  if (n <= 512) return 512;
+  size_t p = 512;
+  while (p < n) p <<= 1;       // smallest power of two >= n
+  const size_t step = p >> 4;  // sixteenths of it = eighths of the octave below
+  return (n + step - 1) / step * step;
+}
+
+void* CtxCore::take_block(size_t rounded) {
+  {
+    std::lock_guard<std::mutex> g(block_mu);
+    auto it = free_blocks.find(rounded);
+    if (it != free_blocks.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      cached_bytes -= rounded;
+      return p;
+    }
+  }
+  HostSpan span("alloc (cudaMallocAsync)");
+  void* p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, rounded, stream);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    drop_cached_blocks();
+    e = cudaMallocAsync(&p, rounded, stream);
+  }
+  if (e != cudaSuccess) fail(FLOCKGPU_ERR_CUDA, "cudaMallocAsync(%zu bytes) -> %s", rounded, cudaGetErrorString(e));
+  return p;
+}
+
+void CtxCore::give_block(void* p, size_t rounded) {
+  std::lock_guard<std::mutex> g(block_mu);
+  free_blocks[rounded].push_back(p);
+  cached_bytes += rounded;
+}
+
+void CtxCore::drop_cached_blocks() {
+  std::lock_guard<std::mutex> g(block_mu);
+  for (auto& kv : free_blocks)
+    for (void* p : kv.second) cudaFreeAsync(p, stream);
+  free_blocks.clear();
+  cached_bytes = 0;
+  cudaStreamSynchronize(stream);
+}
+
 Buffer::Buffer(CtxPtr c, size_t n) : ctx(std::move(c)), bytes(n) {
+  HostSpan span("alloc");
   size_t want = n ? n : 16;
   want = (want + 255) & ~size_t(255);  // room for vector tails: kernels may read up to 16 B past the end
-  FG_CUDA(cudaMallocAsync(&ptr, want + 256, ctx->stream));
+  block_bytes = round_block(want + 256);
+  ptr = ctx->take_block(block_bytes);
 }
 
 Buffer::~Buffer() {
-  if (ptr && !parent) cudaFreeAsync(ptr, ctx->stream);
+  if (ptr && !parent) ctx->give_block(ptr, block_bytes);
 }
 
 BufferPtr alloc(const CtxPtr& ctx, size_t bytes) { return std::make_shared<Buffer>(ctx, bytes); }
@@ -218,6 +297,7 @@ int resident_ctas(const CtxPtr& ctx, const void* kernel, int threads, size_t sme
 }
 
 void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out) {
+  HostSpan span("read_scalars (sync)");
   FG_CUDA(cudaMemcpyAsync(ctx->h_scalars + first, ctx->d_scalars + first, sizeof(unsigned long long) * n,
                           cudaMemcpyDeviceToHost, ctx->stream));
   FG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -227,10 +307,12 @@ void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out) 
 // ---- row counts in flight ------------------------------------------------------------------------
 int64_t PendingRows::wait() {
   if (!done) {
+    HostSpan span("pending wait (sync)");
     cudaSetDevice(ctx->device);
     FG_CUDA(cudaEventSynchronize(ev));
     value = int64_t(ctx->h_scalars[CtxCore::kScalars + slot]);
     done = true;
+    if (h2d_bytes_per_row) ctx->h2d_bytes.fetch_add(value * h2d_bytes_per_row, std::memory_order_relaxed);
   }
   return value;
 }
@@ -373,6 +455,7 @@ struct CopyFan {
     const int i = next;
     next = (next + 1) % CtxCore::kCopyStreams;
     used[i] = true;
+    ctx->h2d_bytes.fetch_add(int64_t(bytes), std::memory_order_relaxed);
     FG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_streams[i]));
   }
   void join() {
@@ -384,6 +467,56 @@ struct CopyFan {
     }
   }
 };
+
+HostRegistration::~HostRegistration() {
+  for (auto& r : ranges) cudaHostUnregister(r.first);
+}
+
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// feed_register: page-locks, in place, the value buffers of the fixed-width columns `cols` of every batch.  Buffers of
+// neighbouring batches may share pages, so the page-aligned ranges are merged before they are registered.
+static std::shared_ptr<HostRegistration> register_sources(const ArrowArray* const* batches, int n_batches, const std::vector<std::pair<int, int>>& cols) {
+  std::vector<std::pair<uintptr_t, uintptr_t>> ranges;
+  const uintptr_t page = 4096;
+  for (const auto& cw : cols)
+    for (int b = 0; b < n_batches; ++b) {
+      const ArrowArray* a = batches[b]->children[cw.first];
+      if (batches[b]->length == 0 || a->n_buffers < 2 || !a->buffers[1]) continue;
+      const char* src = static_cast<const char*>(a->buffers[1]) + (batches[b]->offset + a->offset) * cw.second;
+      if (!is_pageable(src)) continue;
+      const uintptr_t lo = reinterpret_cast<uintptr_t>(src) & ~(page - 1);
+      const uintptr_t hi = (reinterpret_cast<uintptr_t>(src) + size_t(batches[b]->length) * cw.second + page - 1) & ~(page - 1);
+      ranges.emplace_back(lo, hi);
+    }
+  if (ranges.empty()) return nullptr;
+  std::sort(ranges.begin(), ranges.end());
+  auto reg = std::make_shared<HostRegistration>();
+  uintptr_t lo = ranges[0].first, hi = ranges[0].second;
+  auto flush = [&]() {
+    cudaError_t e = cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e == cudaSuccess) reg->ranges.emplace_back(reinterpret_cast<void*>(lo), hi - lo);
+    else cudaGetLastError();  // e.g. a page that is locked already: the column then simply takes the copy path
+  };
+  for (size_t i = 1; i < ranges.size(); ++i) {
+    if (ranges[i].first <= hi) {
+      hi = std::max(hi, ranges[i].second);
+    } else {
+      flush();
+      lo = ranges[i].first;
+      hi = ranges[i].second;
+    }
+  }
+  flush();
+  return reg;
+}
 
 static std::shared_ptr<HostChunks> try_host_chunks(const CtxPtr& ctx, const ArrowArray* const* batches, int n_batches, int p, int w) {
   if (n_batches < 1) return nullptr;
@@ -431,6 +564,11 @@ void Table::dense() const {
   }
 }
 
+namespace {
+void* pin_get(size_t bytes);
+void pin_put(void* p, size_t bytes);
+}  // namespace
+
 TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const ArrowArray* const* batches,
                         int n_batches, const int* projection, int n_projection, bool zero_copy) {
   FG_CHECK(schema && schema->format && !strcmp(schema->format, "+s"), FLOCKGPU_ERR_INVALID,
@@ -443,6 +581,14 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
     for (int i = 0; i < schema->n_children; ++i) proj.push_back(i);
   }
   CopyFan fan(ctx);
+  // page-locked staging blocks of this call (pageable sources); they return to the cache once the copies have drained
+  struct StagedBlocks {
+    std::vector<std::pair<void*, size_t>> v;
+    void emplace_back(void* p, size_t n) { v.emplace_back(p, n); }
+    ~StagedBlocks() {
+      for (auto& b : v) pin_put(b.first, b.second);
+    }
+  } staged;
   int64_t total = 0;
   for (int b = 0; b < n_batches; ++b) {
     FG_CHECK(batches[b] && batches[b]->n_children == schema->n_children, FLOCKGPU_ERR_INVALID,
@@ -457,6 +603,25 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
   t->ctx = ctx;
   t->num_rows = total;
   t->metadata = copy_metadata(schema->metadata);
+  // host -> device copies of the fixed-width columns: collected for ALL columns, then issued together
+  struct Piece {
+    char* dst;
+    const char* src;
+    size_t bytes;
+    size_t stage_off;
+  };
+  std::vector<Piece> pieces;
+  size_t fixed_bytes = 0;
+  std::shared_ptr<HostRegistration> registration;
+  if (zero_copy && ctx->feed_register && total > 0) {
+    std::vector<std::pair<int, int>> fixed;
+    for (int p : proj) {
+      if (p < 0 || p >= schema->n_children) continue;
+      const int dt = dtype_from_format(schema->children[p]->format);
+      if (dt >= 0 && dt != FLOCKGPU_UTF8) fixed.emplace_back(p, dtype_width(dt));
+    }
+    registration = register_sources(batches, n_batches, fixed);
+  }
   for (int p : proj) {
     FG_CHECK(p >= 0 && p < schema->n_children, FLOCKGPU_ERR_INVALID, "table_import: projection index %d out of range", p);
     const ArrowSchema* cs = schema->children[p];
@@ -482,20 +647,20 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
     }
     if (dt != FLOCKGPU_UTF8 && zero_copy && total > 0 && (col.chunks = try_host_chunks(ctx, batches, n_batches, p, dtype_width(dt)))) {
       // stays in page-locked host memory; kernels read it over PCIe or Table::dense() copies it later
+      col.chunks->registration = registration;
     } else if (dt != FLOCKGPU_UTF8) {
       int w = dtype_width(dt);
       col.data = alloc(ctx, size_t(total) * w);
-      fan.fork();
       int64_t row = 0;
       for (int b = 0; b < n_batches; ++b) {
         const ArrowArray* a = batches[b]->children[p];
         int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
         if (len == 0) continue;
         FG_CHECK(a->n_buffers >= 2 && a->buffers[1], FLOCKGPU_ERR_INVALID, "table_import: column \"%s\" has no data buffer", col.name.c_str());
-        fan.copy(static_cast<char*>(col.data->ptr) + row * w, static_cast<const char*>(a->buffers[1]) + off * w, size_t(len) * w);
+        pieces.push_back({static_cast<char*>(col.data->ptr) + row * w, static_cast<const char*>(a->buffers[1]) + off * w, size_t(len) * w, fixed_bytes});
+        fixed_bytes += size_t(len) * w;
         row += len;
       }
-      fan.join();
     } else {
       int64_t bytes = 0;
       for (int b = 0; b < n_batches; ++b) {
@@ -518,6 +683,7 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
         if (len == 0) continue;
         const int32_t* o = static_cast<const int32_t*>(a->buffers[1]) + off;
         int64_t nb = int64_t(o[len]) - int64_t(o[0]);
+        ctx->h2d_bytes.fetch_add(int64_t(len) * 4 + nb, std::memory_order_relaxed);
         FG_CUDA(cudaMemcpyAsync(col.offsets->as<int32_t>() + row, o, size_t(len) * 4, cudaMemcpyHostToDevice, ctx->stream));
         rebase_offsets(ctx, col.offsets->as<int32_t>() + row, len, int32_t(byte - int64_t(o[0])));
         if (nb > 0) {
@@ -531,6 +697,62 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
       set_i32(ctx, col.offsets->as<int32_t>() + total, int32_t(bytes));
     }
     t->cols.push_back(std::move(col));
+  }
+  if (!pieces.empty()) {
+    fan.fork();
+    const int n_thr = int(std::min<size_t>(size_t(ctx->feed_stage_threads), pieces.size()));
+    if (n_thr >= 1 && fixed_bytes >= (size_t(1) << 20) && is_pageable(pieces[0].src)) {
+      // Pageable sources (what arrow-rs hands over): cudaMemcpyAsync would bounce every batch through the driver's own
+      // staging buffer on ONE thread.  Host threads copy the batches into a page-locked block instead and each issues
+      // the DMA of a batch as soon as it has copied it, so the host copies run in parallel with each other and with
+      // the link.
+      char* stage = static_cast<char*>(pin_get(fixed_bytes));
+      staged.emplace_back(stage, fixed_bytes);
+      // DMA chunks: runs of consecutive pieces that are contiguous on both sides (one column's batches), about 4 MB
+      // each.  The workers only copy; THIS thread issues a chunk's DMA as soon as its last piece has been staged
+      // (one cudaMemcpyAsync per chunk: 306 per-batch calls from many threads serialised on the driver's lock).
+      struct Chunk {
+        char* dst;
+        size_t stage_off, bytes;
+        int pieces;
+      };
+      std::vector<Chunk> chunks;
+      std::vector<int> chunk_of(pieces.size());
+      for (size_t i = 0; i < pieces.size(); ++i) {
+        const bool extend = !chunks.empty() && chunks.back().dst + chunks.back().bytes == pieces[i].dst &&
+                            chunks.back().stage_off + chunks.back().bytes == pieces[i].stage_off && chunks.back().bytes < (size_t(4) << 20);
+        if (!extend) chunks.push_back({pieces[i].dst, pieces[i].stage_off, 0, 0});
+        chunks.back().bytes += pieces[i].bytes;
+        chunks.back().pieces += 1;
+        chunk_of[i] = int(chunks.size()) - 1;
+      }
+      std::unique_ptr<std::atomic<int>[]> remaining(new std::atomic<int>[chunks.size()]);
+      for (size_t c = 0; c < chunks.size(); ++c) remaining[c].store(chunks[c].pieces);
+      std::atomic<size_t> next{0};
+      auto worker = [&]() {
+        for (size_t i = next.fetch_add(1); i < pieces.size(); i = next.fetch_add(1)) {
+          memcpy(stage + pieces[i].stage_off, pieces[i].src, pieces[i].bytes);
+          remaining[chunk_of[i]].fetch_sub(1, std::memory_order_release);
+        }
+      };
+      std::vector<std::thread> pool;
+      for (int k = 0; k < n_thr; ++k) pool.emplace_back(worker);
+      cudaError_t issue_err = cudaSuccess;
+      for (size_t c = 0; c < chunks.size(); ++c) {
+        while (remaining[c].load(std::memory_order_acquire) > 0) {
+        }
+        cudaError_t e = cudaMemcpyAsync(chunks[c].dst, stage + chunks[c].stage_off, chunks[c].bytes, cudaMemcpyHostToDevice,
+                                        ctx->copy_streams[c % CtxCore::kCopyStreams]);
+        if (e != cudaSuccess && issue_err == cudaSuccess) issue_err = e;
+      }
+      for (std::thread& th : pool) th.join();
+      FG_CHECK(issue_err == cudaSuccess, FLOCKGPU_ERR_CUDA, "table_import: staged host-to-device copy failed: %s", cudaGetErrorString(issue_err));
+      for (int i = 0; i < CtxCore::kCopyStreams; ++i) fan.used[i] = true;
+      ctx->h2d_bytes.fetch_add(int64_t(fixed_bytes), std::memory_order_relaxed);
+    } else {
+      for (const Piece& pc : pieces) fan.copy(pc.dst, pc.src, pc.bytes);
+    }
+    fan.join();
   }
   // inputs are only borrowed for the call: every copy must have left the host buffers before we return
   FG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -720,6 +942,7 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
         if (c.all_null)
           memset(h, 0, nb);
         else
+          ctx->d2h_bytes.fetch_add(int64_t(nb), std::memory_order_relaxed);
           FG_CUDA(cudaMemcpyAsync(h, static_cast<const char*>(c.values()) + row_begin * w, nb, cudaMemcpyDeviceToHost, ctx->stream));
       }
       priv->buffers = {validity, h};
@@ -732,6 +955,7 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
       priv->blocks.emplace_back(h_val, nb_val ? nb_val : 8);
       if (row_count > 0) {
         if (first_off[i] == 0) {
+          ctx->d2h_bytes.fetch_add(int64_t(nb_off), std::memory_order_relaxed);
           FG_CUDA(cudaMemcpyAsync(h_off, c.offs() + row_begin, nb_off, cudaMemcpyDeviceToHost, ctx->stream));
         } else {
           BufferPtr tmp = alloc(ctx, nb_off);
@@ -742,9 +966,11 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
             shift_offsets_kernel<<<blocks, 256, 0, ctx->stream>>>(c.offs() + row_begin, tmp->as<int32_t>(), row_count + 1);
           }
           count_launch(ctx);
+          ctx->d2h_bytes.fetch_add(int64_t(nb_off), std::memory_order_relaxed);
           FG_CUDA(cudaMemcpyAsync(h_off, tmp->ptr, nb_off, cudaMemcpyDeviceToHost, ctx->stream));
         }
         if (nb_val)
+          ctx->d2h_bytes.fetch_add(int64_t(nb_val), std::memory_order_relaxed);
           FG_CUDA(cudaMemcpyAsync(h_val, static_cast<const char*>(c.values()) + first_off[i], nb_val, cudaMemcpyDeviceToHost, ctx->stream));
       } else {
         h_off[0] = 0;
@@ -933,6 +1159,7 @@ int flockgpu_close(flockgpu_ctx* ctx) {
       cudaStreamSynchronize(ctx->core->stream);
     }
     delete ctx;
+    host_trace_dump(false);
   });
 }
 
@@ -969,6 +1196,11 @@ int flockgpu_timer_elapsed_ms(flockgpu_ctx* ctx, int slot, float* ms) {
 }
 
 int64_t flockgpu_kernel_launches(flockgpu_ctx* ctx) { return ctx && ctx->core ? ctx->core->launches.load() : -1; }
+
+int64_t flockgpu_bytes_moved(flockgpu_ctx* ctx, int32_t direction) {
+  if (!ctx || !ctx->core) return -1;
+  return direction == 0 ? ctx->core->h2d_bytes.load() : ctx->core->d2h_bytes.load();
+}
 
 int flockgpu_host_alloc(flockgpu_ctx* ctx, int64_t bytes, void** out) {
   return guarded([&] {
@@ -1107,6 +1339,9 @@ int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value) {
     std::lock_guard<std::recursive_mutex> g(c->mu);
     if (!strcmp(name, "feed_zero_copy")) c->feed_zero_copy = value != 0;
     else if (!strcmp(name, "compact_mode")) c->compact_mode = int(value);
+    else if (!strcmp(name, "feed_register")) c->feed_register = value != 0;
+    else if (!strcmp(name, "host_trace_dump")) host_trace_dump(value != 0);
+    else if (!strcmp(name, "feed_stage_threads")) c->feed_stage_threads = int(std::max<int64_t>(0, std::min<int64_t>(value, 64)));
     else if (!strcmp(name, "exchange_window_mb")) c->exchange_window_mb = value;
     else fail(FLOCKGPU_ERR_INVALID, "set_option: unknown option \"%s\"", name);
   });

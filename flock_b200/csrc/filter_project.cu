@@ -394,6 +394,23 @@ static void launch_filter(const CtxPtr& ctx, const PredFn& pred, FilterArgs args
 TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* predicate, const std::vector<Expr>& projections,
                         const std::vector<std::string>& names) {
   const Table& in = *in_ptr;
+  // a pure column selection / renaming of a relation that is still in table form (DeferredTable) keeps it there
+  if (in_ptr->deferred && !predicate && !projections.empty()) {
+    std::vector<ColInfo> dinfos = col_infos(in);
+    std::vector<int> src;
+    std::vector<std::string> out_names;
+    bool plain = true;
+    for (size_t i = 0; i < projections.size() && plain; ++i) {
+      CompiledValue v = compile_value(projections[i], dinfos);
+      plain = v.passthrough;
+      src.push_back(v.src_col);
+      out_names.push_back(i < names.size() && !names[i].empty() ? names[i] : (plain ? in.cols[v.src_col].name : std::string()));
+    }
+    if (plain) {
+      std::shared_ptr<DeferredTable> d = in_ptr->deferred;
+      if (TablePtr t = d->project(in, src, out_names)) return t;
+    }
+  }
   in.resolve();
   std::vector<ColInfo> infos = col_infos(in);
   // ---- compile
@@ -580,6 +597,16 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
     pending = reserve_row_count(ctx);
     fa.host_count = pending->host_slot();
   }
+  // zero-copy feed: what this launch reads over the host link (flockgpu_bytes_moved) -- the predicate column whole,
+  // the pass-through columns once per survivor
+  int64_t zc_bytes_per_survivor = 0;
+  if (in.has_host_columns()) {
+    if (cp.fast.kind != FAST_PRED_NONE && in.cols[cp.fast.col].chunks)
+      ctx->h2d_bytes.fetch_add(in.num_rows * int64_t(in.cols[cp.fast.col].width()), std::memory_order_relaxed);
+    for (const CompiledValue& v : vals)
+      if (v.passthrough && in.cols[v.src_col].chunks) zc_bytes_per_survivor += in.cols[v.src_col].width();
+    if (pending) pending->h2d_bytes_per_row = zc_bytes_per_survivor;
+  }
 
   // rows per thread per tile of the vectorised functors (FLOCKGPU_FILTER_ITEMS = 16 | 32 | 64 overrides, for tuning)
   // The smallest tile that still keeps the relation a single wave (<= ~700 tiles of 256 x items rows): small inputs
@@ -635,6 +662,7 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
   if (check_err) FG_CHECK((scalars[8] & 0xffffffffull) == 0, FLOCKGPU_ERR_EXECUTION, "Divide by zero");
   int64_t n_sel = int64_t(scalars[0]);
   FG_CHECK(n_sel >= 0 && n_sel <= in.num_rows, FLOCKGPU_ERR_CUDA, "filter: corrupt survivor count %lld", (long long)n_sel);
+  ctx->h2d_bytes.fetch_add(n_sel * zc_bytes_per_survivor, std::memory_order_relaxed);
   out->num_rows = n_sel;
   for (Column& c : out->cols) c.length = n_sel;
   if (!utf8_outs.empty()) {

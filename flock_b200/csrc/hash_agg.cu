@@ -24,6 +24,7 @@
 //   no keys       agg_global_kernel: register accumulators -> warp shuffle -> one atomic per warp.
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
 
 #include "compact.cuh"
 #include "expr_program.h"
@@ -479,11 +480,80 @@ struct AggHist32Args {
   unsigned long long* part_cursor;
   unsigned long long* key_minmax;
   unsigned long long* slow_rows;
+  // DENSE variant: the flushed counters are added straight into a direct-address table in global memory (L2-resident
+  // for NEXMark: q5's 6.5 M auctions are 26 MB) instead of being written out as (key, count) partials
+  uint32_t* dense;                          // [dense_cap] counts; slot = key - dense_meta[0]
+  const unsigned long long* dense_meta;     // [0] key of slot 0 (device-computed by agg_sample_range_kernel)
+  unsigned long long dense_cap;
+  unsigned long long* overflow;             // rows whose key fell outside the table (the caller then starts over)
 };
 
-// Instruction budget of the common step (all 8192 rows inside the window): per row one subtract, a third of a
-// three-input OR (the window test: every offset < 2^13 iff the OR of the offsets is) and one shared atomic.
-// The key range (min / max) that decides the dense level-2 table is taken from the flushed counters, not per row.
+// meta words of a direct-address count table
+enum DenseMeta : int { DM_FIRST_KEY = 0, DM_OVERFLOW = 1, DM_SAMPLE = 2, DM_SLOTS = 3, DM_MAX = 4, DM_BARRIER1 = 5, DM_BARRIER2 = 6, DM_MATCHES = 7, DM_WORDS = 8 };
+
+// Decides, ON THE DEVICE, which keys the direct-address table covers: the range of a SAMPLE of the key column (the
+// first and last 1024 rows -- ids grow with time, so the extremes sit at the ends -- and 2048 rows spread over the
+// rest) widened by a sixteenth of its span (at least 4096 keys) on both sides, cut to the table's capacity.  The host
+// never learns the range: every later kernel reads it from `meta`, so there is no round trip before the scan starts.
+__global__ void __launch_bounds__(1024) agg_sample_range_kernel(const uint32_t* __restrict__ keys, int64_t n, unsigned long long* meta, unsigned long long cap) {
+  __shared__ unsigned s_min[32], s_max[32];
+  const int tid = threadIdx.x;
+  unsigned lo = ~0u, hi = 0u;
+  auto take = [&](int64_t i) {
+    if (i >= 0 && i < n) {
+      const unsigned k = keys[i];
+      lo = min(lo, k);
+      hi = max(hi, k);
+    }
+  };
+  const int64_t stride = n / 2048 > 0 ? n / 2048 : 1;
+  take(tid);
+  take(n - 1 - tid);
+  take(int64_t(tid) * stride);
+  take(int64_t(tid + 1024) * stride);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, d));
+    hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, d));
+  }
+  if ((tid & 31) == 0) {
+    s_min[tid >> 5] = lo;
+    s_max[tid >> 5] = hi;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    lo = s_min[tid];
+    hi = s_max[tid];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, d));
+      hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, d));
+    }
+    if (tid == 0) {
+      const unsigned long long span = (unsigned long long)hi - lo + 1;
+      unsigned long long margin = span / 16 > 4096 ? span / 16 : 4096;
+      const unsigned long long first = lo > margin ? lo - margin : 0ull;
+      unsigned long long slots = ((unsigned long long)hi - first + 1 + margin + 3) & ~3ull;
+      if (slots > cap) slots = cap;  // keys beyond it count as overflow and the caller starts over
+      meta[DM_FIRST_KEY] = first;
+      meta[DM_OVERFLOW] = 0ull;
+      meta[DM_SAMPLE] = ((unsigned long long)hi << 32) | lo;
+      meta[DM_SLOTS] = slots;
+      meta[DM_MAX] = 0ull;
+      meta[DM_BARRIER1] = 0ull;
+      meta[DM_BARRIER2] = 0ull;
+      meta[DM_MATCHES] = 0ull;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_clear_kernel(uint32_t* table, const unsigned long long* meta) {
+  const unsigned long long n4 = meta[DM_SLOTS] >> 2;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n4; i += (unsigned long long)gridDim.x * blockDim.x)
+    reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
+}
+
+template <bool DENSE>
 __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid_constant__ AggHist32Args a) {
   extern __shared__ __align__(16) unsigned h32_cnt[];  // [H32_WINDOW]
   __shared__ unsigned s_warp[H32_THREADS / 32];
@@ -499,7 +569,7 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
   unsigned base = 0;     // CTA-uniform: key of counter 0
   bool have_base = false;
   unsigned kmin = ~0u, kmax = 0u;
-  unsigned long long slow = 0;
+  unsigned long long slow = 0, overflow = 0;
   const bool has_count = a.has_count != 0;
   __syncthreads();
 
@@ -510,6 +580,32 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
   auto flush = [&]() {
     constexpr int VEC = H32_WINDOW / (H32_THREADS * 4);  // uint4 per thread
     const uint4* cnt4 = reinterpret_cast<const uint4*>(h32_cnt);
+    if (DENSE) {
+      // every non-zero counter becomes one global atomic on the direct-address table (4.9 M per 100 M bids, spread
+      // over the whole scan: they hide behind the streaming loads)
+      const unsigned gbase = unsigned(a.dense_meta[DM_FIRST_KEY]), gslots = unsigned(a.dense_meta[DM_SLOTS]);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int v4 = j * H32_THREADS + tid;
+        const uint4 c = cnt4[v4];
+        if (!(c.x | c.y | c.z | c.w)) continue;
+        const unsigned cs[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!cs[e]) continue;
+          const unsigned idx = base + unsigned(v4) * 4u + unsigned(e) - gbase;
+          if (idx < gslots) {
+            if (has_count) atomicAdd(&a.dense[idx], cs[e]);
+            else a.dense[idx] = 1u;
+          } else {
+            overflow += has_count ? cs[e] : 1u;  // summed per warp at the end: a sparse column must not serialise on one word
+          }
+        }
+        reinterpret_cast<uint4*>(h32_cnt)[v4] = make_uint4(0, 0, 0, 0);
+      }
+      __syncthreads();
+      return;
+    }
     unsigned cnt = 0;
     unsigned smin = ~0u, smax = 0u;
 #pragma unroll
@@ -568,6 +664,15 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
     if (idx < unsigned(H32_WINDOW)) {
       if (has_count) atomicAdd(&h32_cnt[idx], 1u);
       else h32_cnt[idx] = 1u;
+    } else if (DENSE) {
+      const unsigned idx2 = k - unsigned(a.dense_meta[DM_FIRST_KEY]);
+      if (idx2 < unsigned(a.dense_meta[DM_SLOTS])) {
+        if (has_count) atomicAdd(&a.dense[idx2], 1u);
+        else a.dense[idx2] = 1u;
+      } else {
+        ++overflow;
+      }
+      ++slow;
     } else {
       // outside the window even after re-basing (the step spans more than 8 Ki keys)
       unsigned long long pos = atomicAdd(a.part_cursor, 1ull);
@@ -666,14 +771,229 @@ __global__ void __launch_bounds__(H32_THREADS, 4) agg_hist32_kernel(const __grid
     kmin = o1 < kmin ? o1 : kmin;
     kmax = o2 > kmax ? o2 : kmax;
     slow += __shfl_xor_sync(FULL_MASK, slow, d);
+    overflow += __shfl_xor_sync(FULL_MASK, overflow, d);
   }
   if (lane == 0) {
-    if (kmin <= kmax) {
+    if (DENSE && overflow) atomicAdd(a.overflow, overflow);
+    if (!DENSE && kmin <= kmax) {
       atomicMin(a.key_minmax, (unsigned long long)kmin);
       atomicMax(a.key_minmax + 1, (unsigned long long)kmax);
     }
     if (slow) atomicAdd(a.slow_rows, slow);
   }
+}
+
+// ================================================================================================
+// the direct-address count table as a relation of its own (DeferredTable): emit / MAX / "count = v"
+// ================================================================================================
+struct DenseScanArgs {
+  CompactScratch sc;
+  const uint32_t* table;
+  unsigned long long n_slots;
+  const unsigned long long* meta;      // [0] key of slot 0
+  const unsigned long long* eq_value;  // SELECT: keep slots whose count equals *eq_value
+  uint32_t* key_dst;                   // may be NULL
+  unsigned long long* count_dst;       // may be NULL
+  int32_t n_bcast, pad;                // SELECT: columns of the one-row side, repeated for every survivor
+  const void* bcast_src[MAX_IN_COLS];
+  void* bcast_dst[MAX_IN_COLS];
+  int32_t bcast_width[MAX_IN_COLS];
+};
+
+// SELECT = false: every non-empty slot; true: the slots whose count equals *eq_value.  Stable (ascending key).
+template <bool SELECT>
+__global__ void __launch_bounds__(CP_THREADS) dense_scan_kernel(const __grid_constant__ DenseScanArgs a) {
+  constexpr int E = 4, I = 64, G = I / E, TILE = CP_THREADS * I;
+  __shared__ CompactSmem<E, I> sm;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned long long want = SELECT ? *a.eq_value : 0ull;
+  const unsigned gbase = unsigned(a.meta[DM_FIRST_KEY]);
+  const unsigned long long used = a.meta[DM_SLOTS];  // slots in use (device-decided, <= n_slots): the tiles behind them are empty
+  long long tile;
+  for (int it = 0; (tile = cp_next_tile(sm, a.sc, it)) >= 0; ++it) {
+    const unsigned long long tile_base = (unsigned long long)tile * TILE;
+    unsigned long long bits = 0;
+    uint4 c[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const unsigned long long slot0 = tile_base + ((unsigned long long)g * CP_THREADS + tid) * E;
+      c[g] = make_uint4(0, 0, 0, 0);
+      if (slot0 < used) c[g] = *reinterpret_cast<const uint4*>(a.table + slot0);  // slot counts are multiples of 4
+      unsigned nib;
+      if (SELECT) nib = unsigned(c[g].x == want && c[g].x) | (unsigned(c[g].y == want && c[g].y) << 1) | (unsigned(c[g].z == want && c[g].z) << 2) | (unsigned(c[g].w == want && c[g].w) << 3);
+      else nib = unsigned(c[g].x != 0) | (unsigned(c[g].y != 0) << 1) | (unsigned(c[g].z != 0) << 2) | (unsigned(c[g].w != 0) << 3);
+      bits |= (unsigned long long)nib << (g * E);
+    }
+    unsigned lane_prefix[G];
+    cp_rank_tile<E, I>(sm, a.sc, tile, bits, lane_prefix);
+    if (bits && sm.tile_total) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const unsigned nib = unsigned(bits >> (g * E)) & 0xfu;
+        if (!nib) continue;
+        const unsigned long long slot0 = tile_base + ((unsigned long long)g * CP_THREADS + tid) * E;
+        const int64_t pos0 = int64_t(sm.excl) + sm.group_warp[g][warp] + lane_prefix[g];
+        const unsigned cs[4] = {c[g].x, c[g].y, c[g].z, c[g].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!((nib >> e) & 1u)) continue;
+          const int64_t pos = pos0 + __popc(nib & ((1u << e) - 1u));
+          if (a.key_dst) a.key_dst[pos] = gbase + unsigned(slot0) + unsigned(e);
+          if (a.count_dst) a.count_dst[pos] = cs[e];
+          if (SELECT) {
+            for (int b = 0; b < a.n_bcast; ++b) {
+              if (a.bcast_width[b] == 4) static_cast<uint32_t*>(a.bcast_dst[b])[pos] = *static_cast<const uint32_t*>(a.bcast_src[b]);
+              else static_cast<unsigned long long*>(a.bcast_dst[b])[pos] = *static_cast<const unsigned long long*>(a.bcast_src[b]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_max_kernel(const uint32_t* __restrict__ table, const unsigned long long* meta, unsigned long long* out) {
+  unsigned m = 0;
+  const unsigned long long n4 = meta[DM_SLOTS] >> 2;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n4; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 c = reinterpret_cast<const uint4*>(table)[i];
+    m = max(max(m, max(c.x, c.y)), max(c.z, c.w));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, (unsigned long long)m);
+}
+
+// MAX(count) and "count = MAX(count)" in ONE cooperative launch (NEXMark q5's MaxBids subquery and its join): every CTA
+// owns a contiguous range of the table, (1) folds it into the global maximum, (2) after a grid-wide barrier counts
+// its slots that reach the maximum, (3) after a second barrier writes them behind those of the CTAs before it --
+// ascending key order, like the row-by-row path.  The table is L2-resident (it was just built), so the three sweeps
+// cost little; what is saved is a launch, a 8-byte relation and the host's wait for it.
+struct DenseArgmaxArgs {
+  const uint32_t* table;
+  unsigned long long* meta;   // DM_MAX / DM_BARRIER1 / DM_BARRIER2 are zero on entry (agg_sample_range_kernel)
+  unsigned* cta_counts;       // [gridDim.x]
+  uint32_t* key_dst;          // may be NULL
+  unsigned long long* count_dst;
+  int32_t n_max_dst, pad;
+  unsigned long long* max_dst[4];  // columns that repeat the maximum for every output row (the one-row side of the join)
+  unsigned long long* out_count;   // device
+  unsigned long long* host_count;  // page-locked copy (PendingRows)
+};
+
+__device__ __forceinline__ void dense_grid_barrier(unsigned long long* word, unsigned n_ctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(word, 1ull);
+    while (ld_relaxed_u64(word) < n_ctas) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+constexpr int AM_REGS = 16;  // uint4 a thread keeps in registers between the phases (covers 592 x 256 x 16 x 4 = 9.7 M slots)
+
+__global__ void __launch_bounds__(256, 3) dense_argmax_kernel(const __grid_constant__ DenseArgmaxArgs a) {
+  __shared__ unsigned s_cnt[AM_REGS][8];
+  __shared__ unsigned s_part[8];
+  __shared__ unsigned long long s_excl;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long n4 = a.meta[DM_SLOTS] >> 2;
+  const unsigned long long per_cta = (n4 + gridDim.x - 1) / gridDim.x;
+  const unsigned long long lo4 = blockIdx.x * per_cta, hi4 = lo4 + per_cta < n4 ? lo4 + per_cta : n4;
+  const uint4* t4 = reinterpret_cast<const uint4*>(a.table);
+  // element (k, tid) of the CTA's range is uint4 number lo4 + k * 256 + tid: coalesced, and (k, tid) order = key order.
+  // The first AM_REGS rounds stay in registers for the later phases; longer ranges are read again.
+  const bool in_regs = per_cta <= 256ull * AM_REGS;
+  uint4 c[AM_REGS];
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < AM_REGS; ++k) {
+    const unsigned long long i = lo4 + (unsigned long long)k * 256 + tid;
+    c[k] = i < hi4 ? t4[i] : make_uint4(0, 0, 0, 0);
+    m = max(max(m, max(c[k].x, c[k].y)), max(c[k].z, c[k].w));
+  }
+  for (unsigned long long i = lo4 + 256ull * AM_REGS + tid; i < hi4; i += 256) {
+    const uint4 v = t4[i];
+    m = max(max(m, max(v.x, v.y)), max(v.z, v.w));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+  if (lane == 0 && m) atomicMax(a.meta + DM_MAX, (unsigned long long)m);
+  dense_grid_barrier(a.meta + DM_BARRIER1, gridDim.x);
+  const unsigned top = unsigned(ld_relaxed_u64(a.meta + DM_MAX));
+  auto hits = [&](const uint4& v) { return unsigned(v.x == top) + unsigned(v.y == top) + unsigned(v.z == top) + unsigned(v.w == top); };
+  // ---- how many of my slots reach the maximum.  Nearly always none or one in the whole grid: decide per CTA first.
+  unsigned mine = 0;
+  if (top) {
+#pragma unroll
+    for (int k = 0; k < AM_REGS; ++k) mine += hits(c[k]);
+    if (!in_regs)
+      for (unsigned long long i = lo4 + 256ull * AM_REGS + tid; i < hi4; i += 256) mine += hits(t4[i]);
+  }
+  const int any = __syncthreads_or(mine != 0);
+  unsigned total = 0;
+  if (any) {
+    const unsigned w = warp_sum(mine);
+    if (lane == 0) s_part[warp] = w;
+    __syncthreads();
+#pragma unroll
+    for (int x = 0; x < 8; ++x) total += s_part[x];
+  }
+  if (tid == 0) a.cta_counts[blockIdx.x] = total;
+  dense_grid_barrier(a.meta + DM_BARRIER2, gridDim.x);
+  // ---- exclusive prefix over the CTAs
+  unsigned long long part = 0;
+  for (unsigned b = tid; b < blockIdx.x; b += 256) part += *reinterpret_cast<volatile unsigned*>(a.cta_counts + b);
+  part = warp_sum(part);
+  if (lane == 0) s_part[warp] = unsigned(part);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long e = 0;
+    for (int x = 0; x < 8; ++x) e += s_part[x];
+    s_excl = e;
+    if (blockIdx.x == gridDim.x - 1) {
+      *a.out_count = e + total;
+      if (a.host_count) *reinterpret_cast<volatile unsigned long long*>(a.host_count) = e + total;
+    }
+  }
+  __syncthreads();
+  if (!any) return;
+  // ---- the rare CTA that holds a maximum: write its hits in (k, tid) order
+  const unsigned gbase = unsigned(a.meta[DM_FIRST_KEY]);
+  unsigned long long pos = s_excl;
+  const unsigned long long rounds = (per_cta + 255) / 256;
+  for (unsigned long long k = 0; k < rounds; ++k) {
+    const unsigned long long i = lo4 + k * 256 + tid;
+    const uint4 v = i < hi4 ? t4[i] : make_uint4(0, 0, 0, 0);  // L2 / L1 hit: this CTA just read it
+    const unsigned h = top ? hits(v) : 0u;
+    const unsigned incl = warp_inclusive_sum(h);
+    __syncthreads();
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, round_total = 0;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      if (x < warp) before += s_part[x];
+      round_total += s_part[x];
+    }
+    if (h) {
+      unsigned long long p = pos + before + (incl - h);
+      const unsigned cs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (cs[e] == top) {
+          if (a.key_dst) a.key_dst[p] = gbase + unsigned(i * 4) + unsigned(e);
+          if (a.count_dst) a.count_dst[p] = top;
+          for (int q = 0; q < a.n_max_dst; ++q) a.max_dst[q][p] = top;
+          ++p;
+        }
+    }
+    pos += round_total;
+  }
+  (void)s_cnt;
 }
 
 // ================================================================================================
@@ -1146,7 +1466,359 @@ unsigned long long pow2_at_least(unsigned long long n) {
 
 }  // namespace
 
+static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs,
+                                    bool allow_dense);
+
+// ---- COUNT(*) / DISTINCT by one 4-byte key kept in its direct-address table --------------------------------------
+namespace {
+
+struct DenseCore {
+  CtxPtr ctx;
+  TablePtr input;  // kept for the generic path: taken when a key fell outside the table (overflow != 0)
+  int mode = FLOCKGPU_AGG_SINGLE;
+  std::vector<int> group_cols;
+  std::vector<AggSpec> aggs;
+  BufferPtr table, meta;
+  unsigned long long cap = 0;  // capacity in slots; how many are in use is decided on the device (meta[DM_SLOTS])
+  bool has_count = false;
+  std::shared_ptr<PendingRows> overflow;
+  TablePtr full;  // the materialised (key [, count]) rows, produced at most once
+  bool valid() { return overflow->wait() == 0; }
+  TablePtr materialise_full();
+  // the visible columns `kinds` (0 = key, 1 = count) of the materialised relation under `names`
+  TablePtr materialise_as(const std::vector<int>& kinds, const std::vector<std::string>& names, const std::string& metadata) {
+    TablePtr f = materialise_full();
+    auto t = std::make_shared<Table>();
+    t->ctx = ctx;
+    t->metadata = metadata;
+    t->num_rows = f->num_rows;
+    for (size_t i = 0; i < kinds.size(); ++i) {
+      Column c = f->cols[kinds[i]];
+      c.name = names[i];
+      t->cols.push_back(std::move(c));
+    }
+    return t;
+  }
+};
+
+struct DeferredAgg : DeferredTable {
+  std::shared_ptr<DenseCore> core;
+  std::vector<int> kinds;  // per visible column: 0 = the key, 1 = the count
+  void materialise(const Table& self) override;
+  TablePtr project(const Table& self, const std::vector<int>& src_cols, const std::vector<std::string>& names) override;
+  TablePtr global_max(const Table& self, int col, const std::string& out_name) override;
+  TablePtr select_equal(const Table& self, int key_col, const TablePtr& one_row, int one_key, bool self_is_left) override;
+};
+
+// MAX(count) of a DenseCore that nobody has asked the value of yet (one row, one UInt64 column).
+struct DeferredMax : DeferredTable {
+  std::shared_ptr<DenseCore> core;
+  void materialise(const Table& self) override;
+  TablePtr project(const Table& self, const std::vector<int>& src_cols, const std::vector<std::string>& names) override;
+};
+
+// The output of a selection over the table: its buffers are written, its row count is in flight, and whether the
+// table was complete is only known once the overflow word has arrived.  Resolving waits for both; an incomplete
+// table makes it run `fallback` (the same operator on materialised rows) instead.
+struct DeferredChecked : DeferredTable {
+  std::shared_ptr<DenseCore> core;
+  std::shared_ptr<PendingRows> rows;
+  std::function<TablePtr()> fallback;
+  void materialise(const Table& self) override {
+    const int64_t n = rows->wait();
+    if (core->valid()) {
+      self.num_rows = n;
+      for (Column& c : self.cols) c.length = n;
+      return;
+    }
+    TablePtr g = fallback();
+    g->dense();
+    self.num_rows = g->num_rows;
+    for (size_t i = 0; i < self.cols.size(); ++i) {
+      Column c = g->cols[i];
+      c.name = self.cols[i].name;
+      self.cols[i] = std::move(c);
+    }
+  }
+};
+
+DenseScanArgs dense_scan_args(const DenseCore& c) {
+  DenseScanArgs a{};
+  a.table = c.table->as<uint32_t>();
+  a.n_slots = c.cap;
+  a.meta = c.meta->as<unsigned long long>();
+  return a;
+}
+
+template <bool SELECT>
+void launch_dense_scan(const CtxPtr& ctx, DenseScanArgs& a, unsigned long long* out_count, unsigned long long* host_count) {
+  const long long tiles = (long long)((a.n_slots + CP_THREADS * 64 - 1) / (CP_THREADS * 64));
+  auto kernel = dense_scan_kernel<SELECT>;
+  a.sc = prepare_compact(ctx, tiles, resident_ctas(ctx, reinterpret_cast<const void*>(kernel), CP_THREADS), out_count);
+  a.sc.host_count = host_count;
+  {
+    LaunchTimer lt(ctx, SELECT ? "dense_select_kernel" : "dense_emit_kernel");
+    launch_compact(ctx, kernel, a.sc, a);
+  }
+  FG_CUDA(cudaGetLastError());
+  count_launch(ctx);
+}
+
+TablePtr DenseCore::materialise_full() {
+  if (full) return full;
+  if (!valid()) {
+    // a key outside the sampled range: the table is incomplete, aggregate again the general way
+    full = hash_aggregate_impl(ctx, input, mode, group_cols, aggs, false);
+    return full;
+  }
+  const Table& in = *input;
+  const Column& kc = in.cols[group_cols[0]];
+  const int64_t max_groups = int64_t(std::min<unsigned long long>(cap, (unsigned long long)in.num_rows));
+  auto t = std::make_shared<Table>();
+  t->ctx = ctx;
+  t->metadata = in.metadata;
+  Column key;
+  key.name = kc.name;
+  key.dtype = kc.dtype;
+  key.format = kc.format;
+  key.nullable = kc.nullable;
+  key.data = alloc(ctx, size_t(max_groups) * 4);
+  DenseScanArgs a = dense_scan_args(*this);
+  a.key_dst = key.data->as<uint32_t>();
+  Column cnt;
+  if (has_count) {
+    cnt.dtype = FLOCKGPU_UINT64;
+    cnt.format = "L";
+    cnt.nullable = true;
+    cnt.data = alloc(ctx, size_t(max_groups) * 8);
+    a.count_dst = cnt.data->as<unsigned long long>();
+  }
+  launch_dense_scan<false>(ctx, a, ctx->d_scalars + 3, nullptr);
+  unsigned long long n_groups = 0;
+  read_scalars(ctx, 3, 1, &n_groups);
+  FG_CHECK(int64_t(n_groups) <= max_groups, FLOCKGPU_ERR_CUDA, "hash_aggregate: corrupt group count %llu", n_groups);
+  t->num_rows = int64_t(n_groups);
+  key.length = t->num_rows;
+  t->cols.push_back(std::move(key));
+  if (has_count) {
+    cnt.length = t->num_rows;
+    cnt.name = "count";
+    t->cols.push_back(std::move(cnt));
+  }
+  full = t;
+  return full;
+}
+
+void DeferredAgg::materialise(const Table& self) {
+  TablePtr f = core->materialise_full();
+  self.num_rows = f->num_rows;
+  for (size_t i = 0; i < kinds.size(); ++i) {
+    Column c = f->cols[kinds[i]];
+    c.name = self.cols[i].name;
+    self.cols[i] = std::move(c);
+  }
+}
+
+TablePtr deferred_table(const CtxPtr& ctx, const std::shared_ptr<DenseCore>& core, const std::vector<int>& kinds, const std::vector<std::string>& names,
+                        const std::string& metadata) {
+  auto t = std::make_shared<Table>();
+  t->ctx = ctx;
+  t->metadata = metadata;
+  t->num_rows = -1;
+  const Column& kc = core->input->cols[core->group_cols[0]];
+  for (size_t i = 0; i < kinds.size(); ++i) {
+    Column c;
+    c.name = names[i];
+    c.length = -1;
+    if (kinds[i] == 0) {
+      c.dtype = kc.dtype;
+      c.format = kc.format;
+      c.nullable = kc.nullable;
+    } else {
+      c.dtype = FLOCKGPU_UINT64;
+      c.format = "L";
+      c.nullable = true;
+    }
+    t->cols.push_back(std::move(c));
+  }
+  auto d = std::make_shared<DeferredAgg>();
+  d->core = core;
+  d->kinds = kinds;
+  t->deferred = d;
+  return t;
+}
+
+TablePtr DeferredAgg::project(const Table& self, const std::vector<int>& src_cols, const std::vector<std::string>& names) {
+  std::vector<int> k;
+  for (int c : src_cols) k.push_back(kinds[c]);
+  return deferred_table(core->ctx, core, k, names, self.metadata);
+}
+
+TablePtr deferred_max_table(const std::shared_ptr<DenseCore>& core, const std::string& name, const std::string& metadata) {
+  auto t = std::make_shared<Table>();
+  t->ctx = core->ctx;
+  t->metadata = metadata;
+  t->num_rows = 1;
+  Column c;
+  c.name = name;
+  c.dtype = FLOCKGPU_UINT64;
+  c.format = "L";
+  c.nullable = true;
+  c.length = 1;
+  t->cols.push_back(std::move(c));
+  auto d = std::make_shared<DeferredMax>();
+  d->core = core;
+  t->deferred = d;
+  return t;
+}
+
+TablePtr DeferredAgg::global_max(const Table& self, int col, const std::string& out_name) {
+  if (col < 0 || col >= int(kinds.size()) || kinds[col] != 1 || !core->has_count) return nullptr;
+  return deferred_max_table(core, out_name, self.metadata);  // nothing runs until somebody needs the number
+}
+
+void DeferredMax::materialise(const Table& self) {
+  const CtxPtr& ctx = core->ctx;
+  Column& c = self.cols[0];
+  c.data = alloc(ctx, 8);
+  FG_CUDA(cudaMemsetAsync(c.data->ptr, 0, 8, ctx->stream));
+  {
+    LaunchTimer lt(ctx, "dense_max_kernel");
+    dense_max_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(core->table->as<uint32_t>(), core->meta->as<unsigned long long>(), c.data->as<unsigned long long>());
+  }
+  FG_CUDA(cudaGetLastError());
+  count_launch(ctx);
+  if (!core->valid()) {
+    // the table was incomplete: MAX over the materialised counts instead
+    TablePtr f = core->materialise_full();
+    TablePtr m = hash_aggregate_impl(ctx, f, FLOCKGPU_AGG_SINGLE, {}, {AggSpec{FLOCKGPU_AGG_MAX, 1, c.name}}, false);
+    const std::string name = c.name;
+    c = m->cols[0];
+    c.name = name;
+  }
+  self.num_rows = 1;
+  c.length = 1;
+}
+
+TablePtr DeferredMax::project(const Table& self, const std::vector<int>& src_cols, const std::vector<std::string>& names) {
+  if (src_cols.size() != 1 || src_cols[0] != 0) return nullptr;
+  return deferred_max_table(core, names[0], self.metadata);
+}
+
+TablePtr DeferredAgg::select_equal(const Table& self, int key_col, const TablePtr& one_ptr, int one_key, bool self_is_left) {
+  if (key_col < 0 || key_col >= int(kinds.size()) || kinds[key_col] != 1 || !core->has_count) return nullptr;
+  const Table& one_row = *one_ptr;
+  // the other side: MAX(count) of this very table, not computed yet (fused below), or any resolved one-row relation
+  auto* dmax = dynamic_cast<DeferredMax*>(one_row.deferred.get());
+  const bool fused = dmax && dmax->core == core && one_key == 0;
+  if (!fused) one_row.dense();
+  if (one_row.num_rows != 1 || one_row.cols.size() > size_t(fused ? 4 : MAX_IN_COLS)) return nullptr;
+  if (one_key < 0 || one_key >= int(one_row.cols.size()) || one_row.cols[one_key].dtype != FLOCKGPU_UINT64) return nullptr;
+  if (!fused)
+    for (const Column& c : one_row.cols)
+      if (c.all_null || c.dtype == FLOCKGPU_UTF8 || (c.width() != 4 && c.width() != 8) || c.chunks) return nullptr;
+  const CtxPtr& ctx = core->ctx;
+  const int64_t max_rows = int64_t(std::min<unsigned long long>(core->cap, (unsigned long long)core->input->num_rows));
+  std::vector<Column> mine(kinds.size()), theirs(one_row.cols.size());
+  BufferPtr key_buf, cnt_buf;
+  for (size_t i = 0; i < kinds.size(); ++i) {
+    Column& c = mine[i];
+    c = self.cols[i];
+    c.length = -1;
+    BufferPtr& shared = kinds[i] == 0 ? key_buf : cnt_buf;  // the same logical column twice shares one buffer
+    if (!shared) shared = alloc(ctx, size_t(max_rows) * (kinds[i] == 0 ? 4 : 8));
+    c.data = shared;
+  }
+  for (size_t i = 0; i < one_row.cols.size(); ++i) {
+    Column& c = theirs[i];
+    c = one_row.cols[i];
+    c.length = -1;
+    c.data = alloc(ctx, size_t(max_rows) * c.width());
+  }
+  std::shared_ptr<PendingRows> pending = reserve_row_count(ctx);
+  if (fused) {
+    DenseArgmaxArgs a{};
+    a.table = core->table->as<uint32_t>();
+    a.meta = core->meta->as<unsigned long long>();
+    const void* kernel = reinterpret_cast<const void*>(dense_argmax_kernel);
+    const int grid = int(std::min<int64_t>(resident_ctas(ctx, kernel, 256), int64_t(ctx->sm_count) * 4));
+    BufferPtr cta_counts = alloc(ctx, size_t(grid) * 4);
+    a.cta_counts = cta_counts->as<unsigned>();
+    a.key_dst = key_buf ? key_buf->as<uint32_t>() : nullptr;
+    a.count_dst = cnt_buf ? cnt_buf->as<unsigned long long>() : nullptr;
+    a.n_max_dst = int(theirs.size());
+    for (size_t i = 0; i < theirs.size(); ++i) a.max_dst[i] = theirs[i].data->as<unsigned long long>();
+    a.out_count = ctx->d_scalars + 4;
+    a.host_count = pending->host_slot();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(256);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // the CTAs wait for each other: co-residency must be guaranteed
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    {
+      LaunchTimer lt(ctx, "dense_argmax_kernel");
+      FG_CUDA(cudaLaunchKernelEx(&cfg, dense_argmax_kernel, a));
+    }
+    count_launch(ctx);
+    // `cta_counts` may be released now: the block allocator hands it out again in stream order only
+  } else {
+    DenseScanArgs a = dense_scan_args(*core);
+    a.eq_value = static_cast<const unsigned long long*>(one_row.cols[one_key].values());
+    if (key_buf) a.key_dst = key_buf->as<uint32_t>();
+    if (cnt_buf) a.count_dst = cnt_buf->as<unsigned long long>();
+    a.n_bcast = int(one_row.cols.size());
+    for (size_t i = 0; i < one_row.cols.size(); ++i) {
+      a.bcast_src[i] = one_row.cols[i].values();
+      a.bcast_dst[i] = theirs[i].data->ptr;
+      a.bcast_width[i] = theirs[i].width();
+    }
+    launch_dense_scan<true>(ctx, a, ctx->d_scalars + 4, pending->host_slot());
+  }
+  commit_row_count(pending);
+  auto t = std::make_shared<Table>();
+  t->ctx = ctx;
+  t->metadata = self_is_left ? self.metadata : one_row.metadata;
+  t->num_rows = -1;
+  for (Column& c : (self_is_left ? mine : theirs)) t->cols.push_back(std::move(c));
+  for (Column& c : (self_is_left ? theirs : mine)) t->cols.push_back(std::move(c));
+  auto chk = std::make_shared<DeferredChecked>();
+  chk->core = core;
+  chk->rows = pending;
+  std::vector<std::string> my_names;
+  for (const Column& c : self.cols) my_names.push_back(c.name);
+  std::shared_ptr<DenseCore> core_ref = core;
+  std::vector<int> my_kinds = kinds;
+  const std::string md = self.metadata;
+  chk->fallback = [core_ref, my_kinds, my_names, md, one_ptr, key_col, one_key, self_is_left]() {
+    TablePtr me = core_ref->materialise_as(my_kinds, my_names, md);
+    one_ptr->dense();  // a DeferredMax over an incomplete table computes MAX over the materialised rows
+    return self_is_left ? hash_join(core_ref->ctx, me, one_ptr, {key_col}, {one_key}) : hash_join(core_ref->ctx, one_ptr, me, {one_key}, {key_col});
+  };
+  t->deferred = chk;
+  return t;
+}
+
+}  // namespace
+
 TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs) {
+  // MAX over the count column of a group-by that still lives in its direct-address table (NEXMark q5: MAX(num))
+  if (in_ptr->deferred && group_cols.empty() && aggs.size() == 1 && aggs[0].func == FLOCKGPU_AGG_MAX &&
+      (mode == FLOCKGPU_AGG_PARTIAL || mode == FLOCKGPU_AGG_SINGLE)) {
+    std::string name = aggs[0].name.empty() ? std::string("MAX") : aggs[0].name;
+    if (mode == FLOCKGPU_AGG_PARTIAL) name += "[max]";
+    std::shared_ptr<DeferredTable> d = in_ptr->deferred;
+    if (TablePtr t = d->global_max(*in_ptr, aggs[0].col, name)) return t;
+  }
+  return hash_aggregate_impl(ctx, in_ptr, mode, group_cols, aggs, true);
+}
+
+static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs,
+                                    bool allow_dense) {
+  HostSpan agg_span("hash_aggregate (host)");
   in_ptr->dense();
   FG_CHECK(mode >= FLOCKGPU_AGG_PARTIAL && mode <= FLOCKGPU_AGG_SINGLE, FLOCKGPU_ERR_INVALID, "hash_aggregate: bad mode %d", mode);
   // A NULL state column (the state row of an aggregate over no input) merges as "absent": Final over such a row is
@@ -1154,7 +1826,7 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   if ((mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED) && group_cols.empty()) {
     bool null_state = false;
     for (const Column& c : in_ptr->cols) null_state |= c.all_null;
-    if (null_state) return hash_aggregate(ctx, empty_like(ctx, *in_ptr), mode, group_cols, aggs);
+    if (null_state) return hash_aggregate_impl(ctx, empty_like(ctx, *in_ptr), mode, group_cols, aggs, allow_dense);
   }
   const Table& in = *in_ptr;
   for (int g : group_cols) {
@@ -1316,6 +1988,68 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
       part32 = count32;
       bool done_l1 = false;
       static const bool no_hist = getenv("FLOCKGPU_NO_HIST") != nullptr;
+      static const bool no_dense = getenv("FLOCKGPU_NO_DENSE_AGG") != nullptr;
+      if (count32 && !no_hist && !no_dense && allow_dense && n < (int64_t(1) << 32)) {
+        // ---- one pass: the sliding shared-memory histogram adds straight into a direct-address table whose first key a
+        // sample of the column decides ON THE DEVICE (no host round trip); the result stays in table form
+        // (DeferredTable) until somebody needs rows.  A key outside the table counts as overflow, and the first
+        // consumer that finds overflow != 0 aggregates again the general way.
+        const uint32_t* key_col = static_cast<const uint32_t*>(in.cols[kp.col[0]].values());
+        {
+        auto core = std::make_shared<DenseCore>();
+        core->ctx = ctx;
+        core->input = in_ptr;
+        core->mode = mode;
+        core->group_cols = group_cols;
+        core->aggs = aggs;
+        core->has_count = n_acc == 1;
+        // capacity: a direct-address table pays off while it is not much larger than the input; only the slots the
+        // device decides to use are ever cleared or scanned, so a generous capacity costs address space, not time
+        core->cap = (std::min<unsigned long long>(std::max<unsigned long long>(2ull * (unsigned long long)n, 1ull << 16), 1ull << 26) + 3) & ~3ull;
+        core->table = alloc(ctx, size_t(core->cap) * 4);
+        core->meta = alloc(ctx, DM_WORDS * 8);
+        {
+          LaunchTimer lt(ctx, "agg_sample_range_kernel");
+          agg_sample_range_kernel<<<1, 1024, 0, ctx->stream>>>(key_col, n, core->meta->as<unsigned long long>(), core->cap);
+        }
+        FG_CUDA(cudaGetLastError());
+        {
+          LaunchTimer lt(ctx, "dense_clear_kernel");
+          dense_clear_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(core->table->as<uint32_t>(), core->meta->as<unsigned long long>());
+        }
+        FG_CUDA(cudaGetLastError());
+        count_launch(ctx, 2);
+        AggHist32Args h{};
+        h.n_rows = n;
+        h.key_col = key_col;
+        h.has_count = n_acc;
+        h.slow_rows = ctx->d_scalars + 9;
+        h.dense = core->table->as<uint32_t>();
+        h.dense_meta = core->meta->as<unsigned long long>();
+        h.dense_cap = core->cap;  // (the kernels use meta[DM_SLOTS] <= cap)
+        h.overflow = core->meta->as<unsigned long long>() + DM_OVERFLOW;
+        FG_CUDA(cudaMemsetAsync(h.slow_rows, 0, 8, ctx->stream));
+        constexpr size_t h_bytes = size_t(H32_WINDOW) * 4;
+        FG_CUDA(cudaFuncSetAttribute(agg_hist32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h_bytes)));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(agg_hist32_kernel<true>), H32_THREADS, h_bytes), (n + H32_STEP - 1) / H32_STEP)));
+        {
+          LaunchTimer lt(ctx, "agg_hist32_dense_kernel");
+          agg_hist32_kernel<true><<<grid, H32_THREADS, h_bytes, ctx->stream>>>(h);
+        }
+        FG_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        core->overflow = reserve_row_count(ctx);
+        FG_CUDA(cudaMemcpyAsync(core->overflow->host_slot(), h.overflow, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        commit_row_count(core->overflow);
+        std::vector<int> kinds{0};
+        std::vector<std::string> names{in.cols[kp.col[0]].name};
+        if (n_acc == 1) {
+          kinds.push_back(1);
+          names.push_back(outs[0].name);
+        }
+        return deferred_table(ctx, core, kinds, names, in.metadata);
+        }  // dense enough
+      }
       if (count32 && !no_hist) {
         // optimistic dense pass; falls through to the hash kernel when too many rows miss the window
         AggHist32Args h{};
@@ -1330,11 +2064,11 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
         h.slow_rows = ctx->d_scalars + 9;
         FG_CUDA(cudaMemsetAsync(h.slow_rows, 0, 8, ctx->stream));
         constexpr size_t h_bytes = size_t(H32_WINDOW) * 4;
-        FG_CUDA(cudaFuncSetAttribute(agg_hist32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h_bytes)));
-        int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(agg_hist32_kernel), H32_THREADS, h_bytes), (n + H32_STEP - 1) / H32_STEP)));
+        FG_CUDA(cudaFuncSetAttribute(agg_hist32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h_bytes)));
+        int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(agg_hist32_kernel<false>), H32_THREADS, h_bytes), (n + H32_STEP - 1) / H32_STEP)));
         {
           LaunchTimer lt(ctx, "agg_hist32_kernel");
-          agg_hist32_kernel<<<grid, H32_THREADS, h_bytes, ctx->stream>>>(h);
+          agg_hist32_kernel<false><<<grid, H32_THREADS, h_bytes, ctx->stream>>>(h);
         }
         FG_CUDA(cudaGetLastError());
         count_launch(ctx);

@@ -282,6 +282,14 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
                    const std::vector<int>& right_keys) {
   const Table& L = *left_ptr;
   const Table& R = *right_ptr;
+  // one side is a single row and the other a group-by result still in table form (NEXMark q5: num = MAX(num)):
+  // an equality selection over the table, no rows are materialised for the join
+  if (left_keys.size() == 1 && right_keys.size() == 1) {
+    if (std::shared_ptr<DeferredTable> d = left_ptr->deferred)
+      if (TablePtr t = d->select_equal(L, left_keys[0], right_ptr, right_keys[0], true)) return t;
+    if (std::shared_ptr<DeferredTable> d = right_ptr->deferred)
+      if (TablePtr t = d->select_equal(R, right_keys[0], left_ptr, left_keys[0], false)) return t;
+  }
   L.dense();
   R.dense();
   FG_CHECK(!left_keys.empty() && left_keys.size() == right_keys.size(), FLOCKGPU_ERR_INVALID, "hash_join: key lists must be non-empty and of equal length");

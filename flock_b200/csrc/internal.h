@@ -87,6 +87,17 @@ struct CtxCore {
   cudaStream_t copy_streams[kCopyStreams] = {};
   cudaEvent_t copy_fork = nullptr, copy_join[kCopyStreams] = {};
   cudaMemPool_t pool = nullptr;
+  // Freed device blocks by rounded size.  cudaMallocAsync on the stream-ordered pool was measured at 0.5 us most of the
+  // time and 1-100 ms every so often (profiles/r2_q5_host_trace_run6.txt: 454 ms in 353 calls), which no 0.1 ms query
+  // survives; every kernel of a context runs on ONE stream, so a block released by its last owner can be handed to
+  // the next operator at once -- stream order does the rest.  Blocks go back to CUDA when the context closes (or
+  // when a fresh allocation fails).
+  std::mutex block_mu;
+  std::unordered_map<size_t, std::vector<void*>> free_blocks;
+  size_t cached_bytes = 0;
+  void* take_block(size_t rounded);
+  void give_block(void* p, size_t rounded);
+  void drop_cached_blocks();
   int sm_count = 148;
   std::recursive_mutex mu;
 
@@ -104,6 +115,9 @@ struct CtxCore {
   cudaEvent_t timer_start[16] = {};
   cudaEvent_t timer_stop[16] = {};
   std::atomic<int64_t> launches{0};
+  // bytes that crossed the host link on behalf of this context (flockgpu_bytes_moved): copies issued by import /
+  // export plus what kernels read in place from page-locked batches (zero-copy feed)
+  std::atomic<int64_t> h2d_bytes{0}, d2h_bytes{0};
 
   // pinned host blocks handed out by flockgpu_host_alloc and by table export
   std::mutex pin_mu;
@@ -138,6 +152,12 @@ struct CtxCore {
 
   // feed_data_sources keeps page-locked, uniformly batched fixed-width columns in host memory (flockgpu_set_option)
   bool feed_zero_copy = false;
+  // with feed_zero_copy: page-lock ordinary (pageable) batch buffers in place at feed time (cudaHostRegister) and
+  // release them when the fed relation is dropped -- for callers whose Arrow allocator cannot be hooked
+  bool feed_register = false;
+  // pageable sources of a copy feed are staged into a page-locked block by this many host threads, each issuing the
+  // DMA of a batch as soon as it has copied it (0: hand the pageable pointer to cudaMemcpyAsync)
+  int feed_stage_threads = 8;
   // grid-wide prefix protocol of the compaction kernels: 0 = automatic (single wave when every tile is resident,
   // decoupled look-back otherwise), 1 = always decoupled look-back (flockgpu_set_option "compact_mode"; the parity
   // tests run both)
@@ -155,6 +175,16 @@ struct CtxCore {
 };
 using CtxPtr = std::shared_ptr<CtxCore>;
 
+// Host-side wall time per named span, accumulated process-wide when FLOCKGPU_HOST_TRACE is set and printed to stderr
+// by flockgpu_close (where does a 0.3 ms step spend its host time: allocation, waits, launches?).
+struct HostSpan {
+  const char* name;
+  long long t0;
+  explicit HostSpan(const char* n);
+  ~HostSpan();
+};
+void host_trace_dump(bool reset);
+
 // RAII: when profiling is on, brackets ONE kernel launch with events on the context stream.
 struct LaunchTimer {
   CtxCore* ctx;
@@ -168,6 +198,7 @@ struct LaunchTimer {
 struct PendingRows {
   CtxPtr ctx;
   int slot = 0;
+  int64_t h2d_bytes_per_row = 0;  // zero-copy feed: bytes a survivor's pass-through values cost on the host link
   cudaEvent_t ev = nullptr;
   bool done = false;
   int64_t value = 0;
@@ -184,6 +215,7 @@ struct Buffer {
   CtxPtr ctx;
   void* ptr = nullptr;
   size_t bytes = 0;
+  size_t block_bytes = 0;  // size class of an owned block (CtxCore::take_block)
   // A VIEW (a slice of another allocation: one partition of a partition-ordered relation, a column inside a
   // peer-exchange window) keeps its owner alive through `parent` and frees nothing itself.
   std::shared_ptr<const void> parent;
@@ -226,7 +258,14 @@ std::string default_format(int dtype);
 // A fixed-width column that still lives in page-locked HOST memory, one chunk per fed record batch.  The filter
 // kernel reads such a column straight over PCIe (UVA), so a q2 invocation moves each input byte once and never
 // stages the relation in HBM; every other operator materialises it first (Table::dense()).
+// Host ranges this library page-locked on behalf of a fed relation (feed_register); released with the last column.
+struct HostRegistration {
+  std::vector<std::pair<void*, size_t>> ranges;
+  ~HostRegistration();
+};
+
 struct HostChunks {
+  std::shared_ptr<HostRegistration> registration;  // keeps cudaHostRegister'ed sources locked while the column lives
   BufferPtr table;                // device array of chunk base pointers (device-accessible host addresses)
   std::vector<const void*> ptrs;  // the same pointers on the host
   std::vector<int64_t> rows;      // rows per chunk
@@ -251,6 +290,25 @@ struct Column {
   int width() const { return dtype_width(dtype); }
 };
 
+struct Table;
+using TablePtr = std::shared_ptr<const Table>;
+
+// A relation whose rows have not been written out yet: a group-by result that still lives in its direct-address
+// table (hash_agg.cu).  Table::resolve() materialises it; the operators that can work on the table form directly
+// (NEXMark q5: MAX over the counts, then "count = max") ask for that instead and never pay for the 78 MB of
+// (auction, count) rows that the plan would otherwise write and read twice.
+struct DeferredTable {
+  virtual ~DeferredTable() = default;
+  virtual void materialise(const Table& self) = 0;  // fills self.cols / self.num_rows
+  // Fast paths: each returns nullptr when it does not apply (the caller then resolves and takes the generic path).
+  // `out = SELECT self.src_cols AS names`:
+  virtual TablePtr project(const Table& self, const std::vector<int>& src_cols, const std::vector<std::string>& names) { return nullptr; }
+  // one-row relation MAX(self.col) (mode: FLOCKGPU_AGG_PARTIAL state or a final value -- the same number):
+  virtual TablePtr global_max(const Table& self, int col, const std::string& out_name) { return nullptr; }
+  // self JOIN one_row ON self.key_col = one_row.one_key, output columns self ++ one_row (or the reverse):
+  virtual TablePtr select_equal(const Table& self, int key_col, const TablePtr& one_row, int one_key, bool self_is_left) { return nullptr; }
+};
+
 struct Table {
   CtxPtr ctx;
   // `cols[i].length` and `num_rows` are -1 while `pending` is set (a filter's survivor count that has not
@@ -258,6 +316,7 @@ struct Table {
   mutable std::vector<Column> cols;
   mutable int64_t num_rows = 0;
   mutable std::shared_ptr<PendingRows> pending;
+  mutable std::shared_ptr<DeferredTable> deferred;  // see DeferredTable; cols carry names / types only until resolved
   std::string metadata;  // raw Arrow schema metadata block (may be empty)
   // Set on the output of a multi-GPU hash exchange: the NAMES of the columns whose values routed the rows (the
   // routing function of partition.cu over exactly these columns, `partition_world` ranks).  Operators that keep those
@@ -267,6 +326,11 @@ struct Table {
   int partition_world = 0;
   int64_t nbytes() const;
   void resolve() const {
+    if (deferred) {
+      std::shared_ptr<DeferredTable> d = deferred;
+      d->materialise(*this);
+      deferred.reset();
+    }
     if (!pending) return;
     num_rows = pending->wait();
     for (Column& c : cols) c.length = num_rows;
@@ -280,7 +344,6 @@ struct Table {
     return false;
   }
 };
-using TablePtr = std::shared_ptr<const Table>;
 
 }  // namespace fg
 

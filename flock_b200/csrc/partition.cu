@@ -46,30 +46,42 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
   const int64_t end = begin + a.chunk < a.n_rows ? begin + a.chunk : a.n_rows;
   const unsigned lt = lanemask_lt();
   unsigned* mine = h_rows + warp * P;
-  for (int64_t base = begin; base < end; base += PT_THREADS) {
-    const int64_t row = base + tid;
-    const bool valid = row < end;
-    unsigned pid = 0;
-    if (valid) {
-      if (a.dest_rank >= 0) {
-        pid = unsigned(a.dest_rank);
-      } else {
-        const unsigned long long h = a.packed ? fmix64(pack_key(a.pack, a.cols, row)) : hash_row(a.rk, a.cols, row);
-        pid = partition_of(h, uint32_t(P));
+  (void)lt;
+  constexpr int UNROLL = 4;  // rows per thread and iteration: their key loads are independent and in flight together
+  for (int64_t base = begin; base < end; base += PT_THREADS * UNROLL) {
+    unsigned pid[UNROLL];
+    bool valid[UNROLL];
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+      const int64_t row = base + j * PT_THREADS + tid;
+      valid[j] = row < end;
+      pid[j] = 0;
+      if (valid[j]) {
+        if (a.dest_rank >= 0) {
+          pid[j] = unsigned(a.dest_rank);
+        } else {
+          const unsigned long long h = a.packed ? fmix64(pack_key(a.pack, a.cols, row)) : hash_row(a.rk, a.cols, row);
+          pid[j] = partition_of(h, uint32_t(P));
+        }
       }
-      a.pid[row] = uint8_t(pid);
-      for (int u = 0; u < a.n_utf8; ++u) atomicAdd(&h_bytes[u * P + pid], unsigned(a.uoff[u][row + 1] - a.uoff[u][row]));
     }
-    const unsigned vmask = __ballot_sync(FULL_MASK, valid);
-    unsigned m = 0, before = 0;
-    if (valid) {
-      m = __match_any_sync(vmask, pid);
-      before = mine[pid];
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+      const int64_t row = base + j * PT_THREADS + tid;
+      if (valid[j]) {
+        a.pid[row] = uint8_t(pid[j]);
+        for (int u = 0; u < a.n_utf8; ++u) atomicAdd(&h_bytes[u * P + pid[j]], unsigned(a.uoff[u][row + 1] - a.uoff[u][row]));
+      }
+      const unsigned vmask = __ballot_sync(FULL_MASK, valid[j]);
+      unsigned m = 0, before = 0;
+      if (valid[j]) {
+        m = __match_any_sync(vmask, pid[j]);
+        before = mine[pid[j]];
+      }
+      __syncwarp();
+      if (valid[j] && lane == __ffs(m) - 1) mine[pid[j]] = before + __popc(m);
+      __syncwarp();
     }
-    __syncwarp();
-    if (valid && lane == __ffs(m) - 1) mine[pid] = before + __popc(m);
-    __syncwarp();
-    (void)lt;
   }
   __syncthreads();
   for (int p = tid; p < P; p += PT_THREADS) {
@@ -382,8 +394,10 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
   const ScatterSmem L(n_parts, U, n_parts <= PT_DEST_SMEM_PARTS);
   FG_CUDA(cudaFuncSetAttribute(partition_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.total)));
   const int64_t resident = resident_ctas(ctx, reinterpret_cast<const void*>(partition_scatter_kernel), PT_THREADS, L.total);
+  // neither the count nor the scatter kernel waits for another CTA, so several waves are fine: small chunks keep
+  // every SM busy on relations of a few million rows (2.5 M persons are 1221 tiles)
   const int64_t tiles = std::max<int64_t>(1, (ps.n_rows + PT_TILE - 1) / PT_TILE);
-  const int64_t tiles_per_cta = (tiles + resident - 1) / resident;
+  const int64_t tiles_per_cta = (tiles + resident * 4 - 1) / (resident * 4);
   ps.chunk = tiles_per_cta * PT_TILE;
   ps.grid = int((tiles + tiles_per_cta - 1) / tiles_per_cta);
   const size_t cells = size_t(1 + U) * ps.grid * n_parts;

@@ -94,6 +94,10 @@ int flockgpu_timer_stop(flockgpu_ctx* ctx, int slot);              /* records th
 int flockgpu_timer_elapsed_ms(flockgpu_ctx* ctx, int slot, float* ms); /* syncs on the stop event  */
 /* Number of kernels this library has launched on the ctx since it was opened.                     */
 int64_t flockgpu_kernel_launches(flockgpu_ctx* ctx);
+/* Bytes that have crossed the host link for this ctx since it was opened: direction 0 = host -> device (copies issued
+ * by table import / feed_data_sources plus what kernels read in place from page-locked batches under "feed_zero_copy"),
+ * 1 = device -> host (table export).  bench.py's e2e leg reports the difference across its timed region.             */
+int64_t flockgpu_bytes_moved(flockgpu_ctx* ctx, int32_t direction);
 /* Context options.  "feed_zero_copy" (0/1, default 0): flock_context_feed_data_sources leaves fixed-width columns
  * whose buffers are page-locked (flockgpu_host_alloc / cudaHostRegister) and uniformly batched (every batch but the
  * last has the same power-of-two row count >= 4096) in HOST memory; the vectorised filter then reads them in place

@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
         _lib.orc_group_by.restype = C.c_int64
         _lib.orc_hash_join.restype = C.c_int64
         _lib.orc_q2_batch.restype = C.c_int64
+        _lib.orc_q2_collect.restype = C.c_int64
     return _lib
 
 
@@ -422,6 +423,29 @@ def hash_join(left: pa.RecordBatch, right: pa.RecordBatch, lkeys: list[int], rke
 # plan interpreter
 # ------------------------------------------------------------------------------------------------
 Partitions = list  # list[list[pa.RecordBatch]]
+
+
+def q2_collect(batches: list[pa.RecordBatch], n_partitions: int, n_threads: int, modulus: int = 123, rhs: int = 0, repeat: int = 1):
+    """NEXMark q2 over a relation by the native partition-parallel pipeline (orc_q2_collect: native threads, no Python per batch).
+    Returns (result table, seconds per call as a list of `repeat` wall times)."""
+    import time
+    n = len(batches)
+    au = (C.c_void_p * n)(*[b.column("auction").buffers()[1].address + 4 * b.column("auction").offset for b in batches])
+    pr = (C.c_void_p * n)(*[b.column("price").buffers()[1].address + 4 * b.column("price").offset for b in batches])
+    rows = (C.c_int64 * n)(*[b.num_rows for b in batches])
+    total = sum(b.num_rows for b in batches)
+    out_a, out_p = np.empty(max(total, 1), np.int32), np.empty(max(total, 1), np.int32)
+    part = (C.c_int64 * max(n_partitions, 1))()
+    fn = lib().orc_q2_collect
+    times = []
+    m = 0
+    for _ in range(max(repeat, 1)):
+        t = time.perf_counter()
+        m = fn(au, pr, rows, C.c_int32(n), C.c_int64(modulus), C.c_int64(rhs), C.c_int32(n_partitions), C.c_int32(n_threads),
+               out_a.ctypes.data_as(C.c_void_p), out_p.ctypes.data_as(C.c_void_p), part)
+        times.append(time.perf_counter() - t)
+    tbl = pa.table({"auction": pa.array(out_a[:m]), "price": pa.array(out_p[:m])})
+    return tbl, times
 
 
 def _schema_from_json(s: dict) -> pa.Schema:

@@ -23,6 +23,8 @@
 //   hash_join        HashJoinExec Inner: build map on the left, probe right rows in order, verify equality,
 //                    emit (left, right) index pairs probe-row-major (Appendix C.8)
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -522,6 +524,51 @@ int64_t orc_q2_batch(const int32_t* auction, const int32_t* price, int64_t n, in
   for (int64_t k = 0; k < n; ++k)                                                 // filter kernel, column 2
     if (scratch_mask[k]) out_price[m++] = price[k];
   return m;
+}
+
+
+// NEXMark q2 over a whole relation, partition-parallel the way DataFusion runs the plan (planner.rs:120-124 with
+// target_partitions = n, flock/src/configs/flock.toml:113): RepartitionExec(RoundRobinBatch(n)) deals batch b to
+// partition b % n, every partition is one task (here: drawn by a pool of native threads) running FilterExec batch by batch through the
+// same three materialised kernels as orc_q2_batch, CoalesceBatchesExec + ProjectionExec append the survivors to the
+// partition's output, and `collect` concatenates the partitions in partition order.  No Python inside the timed call.
+//   auction[b] / price[b] / rows[b]: the record batches; out_*: room for the total row count.
+//   part_rows[p] receives the output rows of partition p (for the caller's checks).  Returns the output row count.
+int64_t orc_q2_collect(const int32_t* const* auction, const int32_t* const* price, const int64_t* rows, int32_t n_batches, int64_t modulus, int64_t rhs,
+                       int32_t n_partitions, int32_t n_threads, int32_t* out_auction, int32_t* out_price, int64_t* part_rows) {
+  if (n_partitions < 1) n_partitions = 1;
+  if (n_threads < 1) n_threads = 1;
+  std::vector<std::vector<int32_t>> pa(n_partitions), pp(n_partitions);
+  int64_t max_rows = 0;
+  for (int32_t b = 0; b < n_batches; ++b) max_rows = std::max(max_rows, rows[b]);
+  // a pool of n_threads workers draws partitions from a shared counter (this image's gcc ships without libgomp, so
+  // the "OpenMP" arm of BASELINE.md section 3 is std::thread; the schedule is the same dynamic one)
+  std::atomic<int32_t> next{0};
+  auto worker = [&]() {
+    std::vector<int64_t> scratch(size_t(max_rows) + 1);
+    std::vector<uint8_t> mask(size_t(max_rows) + 1);
+    std::vector<int32_t> oa(size_t(max_rows) + 1), op(size_t(max_rows) + 1);
+    for (int32_t p = next.fetch_add(1); p < n_partitions; p = next.fetch_add(1)) {
+      for (int32_t b = p; b < n_batches; b += n_partitions) {
+        const int64_t m = orc_q2_batch(auction[b], price[b], rows[b], modulus, rhs, scratch.data(), mask.data(), oa.data(), op.data());
+        pa[p].insert(pa[p].end(), oa.begin(), oa.begin() + m);
+        pp[p].insert(pp[p].end(), op.begin(), op.begin() + m);
+      }
+    }
+  };
+  const int32_t n_workers = std::min(n_threads, n_partitions);
+  std::vector<std::thread> pool;
+  for (int32_t t = 1; t < n_workers; ++t) pool.emplace_back(worker);
+  worker();
+  for (std::thread& t : pool) t.join();
+  int64_t total = 0;
+  for (int32_t p = 0; p < n_partitions; ++p) {
+    std::copy(pa[p].begin(), pa[p].end(), out_auction + total);
+    std::copy(pp[p].begin(), pp[p].end(), out_price + total);
+    if (part_rows) part_rows[p] = int64_t(pa[p].size());
+    total += int64_t(pa[p].size());
+  }
+  return total;
 }
 
 }  // extern "C"

@@ -294,6 +294,48 @@ def test_hash_join_against_a_single_row(gpu_ctx, key_type, one_row_side):
             assert got["v"].to_pylist() == np.nonzero(k == wanted)[0].tolist()      # probe order preserved
 
 
+# ---- COUNT / DISTINCT by one 4-byte key: the direct-address table as a deferred relation ------------------------------
+@pytest.mark.parametrize("shape", ["dense", "dense_distinct", "sparse", "two_clusters"])
+def test_dense_count_table_and_its_fallback(gpu_ctx, shape):
+    """Large inputs with one Int32 group column aggregate into a direct-address table that stays in table form until a
+    consumer needs rows (hash_agg.cu: DeferredTable).  Keys outside the sampled range (sparse / clustered far apart)
+    make the first consumer start over on the general path: the results must not differ either way."""
+    rng = np.random.default_rng(11)
+    n = 700_000
+    if shape in ("dense", "dense_distinct"):
+        k = (np.arange(n) // 13 + rng.integers(0, 40, n) + 1000).astype(np.int32)      # advancing ids, like NEXMark's
+    elif shape == "sparse":
+        k = rng.integers(-(1 << 31), 1 << 31, n).astype(np.int32)
+    else:
+        k = np.where(rng.integers(0, 2, n) == 0, rng.integers(0, 5000, n), rng.integers(1 << 30, (1 << 30) + 5000, n)).astype(np.int32)
+    b = rb(k=pa.array(k), v=pa.array(rng.integers(0, 1000, n)))
+    t = gpu_ctx.import_batches([b])
+    aggs = [] if shape == "dense_distinct" else [("count", -1, "n")]
+    for mode in ("single", "partial"):
+        got = gpu_ctx.hash_aggregate(t, [0], aggs, mode)
+        want = pa.Table.from_batches([oracle_agg(b, mode.capitalize(), [0], aggs)])
+        assert got.num_rows == want.num_rows == np.unique(k).size
+        oracle.assert_tables_equal(got.to_arrow(), want)
+    # the deferred relation under every kind of consumer
+    d = gpu_ctx.hash_aggregate(t, [0], [("count", -1, "n")], "single")
+    mx = gpu_ctx.hash_aggregate(d, [], [("max", 1, "m")], "single")                     # fast path: MAX over the table
+    counts = np.unique(k, return_counts=True)
+    assert mx.to_arrow()["m"].to_pylist() == [int(counts[1].max())]
+    top = gpu_ctx.hash_join(d, mx, [1], [0]).to_arrow()                                 # fast path: count = max
+    assert sorted(top["k"].to_pylist()) == sorted(counts[0][counts[1] == counts[1].max()].tolist())
+    assert set(top["n"].to_pylist()) == {int(counts[1].max())} and top.schema.names == ["k", "n", "m"]
+    flipped = gpu_ctx.hash_join(mx, d, [0], [1]).to_arrow()
+    assert flipped.schema.names == ["m", "k", "n"] and sorted(flipped["k"].to_pylist()) == sorted(top["k"].to_pylist())
+    d2 = gpu_ctx.hash_aggregate(t, [0], [("count", -1, "n")], "single")
+    kept = gpu_ctx.filter_project(d2, col(1) > lit(13, "uint64")).to_arrow()                           # generic consumer: materialises first
+    assert sorted(kept["k"].to_pylist()) == sorted(counts[0][counts[1] > 13].tolist())
+    renamed = gpu_ctx.filter_project(gpu_ctx.hash_aggregate(t, [0], [("count", -1, "n")], "single"), None, [col(1), col(0)], ["num", "key"])
+    back = renamed.to_arrow()
+    assert back.schema.names == ["num", "key"]
+    order = np.argsort(back["key"].to_numpy(), kind="stable")
+    assert np.array_equal(back["key"].to_numpy()[order], counts[0]) and np.array_equal(back["num"].to_numpy()[order], counts[1].astype(np.uint64))
+
+
 # ---- RepartitionExec: Hash -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("keys", [[0], [5], [6, 0], [1]])
 @pytest.mark.parametrize("n_parts", [2, 8])
