@@ -121,12 +121,16 @@ __device__ __forceinline__ void red_relaxed_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// `group_base`: the launch may run several independent scans at once (gather.cu: the length scans of all Utf8 columns
+// of a take()): tile `tile` of a group only sums the words [group_base, group_base + tile) but everybody waits for
+// all sc.num_tiles arrivals.  `is_last` marks the tile that reports the group's total.
 template <int E, int I>
-__device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned long long total) {
+__device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const CompactScratch& sc, long long tile, unsigned long long total,
+                                               long long group_base = 0, int is_last = -1, unsigned long long* group_out = nullptr) {
   const int tid = threadIdx.x;
   const unsigned long long tag = (unsigned long long)(sc.epoch & 0xfffffu) << 44;
   if (tid == 0) {
-    st_relaxed_u64(sc.counts + tile, tag | EP_PREFIX | total);
+    st_relaxed_u64(sc.counts + group_base + tile, tag | EP_PREFIX | total);
     red_relaxed_add_u32(sc.counters + 1, 1u);
     const unsigned target = sc.arrived_base + unsigned(sc.num_tiles);
     while (int(ld_relaxed_u32(sc.counters + 1) - target) < 0) {
@@ -136,16 +140,18 @@ __device__ __forceinline__ void cp_grid_prefix(CompactSmem<E, I>& s, const Compa
   __syncthreads();
   unsigned long long part = 0;
   for (long long i = tid; i < tile; i += CP_THREADS) {
-    unsigned long long w = ld_relaxed_u64(sc.counts + i);
-    while ((w >> 44) != (tag >> 44)) w = ld_relaxed_u64(sc.counts + i);  // arrival seen before the count: rare
+    unsigned long long w = ld_relaxed_u64(sc.counts + group_base + i);
+    while ((w >> 44) != (tag >> 44)) w = ld_relaxed_u64(sc.counts + group_base + i);  // arrival seen before the count: rare
     part += w & EP_VALUE_MASK;
   }
   const unsigned long long excl = cp_block_sum(s, part);
   if (tid == 0) {
     s.excl = excl;
-    if (tile == sc.num_tiles - 1) {
-      *sc.out_count = excl + total;
-      if (sc.host_count) *reinterpret_cast<volatile unsigned long long*>(sc.host_count) = excl + total;
+    const bool last = is_last < 0 ? tile == sc.num_tiles - 1 : is_last != 0;
+    if (last) {
+      unsigned long long* out = group_out ? group_out : sc.out_count;
+      *out = excl + total;
+      if (sc.host_count && !group_out) *reinterpret_cast<volatile unsigned long long*>(sc.host_count) = excl + total;
     }
   }
   __syncthreads();

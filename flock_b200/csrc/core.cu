@@ -148,6 +148,48 @@ void host_trace_dump(bool reset) {
   if (reset) g_trace.clear();
 }
 
+void StagePool::start(int n, const std::function<void()>* fn) {
+  std::unique_lock<std::mutex> g(mu);
+  while (int(threads.size()) < n) {
+    const int index = int(threads.size());
+    threads.emplace_back([this, index] {
+      uint64_t seen = 0;
+      std::unique_lock<std::mutex> lk(mu);
+      while (true) {
+        wake.wait(lk, [&] { return stop || (generation != seen && index < active); });
+        if (stop) return;
+        seen = generation;
+        const std::function<void()>* fn = job;
+        lk.unlock();
+        (*fn)();
+        lk.lock();
+        if (--running == 0) idle.notify_all();
+      }
+    });
+  }
+  job = fn;
+  active = n;
+  running = n;
+  ++generation;
+  g.unlock();
+  wake.notify_all();
+}
+
+void StagePool::wait() {
+  std::unique_lock<std::mutex> g(mu);
+  idle.wait(g, [&] { return running == 0; });
+  active = 0;
+}
+
+StagePool::~StagePool() {
+  {
+    std::lock_guard<std::mutex> g(mu);
+    stop = true;
+  }
+  wake.notify_all();
+  for (std::thread& t : threads) t.join();
+}
+
 // size classes: eight per power of two (at most 12.5 % slack), 512 bytes at least
 static size_t round_block(size_t n) {
   if (n <= 512) return 512;
@@ -729,14 +771,13 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
       std::unique_ptr<std::atomic<int>[]> remaining(new std::atomic<int>[chunks.size()]);
       for (size_t c = 0; c < chunks.size(); ++c) remaining[c].store(chunks[c].pieces);
       std::atomic<size_t> next{0};
-      auto worker = [&]() {
+      const std::function<void()> worker = [&]() {
         for (size_t i = next.fetch_add(1); i < pieces.size(); i = next.fetch_add(1)) {
           memcpy(stage + pieces[i].stage_off, pieces[i].src, pieces[i].bytes);
           remaining[chunk_of[i]].fetch_sub(1, std::memory_order_release);
         }
       };
-      std::vector<std::thread> pool;
-      for (int k = 0; k < n_thr; ++k) pool.emplace_back(worker);
+      ctx->stage_pool.start(n_thr, &worker);
       cudaError_t issue_err = cudaSuccess;
       for (size_t c = 0; c < chunks.size(); ++c) {
         while (remaining[c].load(std::memory_order_acquire) > 0) {
@@ -745,7 +786,7 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
                                         ctx->copy_streams[c % CtxCore::kCopyStreams]);
         if (e != cudaSuccess && issue_err == cudaSuccess) issue_err = e;
       }
-      for (std::thread& th : pool) th.join();
+      ctx->stage_pool.wait();
       FG_CHECK(issue_err == cudaSuccess, FLOCKGPU_ERR_CUDA, "table_import: staged host-to-device copy failed: %s", cudaGetErrorString(issue_err));
       for (int i = 0; i < CtxCore::kCopyStreams; ++i) fan.used[i] = true;
       ctx->h2d_bytes.fetch_add(int64_t(fixed_bytes), std::memory_order_relaxed);

@@ -10,7 +10,10 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
+#include <thread>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -78,6 +81,21 @@ struct ScanScratch {
   unsigned tickets_issued = 0, arrived = 0, epoch = 0;
 };
 
+// Host threads that stage pageable batch buffers into page-locked memory (core.cu: import_batches).  Kept alive
+// between feeds: creating eight threads costs more than copying their share of a 10 M-row relation.
+struct StagePool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable wake, idle;
+  const std::function<void()>* job = nullptr;
+  uint64_t generation = 0;
+  int active = 0, running = 0;
+  bool stop = false;
+  void start(int n, const std::function<void()>* fn);  // the first n workers run *fn once
+  void wait();                                         // until all of them have returned
+  ~StagePool();
+};
+
 struct CtxCore {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -92,6 +110,7 @@ struct CtxCore {
   // survives; every kernel of a context runs on ONE stream, so a block released by its last owner can be handed to
   // the next operator at once -- stream order does the rest.  Blocks go back to CUDA when the context closes (or
   // when a fresh allocation fails).
+  StagePool stage_pool;
   std::mutex block_mu;
   std::unordered_map<size_t, std::vector<void*>> free_blocks;
   size_t cached_bytes = 0;
@@ -157,7 +176,7 @@ struct CtxCore {
   bool feed_register = false;
   // pageable sources of a copy feed are staged into a page-locked block by this many host threads, each issuing the
   // DMA of a batch as soon as it has copied it (0: hand the pageable pointer to cudaMemcpyAsync)
-  int feed_stage_threads = 8;
+  int feed_stage_threads = 4;
   // grid-wide prefix protocol of the compaction kernels: 0 = automatic (single wave when every tile is resident,
   // decoupled look-back otherwise), 1 = always decoupled look-back (flockgpu_set_option "compact_mode"; the parity
   // tests run both)
@@ -395,6 +414,8 @@ struct AggSpec {
 };
 TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in, int mode, const std::vector<int>& group_cols,
                         const std::vector<AggSpec>& aggs);
+// Estimate from the first 64 Ki rows: fraction of rows that repeat an earlier group key (hash_agg.cu).
+double distinct_sample_duplicates(const CtxPtr& ctx, const TablePtr& in, const std::vector<int>& group_cols);
 TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left, const TablePtr& right,
                    const std::vector<int>& left_keys, const std::vector<int>& right_keys);
 std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in, const std::vector<int>& keys,

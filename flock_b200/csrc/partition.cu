@@ -97,19 +97,44 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
 // step 2: per destination (and per kind: rows, bytes of Utf8 column u) exclusive scan over the CTAs
 // ================================================================================================
 __global__ void __launch_bounds__(1024) partition_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cta_pos,
-                                                              unsigned long long* __restrict__ totals, int grid, int n_parts, int n_items) {
+                                                              unsigned long long* __restrict__ totals, int grid, int n_parts, int n_kinds) {
+  // One kind (rows, or the bytes of one Utf8 column) is a grid x n_parts matrix, row-major; wanted: the exclusive
+  // prefix down every column.  Warp w owns the rows [w * R, (w + 1) * R), lane l the column c0 + l of a block of 32
+  // columns: a thread first sums its R entries (independent loads), the 32 partial sums of a column are combined
+  // through shared memory, and a second sweep writes the prefixes.  (The first version walked each column with one
+  // warp, 32 CTAs per dependent step: 21-25 us for 611 CTAs, profiles/r2_partition_run12.txt.)
+  __shared__ unsigned long long s_part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int item = warp; item < n_items; item += 32) {
-    const int k = item / n_parts, p = item % n_parts;
-    unsigned long long run = 0;
-    for (int c0 = 0; c0 < grid; c0 += 32) {
+  const int R = (grid + 31) / 32;
+  const int r0 = warp * R, r1 = min(grid, r0 + R);
+  for (int k = 0; k < n_kinds; ++k) {
+    const uint32_t* h = hist + int64_t(k) * grid * n_parts;
+    uint32_t* o = cta_pos + int64_t(k) * grid * n_parts;
+    for (int c0 = 0; c0 < n_parts; c0 += 32) {
       const int c = c0 + lane;
-      const unsigned v = c < grid ? hist[(int64_t(k) * grid + c) * n_parts + p] : 0u;
-      const unsigned incl = warp_inclusive_sum(v);
-      if (c < grid) cta_pos[(int64_t(k) * grid + c) * n_parts + p] = unsigned(run) + incl - v;
-      run += __shfl_sync(FULL_MASK, incl, 31);
+      unsigned long long sum = 0;
+      if (c < n_parts)
+        for (int r = r0; r < r1; ++r) sum += h[int64_t(r) * n_parts + c];
+      s_part[warp][lane] = sum;
+      __syncthreads();
+      unsigned long long before = 0, total = 0;
+#pragma unroll 8
+      for (int w = 0; w < 32; ++w) {
+        const unsigned long long v = s_part[w][lane];
+        if (w < warp) before += v;
+        total += v;
+      }
+      if (c < n_parts) {
+        unsigned long long run = before;
+        for (int r = r0; r < r1; ++r) {
+          const unsigned v = h[int64_t(r) * n_parts + c];
+          o[int64_t(r) * n_parts + c] = unsigned(run);
+          run += v;
+        }
+        if (warp == 0) totals[k * n_parts + c] = total;
+      }
+      __syncthreads();
     }
-    if (lane == 0) totals[item] = run;
   }
 }
 
@@ -131,7 +156,7 @@ struct PartScatterArgs {
 
 // dynamic shared memory layout of the scatter kernel (P destinations, U Utf8 columns)
 struct ScatterSmem {
-  size_t wcnt, woff, seg, tot, run, runb, segb, sege, row, pid, wscan, dest, stage, total;
+  size_t wcnt, woff, seg, tot, run, runb, segb, sege, row, pid, wscan, dest, stage, src, total;
   __host__ __device__ ScatterSmem(int P, int U, bool dest_in_smem) {
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -152,12 +177,13 @@ struct ScatterSmem {
     wscan = take(size_t(PT_WARPS + 1) * 4);
     dest = take(dest_in_smem ? size_t(P) * sizeof(PartDest) : 0);
     stage = take(U ? size_t(PT_STAGE_BYTES) : 0);
+    src = take(U ? size_t(PT_STAGE_BYTES) + 32 : 0);
     total = o;
   }
 };
 constexpr int PT_DEST_SMEM_PARTS = 16;  // up to this many destinations the PartDest table is copied to shared memory
 
-__global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __grid_constant__ PartScatterArgs a) {
+__global__ void __launch_bounds__(PT_THREADS, 3) partition_scatter_kernel(const __grid_constant__ PartScatterArgs a) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
   if (a.abort_flag && *reinterpret_cast<const volatile unsigned*>(a.abort_flag)) return;
   const int P = a.n_parts, U = a.n_utf8;
@@ -175,6 +201,7 @@ __global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __g
   unsigned char* s_pid = ps_smem + L.pid;
   unsigned* s_wscan = reinterpret_cast<unsigned*>(ps_smem + L.wscan);
   unsigned char* s_stage = ps_smem + L.stage;
+  unsigned char* s_src = ps_smem + L.src;
   const PartDest* dest = a.dest;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t begin = int64_t(blockIdx.x) * a.chunk;
@@ -200,12 +227,17 @@ __global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __g
     // ---- rank of every row among the rows of its warp with the same destination (rows in input order)
     unsigned char mypid[8];
     unsigned short myrank[8];
+    // the eight destination bytes first: independent loads, all in flight before the (warp-synchronous) ranking starts
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int local = warp * 256 + j * 32 + lane;
+      mypid[j] = local < rows ? a.pid[tile0 + local] : (unsigned char)0;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int local = warp * 256 + j * 32 + lane;
       const bool valid = local < rows;
-      unsigned pid = 0, m = 0, before = 0;
-      if (valid) pid = a.pid[tile0 + local];
+      unsigned pid = mypid[j], m = 0, before = 0;
       const unsigned vmask = __ballot_sync(FULL_MASK, valid);
       if (valid) {
         m = __match_any_sync(vmask, pid);
@@ -214,7 +246,6 @@ __global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __g
       __syncwarp();
       if (valid && lane == __ffs(m) - 1) my_wcnt[pid] = (unsigned short)(before + __popc(m));
       __syncwarp();
-      mypid[j] = (unsigned char)pid;
       myrank[j] = (unsigned short)(before + __popc(m & lt));
     }
     __syncthreads();
@@ -253,13 +284,36 @@ __global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __g
     }
     __syncthreads();
     // ---- fixed-width columns: consecutive threads write consecutive rows of one destination
-    for (int s = tid; s < rows; s += PT_THREADS) {
-      const unsigned p = s_pid[s];
-      const int64_t pos = int64_t(s_run[p]) + (s - int(s_seg[p]));
-      const int64_t row = tile0 + s_row[s];
+    {
+      // slot s = tid + 256 k of the ordered tile: where it goes and where it comes from, for all eight k at once, then
+      // column by column eight loads in flight before their eight stores
+      unsigned pp[8];
+      int64_t pos[8], row[8];
+      bool on[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int sx = tid + k * PT_THREADS;
+        on[k] = sx < rows;
+        pp[k] = on[k] ? s_pid[sx] : 0u;
+        pos[k] = on[k] ? int64_t(s_run[pp[k]]) + (sx - int(s_seg[pp[k]])) : 0;
+        row[k] = on[k] ? tile0 + s_row[sx] : tile0;
+      }
       for (int f = 0; f < a.n_fixed; ++f) {
-        if (a.fwidth[f] == 4) static_cast<uint32_t*>(dest[p].val[f])[pos] = static_cast<const uint32_t*>(a.fsrc[f])[row];
-        else static_cast<unsigned long long*>(dest[p].val[f])[pos] = static_cast<const unsigned long long*>(a.fsrc[f])[row];
+        if (a.fwidth[f] == 4) {
+          uint32_t v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = on[k] ? static_cast<const uint32_t*>(a.fsrc[f])[row[k]] : 0u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (on[k]) static_cast<uint32_t*>(dest[pp[k]].val[f])[pos[k]] = v[k];
+        } else {
+          unsigned long long v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = on[k] ? static_cast<const unsigned long long*>(a.fsrc[f])[row[k]] : 0ull;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (on[k]) static_cast<unsigned long long*>(dest[pp[k]].val[f])[pos[k]] = v[k];
+        }
       }
     }
     // ---- Utf8 columns: a thread owns 8 consecutive slots of the ordered tile
@@ -307,6 +361,20 @@ __global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __g
       }
       __syncthreads();
       const bool staged = tile_bytes <= unsigned(PT_STAGE_BYTES);
+      // The tile's strings are CONTIGUOUS in the source (rows tile0 .. tile0 + rows): the CTA fetches that byte range
+      // with coalesced 16-byte loads into shared memory, and the per-string shuffling into destination order then runs
+      // from shared to shared.  (Fetching string by string from global memory chained ~24 dependent loads per
+      // thread: 70 of the kernel's 86 us on 2.5 M names, profiles/r2_partition_run12.txt.)
+      const int32_t sb0 = a.uoff[u][tile0];
+      unsigned shift = 0;
+      if (staged) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(a.udata[u] + sb0);
+        const uint4* aligned = reinterpret_cast<const uint4*>(addr & ~uintptr_t(15));
+        shift = unsigned(addr & 15);
+        const unsigned n16 = (shift + tile_bytes + 15) >> 4;
+        for (unsigned i = tid; i < n16; i += PT_THREADS) reinterpret_cast<uint4*>(s_src)[i] = __ldg(aligned + i);
+        __syncthreads();
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int s = tid * 8 + k;
@@ -315,11 +383,12 @@ __global__ void __launch_bounds__(PT_THREADS) partition_scatter_kernel(const __g
         const int64_t pos = int64_t(s_run[p]) + (s - int(s_seg[p]));
         const unsigned rel = s_runb[u * P + p] + (bytepos[k] - s_segb[p]);
         dest[p].off[u][pos] = int32_t(dest[p].byte_origin[u] + (long long)rel);
-        const uint8_t* from = a.udata[u] + src[k];
         if (staged) {
+          const unsigned char* from = s_src + shift + (src[k] - sb0);
           unsigned char* to = s_stage + bytepos[k];
           for (int b = 0; b < len[k]; ++b) to[b] = from[b];
         } else {  // a tile of long strings: straight to the destination
+          const uint8_t* from = a.udata[u] + src[k];
           uint8_t* to = dest[p].bytes[u] + rel;
           for (int b = 0; b < len[k]; ++b) to[b] = from[b];
         }
@@ -444,7 +513,7 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
   {
     LaunchTimer lt(ctx, "partition_scan_kernel");
     partition_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ps.hist->as<uint32_t>(), ps.cta_pos->as<uint32_t>(), ps.totals->as<unsigned long long>(), ps.grid,
-                                                       n_parts, (1 + U) * n_parts);
+                                                       n_parts, 1 + U);
   }
   FG_CUDA(cudaGetLastError());
   count_launch(ctx, 2);

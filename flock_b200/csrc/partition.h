@@ -24,7 +24,7 @@ constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_TILE = 2048;        // rows ordered in shared memory at a time (8 per thread)
 constexpr int PT_MAX_PARTS = 255;    // a destination is one byte
 constexpr int PT_MAX_UTF8 = 4;       // Utf8 columns one pass can move
-constexpr int PT_STAGE_BYTES = 40 * 1024;  // shared staging of a tile's string bytes (2048 NEXMark strings are ~25 KB)
+constexpr int PT_STAGE_BYTES = 32 * 1024;  // shared staging of a tile's string bytes, twice: source order and destination order (2048 NEXMark strings are ~25 KB)
 
 // Where THIS source's rows of one destination go.
 struct PartDest {

@@ -44,4 +44,19 @@ elif what == "feed":
             ec.feed_data_sources(src); a = time.perf_counter(); r = ec.execute(); b = time.perf_counter(); ec.clean_data_sources()
             ts.append(((a - t) * 1e3, (b - a) * 1e3, (time.perf_counter() - t) * 1e3))
         print("stage threads", thr, "feed/exec/total ms (median)", [round(float(np.median([x[i] for x in ts[2:]])), 3) for i in range(3)])
+elif what == "partition":
+    n_p, n_a, _ = nexgen.relation_counts(125_000_000)
+    tabs = {"persons(p_id,name)": (ctx.import_batches(nexgen.split_batches(nexgen.persons(n_p, 42, 0, ["p_id", "name"]))), [0]),
+            "sellers": (ctx.import_batches(nexgen.split_batches(nexgen.auctions(n_a, 42, 0, ["seller"]))), [0]),
+            "bids(4 fixed cols, 10 M)": (ctx.import_batches(nexgen.bids_chunked(10_000_000, 42)), [0])}
+    for name, (t, keys) in tabs.items():
+        for parts in (2, 8):
+            for _ in range(3): ctx.hash_partition(t, keys, parts)
+            ctx.profile_begin()
+            ts = []
+            for _ in range(10):
+                ctx.flush_l2(); ctx.timer_start(0); p = ctx.hash_partition(t, keys, parts); ctx.timer_stop(0); ts.append(ctx.timer_ms(0))
+            prof = ctx.profile_end()
+            print(name, "rows", t.num_rows, "bytes", t.nbytes, "parts", parts, "ms median", round(float(np.median(ts)), 4),
+                  {k: round(v["ms"] / v["launches"], 4) for k, v in prof.items()})
 ctx.close()
