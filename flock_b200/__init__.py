@@ -21,7 +21,7 @@ import pyarrow as pa
 from . import _ffi
 from ._ffi import FlockGpuError, lib, check
 
-__all__ = ["Context", "Table", "HostRelation", "ExecutionContext", "FlockGpuError", "col", "lit", "E"]
+__all__ = ["Context", "Table", "HostRelation", "ExecutionContext", "Window", "FlockGpuError", "col", "lit", "E"]
 
 # enum flockgpu_dtype
 BOOL, INT32, INT64, UINT64, FLOAT64, TIMESTAMP, UTF8, UINT32 = range(8)
@@ -204,6 +204,17 @@ class Table:
     def to_arrow(self) -> pa.Table:
         return pa.Table.from_batches([self.to_batch()])
 
+    def to_ipc(self, row_begin: int = 0, row_count: int = -1) -> tuple[bytes, bytes]:
+        """(header, body) of one Arrow IPC record-batch message: the DataFrame the reference's `to_payload` would build."""
+        h, b = C.c_void_p(), C.c_void_p()
+        hl, bl = C.c_int64(), C.c_int64()
+        check(lib.flockgpu_table_export_ipc(self.ctx.handle, self.handle, row_begin, row_count, C.byref(h), C.byref(hl), C.byref(b), C.byref(bl)))
+        try:
+            return C.string_at(h, hl.value), C.string_at(b, bl.value)
+        finally:
+            lib.flockgpu_ipc_free(h)
+            lib.flockgpu_ipc_free(b)
+
     def release(self) -> None:
         if self.handle:
             lib.flockgpu_table_release(self.handle)
@@ -311,6 +322,26 @@ class Context:
             _release_exported(c_schema, arrays, len(batches))
         return Table(self, out.value)
 
+    def import_ipc(self, schema: pa.Schema, frames: Sequence[tuple], projection: Sequence[int] | None = None) -> Table:
+        """frames: [(header, body)] -- the data_header / data_body of Arrow-Flight messages (bytes-like or pyarrow buffers)."""
+        n = len(frames)
+        keep = [(pa.py_buffer(h) if not isinstance(h, pa.Buffer) else h, pa.py_buffer(b) if not isinstance(b, pa.Buffer) else b) for h, b in frames]
+        hp = (C.c_void_p * max(n, 1))(*[h.address for h, _ in keep])
+        hl = (C.c_int64 * max(n, 1))(*[h.size for h, _ in keep])
+        bp = (C.c_void_p * max(n, 1))(*[b.address for _, b in keep])
+        bl = (C.c_int64 * max(n, 1))(*[b.size for _, b in keep])
+        c_schema = _ffi.ArrowSchema()
+        schema._export_to_c(C.addressof(c_schema))
+        try:
+            proj = (C.c_int32 * len(projection))(*projection) if projection is not None else None
+            out = C.c_void_p()
+            check(lib.flockgpu_table_import_ipc(self.handle, C.byref(c_schema), hp, hl, bp, bl, n, proj, len(projection) if projection is not None else 0,
+                                                C.byref(out)))
+        finally:
+            if c_schema.release:
+                C.CFUNCTYPE(None, C.c_void_p)(c_schema.release)(C.addressof(c_schema))
+        return Table(self, out.value)
+
     def concat(self, tables: Sequence[Table]) -> Table:
         hs = (C.c_void_p * len(tables))(*[t.handle for t in tables])
         out = C.c_void_p()
@@ -362,6 +393,24 @@ class Context:
         check(lib.flockgpu_hash_partition(self.handle, table.handle, k, len(key_cols), n_parts, outs))
         return [Table(self, h) for h in outs]
 
+    def sort(self, table: Table, cols: Sequence[int], descending: Sequence[bool] | None = None) -> Table:
+        k = (C.c_int32 * len(cols))(*cols)
+        d = (C.c_int32 * len(cols))(*[1 if x else 0 for x in (descending or [False] * len(cols))])
+        out = C.c_void_p()
+        check(lib.flockgpu_sort(self.handle, table.handle, k, d, len(cols), C.byref(out)))
+        return Table(self, out.value)
+
+    def row_number(self, table: Table, partition_cols: Sequence[int], name: str = "ROW_NUMBER()") -> Table:
+        k = (C.c_int32 * max(len(partition_cols), 1))(*partition_cols)
+        out = C.c_void_p()
+        check(lib.flockgpu_row_number(self.handle, table.handle, k, len(partition_cols), name.encode(), C.byref(out)))
+        return Table(self, out.value)
+
+    def limit(self, table: Table, n: int) -> Table:
+        out = C.c_void_p()
+        check(lib.flockgpu_limit(self.handle, table.handle, n, C.byref(out)))
+        return Table(self, out.value)
+
     # ---- multi-GPU
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -384,6 +433,41 @@ class Context:
         out = C.c_void_p()
         check(lib.flockgpu_hash_exchange(self.handle, table.handle, k, len(key_cols), C.byref(out)))
         return Table(self, out.value)
+
+
+class Window:
+    """Hopping / tumbling window over epoch relations resident in HBM (flockgpu_window_*; hopping.rs:54-74)."""
+
+    def __init__(self, ctx: Context, window_size: int, hop_size: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib.flockgpu_window_open(ctx.handle, window_size, hop_size, C.byref(h)))
+        self.handle = h
+
+    def push(self, epoch: Table) -> None:
+        check(lib.flockgpu_window_push(self.handle, epoch.handle))
+
+    @property
+    def ready(self) -> bool:
+        v = C.c_int32()
+        check(lib.flockgpu_window_ready(self.handle, C.byref(v)))
+        return bool(v.value)
+
+    def next(self) -> tuple[Table, int]:
+        out, first = C.c_void_p(), C.c_int64()
+        check(lib.flockgpu_window_next(self.handle, C.byref(out), C.byref(first)))
+        return Table(self.ctx, out.value), first.value
+
+    def close(self) -> None:
+        if self.handle:
+            lib.flockgpu_window_close(self.handle)
+            self.handle = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def selftest_eval_predicate(batch: pa.RecordBatch, predicate: E):

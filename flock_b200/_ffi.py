@@ -124,16 +124,28 @@ PROTOTYPES = {
     "flockgpu_table_import": (C.c_int, [_P, C.POINTER(ArrowSchema), C.POINTER(C.POINTER(ArrowArray)), C.c_int32, _I32P, C.c_int32, _PP]),
     "flockgpu_table_export": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.POINTER(ArrowSchema), C.POINTER(ArrowArray)]),
     "flockgpu_table_schema": (C.c_int, [_P, _P, C.POINTER(ArrowSchema)]),
+    "flockgpu_table_import_ipc": (C.c_int, [_P, C.POINTER(ArrowSchema), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_int64), C.c_int32, _I32P, C.c_int32, _PP]),
+    "flockgpu_table_export_ipc": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _PP, C.POINTER(C.c_int64), _PP, C.POINTER(C.c_int64)]),
+    "flockgpu_ipc_free": (None, [_P]),
     "flockgpu_table_retain": (C.c_int, [_P]),
     "flockgpu_table_release": (C.c_int, [_P]),
     "flockgpu_table_num_rows": (C.c_int64, [_P]),
     "flockgpu_table_num_columns": (C.c_int32, [_P]),
     "flockgpu_table_nbytes": (C.c_int64, [_P]),
     "flockgpu_table_concat": (C.c_int, [_P, _PP, C.c_int32, _PP]),
+    "flockgpu_window_open": (C.c_int, [_P, C.c_int32, C.c_int32, _PP]),
+    "flockgpu_window_close": (C.c_int, [_P]),
+    "flockgpu_window_push": (C.c_int, [_P, _P]),
+    "flockgpu_window_ready": (C.c_int, [_P, _I32P]),
+    "flockgpu_window_next": (C.c_int, [_P, _PP, C.POINTER(C.c_int64)]),
     "flockgpu_filter_project": (C.c_int, [_P, _P, C.POINTER(Expr), C.POINTER(Expr), C.POINTER(C.c_char_p), C.c_int32, _PP]),
     "flockgpu_hash_aggregate": (C.c_int, [_P, _P, C.c_int32, _I32P, C.c_int32, C.POINTER(AggSpec), C.c_int32, _PP]),
     "flockgpu_hash_join": (C.c_int, [_P, _P, _P, _I32P, _I32P, C.c_int32, _PP]),
     "flockgpu_hash_partition": (C.c_int, [_P, _P, _I32P, C.c_int32, C.c_int32, _PP]),
+    "flockgpu_sort": (C.c_int, [_P, _P, _I32P, _I32P, C.c_int32, _PP]),
+    "flockgpu_row_number": (C.c_int, [_P, _P, _I32P, C.c_int32, C.c_char_p, _PP]),
+    "flockgpu_limit": (C.c_int, [_P, _P, C.c_int64, _PP]),
     "flockgpu_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "flockgpu_comm_init": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     "flockgpu_comm_rank": (C.c_int, [_P, _I32P, _I32P]),

@@ -980,11 +980,12 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
       void* h = pin_get(nb ? nb : 8);
       priv->blocks.emplace_back(h, nb ? nb : 8);
       if (nb) {
-        if (c.all_null)
+        if (c.all_null) {
           memset(h, 0, nb);
-        else
+        } else {
           ctx->d2h_bytes.fetch_add(int64_t(nb), std::memory_order_relaxed);
           FG_CUDA(cudaMemcpyAsync(h, static_cast<const char*>(c.values()) + row_begin * w, nb, cudaMemcpyDeviceToHost, ctx->stream));
+        }
       }
       priv->buffers = {validity, h};
     } else {
@@ -1010,9 +1011,10 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
           ctx->d2h_bytes.fetch_add(int64_t(nb_off), std::memory_order_relaxed);
           FG_CUDA(cudaMemcpyAsync(h_off, tmp->ptr, nb_off, cudaMemcpyDeviceToHost, ctx->stream));
         }
-        if (nb_val)
+        if (nb_val) {
           ctx->d2h_bytes.fetch_add(int64_t(nb_val), std::memory_order_relaxed);
           FG_CUDA(cudaMemcpyAsync(h_val, static_cast<const char*>(c.values()) + first_off[i], nb_val, cudaMemcpyDeviceToHost, ctx->stream));
+        }
       } else {
         h_off[0] = 0;
       }

@@ -509,6 +509,47 @@ TablePtr HashJoinExec::execute(const ExecEnv& env) {
   return fg::hash_join(env.ctx, l, r, lk, rk);
 }
 
+std::string SortExec::fmt_as() const {
+  std::string s = "SortExec: [";
+  for (size_t i = 0; i < expr.size(); ++i) s += (i ? ", " : "") + expr_display(*expr[i].expr) + (expr[i].descending ? " DESC" : " ASC");
+  return s + "]";
+}
+
+TablePtr SortExec::execute(const ExecEnv& env) {
+  TablePtr in = input->execute(env);
+  in->resolve();
+  std::vector<fg::SortKey> keys;
+  for (const Key& k : expr) {
+    if (!is_column_expr(*k.expr)) fail(FLOCKGPU_ERR_UNSUPPORTED, "SortExec: sort expressions must be plain columns on the GPU path");
+    keys.push_back(fg::SortKey{column_of(*k.expr, *in), k.descending, k.nulls_first});
+  }
+  return fg::sort_table(env.ctx, in, keys);
+}
+
+TablePtr GlobalLimitExec::execute(const ExecEnv& env) { return fg::limit_rows(env.ctx, input->execute(env), limit); }
+
+std::string WindowAggExec::fmt_as() const {
+  std::string s = "WindowAggExec: wdw=[";
+  for (size_t i = 0; i < window_expr.size(); ++i) s += (i ? ", " : "") + window_expr[i].name;
+  return s + "]";
+}
+
+TablePtr WindowAggExec::execute(const ExecEnv& env) {
+  TablePtr in = input->execute(env);
+  in->resolve();
+  // several window expressions: each adds its column in front, the first expression ends up first
+  TablePtr out = in;
+  for (auto w = window_expr.rbegin(); w != window_expr.rend(); ++w) {
+    std::vector<int> part;
+    for (const Json* e : w->partition_by) {
+      if (!is_column_expr(*e)) fail(FLOCKGPU_ERR_UNSUPPORTED, "WindowAggExec: PARTITION BY expressions must be plain columns on the GPU path");
+      part.push_back(column_of(*e, *in) + int(out->cols.size() - in->cols.size()));
+    }
+    out = fg::row_number(env.ctx, out, part, w->name);
+  }
+  return out;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan construction from JSON
 // ------------------------------------------------------------------------------------------------
@@ -621,6 +662,44 @@ static PlanPtr build_plan(const Json& j) {
     }
     n->left = build_plan(j.at("left"));
     n->right = build_plan(j.at("right"));
+    return n;
+  }
+  if (tag == "sort_exec") {
+    auto n = std::make_shared<SortExec>();
+    for (const JsonPtr& e : j.at("expr").arr) {
+      SortExec::Key k;
+      k.expr = &e->at("expr");
+      if (const Json* o = e->get("options")) {
+        const Json* d = o->get("descending");
+        const Json* nf = o->get("nulls_first");
+        k.descending = d && d->kind == Json::Bool && d->b;
+        k.nulls_first = nf && nf->kind == Json::Bool && nf->b;
+      }
+      n->expr.push_back(k);
+    }
+    if (n->expr.empty()) fail(FLOCKGPU_ERR_INVALID, "plan JSON: sort_exec without sort expressions");
+    n->input = build_input(j);
+    return n;
+  }
+  if (tag == "global_limit_exec") {
+    auto n = std::make_shared<GlobalLimitExec>();
+    n->limit = j.at("limit").as_int("limit");
+    n->input = build_input(j);
+    return n;
+  }
+  if (tag == "window_agg_exec") {
+    auto n = std::make_shared<WindowAggExec>();
+    for (const JsonPtr& w : j.at("window_expr").arr) {
+      const Json* fun = w->get("fun");
+      if (!fun || !fun->is_string() || fun->str != "RowNumber")
+        fail(FLOCKGPU_ERR_UNSUPPORTED, "plan: window function %s is not supported on the GPU path (ROW_NUMBER only)", fun && fun->is_string() ? fun->str.c_str() : "?");
+      WindowAggExec::Win win;
+      win.name = w->at("name").as_string("window expression name");
+      if (const Json* pb = w->get("partition_by"))
+        for (const JsonPtr& e : pb->arr) win.partition_by.push_back(e.get());
+      n->window_expr.push_back(std::move(win));
+    }
+    n->input = build_input(j);
     return n;
   }
   fail(FLOCKGPU_ERR_UNSUPPORTED, "plan: execution plan node \"%s\" is not supported on the GPU path", tag.c_str());

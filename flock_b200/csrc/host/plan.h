@@ -154,6 +154,39 @@ class HashJoinExec : public ExecutionPlan {
   TablePtr execute(const ExecEnv& env) override;
 };
 
+class SortExec : public UnaryExec {
+ public:
+  struct Key {
+    const Json* expr;
+    bool descending = false, nulls_first = false;
+  };
+  std::vector<Key> expr;
+  const char* name() const override { return "SortExec"; }
+  std::string fmt_as() const override;
+  TablePtr execute(const ExecEnv& env) override;
+};
+
+class GlobalLimitExec : public UnaryExec {
+ public:
+  int64_t limit = 0;
+  const char* name() const override { return "GlobalLimitExec"; }
+  std::string fmt_as() const override { return "GlobalLimitExec: limit=" + std::to_string(limit); }
+  TablePtr execute(const ExecEnv& env) override;
+};
+
+// WindowAggExec with ROW_NUMBER() window expressions (the only window function NEXMark uses, q6)
+class WindowAggExec : public UnaryExec {
+ public:
+  struct Win {
+    std::string name;
+    std::vector<const Json*> partition_by;
+  };
+  std::vector<Win> window_expr;
+  const char* name() const override { return "WindowAggExec"; }
+  std::string fmt_as() const override;
+  TablePtr execute(const ExecEnv& env) override;
+};
+
 // flock::runtime::context::ExecutionContext (only the members that touch the hot path)
 class ExecutionContext {
  public:

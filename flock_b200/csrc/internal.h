@@ -428,6 +428,15 @@ std::vector<int> routing_columns(const Table& in, const std::vector<int>& keys);
 // instead (CoalescePartitionsExec).  Falls back to hash_partition + the NCCL all-to-all when peer windows are
 // unavailable.
 TablePtr hash_exchange(const CtxPtr& ctx, const TablePtr& in, const std::vector<int>& keys, int dest = -1);
+// SortExec / WindowAggExec(ROW_NUMBER) / GlobalLimitExec (sort.cu)
+struct SortKey {
+  int col;
+  bool descending;
+  bool nulls_first;  // no effect: columns with NULLs are not sortable on the GPU path
+};
+TablePtr sort_table(const CtxPtr& ctx, const TablePtr& in, const std::vector<SortKey>& keys);
+TablePtr row_number(const CtxPtr& ctx, const TablePtr& in, const std::vector<int>& partition_cols, const std::string& name);
+TablePtr limit_rows(const CtxPtr& ctx, const TablePtr& in, int64_t limit);
 // Row gather: out.col[c][i] = in.col[c][idx[i]] for every column (fixed width and Utf8).
 TablePtr gather_rows(const CtxPtr& ctx, const Table& in, const std::vector<int>& cols, const uint32_t* d_idx,
                      int64_t n_idx);

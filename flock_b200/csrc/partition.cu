@@ -26,6 +26,7 @@ __host__ __device__ __forceinline__ uint32_t partition_of(uint64_t hash, uint32_
 struct PartCountArgs {
   int64_t n_rows, chunk;
   int32_t n_parts, packed, dest_rank, n_utf8, grid, pad;
+  int32_t digit_col, digit_shift;  // digit_col >= 0: destination = byte `digit_shift / 8` of that UInt64 column (a radix-sort pass)
   KeyPack pack;
   RowKeys rk;
   ColRef cols[MAX_IN_COLS];
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
       if (valid[j]) {
         if (a.dest_rank >= 0) {
           pid[j] = unsigned(a.dest_rank);
+        } else if (a.digit_col >= 0) {
+          pid[j] = unsigned(static_cast<const unsigned long long*>(a.cols[a.digit_col].data)[row] >> a.digit_shift) & 0xffu;
         } else {
           const unsigned long long h = a.packed ? fmix64(pack_key(a.pack, a.cols, row)) : hash_row(a.rk, a.cols, row);
           pid[j] = partition_of(h, uint32_t(P));
@@ -441,11 +444,12 @@ static void fill_colrefs(const Table& in, ColRef* refs) {
   }
 }
 
-PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vector<int>& routing_cols, int n_parts, int dest_rank) {
+PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vector<int>& routing_cols, int n_parts, int dest_rank, int digit_col,
+                              int digit_shift) {
   FG_CHECK(n_parts >= 1 && n_parts <= PT_MAX_PARTS, FLOCKGPU_ERR_INVALID, "hash_partition: n_parts must be in [1, %d], got %d", PT_MAX_PARTS, n_parts);
   FG_CHECK(in.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d columns", MAX_IN_COLS);
-  FG_CHECK(dest_rank >= 0 || (!routing_cols.empty() && routing_cols.size() <= size_t(MAX_KEY_COLS)), FLOCKGPU_ERR_INVALID, "hash_partition: 1..%d key columns",
-           MAX_KEY_COLS);
+  FG_CHECK(dest_rank >= 0 || digit_col >= 0 || (!routing_cols.empty() && routing_cols.size() <= size_t(MAX_KEY_COLS)), FLOCKGPU_ERR_INVALID,
+           "hash_partition: 1..%d key columns", MAX_KEY_COLS);
   PartPass ps;
   ps.n_rows = in.num_rows;
   ps.n_parts = n_parts;
@@ -481,10 +485,12 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
   ca.chunk = ps.chunk;
   ca.n_parts = n_parts;
   ca.dest_rank = dest_rank;
+  ca.digit_col = digit_col;
+  ca.digit_shift = digit_shift;
   ca.n_utf8 = U;
   ca.grid = ps.grid;
   fill_colrefs(in, ca.cols);
-  if (dest_rank < 0) {
+  if (dest_rank < 0 && digit_col < 0) {
     std::vector<int> widths;
     for (int k : routing_cols) {
       FG_CHECK(k >= 0 && k < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "hash_partition: key column %d out of range", k);
@@ -563,7 +569,7 @@ __host__ __device__ __forceinline__ unsigned long long next_partition_base(unsig
 }
 
 struct PlaceLocalArgs {
-  int32_t n_parts, n_fixed, n_utf8, pad;
+  int32_t n_parts, n_fixed, n_utf8, dense;  // dense: partitions back to back, no alignment gaps (radix-sort passes)
   const unsigned long long* totals;  // [(1 + n_utf8)][n_parts]
   void* fdst[MAX_IN_COLS];
   int32_t fwidth[MAX_IN_COLS];
@@ -589,7 +595,7 @@ __global__ void partition_place_local_kernel(const __grid_constant__ PlaceLocalA
       byte_base[u] += bytes;
     }
     a.dest[p] = d;
-    base = next_partition_base(base, rows);
+    base = a.dense ? base + rows : next_partition_base(base, rows);
   }
 }
 
@@ -686,6 +692,44 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
     base = next_partition_base(base, tot[p]);
   }
   return out;
+}
+
+// One stable radix pass: the rows of `in` (fixed-width columns only) reordered by byte `shift / 8` of the UInt64 column
+// `digit_col`, ties in input order -- the multi-way partition with 256 destinations laid out back to back (sort.cu).
+TablePtr radix_pass(const CtxPtr& ctx, const TablePtr& in_ptr, int digit_col, int shift) {
+  const Table& in = *in_ptr;
+  const int64_t n = in.num_rows;
+  if (n <= 1) return in_ptr;
+  PartPass ps = partition_count_scan(ctx, in, {}, 256, -1, digit_col, shift);
+  FG_CHECK(ps.utf8_cols.empty(), FLOCKGPU_ERR_UNSUPPORTED, "radix_pass: Utf8 columns");
+  auto t = std::make_shared<Table>();
+  t->ctx = ctx;
+  t->metadata = in.metadata;
+  t->num_rows = n;
+  t->cols.resize(in.cols.size());
+  PlaceLocalArgs pa{};
+  pa.n_parts = 256;
+  pa.n_fixed = int(ps.fixed_cols.size());
+  pa.n_utf8 = 0;
+  pa.dense = 1;
+  pa.totals = ps.totals->as<unsigned long long>();
+  for (size_t f = 0; f < ps.fixed_cols.size(); ++f) {
+    const Column& src = in.cols[ps.fixed_cols[f]];
+    Column& c = t->cols[ps.fixed_cols[f]];
+    c = src;
+    c.data = alloc(ctx, size_t(n) * src.width());
+    pa.fdst[f] = c.data->ptr;
+    pa.fwidth[f] = src.width();
+  }
+  pa.dest = ps.dest->as<PartDest>();
+  {
+    LaunchTimer lt(ctx, "partition_place_local_kernel");
+    partition_place_local_kernel<<<1, 32, 0, ctx->stream>>>(pa);
+  }
+  FG_CUDA(cudaGetLastError());
+  count_launch(ctx);
+  partition_scatter(ctx, in, ps, nullptr);
+  return t;
 }
 
 }  // namespace fg

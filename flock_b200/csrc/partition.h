@@ -22,7 +22,7 @@ namespace fg {
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_TILE = 2048;        // rows ordered in shared memory at a time (8 per thread)
-constexpr int PT_MAX_PARTS = 255;    // a destination is one byte
+constexpr int PT_MAX_PARTS = 256;    // a destination is one byte
 constexpr int PT_MAX_UTF8 = 4;       // Utf8 columns one pass can move
 constexpr int PT_STAGE_BYTES = 32 * 1024;  // shared staging of a tile's string bytes, twice: source order and destination order (2048 NEXMark strings are ~25 KB)
 
@@ -49,7 +49,10 @@ struct PartPass {
 };
 
 // Steps 1 and 2.  `dest_rank` >= 0 routes every row to that destination (CoalescePartitionsExec) instead of hashing.
-PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vector<int>& routing_cols, int n_parts, int dest_rank = -1);
+PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vector<int>& routing_cols, int n_parts, int dest_rank = -1, int digit_col = -1,
+                              int digit_shift = 0);
+// One stable radix pass over a relation of fixed-width columns (partition.cu; used by SortExec, sort.cu).
+TablePtr radix_pass(const CtxPtr& ctx, const TablePtr& in, int digit_col, int shift);
 // Step 4 (after the caller's place step has filled pass.dest).  `abort_flag` (may be NULL): a non-zero word makes the
 // kernel return without writing (the exchange sets it when the layout could not be agreed).
 void partition_scatter(const CtxPtr& ctx, const Table& in, const PartPass& pass, const unsigned* abort_flag);

@@ -247,8 +247,7 @@ def q7(n: int = TARGET_PARTITIONS) -> dict:
 
 def q6(n: int = TARGET_PARTITIONS) -> dict:
     """benchmarks/src/nexmark/query/q6.sql, types q6_plan.fmt: average selling price of each seller's last ten closed
-    auctions.  Needs SortExec + WindowAggExec(ROW_NUMBER): restated in the ORACLE only so far (SURVEY section 8f rank 3);
-    the GPU plan layer rejects these nodes with FLOCKGPU_ERR_UNSUPPORTED."""
+    auctions.  SortExec + WindowAggExec(ROW_NUMBER) on top of q4's join and BETWEEN filter."""
     a_scan = repartition_rr(memory_exec(AUCTION, [0, 5, 6, 7]), n)     # a_id, a_date_time, expires, seller
     b_scan = repartition_rr(memory_exec(BID, [0, 2, 3]), n)            # auction, price, b_date_time
     lsh = coalesce_batches_exec(repartition_hash(a_scan, [column("a_id", 0)], n))
@@ -280,7 +279,7 @@ def q6(n: int = TARGET_PARTITIONS) -> dict:
 
 
 QUERIES = {"q1": q1, "q2": q2, "q3": q3, "q4": q4, "q5": q5, "q6": q6, "q7": q7, "q8": q8}
-GPU_QUERIES = [q for q in QUERIES if q != "q6"]      # q6 needs SortExec / WindowAggExec: oracle only so far
+GPU_QUERIES = list(QUERIES)
 # relations each query feeds, in feed order (flock/src/datasource/nexmark/nexmark.rs:181-203); q5 scans bid
 # twice, and feed_data_sources hands one source to one leaf (context.rs:293-303), so bid is fed twice.
 SOURCES = {"q1": ["bid"], "q2": ["bid"], "q3": ["auction", "person"], "q4": ["auction", "bid"], "q5": ["bid", "bid"],

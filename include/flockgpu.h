@@ -140,6 +140,22 @@ int flockgpu_table_import(flockgpu_ctx* ctx, const struct ArrowSchema* schema,
 int flockgpu_table_export(flockgpu_ctx* ctx, const flockgpu_table* table, int64_t row_begin,
                           int64_t row_count, struct ArrowSchema* out_schema,
                           struct ArrowArray* out_array);
+/* ---- payload frames: Arrow IPC record-batch messages <-> tables (flock/src/runtime/payload.rs:161-192
+ *      Payload::to_record_batch = flight_data_to_arrow_batch per DataFrame; flock/src/transmute.rs:178-247 to_payload /
+ *      to_bytes = flight_data_from_arrow_batch; the arena hands the frames over, runtime/arena/mod.rs:114-169) ------- */
+/* Host -> HBM from `n_frames` DataFrame { header, body } pairs (Encoding::None): header = the flatbuffer Message of a
+ * RecordBatch (FlightData.data_header), body = its buffers (FlightData.data_body).  Nothing is decoded: the body
+ * buffers are the column buffers, only their extents are read from the header.  `schema` / `projection` as in
+ * flockgpu_table_import; frames with nulls, dictionaries or compressed bodies are rejected (FLOCKGPU_ERR_UNSUPPORTED). */
+int flockgpu_table_import_ipc(flockgpu_ctx* ctx, const struct ArrowSchema* schema, const uint8_t* const* headers, const int64_t* header_lens,
+                              const uint8_t* const* bodies, const int64_t* body_lens, int32_t n_frames, const int32_t* projection,
+                              int32_t n_projection, flockgpu_table** out);
+/* HBM -> one DataFrame for rows [row_begin, row_begin + row_count) (row_count < 0: to the end): *out_header receives a
+ * flatbuffer Message { RecordBatch } (MetadataVersion V5, 8-byte aligned buffers, what arrow-rs writes), *out_body the
+ * buffers.  Both blocks belong to the caller and are released with flockgpu_ipc_free.                                */
+int flockgpu_table_export_ipc(flockgpu_ctx* ctx, const flockgpu_table* table, int64_t row_begin, int64_t row_count, uint8_t** out_header,
+                              int64_t* out_header_len, uint8_t** out_body, int64_t* out_body_len);
+void flockgpu_ipc_free(uint8_t* block);
 /* Schema only (no data movement).                                                                  */
 int flockgpu_table_schema(flockgpu_ctx* ctx, const flockgpu_table* table,
                           struct ArrowSchema* out_schema);
@@ -152,6 +168,23 @@ int64_t flockgpu_table_nbytes(const flockgpu_table* table);
 /* Concatenates tables of identical schema (CoalesceBatchesExec / concat, transmute.rs:55-72).      */
 int flockgpu_table_concat(flockgpu_ctx* ctx, flockgpu_table* const* tables, int32_t n,
                           flockgpu_table** out);
+
+/* ---- window assembly on the device (flock-function/src/aws/window/hopping.rs:54-74, tumbling.rs; the Arena that
+ *      collects a window's pieces: flock/src/runtime/arena/mod.rs:60-85) ------------------------------------------------
+ * A window is `window_size` consecutive epochs (the reference's epochs are seconds); every hop drops the oldest
+ * `hop_size` epochs and waits for as many new ones (hop_size = window_size: tumbling).  Epoch relations stay resident
+ * in HBM between invocations: a hop uploads the new epochs only, and the relation a plan scans is concatenated on
+ * the device.                                                                                                          */
+typedef struct flockgpu_window flockgpu_window;
+int flockgpu_window_open(flockgpu_ctx* ctx, int32_t window_size, int32_t hop_size, flockgpu_window** out);
+int flockgpu_window_close(flockgpu_window* w);
+/* The relation of the next epoch (retained; the caller may release its handle).                                        */
+int flockgpu_window_push(flockgpu_window* w, flockgpu_table* epoch);
+/* *out = 1 when `window_size` epochs are buffered.                                                                      */
+int flockgpu_window_ready(const flockgpu_window* w, int32_t* out);
+/* The next window as one relation (epochs in order); *first_epoch (may be NULL) = number of its first epoch; the
+ * window then moves forward by `hop_size` epochs.                                                                       */
+int flockgpu_window_next(flockgpu_window* w, flockgpu_table** out, int64_t* first_epoch);
 
 /* ---- expressions: the PhysicalExpr trees of FilterExec / ProjectionExec ------------------------
  * A program is the postfix (RPN) encoding of a DataFusion physical expression
@@ -237,6 +270,21 @@ int flockgpu_hash_aggregate(flockgpu_ctx* ctx, const flockgpu_table* in, int32_t
 int flockgpu_hash_join(flockgpu_ctx* ctx, const flockgpu_table* left, const flockgpu_table* right,
                        const int32_t* left_keys, const int32_t* right_keys, int32_t n_keys,
                        flockgpu_table** out);
+
+/* ---- SortExec / WindowAggExec(ROW_NUMBER) / GlobalLimitExec: what NEXMark q6 adds (benchmarks/src/nexmark/query/
+ *      q6.sql, q6_plan.fmt; serialised sort_exec / global_limit_exec: flock/src/tests/data/plan/join.json) ------------- */
+/* Rows ordered by cols[0] (descending[0] != 0: DESC), then cols[1] ...; rows that tie on every sort column are ordered
+ * by the remaining columns, ascending, in column order (the reference leaves ties undefined; this is the oracle's
+ * choice, and it makes the result independent of the input order).  Fixed-width, non-null columns only.               */
+int flockgpu_sort(flockgpu_ctx* ctx, const flockgpu_table* in, const int32_t* cols, const int32_t* descending, int32_t n_keys,
+                  flockgpu_table** out);
+/* ROW_NUMBER() OVER (PARTITION BY partition_cols ORDER BY <the order `in` is sorted in>): `in` must be sorted so that
+ * the rows of a window partition are contiguous (the SortExec DataFusion plans below every WindowAggExec).  The UInt64
+ * window column `name` comes FIRST in the output, then the input columns (WindowAggExec's schema).                       */
+int flockgpu_row_number(flockgpu_ctx* ctx, const flockgpu_table* in, const int32_t* partition_cols, int32_t n_cols, const char* name,
+                        flockgpu_table** out);
+/* The first `limit` rows.                                                                                                */
+int flockgpu_limit(flockgpu_ctx* ctx, const flockgpu_table* in, int64_t limit, flockgpu_table** out);
 
 /* ---- RepartitionExec: Hash([keys], n) (planner.rs:153, :160; call shape
  *      playground/src/distributed_plan/shuffle_writer.rs:105-146) -------------------------------- */

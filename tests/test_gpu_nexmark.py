@@ -29,7 +29,7 @@ def run_gpu(ctx, plan, sources):
     return pa.Table.from_batches(out[0])
 
 
-@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q4", "q5", "q7", "q8"])
+@pytest.mark.parametrize("query", ["q1", "q2", "q3", "q4", "q5", "q6", "q7", "q8"])
 def test_nexmark_matches_oracle(gpu_ctx, query, events_small):
     got = run_gpu(gpu_ctx, plans.QUERIES[query](), sources_for(query, events_small))
     want = oracle.execute_plan(plans.QUERIES[query](), sources_for(query, events_small))
@@ -41,7 +41,7 @@ def test_nexmark_matches_oracle(gpu_ctx, query, events_small):
         oracle.assert_tables_equal(got, one, sort=False)
 
 
-@pytest.mark.parametrize("query", ["q2", "q3", "q4", "q5", "q7", "q8"])
+@pytest.mark.parametrize("query", ["q2", "q3", "q4", "q5", "q6", "q7", "q8"])
 def test_nexmark_seed7_full_batches(gpu_ctx, query, events_seed7):
     got = run_gpu(gpu_ctx, plans.QUERIES[query](), sources_for(query, events_seed7))
     oracle.assert_tables_equal(got, oracle.execute_plan(plans.QUERIES[query](), sources_for(query, events_seed7)))
@@ -51,8 +51,6 @@ def test_golden_vectors(gpu_ctx):
     g = json.loads(goldens.GOLDEN.read_text())
     ev = nexgen.generate(g["n_events"], seed=g["seed"], batch_rows=g["batch_rows"])
     for query, want in g["queries"].items():
-        if query not in plans.GPU_QUERIES:          # q6 (SortExec / WindowAggExec) is restated in the oracle only so far
-            continue
         got = oracle.canonical(run_gpu(gpu_ctx, plans.QUERIES[query](), sources_for(query, ev)))
         assert got.num_rows == want["num_rows"] and got.schema.names == want["columns"], query
         assert goldens._digest(got) == want["digest"], query
@@ -68,6 +66,9 @@ def test_reference_toy_goldens(gpu_ctx):
     out = run_gpu(gpu_ctx, goldens.toy_join_plan(), [[[b1]], [[b2]]])
     rows = sorted(zip(out["a"].to_pylist(), out["b"].to_pylist(), out["d"].to_pylist()))
     assert rows == [("a", 1, 1), ("b", 10, 10), ("c", 10, 10), ("d", 100, 100)]
+    # ... and the fixture in full (global_limit_exec <- sort_exec <- merge_exec on top): ORDER BY a (Utf8) LIMIT 3, order included
+    out = run_gpu(gpu_ctx, goldens.toy_join_sorted_plan(), [[[b1]], [[b2]]])
+    assert list(zip(out["a"].to_pylist(), out["b"].to_pylist(), out["d"].to_pylist())) == [("a", 1, 1), ("b", 10, 10), ("c", 10, 10)]
     # local.rs:169-234
     out = run_gpu(gpu_ctx, goldens.toy_global_plan(), [[[goldens.toy_batch()]]])
     assert [out.column(i).to_pylist() for i in range(3)] == [[90], [37.125], [8]]
@@ -144,6 +145,33 @@ def test_zero_copy_feed_of_pinned_batches(gpu_ctx):
         assert np.array_equal(got["p1"].to_numpy(), full["price"].to_numpy()[keep] + 1)
     finally:
         gpu_ctx.set_option("feed_zero_copy", 0)
+
+
+def test_hopping_windows_assembled_on_the_device(gpu_ctx):
+    """q5 over Hopping(size 4, hop 2) windows (benchmarks/src/nexmark/main.rs:116-123 runs it as Hopping(10 s, 5 s)): every
+    epoch is uploaded ONCE, windows are concatenated from resident epochs (hopping.rs:54-74), and each window's hot items
+    equal the oracle's over the same epochs.  hop = size is the tumbling case (q7 / q8)."""
+    epochs = [nexgen.bids(20_000 + 1000 * e, seed=70 + e, first_bid=100_000 * e) for e in range(9)]
+    ec = fb.ExecutionContext(gpu_ctx, plans.q5())
+    for size, hop in ((4, 2), (3, 3)):
+        w = fb.Window(gpu_ctx, size, hop)
+        seen = []
+        for e, b in enumerate(epochs):
+            w.push(gpu_ctx.import_batches([b]))
+            while w.ready:
+                t, first = w.next()
+                seen.append(first)
+                span = epochs[first:first + size]
+                assert t.num_rows == sum(x.num_rows for x in span)
+                assert t.to_batch().equals(pa.Table.from_batches(span).combine_chunks().to_batches()[0])
+                ec.feed_tables([t, t])
+                got = ec.execute_device(0).to_arrow()
+                oracle.assert_tables_equal(got, oracle.execute_plan(plans.q5(), [[span], [span]]))
+        assert seen == list(range(0, len(epochs) - size + 1, hop))
+        w.close()
+    ec.close()
+    with pytest.raises(fb.FlockGpuError):
+        fb.Window(gpu_ctx, 2, 3)                  # hop > size: rejected like hopping.rs:38-43
 
 
 def test_device_resident_feed(gpu_ctx, events_small):

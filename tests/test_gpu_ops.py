@@ -52,6 +52,41 @@ def test_import_export_roundtrip(gpu_ctx, n):
         assert both.to_batch().equals(pa.Table.from_batches([b, b]).combine_chunks().to_batches()[0])
 
 
+def _ipc_frame(batch: pa.RecordBatch):
+    """(data_header, data_body) of the batch as arrow-rs / pyarrow write it (the DataFrame of flock's Payload)."""
+    msg = pa.ipc.read_message(batch.serialize())
+    return msg.metadata, msg.body
+
+
+def _read_frame(schema: pa.Schema, header: bytes, body: bytes) -> pa.RecordBatch:
+    import struct
+    stream = struct.pack("<Ii", 0xFFFFFFFF, len(header)) + header + body       # encapsulated message (header is 8-byte padded)
+    return pa.ipc.read_record_batch(pa.ipc.read_message(stream), schema)
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 70_001])
+def test_ipc_frames_roundtrip(gpu_ctx, n):
+    """Payload frames in (pyarrow writes them) = the table a batch import gives; frames out are read back by pyarrow's own
+    IPC reader.  Byte-for-byte the buffers are the column buffers."""
+    b = mixed_batch(n, seed=n + 3)
+    pieces = [b] if n < 10 else [b.slice(0, n // 3), b.slice(n // 3)]
+    t = gpu_ctx.import_ipc(b.schema, [_ipc_frame(p) for p in pieces])
+    assert t.num_rows == n and t.to_batch().equals(b)
+    proj = gpu_ctx.import_ipc(b.schema, [_ipc_frame(p) for p in pieces], projection=[5, 0])
+    assert proj.to_batch().equals(b.select(["s", "i32"]))
+    header, body = t.to_ipc()
+    assert _read_frame(b.schema, header, body).equals(b)
+    assert len(header) % 8 == 0 and len(body) % 8 == 0
+    if n > 100:
+        header, body = t.to_ipc(37, 50)                                          # Utf8 offsets rebased, like arrow-rs
+        assert _read_frame(b.schema, header, body).equals(b.slice(37, 50))
+        # a frame our writer produced is a frame our reader takes
+        again = gpu_ctx.import_ipc(b.schema, [t.to_ipc(0, 64), t.to_ipc(64, -1)])
+        assert again.to_batch().equals(b)
+    with pytest.raises(fb.FlockGpuError):
+        gpu_ctx.import_ipc(b.schema, [(b"\x00" * 4, b"")])
+
+
 def test_import_rejects_nulls_and_unknown_types(gpu_ctx):
     with pytest.raises(fb.FlockGpuError) as info:
         gpu_ctx.import_batches([rb(x=pa.array([1, None, 3], pa.int32()))])
@@ -334,6 +369,47 @@ def test_dense_count_table_and_its_fallback(gpu_ctx, shape):
     assert back.schema.names == ["num", "key"]
     order = np.argsort(back["key"].to_numpy(), kind="stable")
     assert np.array_equal(back["key"].to_numpy()[order], counts[0]) and np.array_equal(back["num"].to_numpy()[order], counts[1].astype(np.uint64))
+
+
+# ---- SortExec / WindowAggExec(ROW_NUMBER) / GlobalLimitExec ---------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 2, 1000, 200_003])
+def test_sort_row_number_limit(gpu_ctx, n):
+    rng = np.random.default_rng(n + 1)
+    b = rb(g=pa.array(rng.integers(-5, 40, n).astype(np.int32)), t=pa.array(rng.integers(1_436_918_400_000, 1_436_918_400_500, n), pa.timestamp("ms")),
+           p=pa.array(rng.integers(0, 1 << 40, n)), u=pa.array(rng.integers(0, 1 << 63, n).astype(np.uint64)), f=pa.array(rng.normal(0, 100, n)),
+           k=pa.array(rng.integers(0, 3, n).astype(np.int32)))
+    t = gpu_ctx.import_batches([b])
+    for cols, desc in (([0], [False]), ([0, 1], [False, True]), ([4], [True]), ([5, 3], [True, False]), ([1, 2], [True, True])):
+        got = gpu_ctx.sort(t, cols, desc).to_batch()
+        spec = [{"expr": plans.column(b.schema.names[c], c), "options": {"descending": d, "nulls_first": d}} for c, d in zip(cols, desc)]
+        want = oracle.sort_batch(b, spec)
+        assert got.equals(want), (cols, desc)
+    # ROW_NUMBER over the sorted relation, then the filter / limit q6 puts on top
+    s = gpu_ctx.sort(t, [0, 2], [False, True])
+    w = gpu_ctx.row_number(s, [0], "rn")
+    got = w.to_batch()
+    want = oracle.window_batch(oracle.sort_batch(b, [{"expr": plans.column("g", 0), "options": {"descending": False}},
+                                                     {"expr": plans.column("p", 2), "options": {"descending": True}}]),
+                               [{"fun": "RowNumber", "name": "rn", "partition_by": [plans.column("g", 0)], "order_by": []}])
+    assert got.schema.names == ["rn", "g", "t", "p", "u", "f", "k"] and got.equals(want)
+    both = gpu_ctx.row_number(gpu_ctx.sort(t, [0, 5, 1], [False, False, False]), [0, 5], "rn2").to_batch()
+    keys = list(zip(both["g"].to_pylist(), both["k"].to_pylist()))
+    seen = {}
+    for key, r in zip(keys, both["rn2"].to_pylist()):
+        seen[key] = seen.get(key, 0) + 1
+        assert r == seen[key]
+    for lim in (0, 1, 7, n, n + 5):
+        assert gpu_ctx.limit(s, lim).to_batch().equals(s.to_batch().slice(0, min(lim, n)))
+    names = rb(s=pa.array(["b", "a", "c"]), v=pa.array([1, 2, 3]))
+    assert gpu_ctx.limit(gpu_ctx.import_batches([names]), 2).to_batch().equals(names.slice(0, 2))
+    # Utf8 sort keys and tie-breakers: byte order, shorter first, embedded NUL, multi-byte characters, > 8 bytes
+    words = ["", "a", "a\0", "ab", "abcdefgh", "abcdefghi", "abcdefgh\0", "b", "émile", "日本", "zzzzzzzzzzzzzzzzzzzzzzzzzq", "zzzzzzzzzzzzzzzzzzzzzzzzzp"]
+    m = max(n, 1)
+    sb = rb(s=pa.array([words[i] for i in rng.integers(0, len(words), m)]), v=pa.array(rng.integers(0, 4, m)))
+    st = gpu_ctx.import_batches([sb])
+    for cols, desc in (([0], [False]), ([0], [True]), ([1], [False]), ([1, 0], [True, True])):
+        spec = [{"expr": plans.column(sb.schema.names[c], c), "options": {"descending": d}} for c, d in zip(cols, desc)]
+        assert gpu_ctx.sort(st, cols, desc).to_batch().equals(oracle.sort_batch(sb, spec)), (cols, desc)
 
 
 # ---- RepartitionExec: Hash -------------------------------------------------------------------------------------------

@@ -68,13 +68,17 @@ def test_unmarshal_nexmark_plans(query):
         assert "HashJoinExec: mode=Partitioned, join_type=Inner, on=[(price, maxprice)]" in s and "mode=Final, gby=[]" in s
 
 
-def test_q6_is_rejected_not_emulated():
-    """q6 needs SortExec + WindowAggExec, which only the oracle restates so far: the GPU plan layer must refuse the plan
-    (the Rust shim then keeps the CPU nodes) instead of falling back to anything."""
+def test_q6_plan_is_accepted():
+    """q6 = SortExec + WindowAggExec(ROW_NUMBER) + the operators of q4: the GPU plan layer builds all of it."""
+    s = fb.ExecutionContext(None, plans.q6()).plan_str()
+    assert s.count("SortExec: [") == 3 and s.count("WindowAggExec: wdw=[ROW_NUMBER()") == 2
+    assert "SortExec: [a_id@0 ASC, price@5 DESC]" in s and "aggr=[AVG(R.price)]" in s
+    # other window functions are refused, not emulated
+    bad = plans.row_number_window("r", [plans.column("a_id", 0)], [], plans.memory_exec(nexgen.auction_schema(), [0]))
+    bad["window_expr"][0]["fun"] = "Rank"
     with pytest.raises(fb.FlockGpuError) as info:
-        fb.ExecutionContext(None, plans.q6())
-    assert info.value.code == _ffi.ERR_UNSUPPORTED
-    assert "sort_exec" in info.value.message or "window_agg_exec" in info.value.message
+        fb.ExecutionContext(None, bad)
+    assert info.value.code == _ffi.ERR_UNSUPPORTED and "Rank" in info.value.message
 
 
 def test_shuffle_stage_and_marshalled_context():
@@ -86,10 +90,10 @@ def test_shuffle_stage_and_marshalled_context():
 
 
 def test_unsupported_nodes_fail_loudly():
-    sort = {"execution_plan": "sort_exec", "input": plans.q2(), "expr": []}
+    cross = {"execution_plan": "cross_join_exec", "left": plans.q2(), "right": plans.q2()}
     with pytest.raises(fb.FlockGpuError) as info:
-        fb.ExecutionContext(None, sort)
-    assert info.value.code == _ffi.ERR_UNSUPPORTED and "sort_exec" in info.value.message
+        fb.ExecutionContext(None, cross)
+    assert info.value.code == _ffi.ERR_UNSUPPORTED and "cross_join_exec" in info.value.message
     with pytest.raises(fb.FlockGpuError):
         fb.ExecutionContext(None, "{not json")
 
@@ -103,9 +107,9 @@ def test_reference_plan_fixtures_parse():
     s = ec.plan_str(0)
     assert "HashAggregateExec: mode=FinalPartitioned, gby=[c3 as c3], aggr=[MAX(c1), MIN(c2)]" in s
     assert "FilterExec: c2 < CAST(99 AS Float64)" in s
-    with pytest.raises(fb.FlockGpuError) as info:      # join.json carries global_limit_exec + sort_exec
-        fb.ExecutionContext(None, (REFERENCE_PLANS / "join.json").read_text())
-    assert info.value.code == _ffi.ERR_UNSUPPORTED
+    s = fb.ExecutionContext(None, (REFERENCE_PLANS / "join.json").read_text()).plan_str(0)      # global_limit_exec <- sort_exec <- merge_exec <- ...
+    assert s.startswith("GlobalLimitExec: limit=3\n  SortExec: [b ASC]\n    CoalescePartitionsExec")
+    assert "HashJoinExec: mode=Partitioned, join_type=Inner, on=[(a, c)]" in s
 
 
 # ---- expression lowering ---------------------------------------------------------------------------------

@@ -75,6 +75,18 @@ def toy_join_plan(n=8):
                                  plans.coalesce_batches_exec(j))
 
 
+def toy_join_sorted_plan(n=8):
+    """The whole of flock/src/tests/data/plan/join.json: ... ORDER BY a LIMIT 3 (global_limit_exec <- sort_exec <- merge_exec)."""
+    return plans.global_limit_exec(plans.sort_exec([(plans.column("a", 0), False, False)], plans.coalesce_partitions_exec(toy_join_plan(n))), 3)
+
+
+def test_golden_join_sort_limit():
+    # context.rs:508-592 in full: the expected table of :578-586, order included
+    b1, b2 = toy_join_inputs()
+    out = oracle.execute_plan(toy_join_sorted_plan(), [[[b1]], [[b2]]])
+    assert list(zip(out["a"].to_pylist(), out["b"].to_pylist(), out["d"].to_pylist())) == [("a", 1, 1), ("b", 10, 10), ("c", 10, 10)]
+
+
 def test_golden_feed_two_data_sources():
     # expected table of context.rs:578-586 (ORDER BY a LIMIT 3 applied here on the host)
     b1, b2 = toy_join_inputs()
