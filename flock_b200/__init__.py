@@ -342,6 +342,19 @@ class Context:
                 C.CFUNCTYPE(None, C.c_void_p)(c_schema.release)(C.addressof(c_schema))
         return Table(self, out.value)
 
+    def import_ndjson(self, schema: pa.Schema, text: bytes) -> Table:
+        """One flat JSON object per line -> table (event_bytes_to_batch, flock/src/transmute.rs:255-266)."""
+        buf = pa.py_buffer(text)
+        c_schema = _ffi.ArrowSchema()
+        schema._export_to_c(C.addressof(c_schema))
+        try:
+            out = C.c_void_p()
+            check(lib.flockgpu_table_import_ndjson(self.handle, C.byref(c_schema), C.c_void_p(buf.address), buf.size, C.byref(out)))
+        finally:
+            if c_schema.release:
+                C.CFUNCTYPE(None, C.c_void_p)(c_schema.release)(C.addressof(c_schema))
+        return Table(self, out.value)
+
     def concat(self, tables: Sequence[Table]) -> Table:
         hs = (C.c_void_p * len(tables))(*[t.handle for t in tables])
         out = C.c_void_p()

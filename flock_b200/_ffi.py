@@ -128,6 +128,7 @@ PROTOTYPES = {
                                            C.POINTER(C.c_int64), C.c_int32, _I32P, C.c_int32, _PP]),
     "flockgpu_table_export_ipc": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _PP, C.POINTER(C.c_int64), _PP, C.POINTER(C.c_int64)]),
     "flockgpu_ipc_free": (None, [_P]),
+    "flockgpu_table_import_ndjson": (C.c_int, [_P, C.POINTER(ArrowSchema), _P, C.c_int64, _PP]),
     "flockgpu_table_retain": (C.c_int, [_P]),
     "flockgpu_table_release": (C.c_int, [_P]),
     "flockgpu_table_num_rows": (C.c_int64, [_P]),

@@ -156,6 +156,15 @@ int flockgpu_table_import_ipc(flockgpu_ctx* ctx, const struct ArrowSchema* schem
 int flockgpu_table_export_ipc(flockgpu_ctx* ctx, const flockgpu_table* table, int64_t row_begin, int64_t row_count, uint8_t** out_header,
                               int64_t* out_header_len, uint8_t** out_body, int64_t* out_body_len);
 void flockgpu_ipc_free(uint8_t* block);
+/* ---- NDJSON events -> table: event_bytes_to_batch (flock/src/transmute.rs:255-266; call sites flock/src/datasource/
+ *      nexmark/nexmark.rs:181-203), the schema-driven arrow json::Reader over the generator's serde_json lines ---------
+ * One flat JSON object per line; fields are matched BY NAME in any order, unknown fields (nested values included) are
+ * skipped; Int32/UInt32/Int64/UInt64/Timestamp columns take JSON integers in range, Float64 numbers of at most 15
+ * significant digits and |exponent| <= 22 (exact with one IEEE operation), Utf8 JSON strings (unescaped, \uXXXX and
+ * surrogate pairs to UTF-8).  A malformed line, a missing field or a null fails the call with FLOCKGPU_ERR_EXECUTION
+ * naming the first bad line.  `data` is borrowed for the call.                                                          */
+int flockgpu_table_import_ndjson(flockgpu_ctx* ctx, const struct ArrowSchema* schema, const uint8_t* data, int64_t n_bytes,
+                                 flockgpu_table** out);
 /* Schema only (no data movement).                                                                  */
 int flockgpu_table_schema(flockgpu_ctx* ctx, const flockgpu_table* table,
                           struct ArrowSchema* out_schema);

@@ -40,6 +40,31 @@ extern "C" {
         out_array: *mut FFI_ArrowArray,
     ) -> c_int;
     pub fn flockgpu_table_release(table: *mut flockgpu_table) -> c_int;
+    /// Payload frames (FlightData.data_header / data_body, Encoding::None) straight to a device table and back.
+    pub fn flockgpu_table_import_ipc(
+        ctx: *mut flockgpu_ctx,
+        schema: *const FFI_ArrowSchema,
+        headers: *const *const u8,
+        header_lens: *const i64,
+        bodies: *const *const u8,
+        body_lens: *const i64,
+        n_frames: i32,
+        projection: *const i32,
+        n_projection: i32,
+        out: *mut *mut flockgpu_table,
+    ) -> c_int;
+    pub fn flockgpu_table_export_ipc(
+        ctx: *mut flockgpu_ctx,
+        table: *const flockgpu_table,
+        row_begin: i64,
+        row_count: i64,
+        out_header: *mut *mut u8,
+        out_header_len: *mut i64,
+        out_body: *mut *mut u8,
+        out_body_len: *mut i64,
+    ) -> c_int;
+    pub fn flockgpu_ipc_free(block: *mut u8);
+    pub fn flock_context_feed_tables(ec: *mut flock_context, tables: *const *mut flockgpu_table, n_sources: i32) -> c_int;
     pub fn flockgpu_table_num_rows(table: *const flockgpu_table) -> i64;
 
     // flock::runtime::context::ExecutionContext on the GPU

@@ -8,10 +8,15 @@
 //! `GpuPlanExec` wraps a whole plan (or sub-plan): its serde-JSON form -- the very string
 //! `flock::runtime::context::marshal` produces (flock/src/runtime/context.rs:366-381) -- is handed to
 //! `flock_context_unmarshal`; `execute()` exports the batches of its MemoryExec leaves through the Arrow C
-//! Data Interface, calls the GPU executor and wraps the result in a one-batch stream.  If the GPU library
-//! answers FLOCKGPU_ERR_UNSUPPORTED (sort, limit, window functions, nullable input ...) `try_new` returns
-//! `None` and the caller keeps the original CPU plan.
+//! Data Interface, calls the GPU executor and wraps the result in a one-batch stream.
+//!
+//! Two fallbacks keep the Lambda alive whatever the data looks like:
+//!   * plan time: `rewrite_for_gpu` wraps the LARGEST sub-plans a parse-only `flock_context_unmarshal(NULL, json)`
+//!     accepts; nodes the GPU path does not implement stay DataFusion nodes with GPU sub-plans below them;
+//!   * run time: data-dependent refusals (a column with NULLs, LargeUtf8, a dictionary ...) surface as
+//!     FLOCKGPU_ERR_UNSUPPORTED from feed / execute; `GpuPlanExec::execute` then runs the wrapped CPU plan instead.
 pub mod ffi;
+pub mod pinned;
 
 use async_trait::async_trait;
 use datafusion::arrow::array::{make_array_from_raw, ArrayRef, StructArray};
@@ -118,7 +123,7 @@ impl ExecutionPlan for GpuPlanExec {
         }
         let schema = self.schema();
         // 2. the blocking GPU call runs off the async executor
-        let batches = tokio::task::spawn_blocking(move || -> Result<Vec<RecordBatch>> {
+        let batches = tokio::task::spawn_blocking(move || -> Result<Option<Vec<RecordBatch>>> {
             let mut ec = std::ptr::null_mut();
             if unsafe { ffi::flock_context_unmarshal(ctx, json.as_ptr(), &mut ec) } != 0 {
                 return Err(last_error());
@@ -145,6 +150,11 @@ impl ExecutionPlan for GpuPlanExec {
                 }
                 rc
             };
+            if rc == ffi::FLOCKGPU_ERR_UNSUPPORTED {
+                // the DATA is outside what the GPU path implements (NULLs, LargeUtf8 ...): not an error, the CPU plan runs
+                unsafe { ffi::flock_context_free(ec) };
+                return Ok(None);
+            }
             if rc != 0 {
                 unsafe { ffi::flock_context_free(ec) };
                 return Err(last_error());
@@ -163,11 +173,17 @@ impl ExecutionPlan for GpuPlanExec {
             }
             let array: ArrayRef = unsafe { make_array_from_raw(&out_array, &out_schema) }.map_err(DataFusionError::ArrowError)?;
             let s = array.as_any().downcast_ref::<StructArray>().expect("struct array");
-            Ok(vec![RecordBatch::from(s)])
+            Ok(Some(vec![RecordBatch::from(s)]))
         })
         .await
         .map_err(|e| DataFusionError::Execution(e.to_string()))??;
-        Ok(Box::pin(MemoryStream::try_new(batches, schema, None)?))
+        match batches {
+            Some(batches) => Ok(Box::pin(MemoryStream::try_new(batches, schema, None)?)),
+            // run-time fallback: the wrapped DataFusion plan, leaves already fed by feed_data_sources
+            None => datafusion::physical_plan::collect(self.plan.clone()).await.and_then(|b| {
+                Ok(Box::pin(MemoryStream::try_new(b, schema, None)?) as SendableRecordBatchStream)
+            }),
+        }
     }
 
     fn fmt_as(&self, _t: DisplayFormatType, f: &mut std::fmt::Formatter) -> std::fmt::Result {
@@ -178,11 +194,33 @@ impl ExecutionPlan for GpuPlanExec {
     }
 }
 
-/// Plan rewrite: called where Flock builds the per-function plan (flock/src/runtime/plan.rs:221-228).
-/// Wraps the whole plan when the GPU path supports it, otherwise returns the plan untouched.
-pub fn rewrite_for_gpu(plan: Arc<dyn ExecutionPlan>) -> Arc<dyn ExecutionPlan> {
-    match GpuPlanExec::try_new(plan.clone()) {
-        Some(gpu) => Arc::new(gpu),
-        None => plan,
+/// The fork's `LambdaExecPlan` (implemented in-tree by `ShuffleWriterExec`,
+/// playground/src/distributed_plan/shuffle_writer.rs:157-161): a node whose input arrives as batches, not as a child.
+impl datafusion::physical_plan::LambdaExecPlan for GpuPlanExec {
+    fn feed_batches(&mut self, partitions: Vec<Vec<RecordBatch>>) {
+        // hand the batches to the first MemoryExec leaf of the wrapped plan, exactly what feed_data_sources does for
+        // a one-relation plan (flock/src/runtime/context.rs:293-303)
+        if let Some(leaf) = self.leaves().into_iter().next() {
+            unsafe {
+                let mem = Arc::get_mut_unchecked(&mut leaf.clone());
+                if let Some(m) = mem.as_mut_any().downcast_mut::<MemoryExec>() {
+                    m.set_partitions(partitions);
+                }
+            }
+        }
     }
+}
+
+/// Plan rewrite: called where Flock builds the per-function plan (flock/src/runtime/plan.rs:221-228).
+/// Wraps the largest sub-plans the GPU path supports; everything else stays as DataFusion planned it.
+pub fn rewrite_for_gpu(plan: Arc<dyn ExecutionPlan>) -> Arc<dyn ExecutionPlan> {
+    if plan.children().is_empty() {
+        return plan; // a bare MemoryExec gains nothing
+    }
+    if let Some(gpu) = GpuPlanExec::try_new(plan.clone()) {
+        return Arc::new(gpu);
+    }
+    // this node (or something below it) is not implemented on the GPU: keep the node, rewrite its inputs
+    let children: Vec<_> = plan.children().into_iter().map(rewrite_for_gpu).collect();
+    plan.with_new_children(children).unwrap_or(plan)
 }

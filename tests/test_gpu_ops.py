@@ -87,6 +87,63 @@ def test_ipc_frames_roundtrip(gpu_ctx, n):
         gpu_ctx.import_ipc(b.schema, [(b"\x00" * 4, b"")])
 
 
+def _ndjson(batch: pa.RecordBatch, shuffle_keys: bool = False, seed: int = 0) -> bytes:
+    """The lines serde_json writes for NEXMark events: one compact object per row (timestamps as integer milliseconds)."""
+    import json, random
+    cols = {}
+    for f in batch.schema:
+        c = batch.column(f.name)
+        cols[f.name] = c.cast(pa.int64()).to_pylist() if pa.types.is_timestamp(f.type) else c.to_pylist()
+    rnd = random.Random(seed)
+    lines = []
+    for i in range(batch.num_rows):
+        keys = list(cols)
+        if shuffle_keys:
+            rnd.shuffle(keys)
+        lines.append(json.dumps({k: cols[k][i] for k in keys}, separators=(",", ":"), ensure_ascii=bool(i & 1)))
+    return ("\n".join(lines) + ("\n" if lines else "")).encode("utf-8")
+
+
+@pytest.mark.parametrize("relation", ["bid", "person", "auction"])
+def test_ndjson_events_to_table(gpu_ctx, relation):
+    """event_bytes_to_batch (transmute.rs:255-266): NEXMark events as NDJSON parse into exactly the batch they came from."""
+    ev = nexgen.generate(60_000, seed=5, batch_rows=1 << 20)
+    b = ev[relation][0]
+    assert b.num_rows > 1000
+    got = gpu_ctx.import_ndjson(b.schema, _ndjson(b)).to_batch()
+    assert got.equals(b)
+    got = gpu_ctx.import_ndjson(b.schema, _ndjson(b, shuffle_keys=True, seed=3)).to_batch()      # fields are found by name
+    assert got.equals(b)
+    part = pa.schema([b.schema.field(i) for i in (b.num_columns - 1, 0)], metadata=b.schema.metadata)  # the rest is skipped
+    assert gpu_ctx.import_ndjson(part, _ndjson(b)).to_batch().equals(b.select([b.num_columns - 1, 0]))
+
+
+def test_ndjson_syntax_corners_match_arrow(gpu_ctx):
+    import pyarrow.json as pj, io
+    schema = pa.schema([("i", pa.int32()), ("l", pa.int64()), ("u", pa.uint64()), ("f", pa.float64()), ("s", pa.utf8()), ("t", pa.timestamp("ms"))])
+    arrow_schema = pa.schema([f if f.name != "t" else pa.field("t", pa.int64()) for f in schema])      # Arrow C++ wants timestamp STRINGS; epochs go in as integers
+    lines = [
+        r'{"i":-2147483648,"l":-9223372036854775808,"u":18446744073709551615,"f":-0.5,"s":"","t":0}',
+        r'{ "s" : "a\"b\\c\/d\n\té日😀" , "i":7, "extra":{"x":[1,{"y":"}"}],"z":null}, "l":1,"u":0,"f":1e3,"t":1436918400000}',
+        '{"i":2147483647,"l":9223372036854775807,"u":1,"f":123456789012345,"s":"é日 plain utf-8","t":-1,"tail":[true,false]}',
+        r'{"i":1,"l":1,"u":1,"f":1,"s":"\u00e9\u65e5\ud83d\ude00 \u0041","t":1}',
+        '{"f":2.5E-3,"s":"x","i":0,"l":0,"u":0,"t":5}\r',
+    ]
+    text = ("\n".join(lines) + "\n").encode("utf-8")
+    want = pj.read_json(io.BytesIO(text), parse_options=pj.ParseOptions(explicit_schema=arrow_schema, unexpected_field_behavior="ignore"))
+    got = gpu_ctx.import_ndjson(schema, text).to_arrow()
+    assert got.equals(want.select(got.schema.names).cast(got.schema))
+    assert got["s"].to_pylist()[1] == 'a"b\\c/d\n\té日😀'
+    assert gpu_ctx.import_ndjson(schema, b"").num_rows == 0
+    assert gpu_ctx.import_ndjson(schema, text[:-1]).num_rows == 5                      # no newline behind the last line
+    for bad, why in ((b'{"i":1}\n', "missing"), (b'{"i":1.5,"l":1,"u":1,"f":1,"s":"","t":1}\n', "type"), (b'{"i":3000000000,"l":1,"u":1,"f":1,"s":"","t":1}\n', "range"),
+                     (b'{"i":1,"l":1,"u":1,"f":1,"s":null,"t":1}\n', "null"), (b'{"i":1,"l":1,"u":1,"f":1,"s":"abc,"t":1}\n', "malformed"),
+                     (b'{"i":1,"l":1,"u":1,"f":0.1234567890123456789,"s":"","t":1}\n', "significant")):
+        with pytest.raises(fb.FlockGpuError) as info:
+            gpu_ctx.import_ndjson(schema, text + bad)
+        assert info.value.code == -5 and "line 6" in info.value.message and why in info.value.message, info.value.message
+
+
 def test_import_rejects_nulls_and_unknown_types(gpu_ctx):
     with pytest.raises(fb.FlockGpuError) as info:
         gpu_ctx.import_batches([rb(x=pa.array([1, None, 3], pa.int32()))])

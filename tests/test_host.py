@@ -81,6 +81,18 @@ def test_q6_plan_is_accepted():
     assert info.value.code == _ffi.ERR_UNSUPPORTED and "Rank" in info.value.message
 
 
+def test_header_is_c_and_the_c_program_links(tmp_path):
+    """include/flockgpu.h compiles as C11 (not only as C++), and tests/cabi/q2_cabi.c links against libflockgpu.so --
+    every symbol it uses is exported with C linkage.  (It runs on the GPU box: tests/test_gpu_cabi.py.)"""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", str(root / "include" / "flockgpu.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from test_gpu_cabi import build_cabi_program
+    build_cabi_program(tmp_path / "q2_cabi")
+    assert (tmp_path / "q2_cabi").exists()
+
+
 def test_shuffle_stage_and_marshalled_context():
     a, p = plans.q3_stage0()
     ec = fb.ExecutionContext(None, [a, p])
