@@ -92,6 +92,7 @@ TablePtr all_to_all(const CtxPtr& ctx, const std::vector<TablePtr>& parts) {
     for (size_t c = 0; c < ncol; ++c) {
       FG_CHECK(p->cols[c].dtype == proto.cols[c].dtype, FLOCKGPU_ERR_INVALID, "all_to_all: partitions differ in column types");
       FG_CHECK(!p->cols[c].all_null, FLOCKGPU_ERR_UNSUPPORTED, "all_to_all: NULL column");
+      require_no_nulls(p->cols[c], "all_to_all (NCCL fallback; the peer-window exchange carries validity)");
     }
   }
   // ---- sizes: M values per destination = rows + value bytes of every Utf8 column

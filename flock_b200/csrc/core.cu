@@ -677,17 +677,32 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
     col.format = cs->format;
     col.nullable = (cs->flags & ARROW_FLAG_NULLABLE) != 0;
     col.length = total;
-    // validity check (no nulls on the GPU path)
-    for (int b = 0; b < n_batches; ++b) {
+    // validity: Arrow's bitmaps (bit offset = array offset) become one byte per row, only when some batch has a NULL
+    bool has_null = false;
+    for (int b = 0; b < n_batches && !has_null; ++b) {
       const ArrowArray* a = batches[b]->children[p];
       int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
-      bool has_null = a->null_count > 0;
-      if (a->null_count < 0 && a->n_buffers > 0 && a->buffers[0])
-        has_null = range_has_null(static_cast<const uint8_t*>(a->buffers[0]), off, len);
-      FG_CHECK(!has_null, FLOCKGPU_ERR_UNSUPPORTED,
-               "table_import: column \"%s\" contains nulls; the GPU path handles non-null columns only", col.name.c_str());
+      has_null = a->null_count > 0;
+      if (a->null_count < 0 && a->n_buffers > 0 && a->buffers[0]) has_null = range_has_null(static_cast<const uint8_t*>(a->buffers[0]), off, len);
     }
-    if (dt != FLOCKGPU_UTF8 && zero_copy && total > 0 && (col.chunks = try_host_chunks(ctx, batches, n_batches, p, dtype_width(dt)))) {
+    if (has_null) {
+      uint8_t* bytes = static_cast<uint8_t*>(pin_get(size_t(total)));
+      staged.emplace_back(bytes, size_t(total));
+      int64_t row = 0;
+      for (int b = 0; b < n_batches; ++b) {
+        const ArrowArray* a = batches[b]->children[p];
+        const int64_t off = batches[b]->offset + a->offset, len = batches[b]->length;
+        const uint8_t* bits = a->n_buffers > 0 ? static_cast<const uint8_t*>(a->buffers[0]) : nullptr;
+        if (!bits || a->null_count == 0) memset(bytes + row, 1, size_t(len));
+        else
+          for (int64_t i = 0; i < len; ++i) bytes[row + i] = (bits[(off + i) >> 3] >> ((off + i) & 7)) & 1;
+        row += len;
+      }
+      col.validity = alloc(ctx, size_t(total));
+      ctx->h2d_bytes.fetch_add(total, std::memory_order_relaxed);
+      FG_CUDA(cudaMemcpyAsync(col.validity->ptr, bytes, size_t(total), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (dt != FLOCKGPU_UTF8 && zero_copy && !has_null && total > 0 && (col.chunks = try_host_chunks(ctx, batches, n_batches, p, dtype_width(dt)))) {
       // stays in page-locked host memory; kernels read it over PCIe or Table::dense() copies it later
       col.chunks->registration = registration;
     } else if (dt != FLOCKGPU_UTF8) {
@@ -959,6 +974,13 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
   }
 
   std::vector<BufferPtr> keep;  // device temporaries alive until the final sync
+  struct PackJob {
+    const uint8_t* bytes;
+    uint8_t* bits;
+    int64_t n;
+    ArrowArray* array;
+  };
+  std::vector<PackJob> pack_jobs;
   for (size_t i = 0; i < t.cols.size(); ++i) {
     const Column& c = t.cols[i];
     auto priv = std::make_unique<ArrayPrivate>();
@@ -973,6 +995,17 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
       memset(validity, 0, nb);
       priv->blocks.emplace_back(validity, nb);
       a.null_count = row_count;
+    } else if (c.validity && row_count > 0) {
+      // bytes to the host now, packed into Arrow's bitmap after the final sync (pack_jobs)
+      uint8_t* bytes = static_cast<uint8_t*>(pin_get(size_t(row_count)));
+      priv->blocks.emplace_back(bytes, size_t(row_count));
+      size_t nb = size_t((row_count + 7) / 8);
+      validity = pin_get(nb);
+      memset(validity, 0, nb);
+      priv->blocks.emplace_back(validity, nb);
+      ctx->d2h_bytes.fetch_add(row_count, std::memory_order_relaxed);
+      FG_CUDA(cudaMemcpyAsync(bytes, c.valid() + row_begin, size_t(row_count), cudaMemcpyDeviceToHost, ctx->stream));
+      pack_jobs.push_back({bytes, static_cast<uint8_t*>(validity), row_count, &a});
     }
     if (c.dtype != FLOCKGPU_UTF8) {
       int w = c.width();
@@ -1029,6 +1062,14 @@ void export_table(const CtxPtr& ctx, const Table& t, int64_t row_begin, int64_t 
     a.private_data = priv.release();
   }
   FG_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (const PackJob& j : pack_jobs) {
+    int64_t nulls = 0;
+    for (int64_t r = 0; r < j.n; ++r) {
+      if (j.bytes[r]) j.bits[r >> 3] |= uint8_t(1u << (r & 7));
+      else ++nulls;
+    }
+    j.array->null_count = nulls;
+  }
 
   for (auto& c : top->children) top->child_ptrs.push_back(&c);
   top->buffers = {nullptr};
@@ -1094,6 +1135,20 @@ TablePtr concat_tables(const CtxPtr& ctx, const std::vector<TablePtr>& tables) {
     c.format = first.cols[i].format;
     c.nullable = first.cols[i].nullable;
     c.length = total;
+    bool any_validity = false;
+    for (const TablePtr& t : tables) any_validity |= t->cols[i].validity != nullptr;
+    if (any_validity) {
+      c.validity = alloc(ctx, size_t(total));
+      int64_t row = 0;
+      for (const TablePtr& t : tables) {
+        const Column& s = t->cols[i];
+        if (s.length) {
+          if (s.validity) FG_CUDA(cudaMemcpyAsync(c.validity->as<uint8_t>() + row, s.valid(), size_t(s.length), cudaMemcpyDeviceToDevice, ctx->stream));
+          else FG_CUDA(cudaMemsetAsync(c.validity->as<uint8_t>() + row, 1, size_t(s.length), ctx->stream));
+        }
+        row += s.length;
+      }
+    }
     if (c.dtype != FLOCKGPU_UTF8) {
       int w = c.width();
       c.data = alloc(ctx, size_t(total) * w);

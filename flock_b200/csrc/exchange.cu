@@ -371,7 +371,7 @@ TablePtr hash_exchange(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vec
   if (!pw.enabled || n_utf8 > size_t(PT_MAX_UTF8)) {
     result = exchange_fallback(ctx, in_ptr, dest < 0 ? routing : keys, dest);
   } else {
-    PartPass ps = partition_count_scan(ctx, in, routing, W, dest);
+    PartPass ps = partition_count_scan(ctx, in, routing, W, dest, -1, 0, /*ship_nullable=*/true);
     const int U = int(ps.utf8_cols.size());
     const unsigned long long seq = ++pw.seq;
     const size_t region_off = (pw.cursor + 255) & ~size_t(255);
@@ -382,9 +382,10 @@ TablePtr hash_exchange(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vec
     pa.seq = seq;
     pa.me = me;
     pa.world = W;
-    pa.n_fixed = int(ps.fixed_cols.size());
+    pa.n_fixed = int(ps.fixed_cols.size() + ps.valid_cols.size());  // validity bytes travel as 1-byte columns behind the values
     pa.n_utf8 = U;
     for (size_t f = 0; f < ps.fixed_cols.size(); ++f) pa.fwidth[f] = in.cols[ps.fixed_cols[f]].width();
+    for (size_t k = 0; k < ps.valid_cols.size(); ++k) pa.fwidth[ps.fixed_cols.size() + k] = 1;
     pa.my_counts = ps.totals->as<unsigned long long>();
     pa.region_off = region_off;
     pa.region_cap = pw.window_bytes - region_off;
@@ -459,6 +460,8 @@ TablePtr hash_exchange(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vec
       c.data = std::make_shared<Buffer>(ctx, base + lay.bytes[u], size_t(bytes[u]), owner);
       c.values_bytes = int64_t(bytes[u]);
     }
+    for (size_t k = 0; k < ps.valid_cols.size(); ++k)
+      t->cols[ps.valid_cols[k]].validity = std::make_shared<Buffer>(ctx, base + lay.val[ps.fixed_cols.size() + k], size_t(rows), owner);
     result = t;
   }
   if (dest < 0) {

@@ -440,21 +440,64 @@ CompiledPredicate compile_predicate(const Expr& e, const std::vector<ColInfo>& c
         ChainBuilder::convert(term.rhs, r.dtype, FLOCKGPU_FLOAT64);
       }
     }
+    // which input columns make this comparison NULL
+    {
+      std::function<void(int)> cols_of = [&](int i) {
+        const Node& x = t.nodes[i];
+        if (x.op == FLOCKGPU_OP_COLUMN) {
+          if (x.col >= 0 && x.col < 32 && cols[x.col].has_nulls) term.null_cols |= 1u << x.col;
+          return;
+        }
+        if (x.l >= 0) cols_of(x.l);
+        if (x.r >= 0) cols_of(x.r);
+      };
+      term.null_cols = 0;
+      cols_of(n.l);
+      cols_of(n.r);
+    }
     term_of_node[idx] = p.n_terms++;
   };
   collect(t.root);
   p.has_div_by_col = b.div_by_col ? 1 : 0;
+  bool any_null = false;
+  for (int i = 0; i < p.n_terms; ++i) any_null |= p.terms[i].null_cols != 0;
 
-  // truth table over the term bits
-  std::function<bool(int, unsigned)> truth = [&](int idx, unsigned bits) -> bool {
-    const Node& n = t.nodes[idx];
-    if (n.op == FLOCKGPU_OP_AND) return truth(n.l, bits) && truth(n.r, bits);
-    if (n.op == FLOCKGPU_OP_OR) return truth(n.l, bits) || truth(n.r, bits);
-    if (n.op == FLOCKGPU_OP_NOT) return !truth(n.l, bits);
-    return (bits >> term_of_node[idx]) & 1u;
-  };
-  for (unsigned bits = 0; bits < (1u << p.n_terms); ++bits)
-    if (truth(t.root, bits)) p.lut[bits >> 5] |= 1u << (bits & 31);
+  if (!any_null) {
+    // truth table over the term bits
+    std::function<bool(int, unsigned)> truth = [&](int idx, unsigned bits) -> bool {
+      const Node& n = t.nodes[idx];
+      if (n.op == FLOCKGPU_OP_AND) return truth(n.l, bits) && truth(n.r, bits);
+      if (n.op == FLOCKGPU_OP_OR) return truth(n.l, bits) || truth(n.r, bits);
+      if (n.op == FLOCKGPU_OP_NOT) return !truth(n.l, bits);
+      return (bits >> term_of_node[idx]) & 1u;
+    };
+    for (unsigned bits = 0; bits < (1u << p.n_terms); ++bits)
+      if (truth(t.root, bits)) p.lut[bits >> 5] |= 1u << (bits & 31);
+  } else {
+    // SQL three-valued logic (strong Kleene): 1 = TRUE, 0 = FALSE, 2 = NULL; the row is kept iff the root is TRUE
+    FG_CHECK(p.n_terms <= 4, FLOCKGPU_ERR_UNSUPPORTED, "filter: more than 4 comparison terms over columns with NULLs");
+    p.kleene = 1;
+    std::function<int(int, unsigned)> k3 = [&](int idx, unsigned bits) -> int {
+      const Node& n = t.nodes[idx];
+      if (n.op == FLOCKGPU_OP_AND) {
+        const int a = k3(n.l, bits), c = k3(n.r, bits);
+        return (a == 0 || c == 0) ? 0 : (a == 2 || c == 2) ? 2 : 1;
+      }
+      if (n.op == FLOCKGPU_OP_OR) {
+        const int a = k3(n.l, bits), c = k3(n.r, bits);
+        return (a == 1 || c == 1) ? 1 : (a == 2 || c == 2) ? 2 : 0;
+      }
+      if (n.op == FLOCKGPU_OP_NOT) {
+        const int a = k3(n.l, bits);
+        return a == 2 ? 2 : 1 - a;
+      }
+      const int tix = term_of_node[idx];
+      return ((bits >> (4 + tix)) & 1u) ? 2 : int((bits >> tix) & 1u);
+    };
+    for (unsigned bits = 0; bits < 256; ++bits)
+      if (k3(t.root, bits) == 1) p.lut[bits >> 5] |= 1u << (bits & 31);
+    return out;  // no vectorised shape reads validity
+  }
 
   // fast shapes: one term over one Int32 column against literals
   // (a single term has a 2-entry truth table: 0b10 = the term itself, 0b01 = NOT term; constants keep the interpreter)

@@ -14,6 +14,7 @@ struct ColInfo {
   int dtype;
   std::string name;
   std::string format;
+  bool has_nulls = false;  // the column carries validity bytes: comparisons over it are three-valued
 };
 
 // Shapes with a hand-specialised kernel (everything else runs the generic term interpreter).

@@ -49,6 +49,7 @@ struct ColRef {
   int32_t dtype;
   int32_t chunk_shift;     // chunked: rows per chunk = 1 << chunk_shift
   const void* const* chunks;  // chunked: base pointer of every chunk (device-accessible host memory)
+  const uint8_t* validity;  // one byte per row, 1 = valid; NULL when the column has no NULLs
 };
 
 struct ChainStep {
@@ -74,11 +75,18 @@ struct Term {
   // DOM_UTF8: column lhs_col compared with a pooled literal (rhs_col < 0) or another column
   int32_t lhs_col, rhs_col;
   int32_t lit_off, lit_len;
+  uint32_t null_cols;  // bit c: a NULL in input column c makes this comparison NULL (Predicate::kleene)
+  int32_t pad;
 };
 
 struct Predicate {
   int32_t n_terms;
   int32_t has_div_by_col;  // a division/modulo by a column: the kernel reports divide-by-zero
+  // kleene = 1 (some referenced column has NULLs; at most 4 terms): the table is indexed by the terms' VALUE bits
+  // (0 where the term is NULL) | their NULL bits << 4, and holds "the predicate is TRUE under SQL's three-valued
+  // logic" -- FilterExec keeps a row only then (a NULL predicate drops the row)
+  int32_t kleene;
+  int32_t pad;
   uint32_t lut[8];         // bit (b) of the table = truth value when the term bits spell b
   Term terms[MAX_TERMS];
   char strpool[STRPOOL_BYTES];
@@ -268,6 +276,19 @@ FG_HD unsigned eval_predicate(const Predicate& p, const ColRef* cols, const int6
       eval_chain<R>(term.rhs, cols, rows, b, err);
 #pragma unroll
       for (int j = 0; j < R; ++j) bits[j] |= unsigned(compare_vals(term.domain, term.cmp, a[j], b[j])) << t;
+    }
+  }
+  if (p.kleene) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (rows[j] < 0) continue;
+      unsigned nulls = 0;
+      for (int t = 0; t < p.n_terms; ++t) {
+        const unsigned m = p.terms[t].null_cols;
+        for (int c = 0; m >> c; ++c)
+          if (((m >> c) & 1u) && cols[c].validity && !cols[c].validity[rows[j]]) nulls |= 1u << t;
+      }
+      bits[j] = (bits[j] & ~nulls & 0xfu) | (nulls << 4);
     }
   }
   unsigned sel = 0;

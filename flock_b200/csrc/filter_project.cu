@@ -333,12 +333,22 @@ __global__ void __launch_bounds__(PJ_THREADS) project_i32_to_f64_mul_kernel(cons
   }
 }
 
+__global__ void __launch_bounds__(256) and_validity_kernel(const uint8_t* a, const uint8_t* b, const uint8_t* c, const uint8_t* d, uint8_t* out, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    uint8_t v = a[i];
+    if (b) v &= b[i];
+    if (c) v &= c[i];
+    if (d) v &= d[i];
+    out[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static std::vector<ColInfo> col_infos(const Table& t) {
   std::vector<ColInfo> v;
-  for (const Column& c : t.cols) v.push_back({c.dtype, c.name, c.format});
+  for (const Column& c : t.cols) v.push_back({c.dtype, c.name, c.format, c.validity != nullptr});
   return v;
 }
 
@@ -351,6 +361,7 @@ static void fill_colrefs(const Table& t, ColRef* refs) {
     refs[i].dtype = t.cols[i].dtype;
     refs[i].chunk_shift = t.cols[i].chunks ? t.cols[i].chunks->shift : 0;
     refs[i].chunks = t.cols[i].chunks ? static_cast<const void* const*>(t.cols[i].chunks->table->ptr) : nullptr;
+    refs[i].validity = t.cols[i].valid();
   }
 }
 
@@ -475,7 +486,29 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
         c.offsets = s.offsets;
         c.values_bytes = s.values_bytes;
         c.all_null = s.all_null;
+        c.validity = s.validity;
       } else {
+        // a computed value is NULL where any column it reads is NULL
+        std::vector<const uint8_t*> srcs;
+        auto note = [&](int col) {
+          if (col >= 0 && in.cols[col].validity) srcs.push_back(in.cols[col].valid());
+        };
+        note(v.chain.start_col);
+        for (int st = 0; st < v.chain.n_steps; ++st)
+          if (v.chain.steps[st].src == 1) note(v.chain.steps[st].col);
+        if (!srcs.empty() && in.num_rows > 0) {
+          FG_CHECK(srcs.size() <= 4, FLOCKGPU_ERR_UNSUPPORTED, "projection: an expression over more than 4 columns with NULLs");
+          c.validity = alloc(ctx, size_t(in.num_rows));
+          c.nullable = true;
+          int grid = int(std::min<int64_t>((in.num_rows + 255) / 256, int64_t(ctx->sm_count) * 8));
+          {
+            LaunchTimer lt(ctx, "and_validity_kernel");
+            and_validity_kernel<<<grid, 256, 0, ctx->stream>>>(srcs[0], srcs.size() > 1 ? srcs[1] : nullptr, srcs.size() > 2 ? srcs[2] : nullptr,
+                                                           srcs.size() > 3 ? srcs[3] : nullptr, c.validity->as<uint8_t>(), in.num_rows);
+          }
+          FG_CUDA(cudaGetLastError());
+          count_launch(ctx);
+        }
         c.data = alloc(ctx, size_t(in.num_rows) * dtype_width(v.dtype));
         if (in.num_rows > 0) {
           if (v.fast == FAST_VAL_I32_TO_F64_MUL) {
@@ -566,7 +599,17 @@ TablePtr filter_project(const CtxPtr& ctx, const TablePtr& in_ptr, const Expr* p
     c.dtype = v.dtype;
     c.format = v.format;
     if (v.passthrough) c.nullable = in.cols[v.src_col].nullable;
-    if (v.dtype == FLOCKGPU_UTF8) {
+    if (!v.passthrough) {
+      // a computed output inside the fused filter kernel cannot carry NULLs (no validity output there)
+      auto refuse = [&](int col) {
+        if (col >= 0) require_no_nulls(in.cols[col], "filter: computed projection");
+      };
+      refuse(v.chain.start_col);
+      for (int st = 0; st < v.chain.n_steps; ++st)
+        if (v.chain.steps[st].src == 1) refuse(v.chain.steps[st].col);
+    }
+    if (v.dtype == FLOCKGPU_UTF8 || (v.passthrough && in.cols[v.src_col].validity)) {
+      // Utf8 outputs and outputs with validity bytes are taken through the selection vector behind the kernel
       need_sel = true;
       utf8_outs.push_back(int(i));
     } else {

@@ -260,12 +260,35 @@ __global__ void __launch_bounds__(GA_THREADS) gather_utf8_copy_multi_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------
-static int stream_grid(const CtxPtr& ctx, int64_t items, int per_block, int blocks_per_sm = 8) {
+static int stream_grid(const CtxPtr& ctx, int64_t items, int per_block, int blocks_per_sm) {
   int64_t g = (items + per_block - 1) / per_block;
   return int(std::max<int64_t>(1, std::min<int64_t>(g, int64_t(ctx->sm_count) * blocks_per_sm)));
 }
 
+static int stream_grid(const CtxPtr& ctx, int64_t items, int per_block, int blocks_per_sm = 8);
+// the validity bytes of a taken column: one more 1-byte gather
+static void gather_validity(const CtxPtr& ctx, const Column& in, Column& out, const uint32_t* d_idx, int64_t n) {
+  if (!in.validity) return;
+  out.validity = alloc(ctx, size_t(n));
+  if (n > 0) {
+    {
+      LaunchTimer lt(ctx, "gather_fixed_kernel<uint8_t>");
+      gather_fixed_kernel<uint8_t><<<stream_grid(ctx, n, GA_THREADS * 4), GA_THREADS, 0, ctx->stream>>>(in.valid(), d_idx, out.validity->as<uint8_t>(), n);
+    }
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
+  }
+}
+
+static Column gather_column_values(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx, int64_t n);
+
 Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx, int64_t n) {
+  Column out = gather_column_values(ctx, in, d_idx, n);
+  gather_validity(ctx, in, out, d_idx, n);
+  return out;
+}
+
+static Column gather_column_values(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx, int64_t n) {
   FG_CHECK(!in.all_null, FLOCKGPU_ERR_UNSUPPORTED, "gather: NULL column \"%s\"", in.name.c_str());
   Column out;
   out.dtype = in.dtype;
@@ -337,7 +360,15 @@ Column gather_column(const CtxPtr& ctx, const Column& in, const uint32_t* d_idx,
 
 // take() of several columns through one index vector: one launch for all fixed-width columns; the Utf8 columns' length
 // scans are launched back to back and their byte totals read with ONE host round trip (each used to cost its own).
+static std::vector<Column> gather_columns_values(const CtxPtr& ctx, const std::vector<const Column*>& in, const uint32_t* d_idx, int64_t n);
+
 std::vector<Column> gather_columns(const CtxPtr& ctx, const std::vector<const Column*>& in, const uint32_t* d_idx, int64_t n) {
+  std::vector<Column> out = gather_columns_values(ctx, in, d_idx, n);
+  for (size_t k = 0; k < in.size(); ++k) gather_validity(ctx, *in[k], out[k], d_idx, n);
+  return out;
+}
+
+static std::vector<Column> gather_columns_values(const CtxPtr& ctx, const std::vector<const Column*>& in, const uint32_t* d_idx, int64_t n) {
   std::vector<Column> out(in.size());
   std::vector<size_t> fixed, utf8;
   for (size_t k = 0; k < in.size(); ++k) {

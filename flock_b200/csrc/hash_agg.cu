@@ -52,6 +52,8 @@ struct EmitDesc {
   int32_t a0, a1;     // accumulator indices (AVG: a0 = count, a1 = sum)
   int32_t out_dtype;
   void* dst;
+  uint8_t* valid_dst;  // not NULL: the output is NULL for groups whose accumulator `valid_acc` (a count of non-NULL inputs) is 0
+  int32_t valid_acc, pad;
 };
 
 __host__ __device__ __forceinline__ unsigned long long acc_identity(int op) {
@@ -111,10 +113,15 @@ __device__ __forceinline__ Val acc_combine(int op, Val a, Val b) {
   return r;
 }
 
+// false: the argument is NULL in this row, and NULL arguments are skipped by every aggregate
+__device__ __forceinline__ bool acc_input_valid(const AccDesc& d, const ColRef* cols, int64_t row) {
+  return d.col < 0 || !cols[d.col].validity || cols[d.col].validity[row] != 0;
+}
+
 __device__ __forceinline__ Val load_acc_input(const AccDesc& d, const ColRef* cols, int64_t row) {
   Val v;
   v.u = 0;
-  if (d.col >= 0) {
+  if (d.col >= 0 && d.op != ACC_COUNT) {
     v = load_val(cols[d.col], row);
     if (d.cvt == CVT_I2F) v.d = __ll2double_rn(v.i);
     else if (d.cvt == CVT_U2F) v.d = __ull2double_rn(v.u);
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(AL_THREADS) agg_local_kernel(const __grid_cons
           Val v = load_acc_input(a.acc[c], a.cols, row[u]);
           Val id;
           id.u = acc_identity(a.acc[c].op);
-          a.part_acc[int64_t(c) * a.part_capacity + pos] = acc_combine(a.acc[c].op, id, v).u;
+          a.part_acc[int64_t(c) * a.part_capacity + pos] = acc_input_valid(a.acc[c], a.cols, row[u]) ? acc_combine(a.acc[c].op, id, v).u : id.u;
         }
         continue;
       }
@@ -248,7 +255,8 @@ __global__ void __launch_bounds__(AL_THREADS) agg_local_kernel(const __grid_cons
         }
         slot = (slot + 1) & (AL_SLOTS - 1);
       }
-      for (int c = 0; c < a.n_acc; ++c) acc_apply(&s_acc[c * AL_SLOTS + slot], a.acc[c].op, load_acc_input(a.acc[c], a.cols, row[u]));
+      for (int c = 0; c < a.n_acc; ++c)
+        if (acc_input_valid(a.acc[c], a.cols, row[u])) acc_apply(&s_acc[c * AL_SLOTS + slot], a.acc[c].op, load_acc_input(a.acc[c], a.cols, row[u]));
     }
     // the decision must be CTA-uniform: s_occ is bumped again by fast warps in the next step, so every thread
     // reads it between two barriers
@@ -1148,6 +1156,7 @@ __global__ void __launch_bounds__(256) agg_insert_kernel(const __grid_constant__
         v.u = a.part32 ? (unsigned long long)reinterpret_cast<const uint32_t*>(a.part_acc)[i] : a.part_acc[int64_t(c) * a.part_capacity + i];
         op = acc_merge_op(a.acc[c].op);
       } else {
+        if (!acc_input_valid(a.acc[c], a.cols, i)) continue;
         v = load_acc_input(a.acc[c], a.cols, i);
         op = a.acc[c].op;
       }
@@ -1197,7 +1206,8 @@ __global__ void __launch_bounds__(256) agg_insert_rows_kernel(const __grid_const
       if (rows_equal(a.keys, a.cols, int64_t(cur), a.keys, a.cols, row)) break;
       slot = (slot + 1) & (a.cap - 1);
     }
-    for (int c = 0; c < a.n_acc; ++c) acc_apply(&a.tacc[c * a.cap + slot], a.acc[c].op, load_acc_input(a.acc[c], a.cols, row));
+    for (int c = 0; c < a.n_acc; ++c)
+      if (acc_input_valid(a.acc[c], a.cols, row)) acc_apply(&a.tacc[c * a.cap + slot], a.acc[c].op, load_acc_input(a.acc[c], a.cols, row));
   }
   claimed = warp_sum(claimed);
   if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(a.n_groups, (unsigned long long)claimed);
@@ -1235,6 +1245,7 @@ __device__ __forceinline__ void emit_values(const EmitDesc* emit, int n_emit, co
       v.d = __ddiv_rn(s.d, __ull2double_rn(v.u));
     }
     store_val(d.dst, d.out_dtype, pos, v);
+    if (d.valid_dst) d.valid_dst[pos] = acc[d.valid_acc * stride + slot] != 0ull;
   }
 }
 
@@ -1342,6 +1353,12 @@ __global__ void __launch_bounds__(CP_THREADS) agg_emit_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e].d = __ddiv_rn(sv[e].d, __ull2double_rn(v[e].u));
           }
+          if (d.valid_dst) {
+            const unsigned long long* pv = a.acc + d.valid_acc * a.acc_stride + slot0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if ((nib >> e) & 1u) d.valid_dst[pos[e]] = pv[e] != 0ull;
+          }
           // one uniform width branch per column instead of a type switch per element
           if (d.out_dtype == FLOCKGPU_INT32 || d.out_dtype == FLOCKGPU_UINT32) {
 #pragma unroll
@@ -1386,13 +1403,14 @@ __global__ void __launch_bounds__(256) agg_global_kernel(const __grid_constant__
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = load_acc_input(a.acc[c], a.cols, row + u * stride);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) local[c] = acc_combine(a.acc[c].op, local[c], v[u]);
+      for (int u = 0; u < 4; ++u)
+        if (acc_input_valid(a.acc[c], a.cols, row + u * stride)) local[c] = acc_combine(a.acc[c].op, local[c], v[u]);
     }
   }
   for (; row < a.n_rows; row += stride) {
 #pragma unroll
     for (int c = 0; c < MAX_ACC; ++c)
-      if (c < a.n_acc) local[c] = acc_combine(a.acc[c].op, local[c], load_acc_input(a.acc[c], a.cols, row));
+      if (c < a.n_acc && acc_input_valid(a.acc[c], a.cols, row)) local[c] = acc_combine(a.acc[c].op, local[c], load_acc_input(a.acc[c], a.cols, row));
   }
 #pragma unroll
   for (int c = 0; c < MAX_ACC; ++c) {
@@ -1431,6 +1449,7 @@ struct OutPlan {
   int dtype;
   std::string format;
   int kind, a0, a1;
+  int valid_acc = -1;  // accumulator counting the non-NULL inputs of this aggregate: 0 at the end = the result is NULL
 };
 
 const char* func_name(int f) {
@@ -1464,6 +1483,9 @@ void plan_aggregates(const Table& in, int mode, const std::vector<AggSpec>& aggs
     FG_CHECK(!in.cols[col].all_null, FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: NULL input column");
     return in.cols[col].dtype;
   };
+  // an argument (or state) column with NULLs: the aggregate skips them, and a group that saw nothing else is NULL
+  auto nulls_in = [&](int col) { return col >= 0 && col < int(in.cols.size()) && in.cols[col].validity != nullptr; };
+  auto valid_counter = [&](int col) { return nulls_in(col) ? add_acc(ACC_COUNT, col, CVT_NONE) : -1; };
   for (const AggSpec& s : aggs) {
     const std::string base = s.name.empty() ? std::string(func_name(s.func)) : s.name;
     switch (s.func) {
@@ -1474,7 +1496,7 @@ void plan_aggregates(const Table& in, int mode, const std::vector<AggSpec>& aggs
           a = add_acc(ACC_ADD_I, s.col, CVT_NONE);
         } else {
           if (s.col >= 0) col_dtype(s.col, "COUNT");
-          a = add_acc(ACC_COUNT, -1, CVT_NONE);
+          a = add_acc(ACC_COUNT, nulls_in(s.col) ? s.col : -1, CVT_NONE);  // COUNT(col) counts the non-NULL values
         }
         outs->push_back({partial_out ? base + "[count]" : base, FLOCKGPU_UINT64, "L", EMIT_RAW, a, 0});
         break;
@@ -1487,7 +1509,7 @@ void plan_aggregates(const Table& in, int mode, const std::vector<AggSpec>& aggs
         else if (dt == FLOCKGPU_INT32 || dt == FLOCKGPU_INT64) { out_dt = FLOCKGPU_INT64; op = ACC_ADD_I; }
         else fail(FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: SUM over %s", dtype_name(dt));
         int a = add_acc(op, s.col, CVT_NONE);
-        outs->push_back({partial_out ? base + "[sum]" : base, out_dt, default_format(out_dt), EMIT_RAW, a, 0});
+        outs->push_back({partial_out ? base + "[sum]" : base, out_dt, default_format(out_dt), EMIT_RAW, a, 0, valid_counter(s.col)});
         break;
       }
       case FLOCKGPU_AGG_MIN:
@@ -1495,7 +1517,7 @@ void plan_aggregates(const Table& in, int mode, const std::vector<AggSpec>& aggs
         bool is_min = s.func == FLOCKGPU_AGG_MIN;
         int dt = col_dtype(s.col, is_min ? "MIN" : "MAX");
         int a = add_acc(minmax_op(dt, is_min, is_min ? "MIN" : "MAX"), s.col, CVT_NONE);
-        outs->push_back({partial_out ? base + (is_min ? "[min]" : "[max]") : base, dt, in.cols[s.col].format, EMIT_RAW, a, 0});
+        outs->push_back({partial_out ? base + (is_min ? "[min]" : "[max]") : base, dt, in.cols[s.col].format, EMIT_RAW, a, 0, valid_counter(s.col)});
         break;
       }
       case FLOCKGPU_AGG_AVG: {
@@ -1508,14 +1530,16 @@ void plan_aggregates(const Table& in, int mode, const std::vector<AggSpec>& aggs
         } else {
           int dt = col_dtype(s.col, "AVG");
           FG_CHECK(dt != FLOCKGPU_UTF8 && dt != FLOCKGPU_TIMESTAMP, FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: AVG over %s", dtype_name(dt));
-          a_cnt = add_acc(ACC_COUNT, -1, CVT_NONE);
+          a_cnt = add_acc(ACC_COUNT, nulls_in(s.col) ? s.col : -1, CVT_NONE);  // AVG divides by the number of non-NULL values
           a_sum = add_acc(ACC_ADD_F, s.col, dt == FLOCKGPU_FLOAT64 ? CVT_NONE : (is_unsigned_dt(dt) ? CVT_U2F : CVT_I2F));
         }
         if (partial_out) {
           outs->push_back({base + "[count]", FLOCKGPU_UINT64, "L", EMIT_RAW, a_cnt, 0});
           outs->push_back({base + "[sum]", FLOCKGPU_FLOAT64, "g", EMIT_RAW, a_sum, 0});
         } else {
-          outs->push_back({base, FLOCKGPU_FLOAT64, "g", EMIT_AVG, a_cnt, a_sum});
+          // no non-NULL value at all: AVG is NULL (0 / 0 otherwise); with states, the merged count tells
+          const bool maybe_empty = from_states ? (nulls_in(s.col) || nulls_in(s.col + 1)) : nulls_in(s.col);
+          outs->push_back({base, FLOCKGPU_FLOAT64, "g", EMIT_AVG, a_cnt, a_sum, maybe_empty ? a_cnt : -1});
         }
         break;
       }
@@ -1533,6 +1557,7 @@ void fill_cols(const Table& t, ColRef* refs) {
     refs[i].dtype = t.cols[i].dtype;
     refs[i].chunk_shift = 0;
     refs[i].chunks = nullptr;
+    refs[i].validity = t.cols[i].valid();
   }
 }
 
@@ -1854,7 +1879,7 @@ TablePtr DeferredAgg::select_equal(const Table& self, int key_col, const TablePt
   if (one_key < 0 || one_key >= int(one_row.cols.size()) || one_row.cols[one_key].dtype != FLOCKGPU_UINT64) return nullptr;
   if (!fused)
     for (const Column& c : one_row.cols)
-      if (c.all_null || c.dtype == FLOCKGPU_UTF8 || (c.width() != 4 && c.width() != 8) || c.chunks) return nullptr;
+      if (c.all_null || c.validity || c.dtype == FLOCKGPU_UTF8 || (c.width() != 4 && c.width() != 8) || c.chunks) return nullptr;
   const CtxPtr& ctx = core->ctx;
   const int64_t max_rows = int64_t(std::min<unsigned long long>(core->cap, (unsigned long long)core->input->num_rows));
   std::vector<Column> mine(kinds.size()), theirs(one_row.cols.size());
@@ -1994,7 +2019,14 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
   auto fill_emit = [&](EmitDesc* emit, int* n_emit, std::vector<Column>& cols) {
     FG_CHECK(outs.size() <= size_t(2 * MAX_ACC), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: too many output columns");
     *n_emit = int(outs.size());
-    for (size_t i = 0; i < outs.size(); ++i) emit[i] = EmitDesc{outs[i].kind, outs[i].a0, outs[i].a1, outs[i].dtype, cols[i].data->ptr};
+    for (size_t i = 0; i < outs.size(); ++i) {
+      emit[i] = EmitDesc{outs[i].kind, outs[i].a0, outs[i].a1, outs[i].dtype, cols[i].data->ptr, nullptr, 0, 0};
+      if (outs[i].valid_acc >= 0) {
+        cols[i].validity = alloc(ctx, size_t(std::max<int64_t>(cols[i].length, 1)));
+        emit[i].valid_dst = cols[i].validity->as<uint8_t>();
+        emit[i].valid_acc = outs[i].valid_acc;
+      }
+    }
   };
   unsigned long long ident[MAX_ACC] = {};
   for (int c = 0; c < n_acc; ++c) ident[c] = acc_identity(accs[c].op);
@@ -2077,6 +2109,7 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
   for (int g : group_cols) {
     int w = in.cols[g].width();
     if (w == 0) packed = false;
+    if (in.cols[g].validity) packed = false;  // a NULL key is a group of its own: the row-representative table compares validity too
     key_bytes += w;
   }
   if (group_cols.size() == 2 && key_bytes != 8) packed = false;
@@ -2122,7 +2155,7 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
       FG_CUDA(cudaMemsetAsync(la.key_minmax, 0xff, 8, ctx->stream));   // min = ~0
       FG_CUDA(cudaMemsetAsync(la.key_minmax + 1, 0, 8, ctx->stream));  // max = 0
       FG_CUDA(cudaFuncSetAttribute(agg_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(local_smem)));
-      const bool count32 = kp.n == 1 && kp.width[0] == 4 && (n_acc == 0 || (n_acc == 1 && accs[0].op == ACC_COUNT));
+      const bool count32 = kp.n == 1 && kp.width[0] == 4 && (n_acc == 0 || (n_acc == 1 && accs[0].op == ACC_COUNT && accs[0].col < 0));
       part32 = count32;
       bool done_l1 = false;
       static const bool no_hist = getenv("FLOCKGPU_NO_HIST") != nullptr;

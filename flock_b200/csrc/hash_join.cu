@@ -36,6 +36,8 @@ struct JoinSide {
   int32_t packed;
   int32_t pad;
   const void* key0;  // the key column when the join has ONE fixed-width key (kernels instantiated with KW = 4 / 8)
+  int32_t n_null_cols, pad2;  // key columns that carry validity bytes: a row with a NULL key matches nothing (NULL != NULL)
+  const uint8_t* key_valid[MAX_KEY_COLS];
   KeyPack pack;
   RowKeys rk;
   ColRef cols[MAX_IN_COLS];
@@ -52,6 +54,12 @@ struct JoinTable {
 // KW = 4 / 8: one fixed-width key column, read straight from JoinSide::key0 (every NEXMark join); KW = 0: the general
 // form (two packed columns, or row comparison for Utf8 / wide keys).  The general form cost ~140 lane-instructions per
 // probe row on q5 (dynamic indexing of the column table in parameter space, width and mode branches).
+__device__ __forceinline__ bool key_is_null(const JoinSide& s, int64_t row) {
+  for (int i = 0; i < s.n_null_cols; ++i)
+    if (!s.key_valid[i][row]) return true;
+  return false;
+}
+
 template <int KW>
 __device__ __forceinline__ unsigned long long side_hash(const JoinSide& s, int64_t row, unsigned long long* key) {
   if (KW == 4) {
@@ -81,6 +89,7 @@ __device__ __forceinline__ bool build_row_matches(const JoinSide& build, unsigne
 template <int KW>
 __global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__ JoinSide build, const JoinTable t) {
   for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < build.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
+    if (key_is_null(build, row)) continue;  // never enters the table: nothing can match it
     unsigned long long key;
     unsigned long long slot = side_hash<KW>(build, row, &key) & (t.cap - 1);
     while (true) {
@@ -100,6 +109,7 @@ __global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__
 // Slot of the key of probe row `row`, or ~0 when no build row has it.
 template <int KW>
 __device__ __forceinline__ unsigned long long find_slot(const JoinSide& build, const JoinSide& probe, const JoinTable& t, int64_t row) {
+  if (key_is_null(probe, row)) return ~0ull;
   unsigned long long key;
   unsigned long long slot = side_hash<KW>(probe, row, &key) & (t.cap - 1);
   while (true) {
@@ -262,9 +272,14 @@ static void fill_side(const Table& t, const std::vector<int>& keys, bool packed,
     s->cols[i].dtype = t.cols[i].dtype;
     s->cols[i].chunk_shift = 0;
     s->cols[i].chunks = nullptr;
+    s->cols[i].validity = nullptr;  // key equality between the sides is value equality: rows with NULL keys are skipped up front
   }
   s->rk.n = int(keys.size());
-  for (size_t i = 0; i < keys.size(); ++i) s->rk.col[i] = keys[i];
+  s->n_null_cols = 0;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    s->rk.col[i] = keys[i];
+    if (t.cols[keys[i]].validity) s->key_valid[s->n_null_cols++] = t.cols[keys[i]].valid();
+  }
   if (packed) {
     s->pack.n = int(keys.size());
     for (size_t i = 0; i < keys.size(); ++i) {
@@ -335,7 +350,7 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
       else if (kw == 8) f(std::integral_constant<int, 8>{});
       else f(std::integral_constant<int, 0>{});
     };
-    if (kw && B.num_rows == 1) {
+    if (kw && B.num_rows == 1 && bs.n_null_cols == 0 && ps.n_null_cols == 0) {
       // one build row: equality filter over the probe side (see join_one_kernel)
       probe_idx = alloc(ctx, size_t(P.num_rows) * 4);
       JoinOneArgs oa{};

@@ -226,8 +226,9 @@ void export_ipc_frame(const CtxPtr& ctx, const Table& t, int64_t row_begin, int6
   for (size_t i = 0; i < t.cols.size(); ++i) {
     const Column& c = t.cols[i];
     const bool all_null = c.all_null && row_count > 0;
-    nodes.emplace_back(row_count, all_null ? row_count : 0);
-    const int64_t vbytes = all_null ? (row_count + 7) / 8 : 0;  // validity: empty when there is no NULL
+    const bool some_null = !all_null && c.validity && row_count > 0;
+    nodes.emplace_back(row_count, all_null ? row_count : 0);  // (null_count of `some_null` columns is filled in once the bytes are here)
+    const int64_t vbytes = (all_null || some_null) ? (row_count + 7) / 8 : 0;  // validity: empty when there is no NULL
     buffers.emplace_back(body_len, vbytes);
     body_len += pad8(vbytes);
     if (c.dtype == FLOCKGPU_UTF8) {
@@ -243,10 +244,16 @@ void export_ipc_frame(const CtxPtr& ctx, const Table& t, int64_t row_begin, int6
   uint8_t* body = static_cast<uint8_t*>(calloc(size_t(body_len ? body_len : 8), 1));
   FG_CHECK(body, FLOCKGPU_ERR_INVALID, "table_export_ipc: out of host memory (%lld bytes)", (long long)body_len);
   std::unique_ptr<uint8_t, void (*)(void*)> guard(body, free);
+  std::vector<std::vector<uint8_t>> vbytes_host(t.cols.size());
   size_t b = 0;
   for (size_t i = 0; i < t.cols.size(); ++i) {
     const Column& c = t.cols[i];
-    ++b;  // validity stays zero (all NULL) or absent
+    if (c.validity && !c.all_null && row_count > 0) {  // byte per row now, packed into the body's bitmap after the sync
+      vbytes_host[i].resize(size_t(row_count));
+      ctx->d2h_bytes.fetch_add(row_count, std::memory_order_relaxed);
+      FG_CUDA(cudaMemcpyAsync(vbytes_host[i].data(), c.valid() + row_begin, size_t(row_count), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ++b;  // validity: zero (all NULL), absent, or packed below
     if (c.dtype == FLOCKGPU_UTF8) {
       int32_t* off = reinterpret_cast<int32_t*>(body + buffers[b].first);
       if (row_count > 0) {
@@ -267,6 +274,19 @@ void export_ipc_frame(const CtxPtr& ctx, const Table& t, int64_t row_begin, int6
     }
   }
   FG_CUDA(cudaStreamSynchronize(ctx->stream));
+  b = 0;
+  for (size_t i = 0; i < t.cols.size(); ++i) {
+    if (!vbytes_host[i].empty()) {
+      uint8_t* bits = body + buffers[b].first;
+      int64_t nulls = 0;
+      for (int64_t r = 0; r < row_count; ++r) {
+        if (vbytes_host[i][size_t(r)]) bits[r >> 3] |= uint8_t(1u << (r & 7));
+        else ++nulls;
+      }
+      nodes[i].second = nulls;
+    }
+    b += t.cols[i].dtype == FLOCKGPU_UTF8 ? 3 : 2;
+  }
   // Utf8 offsets of a row range start at offsets[row_begin]: rebase them to 0 (Arrow IPC does not require it, arrow-rs
   // and pyarrow both write them rebased, and readers of older versions expect it)
   b = 0;

@@ -301,8 +301,13 @@ struct Column {
   std::shared_ptr<HostChunks> chunks;  // host-resident form (zero-copy feed); see HostChunks
   BufferPtr offsets;   // Utf8 only: int32[length + 1]; offsets[0] may be > 0
   int64_t values_bytes = 0;  // Utf8: number of value bytes addressed by offsets
-  // Only the one-row result of a global aggregate over empty input carries a NULL.
+  // The one-row result of a global aggregate over empty input is NULL as a whole.
   bool all_null = false;
+  // Row-wise NULLs: one byte per row, 1 = valid; no buffer = no NULL in the column.  (Arrow's bit-packed bitmap is
+  // expanded at import and packed again at export: every kernel that moves rows moves these bytes like one more
+  // 1-byte column.)
+  BufferPtr validity;
+  const uint8_t* valid() const { return validity ? validity->as<uint8_t>() : nullptr; }
 
   const void* values() const { return data ? data->ptr : nullptr; }
   const int32_t* offs() const { return offsets ? offsets->as<int32_t>() : nullptr; }
@@ -385,6 +390,12 @@ inline const Table& deref(const flockgpu_table* t) {
 inline CtxPtr core_of(flockgpu_ctx* c) {
   if (!c || !c->core) fail(FLOCKGPU_ERR_INVALID, "null context handle");
   return c->core;
+}
+
+// Operators that do not implement NULL semantics for some input refuse it (FLOCKGPU_ERR_UNSUPPORTED): the Rust shim then
+// keeps the CPU plan for that data.  Never a silent wrong answer.
+inline void require_no_nulls(const Column& c, const char* what) {
+  if (c.validity) fail(FLOCKGPU_ERR_UNSUPPORTED, "%s: column \"%s\" contains NULLs, which this operator does not handle on the GPU path", what, c.name.c_str());
 }
 
 // ---- operators (implemented in the .cu files; called by the ABI layer and by the plan layer) ----

@@ -302,7 +302,14 @@ __global__ void __launch_bounds__(PT_THREADS, 3) partition_scatter_kernel(const 
         row[k] = on[k] ? tile0 + s_row[sx] : tile0;
       }
       for (int f = 0; f < a.n_fixed; ++f) {
-        if (a.fwidth[f] == 4) {
+        if (a.fwidth[f] == 1) {
+          uint8_t v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = on[k] ? static_cast<const uint8_t*>(a.fsrc[f])[row[k]] : uint8_t(0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (on[k]) static_cast<uint8_t*>(dest[pp[k]].val[f])[pos[k]] = v[k];
+        } else if (a.fwidth[f] == 4) {
           uint32_t v[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = on[k] ? static_cast<const uint32_t*>(a.fsrc[f])[row[k]] : 0u;
@@ -441,11 +448,12 @@ static void fill_colrefs(const Table& in, ColRef* refs) {
     refs[i].dtype = in.cols[i].dtype;
     refs[i].chunk_shift = 0;
     refs[i].chunks = nullptr;
+    refs[i].validity = in.cols[i].valid();
   }
 }
 
 PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vector<int>& routing_cols, int n_parts, int dest_rank, int digit_col,
-                              int digit_shift) {
+                              int digit_shift, bool ship_nullable) {
   FG_CHECK(n_parts >= 1 && n_parts <= PT_MAX_PARTS, FLOCKGPU_ERR_INVALID, "hash_partition: n_parts must be in [1, %d], got %d", PT_MAX_PARTS, n_parts);
   FG_CHECK(in.cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d columns", MAX_IN_COLS);
   FG_CHECK(dest_rank >= 0 || digit_col >= 0 || (!routing_cols.empty() && routing_cols.size() <= size_t(MAX_KEY_COLS)), FLOCKGPU_ERR_INVALID,
@@ -462,6 +470,20 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
     }
   }
   FG_CHECK(ps.utf8_cols.size() <= size_t(PT_MAX_UTF8), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d Utf8 columns", PT_MAX_UTF8);
+  for (size_t i = 0; i < in.cols.size(); ++i) {
+    const Column& c = in.cols[i];
+    if (!c.validity && !(ship_nullable && c.nullable)) continue;
+    ps.valid_cols.push_back(int(i));
+    if (c.validity) {
+      ps.valid_src.push_back(c.validity);
+    } else {
+      BufferPtr ones = alloc(ctx, size_t(std::max<int64_t>(in.num_rows, 1)));
+      FG_CUDA(cudaMemsetAsync(ones->ptr, 1, size_t(std::max<int64_t>(in.num_rows, 1)), ctx->stream));
+      ps.valid_src.push_back(ones);
+    }
+  }
+  FG_CHECK(ps.fixed_cols.size() + ps.valid_cols.size() <= size_t(MAX_IN_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_partition: more than %d value + validity columns",
+           MAX_IN_COLS);
   const int U = int(ps.utf8_cols.size());
   // geometry: as many CTAs as stay resident, each owning a contiguous, tile-aligned range of rows
   const ScatterSmem L(n_parts, U, n_parts <= PT_DEST_SMEM_PARTS);
@@ -497,6 +519,8 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
       widths.push_back(in.cols[k].width());
     }
     ca.packed = keys_packable(widths.data(), int(widths.size())) ? 1 : 0;
+    for (int k : routing_cols)
+      if (in.cols[k].validity) ca.packed = 0;  // a NULL key routes by hash_row's fixed NULL contribution, not by the bytes underneath
     ca.rk.n = int(routing_cols.size());
     for (size_t i = 0; i < routing_cols.size(); ++i) ca.rk.col[i] = routing_cols[i];
     if (ca.packed) {
@@ -540,6 +564,11 @@ void partition_scatter(const CtxPtr& ctx, const Table& in, const PartPass& ps, c
     sa.fsrc[f] = in.cols[ps.fixed_cols[f]].values();
     sa.fwidth[f] = in.cols[ps.fixed_cols[f]].width();
   }
+  for (size_t k = 0; k < ps.valid_cols.size(); ++k) {  // validity bytes: one more column of width 1 each
+    sa.fsrc[ps.fixed_cols.size() + k] = ps.valid_src[k]->ptr;
+    sa.fwidth[ps.fixed_cols.size() + k] = 1;
+  }
+  sa.n_fixed = int(ps.fixed_cols.size() + ps.valid_cols.size());
   for (int u = 0; u < U; ++u) {
     sa.uoff[u] = in.cols[ps.utf8_cols[u]].offs();
     sa.udata[u] = static_cast<const uint8_t*>(in.cols[ps.utf8_cols[u]].values());
@@ -622,10 +651,15 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
   const int U = int(ps.utf8_cols.size());
   // ---- output buffers: every column once, partitions one behind the other (5 spare rows per partition at most)
   const size_t cap_rows = size_t(n) + 5 * size_t(n_parts) + 4;
-  std::vector<BufferPtr> fbuf(ps.fixed_cols.size()), obuf(U), bbuf(U);
+  std::vector<BufferPtr> fbuf(ps.fixed_cols.size()), obuf(U), bbuf(U), vbuf(ps.valid_cols.size());
   PlaceLocalArgs pa{};
   pa.n_parts = n_parts;
-  pa.n_fixed = int(ps.fixed_cols.size());
+  pa.n_fixed = int(ps.fixed_cols.size() + ps.valid_cols.size());
+  for (size_t k = 0; k < ps.valid_cols.size(); ++k) {
+    vbuf[k] = alloc(ctx, cap_rows);
+    pa.fdst[ps.fixed_cols.size() + k] = vbuf[k]->ptr;
+    pa.fwidth[ps.fixed_cols.size() + k] = 1;
+  }
   pa.n_utf8 = U;
   pa.totals = ps.totals->as<unsigned long long>();
   for (size_t f = 0; f < ps.fixed_cols.size(); ++f) {
@@ -688,6 +722,7 @@ std::vector<TablePtr> hash_partition(const CtxPtr& ctx, const TablePtr& in_ptr, 
       c.values_bytes = int64_t(bytes);
       byte_base[u] += bytes;
     }
+    for (size_t k = 0; k < ps.valid_cols.size(); ++k) t->cols[ps.valid_cols[k]].validity = view_of(vbuf[k], size_t(base), size_t(rows));
     out.push_back(std::move(t));
     base = next_partition_base(base, tot[p]);
   }

@@ -41,6 +41,11 @@ struct PartPass {
   int grid = 1;
   int n_parts = 1;
   std::vector<int> fixed_cols, utf8_cols;  // input columns by kind, in input order
+  // columns whose validity bytes travel with the rows: they are moved like 1-byte fixed-width columns, behind the
+  // value columns (destination slot fixed_cols.size() + k).  valid_src[k] = the bytes (all ones, synthesised, when an
+  // exchange ships the validity of a nullable column that happens to hold no NULL on this rank)
+  std::vector<int> valid_cols;
+  std::vector<BufferPtr> valid_src;
   BufferPtr pid;       // u8  [n_rows]
   BufferPtr hist;      // u32 [(1 + n_utf8)][grid][n_parts]: rows, then bytes per Utf8 column
   BufferPtr cta_pos;   // u32 same shape: exclusive scan over the CTAs (offset inside my contribution to a destination)
@@ -49,8 +54,10 @@ struct PartPass {
 };
 
 // Steps 1 and 2.  `dest_rank` >= 0 routes every row to that destination (CoalescePartitionsExec) instead of hashing.
+// `ship_nullable`: move validity for every column the SCHEMA calls nullable (an exchange must lay out the same buffers
+// on every rank, whatever the data), not only for the columns that hold a NULL here.
 PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vector<int>& routing_cols, int n_parts, int dest_rank = -1, int digit_col = -1,
-                              int digit_shift = 0);
+                              int digit_shift = 0, bool ship_nullable = false);
 // One stable radix pass over a relation of fixed-width columns (partition.cu; used by SortExec, sort.cu).
 TablePtr radix_pass(const CtxPtr& ctx, const TablePtr& in, int digit_col, int shift);
 // Step 4 (after the caller's place step has filled pass.dest).  `abort_flag` (may be NULL): a non-zero word makes the

@@ -44,6 +44,10 @@ __device__ __forceinline__ unsigned long long hash_row(const RowKeys& k, const C
   unsigned long long h = 0x9e3779b97f4a7c15ull;
   for (int i = 0; i < k.n; ++i) {
     const ColRef& c = cols[k.col[i]];
+    if (c.validity && !c.validity[row]) {  // NULL: one fixed contribution, whatever bytes lie underneath
+      h = fmix64(h ^ 0x6e756c6c6e756c6cull);
+      continue;
+    }
     if (c.dtype == FLOCKGPU_UTF8) {
       int32_t lo = c.offsets[row], hi = c.offsets[row + 1];
       h = hash_bytes(static_cast<const uint8_t*>(c.data) + lo, hi - lo, h);
@@ -59,6 +63,10 @@ __device__ __forceinline__ bool rows_equal(const RowKeys& k1, const ColRef* cols
   for (int i = 0; i < k1.n; ++i) {
     const ColRef& c1 = cols1[k1.col[i]];
     const ColRef& c2 = cols2[k2.col[i]];
+    // grouping semantics: NULL equals NULL and nothing else (joins never get here with a NULL key: they skip such rows)
+    const bool v1 = !c1.validity || c1.validity[r1], v2 = !c2.validity || c2.validity[r2];
+    if (v1 != v2) return false;
+    if (!v1) continue;
     if (c1.dtype == FLOCKGPU_UTF8) {
       int32_t lo1 = c1.offsets[r1], n1 = c1.offsets[r1 + 1] - lo1;
       int32_t lo2 = c2.offsets[r2], n2 = c2.offsets[r2 + 1] - lo2;

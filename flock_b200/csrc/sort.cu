@@ -124,6 +124,7 @@ TablePtr sort_table(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vector
     const Column& c = in.cols[k.col];
     FG_CHECK(!c.all_null, FLOCKGPU_ERR_UNSUPPORTED, "sort: NULL column \"%s\"", c.name.c_str());
     FG_CHECK(!c.chunks, FLOCKGPU_ERR_INVALID, "sort: host-resident column");
+    require_no_nulls(c, "sort");
   }
   if (n <= 1) return in_ptr;
 
@@ -251,6 +252,7 @@ TablePtr row_number(const CtxPtr& ctx, const TablePtr& in_ptr, const std::vector
     FG_CHECK(c >= 0 && c < int(in.cols.size()), FLOCKGPU_ERR_INVALID, "ROW_NUMBER: partition column %d out of range", c);
     FG_CHECK(in.cols[c].dtype != FLOCKGPU_UTF8 && !in.cols[c].all_null, FLOCKGPU_ERR_UNSUPPORTED, "ROW_NUMBER: PARTITION BY column \"%s\" must be fixed width",
              in.cols[c].name.c_str());
+    require_no_nulls(in.cols[c], "ROW_NUMBER: PARTITION BY");
     a.key[k].data = in.cols[c].values();
     a.key[k].dtype = in.cols[c].dtype;
   }

@@ -71,6 +71,36 @@ def _worker(rank, world, port, out_dir, mode):
     assert dict(zip(agg["src"].to_pylist(), agg["n"].to_pylist())) == {s: n for s, n in per_src.items() if n}
     del held
 
+    # ---- NULLs cross the exchange with their rows: rank 0 holds NULLs (key and payload), rank 1 the same nullable
+    # schema without a single NULL (every rank lays out the same buffers); rows with a NULL key meet on one rank
+    nn = 30_000 + 7 * rank
+    holes = rank == 0 or mode == "nccl"              # (the fallback refuses per rank: give every rank a NULL so none waits for a peer that raised)
+    mask_k = (np.arange(nn) % 9 == 0) if holes else np.zeros(nn, bool)
+    mask_s = (np.arange(nn) % 4 == 1) if holes else np.zeros(nn, bool)
+    nb = pa.RecordBatch.from_arrays([pa.array(rng.integers(0, 5000, nn).astype(np.int32), mask=mask_k),
+                                     pa.array([None if m else words[k] for k, m in zip(rng.integers(0, 5, nn), mask_s)], pa.utf8()),
+                                     pa.array(rng.integers(0, 1 << 40, nn), mask=mask_s[::-1].copy()), pa.array(np.full(nn, rank, np.int32))],
+                                    names=["k", "s", "v", "src"])
+    dist.barrier()
+    if mode == "peer":
+        moved = ctx.hash_exchange(ctx.import_batches([nb]), [0]).to_arrow()
+        everything = [None] * world
+        dist.all_gather_object(everything, (_ipc(pa.Table.from_batches([nb])), _ipc(moved)))
+        if rank == 0:
+            sent = pa.concat_tables([pa.ipc.open_stream(e[0]).read_all() for e in everything])
+            landed = [pa.ipc.open_stream(e[1]).read_all() for e in everything]
+            import oracle
+            oracle.assert_tables_equal(pa.concat_tables(landed), sent)
+            homes = {}
+            for r, part in enumerate(landed):
+                for k in set(part["k"].to_pylist()):
+                    assert homes.setdefault(k, r) == r
+            assert None in homes
+    else:
+        with pytest.raises(fb.FlockGpuError) as info:       # the NCCL fallback moves values only and says so
+            ctx.hash_exchange(ctx.import_batches([nb]), [0])
+        assert info.value.code == -2
+
     # ---- a global aggregate with one EMPTY shard: rank 1 scans no bids; MAX must come out of rank 0's state alone, and
     # with every shard empty the merged MAX is NULL while COUNT is 0
     bids = nexgen.split_batches(nexgen.bids(50_000, seed=9), 8192)

@@ -144,13 +144,106 @@ def test_ndjson_syntax_corners_match_arrow(gpu_ctx):
         assert info.value.code == -5 and "line 6" in info.value.message and why in info.value.message, info.value.message
 
 
-def test_import_rejects_nulls_and_unknown_types(gpu_ctx):
-    with pytest.raises(fb.FlockGpuError) as info:
-        gpu_ctx.import_batches([rb(x=pa.array([1, None, 3], pa.int32()))])
-    assert info.value.code == -2 and "nulls" in info.value.message
+def test_import_rejects_unknown_types(gpu_ctx):
     with pytest.raises(fb.FlockGpuError) as info:
         gpu_ctx.import_batches([rb(x=pa.array([1.0, 2.0], pa.float32()))])
     assert info.value.code == -2
+
+
+# ---- NULLs: validity travels with the rows, and every operator follows SQL / DataFusion semantics (App. C.3 / C.7 / C.8) --------
+def nullable_batch(n, seed, null_every=(5, 7, 3, 11)):
+    rng = np.random.default_rng(seed)
+    words = ["", "a", "or", "id", "portland", "x" * 21, "日本"]
+    def holes(arr, k, offset=0):
+        mask = (np.arange(n) + offset) % k == 0
+        return pa.array(arr, mask=mask) if isinstance(arr, np.ndarray) else pa.array([None if m else v for v, m in zip(arr, mask)])
+    return pa.RecordBatch.from_arrays([
+        holes(rng.integers(0, 12, n).astype(np.int32), null_every[0]),                      # g: group / join key with NULLs
+        holes(rng.integers(-1000, 1000, n), null_every[1], 2),                             # v: Int64 with NULLs
+        holes(rng.normal(0, 50, n).round(0), null_every[2], 1),                            # f: Float64 (integral values: exact sums)
+        holes([words[k] for k in rng.integers(0, len(words), n)], null_every[3], 4),       # s: Utf8 with NULLs
+        pa.array(np.arange(n, dtype=np.int32)),                                            # id: no NULLs
+    ], names=["g", "v", "f", "s", "id"])
+
+
+@pytest.mark.parametrize("n", [1, 9, 5000, 150_001])
+def test_nulls_roundtrip_filter_take(gpu_ctx, n):
+    b = nullable_batch(n, n)
+    pieces = [b] if n < 20 else [b.slice(0, 3), b.slice(3, n // 2), b.slice(3 + n // 2)]          # bit offsets that are not byte aligned
+    t = gpu_ctx.import_batches(pieces)
+    assert t.to_batch().equals(b) and t.to_batch(min(1, n - 1), max(n - 3, 0)).equals(b.slice(min(1, n - 1), max(n - 3, 0)))
+    # frames with validity in, frames with validity out
+    h, body = t.to_ipc()
+    assert _read_frame(b.schema, h, body).equals(b)
+    assert gpu_ctx.import_ipc(b.schema, [_ipc_frame(p) for p in pieces]).to_batch().equals(b)
+    # FilterExec: a NULL predicate drops the row (three-valued AND / OR / NOT), NULL payload survives as NULL
+    cases = [
+        (col(1) > 0, pc.greater(b["v"], 0)),
+        ((col(1) > 0) | (col(0) == 3), pc.or_kleene(pc.greater(b["v"], 0), pc.equal(b["g"], 3))),
+        ((col(1) > 0) & ~(col(2) < 10.0), pc.and_kleene(pc.greater(b["v"], 0), pc.invert(pc.less(b["f"], 10.0)))),
+        ((col(3) == "or") | (col(4) % 2 == 0), pc.or_kleene(pc.equal(b["s"], "or"), pc.equal(pc.bit_wise_and(b["id"], 1), 0))),
+        (~(col(0) == 3), pc.invert(pc.equal(b["g"], 3))),
+    ]
+    for pred, mask in cases:
+        got = gpu_ctx.filter_project(t, pred).to_batch()
+        want = b.filter(mask.fill_null(False))
+        assert got.equals(want)
+    # take through a selection, then concat: validity is one more column
+    kept = gpu_ctx.filter_project(t, col(4) % 3 == 0)
+    both = gpu_ctx.concat([kept, t]).to_batch()
+    assert both.equals(pa.Table.from_batches([b.filter(pc.equal(pc.subtract(b["id"], pc.multiply(pc.divide(b["id"], 3), 3)), 0)), b]).combine_chunks().to_batches()[0])
+    # ProjectionExec: a computed value is NULL where an input is NULL
+    proj = gpu_ctx.filter_project(t, None, [col(1) * 2 + col(4), col(2) * 0.5, col(4)], ["a", "h", "id"]).to_batch()
+    assert proj["a"].equals(pc.add(pc.multiply(b["v"], 2), pc.cast(b["id"], pa.int64()))) and proj["h"].equals(pc.multiply(b["f"], 0.5))
+
+
+@pytest.mark.parametrize("n", [7, 4000, 300_017])
+def test_nulls_aggregate_join_partition(gpu_ctx, n):
+    b = nullable_batch(n, n + 1)
+    t = gpu_ctx.import_batches([b])
+    tbl = pa.Table.from_batches([b])
+    # HashAggregateExec: NULL arguments are skipped, a group of only NULLs yields NULL, the NULL key is a group
+    aggs = [("count", -1, "n"), ("count", 1, "nv"), ("sum", 1, "sv"), ("min", 2, "mf"), ("max", 1, "xv"), ("avg", 2, "af")]
+    want = tbl.group_by("g", use_threads=False).aggregate([([], "count_all"), ("v", "count"), ("v", "sum"), ("f", "min"), ("v", "max"), ("f", "mean")])
+    for mode_path in ("single", "two_phase"):
+        if mode_path == "single":
+            got = gpu_ctx.hash_aggregate(t, [0], aggs, "single").to_arrow()
+        else:
+            part = gpu_ctx.hash_aggregate(t, [0], aggs, "partial")
+            state = 1
+            fin = []
+            for f, _, name in aggs:
+                fin.append((f, state, name))
+                state += 2 if f == "avg" else 1
+            got = gpu_ctx.hash_aggregate(part, [0], fin, "final_partitioned").to_arrow()
+        key = lambda tb, names: sorted(zip(*[tb[c].to_pylist() for c in names]), key=lambda r: (r[0] is None, r[0] if r[0] is not None else 0))
+        assert key(got, ["g", "n", "nv", "sv", "mf", "xv", "af"]) == key(want, ["g", "count_all", "v_count", "v_sum", "f_min", "v_max", "f_mean"])
+    # global aggregate over a column that is NULL throughout
+    allnull = gpu_ctx.import_batches([rb(x=pa.array([None] * 5, pa.int64()), y=pa.array([1, 2, 3, 4, 5]))])
+    one = gpu_ctx.hash_aggregate(allnull, [], [("max", 0, "m"), ("count", 0, "c"), ("count", -1, "n"), ("sum", 1, "s")], "single").to_arrow()
+    assert [one.column(i).to_pylist() for i in range(4)] == [[None], [0], [5], [15]]
+    # HashJoinExec: NULL keys match nothing (not even each other); NULL payload columns come through
+    r = nullable_batch(min(max(n // 3, 4), 40), n + 2, null_every=(4, 5, 6, 7))
+    r = r.rename_columns(["g2", "v2", "f2", "s2", "id2"])
+    got = gpu_ctx.hash_join(t, gpu_ctx.import_batches([r]), [0], [0]).to_arrow()
+    want = tbl.join(pa.Table.from_batches([r]), keys="g", right_keys="g2", join_type="inner", coalesce_keys=False, use_threads=False)
+    oracle.assert_tables_equal(got, want.select(got.schema.names), check_names=False)
+    assert got["g"].null_count == 0 and got["v"].null_count > 0
+    got2 = gpu_ctx.hash_join(t, gpu_ctx.import_batches([r]), [3, 0], [3, 0]).to_arrow()                      # Utf8 + Int32 key, both with NULLs
+    want2 = tbl.join(pa.Table.from_batches([r]), keys=["s", "g"], right_keys=["s2", "g2"], join_type="inner", coalesce_keys=False, use_threads=False)
+    oracle.assert_tables_equal(got2, want2.select(got2.schema.names), check_names=False)
+    # RepartitionExec(Hash): rows with a NULL key land together; validity moves with the rows; nothing is lost
+    parts = [p.to_batch() for p in gpu_ctx.hash_partition(t, [0], 5)]
+    assert sum(p.num_rows for p in parts) == n
+    home = {}
+    for q, p in enumerate(parts):
+        for g in set(p["g"].to_pylist()):
+            assert home.setdefault(g, q) == q
+    oracle.assert_tables_equal(pa.Table.from_batches(parts), tbl)
+    # operators without NULL semantics refuse loudly
+    with pytest.raises(fb.FlockGpuError) as info:
+        gpu_ctx.sort(t, [1])
+    assert info.value.code == -2 and "NULL" in info.value.message
 
 
 # ---- FilterExec / ProjectionExec ----------------------------------------------------------------------------
