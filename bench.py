@@ -641,6 +641,11 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
     names = sorted(PHASES) + ["other"]
     mx = dist.max(*[ph.get(n, 0.0) for n in names])
     phases = {n: round(v, 5) for n, v in zip(names, mx) if v}
+    # how long each rank sat in the exchange waiting for its peers' counts (exchange_place_kernel = push my counts,
+    # wait for everybody's, lay the windows out) and its own step time: rank skew shows up here, not in the kernels
+    per_rank = dist.gather_objects({"rank": dist.rank, "step_ms": round(ctx.timer_ms(0) / args.steps, 5),
+                                    "exchange_place_ms": round(prof.get("exchange_place_kernel", {}).get("ms", 0.0), 5),
+                                    "exchange_finish_ms": round(prof.get("exchange_finish_kernel", {}).get("ms", 0.0), 5)})
 
     # ---- the same share on one GPU, no communicator (what weak scaling is measured against), same protocol
     def step_alone():
@@ -701,7 +706,7 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
                   "single_share_ms_per_step": alone_ms / args.steps, "rows_out": rows_out},
         "e2e": {"value": events * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (h1 - h0) // e2e_steps, "d2h_bytes_per_step": (d1 - d0) // e2e_steps,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "feed": "pageable Arrow batches per rank, result exported per rank"},
-        "gpu_launches": int(launches), "launches_per_step_rank0": launches / args.steps, "kernels": prof, "phases_ms": phases, "clocks": clocks,
+        "gpu_launches": int(launches), "launches_per_step_rank0": launches / args.steps, "kernels": prof, "phases_ms": phases, "per_rank": per_rank, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(alg / (dev_ms / args.steps * 1e-3) / 1e9, 1), "peak": peak * world, "unit": "GB/s",
                      "frac": round(alg / (dev_ms / args.steps * 1e-3) / 1e9 / (peak * world), 4), "traffic": None, "kernel": k, "kernel_ms": round(k_ms, 5),
                      "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src + f" x {world} GPUs",

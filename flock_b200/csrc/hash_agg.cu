@@ -1474,6 +1474,11 @@ void plan_aggregates(const Table& in, int mode, const std::vector<AggSpec>& aggs
   const bool from_states = mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED;
   const bool partial_out = mode == FLOCKGPU_AGG_PARTIAL;
   auto add_acc = [&](int op, int col, int cvt) {
+    // "how many non-NULL values of column c" is wanted by COUNT(c) and by the validity of SUM / MIN / MAX / AVG over c:
+    // one accumulator serves them all
+    if (op == ACC_COUNT && col >= 0)
+      for (size_t i = 0; i < accs->size(); ++i)
+        if ((*accs)[i].op == ACC_COUNT && (*accs)[i].col == col && (*accs)[i].cvt == cvt) return int(i);
     FG_CHECK(accs->size() < size_t(MAX_ACC), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: more than %d accumulators", MAX_ACC);
     accs->push_back(AccDesc{op, col, cvt, 0});
     return int(accs->size()) - 1;
@@ -1979,6 +1984,69 @@ TablePtr hash_aggregate(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, con
   return hash_aggregate_impl(ctx, in_ptr, mode, group_cols, aggs, true);
 }
 
+// One pass over a 4-byte key column: the sliding shared-memory histogram adds straight into the direct-address count
+// table `table` (capacity `cap` slots) whose first key a sample of the column decides ON THE DEVICE.  `meta`
+// (DM_WORDS words, zeroed by the caller on the stream) receives the range, the rows that fell outside (DM_OVERFLOW)
+// and, with has_count, the largest count (DM_MAX).
+static void launch_dense_hist(const CtxPtr& ctx, const uint32_t* key_col, int64_t n, int has_count, uint32_t* table, unsigned long long* meta,
+                              unsigned long long cap) {
+  // FLOCKGPU_DENSE_VARIANT (tuning): 1 = sampling and clearing inside a cooperative scan kernel (default),
+  // 0 = sample / clear / scan as three launches, 2 = like 1 but launched non-cooperatively (measurement only).
+  // Measured equal within the box-to-box spread (profiles/r2_q5_variants_run12.txt); 1 has the fewest launches.
+  static const int variant = getenv("FLOCKGPU_DENSE_VARIANT") ? atoi(getenv("FLOCKGPU_DENSE_VARIANT")) : 1;
+  if (variant == 0) {
+    {
+      LaunchTimer lt(ctx, "agg_sample_range_kernel");
+      agg_sample_range_kernel<<<1, 256, 0, ctx->stream>>>(key_col, n, meta, cap);
+    }
+    {
+      LaunchTimer lt(ctx, "dense_clear_kernel");
+      dense_clear_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(table, meta);
+    }
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx, 2);
+  }
+  AggHist32Args h{};
+  h.n_rows = n;
+  h.key_col = key_col;
+  h.has_count = has_count;
+  h.slow_rows = ctx->d_scalars + 9;
+  h.dense = table;
+  h.dense_meta = meta;
+  h.dense_cap = cap;  // (the kernels use meta[DM_SLOTS] <= cap)
+  h.overflow = meta + DM_OVERFLOW;
+  h.fused = variant != 0;
+  FG_CUDA(cudaMemsetAsync(h.slow_rows, 0, 8, ctx->stream));
+  constexpr size_t h_bytes = size_t(H32_WINDOW) * 4;
+  // FLOCKGPU_HIST_TMA=1 selects the bulk-copy ring instead of the register-staged loads.  Measured on q5's
+  // 100 M bids (profiles/r2_q5_tma_ab.txt): ring of 3 x 16 KB at 2 CTAs/SM 134 us, ring of 2 x 16 KB at 3 CTAs/SM
+  // 117 us, registers at 4 CTAs/SM 104 us -- the scan is bound by its shared-memory atomics and step barriers as
+  // much as by load latency, and the ring's shared memory costs the occupancy that hides those.  Registers stay
+  // the default; the ring stays selectable so the comparison can be repeated.
+  static const bool use_tma = getenv("FLOCKGPU_HIST_TMA") && atoi(getenv("FLOCKGPU_HIST_TMA")) == 1;
+  const bool tma_ok = use_tma && (reinterpret_cast<uintptr_t>(key_col) & 15) == 0;
+  const size_t h_bytes_used = tma_ok ? h_bytes + size_t(H32_STAGES) * H32_STEP * 4 : h_bytes;
+  auto hist_kernel = tma_ok ? agg_hist32_kernel<true, true> : agg_hist32_kernel<true, false>;
+  FG_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h_bytes_used)));
+  int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(hist_kernel), H32_THREADS, h_bytes_used), (n + H32_STEP - 1) / H32_STEP)));
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(H32_THREADS);
+    cfg.dynamicSmemBytes = h_bytes_used;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // fused: the CTAs wait for each other's slice of the clearing
+    attr[0].val.cooperative = variant == 1 ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LaunchTimer lt(ctx, "agg_hist32_dense_kernel");
+    FG_CUDA(cudaLaunchKernelEx(&cfg, hist_kernel, h));
+  }
+  FG_CUDA(cudaGetLastError());
+  count_launch(ctx);
+}
+
 static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, int mode, const std::vector<int>& group_cols, const std::vector<AggSpec>& aggs,
                                     bool allow_dense) {
   HostSpan agg_span("hash_aggregate (host)");
@@ -2137,6 +2205,9 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
     // Final* inputs are partial states: every key occurs at most once per producer, so a CTA-local pre-aggregation
     // finds nothing to merge (measured: 0.27 ms of agg_local_kernel on q5's 2-GPU final stage for no reduction)
     const bool states_in = mode == FLOCKGPU_AGG_FINAL || mode == FLOCKGPU_AGG_FINAL_PARTITIONED;
+    // (also right for the Final* stage of a DISTINCT, which has no states: its input arrives hash-routed, 1/W of the
+    // keys spread over the WHOLE key range -- no locality for a sliding window, no density for a direct-address table;
+    // tried in run 21: the dense table overflowed and the stage paid both paths)
     if (n >= (int64_t(1) << 18) && local_smem <= 200 * 1024 && !states_in) {
       AggLocalArgs la{};
       la.n_rows = n;
@@ -2180,63 +2251,9 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
         core->table = alloc(ctx, size_t(core->cap) * 4);
         core->meta = alloc(ctx, DM_WORDS * 8);
         FG_CUDA(cudaMemsetAsync(core->meta->ptr, 0, DM_WORDS * 8, ctx->stream));
-        // FLOCKGPU_DENSE_VARIANT (tuning): 1 = sampling and clearing inside a cooperative scan kernel (default),
-        // 0 = sample / clear / scan as three launches, 2 = like 1 but launched non-cooperatively (measurement only).
-        // Measured equal within the box-to-box spread (profiles/r2_q5_variants_run12.txt); 1 has the fewest launches.
-        static const int variant = getenv("FLOCKGPU_DENSE_VARIANT") ? atoi(getenv("FLOCKGPU_DENSE_VARIANT")) : 1;
-        if (variant == 0) {
-          {
-            LaunchTimer lt(ctx, "agg_sample_range_kernel");
-            agg_sample_range_kernel<<<1, 256, 0, ctx->stream>>>(key_col, n, core->meta->as<unsigned long long>(), core->cap);
-          }
-          {
-            LaunchTimer lt(ctx, "dense_clear_kernel");
-            dense_clear_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(core->table->as<uint32_t>(), core->meta->as<unsigned long long>());
-          }
-          FG_CUDA(cudaGetLastError());
-          count_launch(ctx, 2);
-        }
-        AggHist32Args h{};
-        h.n_rows = n;
-        h.key_col = key_col;
-        h.has_count = n_acc;
-        h.slow_rows = ctx->d_scalars + 9;
-        h.dense = core->table->as<uint32_t>();
-        h.dense_meta = core->meta->as<unsigned long long>();
-        h.dense_cap = core->cap;  // (the kernels use meta[DM_SLOTS] <= cap)
-        h.overflow = core->meta->as<unsigned long long>() + DM_OVERFLOW;
-        h.fused = variant != 0;
-        FG_CUDA(cudaMemsetAsync(h.slow_rows, 0, 8, ctx->stream));
-        constexpr size_t h_bytes = size_t(H32_WINDOW) * 4;
-        // FLOCKGPU_HIST_TMA=1 selects the bulk-copy ring instead of the register-staged loads.  Measured on q5's
-        // 100 M bids (profiles/r2_q5_tma_ab.txt): ring of 3 x 16 KB at 2 CTAs/SM 134 us, ring of 2 x 16 KB at 3 CTAs/SM
-        // 117 us, registers at 4 CTAs/SM 104 us -- the scan is bound by its shared-memory atomics and step barriers as
-        // much as by load latency, and the ring's shared memory costs the occupancy that hides those.  Registers stay
-        // the default; the ring stays selectable so the comparison can be repeated.
-        static const bool use_tma = getenv("FLOCKGPU_HIST_TMA") && atoi(getenv("FLOCKGPU_HIST_TMA")) == 1;
-        const bool tma_ok = use_tma && (reinterpret_cast<uintptr_t>(key_col) & 15) == 0;
-        const size_t h_bytes_used = tma_ok ? h_bytes + size_t(H32_STAGES) * H32_STEP * 4 : h_bytes;
-        auto hist_kernel = tma_ok ? agg_hist32_kernel<true, true> : agg_hist32_kernel<true, false>;
-        FG_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h_bytes_used)));
-        int grid = int(std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, reinterpret_cast<const void*>(hist_kernel), H32_THREADS, h_bytes_used), (n + H32_STEP - 1) / H32_STEP)));
-        {
-          cudaLaunchConfig_t cfg{};
-          cfg.gridDim = dim3(unsigned(grid));
-          cfg.blockDim = dim3(H32_THREADS);
-          cfg.dynamicSmemBytes = h_bytes_used;
-          cfg.stream = ctx->stream;
-          cudaLaunchAttribute attr[1];
-          attr[0].id = cudaLaunchAttributeCooperative;  // fused: the CTAs wait for each other's slice of the clearing
-          attr[0].val.cooperative = variant == 1 ? 1 : 0;
-          cfg.attrs = attr;
-          cfg.numAttrs = 1;
-          LaunchTimer lt(ctx, "agg_hist32_dense_kernel");
-          FG_CUDA(cudaLaunchKernelEx(&cfg, hist_kernel, h));
-        }
-        FG_CUDA(cudaGetLastError());
-        count_launch(ctx);
+        launch_dense_hist(ctx, key_col, n, n_acc, core->table->as<uint32_t>(), core->meta->as<unsigned long long>(), core->cap);
         core->overflow = reserve_row_count(ctx);
-        FG_CUDA(cudaMemcpyAsync(core->overflow->host_slot(), h.overflow, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(cudaMemcpyAsync(core->overflow->host_slot(), core->meta->as<unsigned long long>() + DM_OVERFLOW, 8, cudaMemcpyDeviceToHost, ctx->stream));
         commit_row_count(core->overflow);
         std::vector<int> kinds{0};
         std::vector<std::string> names{in.cols[kp.col[0]].name};
@@ -2371,6 +2388,48 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
     ea.key_width[1] = kp.width[1];
   } else {
     FG_CHECK(group_cols.size() <= size_t(MAX_KEY_COLS), FLOCKGPU_ERR_UNSUPPORTED, "hash_aggregate: more than %d group columns", MAX_KEY_COLS);
+    auto all_rows_distinct = [&]() {
+      out->num_rows = n;
+      for (int g : group_cols) out->cols.push_back(in.cols[g]);  // zero-copy
+      if (!in.partitioned_on.empty()) {
+        bool kept = true;
+        for (const std::string& p : in.partitioned_on) {
+          bool found = false;
+          for (int g : group_cols) found |= in.cols[g].name == p;
+          kept &= found;
+        }
+        if (kept) {
+          out->partitioned_on = in.partitioned_on;
+          out->partition_world = in.partition_world;
+        }
+      }
+      return out;
+    };
+    // ---- DISTINCT whose key holds a 4-byte column: if THAT column alone never repeats, no key does, and the answer is
+    // the input.  One streaming count of the column into a direct-address table (the q5 kernel: MAX(count) == 1 and no
+    // row outside the table) settles it for a quarter of what hashing and comparing the Utf8 keys costs (q8's persons
+    // by (p_id, name): 2.5 M rows, 107 us of row-table build before); when the column does repeat, the general path
+    // below runs as before.
+    static const bool no_probe = getenv("FLOCKGPU_NO_UNIQUE_PROBE") != nullptr;
+    if (n_acc == 0 && !no_probe && n >= (int64_t(1) << 18) && n < (int64_t(1) << 32)) {
+      int probe_col = -1;
+      for (int g : group_cols)
+        if (in.cols[g].dtype != FLOCKGPU_UTF8 && in.cols[g].width() == 4 && !in.cols[g].validity) {
+          probe_col = g;
+          break;
+        }
+      if (probe_col >= 0) {
+        constexpr int kProbeMeta = 64;  // d_scalars[64 .. 64 + DM_WORDS)
+        const unsigned long long pcap = (std::min<unsigned long long>(std::max<unsigned long long>(2ull * (unsigned long long)n, 1ull << 16), 1ull << 26) + 3) & ~3ull;
+        BufferPtr ptable = alloc(ctx, size_t(pcap) * 4);
+        unsigned long long* pmeta = ctx->d_scalars + kProbeMeta;
+        FG_CUDA(cudaMemsetAsync(pmeta, 0, DM_WORDS * 8, ctx->stream));
+        launch_dense_hist(ctx, static_cast<const uint32_t*>(in.cols[probe_col].values()), n, 1, ptable->as<uint32_t>(), pmeta, pcap);
+        unsigned long long m[DM_WORDS] = {};
+        read_scalars(ctx, kProbeMeta, DM_WORDS, m);
+        if (m[DM_OVERFLOW] == 0 && m[DM_MAX] == 1) return all_rows_distinct();
+      }
+    }
     const unsigned long long cap = std::max<unsigned long long>(4, pow2_at_least(2ull * (unsigned long long)n));
     n_slots = cap;
     acc_stride = cap;
@@ -2409,23 +2468,7 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
       // Utf8 names cost more than building the table)
       unsigned long long distinct = 0;
       read_scalars(ctx, 7, 1, &distinct);
-      if (int64_t(distinct) == n) {
-        out->num_rows = n;
-        for (int g : group_cols) out->cols.push_back(in.cols[g]);  // zero-copy
-        if (!in.partitioned_on.empty()) {
-          bool kept = true;
-          for (const std::string& p : in.partitioned_on) {
-            bool found = false;
-            for (int g : group_cols) found |= in.cols[g].name == p;
-            kept &= found;
-          }
-          if (kept) {
-            out->partitioned_on = in.partitioned_on;
-            out->partition_world = in.partition_world;
-          }
-        }
-        return out;
-      }
+      if (int64_t(distinct) == n) return all_rows_distinct();
     }
     ea.owner = towner->as<unsigned>();
     ea.acc = tacc->as<unsigned long long>();

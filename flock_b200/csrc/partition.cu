@@ -11,6 +11,7 @@
 #include "partition.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 
@@ -25,7 +26,7 @@ __host__ __device__ __forceinline__ uint32_t partition_of(uint64_t hash, uint32_
 // ================================================================================================
 struct PartCountArgs {
   int64_t n_rows, chunk;
-  int32_t n_parts, packed, dest_rank, n_utf8, grid, pad;
+  int32_t n_parts, packed, dest_rank, n_utf8, grid, key_nulls;
   int32_t digit_col, digit_shift;  // digit_col >= 0: destination = byte `digit_shift / 8` of that UInt64 column (a radix-sort pass)
   KeyPack pack;
   RowKeys rk;
@@ -33,7 +34,48 @@ struct PartCountArgs {
   const int32_t* uoff[PT_MAX_UTF8];
   uint8_t* pid;
   uint32_t* hist;  // [(1 + n_utf8)][grid][n_parts]
+  // fused scan (step 2 inside this kernel): the CTA that arrives last scans the histograms of all CTAs
+  unsigned* arrive;           // zero on entry, left zero (NULL: the scan is a launch of its own)
+  uint32_t* cta_pos;
+  unsigned long long* totals;
 };
+
+constexpr int kPartitionArriveSlot = 80;  // d_scalars[80]: arrival counter of the fused scan (zero between launches)
+constexpr int PT_FUSED_SCAN_COLS = 64;  // (1 + n_utf8) * n_parts up to which the last CTA scans (>= 4 row blocks of threads)
+
+// Step 2 by ONE CTA of PT_THREADS threads, for matrices of few columns (an exchange over <= 16 ranks): thread (g, c)
+// sums a block of rows of column c, the blocks' sums are combined through shared memory, a second sweep writes the
+// exclusive prefixes.  `s_part` holds PT_THREADS words.
+__device__ __forceinline__ void scan_hist_cta(const uint32_t* hist, uint32_t* cta_pos, unsigned long long* totals, int grid, int P, int kinds,
+                                              unsigned long long* s_part) {
+  const int tid = threadIdx.x;
+  const int C = kinds * P, G = PT_THREADS / C;
+  const int c = tid % C, g = tid / C;
+  const int kind = c / P, p = c - kind * P;
+  const int R = (grid + G - 1) / G;
+  const int r0 = g * R, r1 = g < G ? min(grid, r0 + R) : r0;
+  const uint32_t* h = hist + int64_t(kind) * grid * P + p;
+  uint32_t* o = cta_pos + int64_t(kind) * grid * P + p;
+  unsigned long long sum = 0;
+  for (int r = r0; r < r1; ++r) sum += __ldcg(h + int64_t(r) * P);
+  s_part[tid] = sum;
+  __syncthreads();
+  if (g < G) {
+    unsigned long long before = 0, total = 0;
+    for (int gg = 0; gg < G; ++gg) {
+      const unsigned long long v = s_part[gg * C + c];
+      if (gg < g) before += v;
+      total += v;
+    }
+    unsigned long long run = before;
+    for (int r = r0; r < r1; ++r) {
+      const unsigned v = __ldcg(h + int64_t(r) * P);
+      o[int64_t(r) * P] = uint32_t(run);
+      run += v;
+    }
+    if (g == 0) totals[kind * P + p] = total;
+  }
+}
 
 __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __grid_constant__ PartCountArgs a) {
   extern __shared__ __align__(16) unsigned pc_smem[];
@@ -49,6 +91,16 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
   unsigned* mine = h_rows + warp * P;
   (void)lt;
   constexpr int UNROLL = 4;  // rows per thread and iteration: their key loads are independent and in flight together
+  const bool small = P <= 8;
+  unsigned long long acc8 = 0;
+  int since = 0;
+  auto flush_acc8 = [&]() {
+    for (int p = 0; p < P; ++p) {
+      const unsigned total = __reduce_add_sync(FULL_MASK, unsigned(acc8 >> (8 * p)) & 0xffu);
+      if (lane == 0) mine[p] += total;
+    }
+    acc8 = 0;
+  };
   for (int64_t base = begin; base < end; base += PT_THREADS * UNROLL) {
     unsigned pid[UNROLL];
     bool valid[UNROLL];
@@ -63,7 +115,16 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
         } else if (a.digit_col >= 0) {
           pid[j] = unsigned(static_cast<const unsigned long long*>(a.cols[a.digit_col].data)[row] >> a.digit_shift) & 0xffu;
         } else {
-          const unsigned long long h = a.packed ? fmix64(pack_key(a.pack, a.cols, row)) : hash_row(a.rk, a.cols, row);
+          // a row with a NULL key takes hash_row's fixed NULL contribution on every rank; any other row of a packable
+          // key hashes its packed word whether or not the column carries validity HERE (a peer's slice of the same
+          // column may hold no NULL and so no validity: both must route a key alike)
+          bool null_key = false;
+          if (a.packed && a.key_nulls)
+            for (int i = 0; i < a.rk.n; ++i) {
+              const uint8_t* v = a.cols[a.rk.col[i]].validity;
+              null_key |= v && !v[row];
+            }
+          const unsigned long long h = a.packed && !null_key ? fmix64(pack_key(a.pack, a.cols, row)) : hash_row(a.rk, a.cols, row);
           pid[j] = partition_of(h, uint32_t(P));
         }
       }
@@ -75,6 +136,10 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
         a.pid[row] = uint8_t(pid[j]);
         for (int u = 0; u < a.n_utf8; ++u) atomicAdd(&h_bytes[u * P + pid[j]], unsigned(a.uoff[u][row + 1] - a.uoff[u][row]));
       }
+      if (small) {  // up to 8 destinations: eight 8-bit counters in one register, emptied before any can wrap
+        if (valid[j]) acc8 += 1ull << (8 * pid[j]);
+        continue;
+      }
       const unsigned vmask = __ballot_sync(FULL_MASK, valid[j]);
       unsigned m = 0, before = 0;
       if (valid[j]) {
@@ -85,7 +150,12 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
       if (valid[j] && lane == __ffs(m) - 1) mine[pid[j]] = before + __popc(m);
       __syncwarp();
     }
+    if (small && ++since == 255 / UNROLL) {
+      flush_acc8();
+      since = 0;
+    }
   }
+  if (small) flush_acc8();
   __syncthreads();
   for (int p = tid; p < P; p += PT_THREADS) {
     unsigned rows = 0;
@@ -93,6 +163,20 @@ __global__ void __launch_bounds__(PT_THREADS) partition_count_kernel(const __gri
     for (int w = 0; w < PT_WARPS; ++w) rows += h_rows[w * P + p];
     a.hist[(int64_t(0) * a.grid + blockIdx.x) * P + p] = rows;
     for (int u = 0; u < a.n_utf8; ++u) a.hist[(int64_t(1 + u) * a.grid + blockIdx.x) * P + p] = h_bytes[u * P + p];
+  }
+  if (a.arrive) {
+    // the histograms of this CTA are visible before its arrival is; whoever counts the last arrival reads them all
+    __shared__ unsigned s_last;
+    __shared__ unsigned long long s_part[PT_THREADS];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.arrive, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      scan_hist_cta(a.hist, a.cta_pos, a.totals, a.grid, P, 1 + a.n_utf8, s_part);
+      if (tid == 0) *a.arrive = 0u;  // ready for the next pass on this context's stream
+    }
   }
 }
 
@@ -520,7 +604,7 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
     }
     ca.packed = keys_packable(widths.data(), int(widths.size())) ? 1 : 0;
     for (int k : routing_cols)
-      if (in.cols[k].validity) ca.packed = 0;  // a NULL key routes by hash_row's fixed NULL contribution, not by the bytes underneath
+      if (in.cols[k].validity) ca.key_nulls = 1;  // a NULL key routes by hash_row's fixed NULL contribution, not by the bytes underneath
     ca.rk.n = int(routing_cols.size());
     for (size_t i = 0; i < routing_cols.size(); ++i) ca.rk.col[i] = routing_cols[i];
     if (ca.packed) {
@@ -535,18 +619,29 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
   ca.pid = ps.pid->as<uint8_t>();
   ca.hist = ps.hist->as<uint32_t>();
   const size_t count_smem = size_t(PT_WARPS + U) * n_parts * 4;
+  // few destinations (an exchange): the CTA that finishes last also scans -- one launch, no 1-CTA kernel in the chain
+  static const bool no_fused_scan = getenv("FLOCKGPU_NO_FUSED_SCAN") != nullptr;
+  const bool fused_scan = !no_fused_scan && (1 + U) * n_parts <= PT_FUSED_SCAN_COLS;
+  if (fused_scan) {
+    ca.arrive = reinterpret_cast<unsigned*>(ctx->d_scalars + kPartitionArriveSlot);
+    ca.cta_pos = ps.cta_pos->as<uint32_t>();
+    ca.totals = ps.totals->as<unsigned long long>();
+  }
   {
     LaunchTimer lt(ctx, "partition_count_kernel");
     partition_count_kernel<<<ps.grid, PT_THREADS, count_smem, ctx->stream>>>(ca);
   }
   FG_CUDA(cudaGetLastError());
-  {
-    LaunchTimer lt(ctx, "partition_scan_kernel");
-    partition_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ps.hist->as<uint32_t>(), ps.cta_pos->as<uint32_t>(), ps.totals->as<unsigned long long>(), ps.grid,
-                                                       n_parts, 1 + U);
+  count_launch(ctx);
+  if (!fused_scan) {
+    {
+      LaunchTimer lt(ctx, "partition_scan_kernel");
+      partition_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ps.hist->as<uint32_t>(), ps.cta_pos->as<uint32_t>(), ps.totals->as<unsigned long long>(), ps.grid,
+                                                         n_parts, 1 + U);
+    }
+    FG_CUDA(cudaGetLastError());
+    count_launch(ctx);
   }
-  FG_CUDA(cudaGetLastError());
-  count_launch(ctx, 2);
   return ps;
 }
 

@@ -31,6 +31,18 @@ def _ipc(t: pa.Table) -> bytes:
 
 
 def _worker(rank, world, port, out_dir, mode):
+    """Every rank leaves its own traceback behind: mp.spawn reports one failing process only, and usually the one
+    that merely lost its peer."""
+    try:
+        _worker_body(rank, world, port, out_dir, mode)
+    except BaseException:
+        import traceback
+        with open(os.path.join(out_dir, f"rank{rank}.err"), "w") as f:
+            traceback.print_exc(file=f)
+        raise
+
+
+def _worker_body(rank, world, port, out_dir, mode):
     import torch.distributed as dist
     import flock_b200 as fb
     from flock_b200 import nexgen, plans, sharding
@@ -151,7 +163,11 @@ def test_two_gpu_exchange_and_plans(tmp_path, mode):
     import oracle
     from flock_b200 import nexgen, plans
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
+    try:
+        mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
+    except Exception as e:
+        traces = "\n".join(f"---- {f.name}\n{f.read_text()}" for f in sorted(tmp_path.glob("rank*.err")))
+        raise AssertionError(f"{e}\n{traces}") from None
     ev = nexgen.generate(400_000, seed=21, batch_rows=4096)
     for q in ("q8", "q5", "q3"):
         parts = [pa.ipc.open_stream((tmp_path / f"{q}_rank{r}.arrow").read_bytes()).read_all() for r in range(world)]
