@@ -568,11 +568,25 @@ def phase_times(prof: dict) -> dict:
     return out
 
 
+def bind_to_gpu_numa_node(device: int) -> str:
+    """Pins this process to the CPU cores next to its GPU (NVML's ideal affinity: `nvidia-smi topo -m` shows GPUs 0-3 on
+    NUMA node 0 and 4-7 on node 1 on these boxes).  torchrun does not bind ranks, and a rank whose host thread sits on
+    the far socket reaches every exchange late -- its peers then wait inside exchange_place_kernel."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device))
+        return f"{len(os.sched_getaffinity(0))} cores"
+    except Exception as e:                           # affinity is a tuning aid, never a requirement
+        return f"unbound ({type(e).__name__})"
+
+
 def run_gpu_q8(args, dist: Dist) -> dict | None:
     import flock_b200 as fb
     from flock_b200 import nexgen, plans
 
     rank, world, local = dist.rank, dist.world, dist.local
+    numa = bind_to_gpu_numa_node(local)
     ctx = fb.Context(local)
     ctx.comm_init(dist.broadcast_object(fb.Context.comm_unique_id() if rank == 0 else None), rank, world)
     alone = fb.Context(local)                       # the same share WITHOUT a communicator: what one GPU does on its own
@@ -633,10 +647,14 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
     launches = ctx.kernel_launches - launches0
     del keep
     # per-phase kernel times of one more step (max over ranks per phase)
+    # (five steps, per-step mean: the ranks leave the barrier tens of microseconds apart, and a single profiled step
+    # books that skew as waiting time inside the first exchange -- run 23 showed 150 us on rank 0 against 27 us on rank 1)
+    PROFILED_STEPS = 5
     dist.barrier()
     ctx.profile_begin()
-    step().num_rows
-    prof = ctx.profile_end()
+    for _ in range(PROFILED_STEPS):
+        step().num_rows
+    prof = {k: {"launches": v["launches"] / PROFILED_STEPS, "ms": v["ms"] / PROFILED_STEPS} for k, v in ctx.profile_end().items()}
     ph = phase_times(prof)
     names = sorted(PHASES) + ["other"]
     mx = dist.max(*[ph.get(n, 0.0) for n in names])
@@ -706,7 +724,7 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
                   "single_share_ms_per_step": alone_ms / args.steps, "rows_out": rows_out},
         "e2e": {"value": events * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (h1 - h0) // e2e_steps, "d2h_bytes_per_step": (d1 - d0) // e2e_steps,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "feed": "pageable Arrow batches per rank, result exported per rank"},
-        "gpu_launches": int(launches), "launches_per_step_rank0": launches / args.steps, "kernels": prof, "phases_ms": phases, "per_rank": per_rank, "clocks": clocks,
+        "gpu_launches": int(launches), "launches_per_step_rank0": launches / args.steps, "kernels": prof, "phases_ms": phases, "per_rank": per_rank, "cpu_affinity": numa, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(alg / (dev_ms / args.steps * 1e-3) / 1e9, 1), "peak": peak * world, "unit": "GB/s",
                      "frac": round(alg / (dev_ms / args.steps * 1e-3) / 1e9 / (peak * world), 4), "traffic": None, "kernel": k, "kernel_ms": round(k_ms, 5),
                      "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src + f" x {world} GPUs",

@@ -495,7 +495,7 @@ struct AggHist32Args {
   unsigned long long dense_cap;
   unsigned long long* overflow;             // rows whose key fell outside the table (the caller then starts over)
   int32_t fused;                            // 1: CTA 0 samples the range and every CTA clears its slice inside the scan kernel
-  int32_t pad2;
+  int32_t relaxed;                          // 1: DENSE, register-staged loads: the CTA-wide window vote only every H32_SYNC_EVERY steps
 };
 
 // meta words of a direct-address count table
@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(256) dense_clear_kernel(uint32_t* table, const
 // shows 45 % of its stall samples on the first use of the loaded keys and on the step barrier at 68 % of DRAM peak;
 // it did NOT win (see the launch site for the numbers), so it is an opt-in variant.
 constexpr int H32_STAGES = 2;
+constexpr int H32_SYNC_EVERY = 4;  // relaxed protocol: steps between two CTA-wide window votes
 template <bool DENSE, bool TMA>
 __global__ void __launch_bounds__(H32_THREADS, TMA ? 3 : 4) agg_hist32_kernel(const __grid_constant__ AggHist32Args a) {
   extern __shared__ __align__(128) unsigned h32_cnt[];  // [H32_WINDOW], then (TMA) H32_STAGES x H32_STEP keys
@@ -581,8 +582,10 @@ __global__ void __launch_bounds__(H32_THREADS, TMA ? 3 : 4) agg_hist32_kernel(co
   __shared__ unsigned s_warp[H32_THREADS / 32];
   __shared__ unsigned long long s_base_pos;
   __shared__ unsigned s_min;
+  __shared__ unsigned s_need;  // relaxed protocol: a warp met rows outside the window since the last vote
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int s = tid; s < H32_WINDOW; s += H32_THREADS) h32_cnt[s] = 0;
+  if (tid == 0) s_need = 0u;
 
   int64_t per_cta = (a.n_rows + gridDim.x - 1) / gridDim.x;
   per_cta = (per_cta + H32_STEP - 1) / H32_STEP * H32_STEP;
@@ -801,6 +804,7 @@ __global__ void __launch_bounds__(H32_THREADS, TMA ? 3 : 4) agg_hist32_kernel(co
   }
   if (DENSE && a.fused) clear_my_slice();  // the first steps' loads are in flight meanwhile
   int64_t k_step = 0;
+  bool relaxed_mode = false;  // CTA-uniform
   for (; step + H32_STEP <= end; step += H32_STEP, ++k_step) {
     const bool more = step + 2 * int64_t(H32_STEP) <= end;
     if (TMA) {
@@ -810,6 +814,63 @@ __global__ void __launch_bounds__(H32_THREADS, TMA ? 3 : 4) agg_hist32_kernel(co
       for (int j = 0; j < H32_LOADS; ++j) v[j] = st[j * H32_THREADS + tid];
     } else if (more) {
       load_step(nxt, step + H32_STEP);  // in flight while this step waits at the barrier and counts
+    }
+    if (DENSE && !TMA && relaxed_mode) {
+      // ---- relaxed protocol: a warp whose rows all fall into the window counts them without asking anybody; a warp
+      // that meets a row outside sends such rows straight to the table (global atomic) and raises s_need; only every
+      // H32_SYNC_EVERY steps do the warps meet, and move the window when somebody asked for it.  (The per-step
+      // barrier of the strict protocol was the second largest stall of the kernel: profiles/r2_q5_hist_ncu.md.)
+      if ((k_step % H32_SYNC_EVERY) == 0) {
+        unsigned o2 = 0;
+#pragma unroll
+        for (int j = 0; j < H32_LOADS; ++j) o2 |= (v[j].x - base) | (v[j].y - base) | (v[j].z - base) | (v[j].w - base);
+        // move the window EARLY -- as soon as a key of this step lies in its upper half: the steps until the next
+        // vote then still fit (q5 advances ~270 ids per step), and no warp has to take the row-by-row path, which
+        // costs ten fast steps (run 24: waiting for the window to be exhausted made the kernel 179 us instead of 107)
+        if (__syncthreads_or(int(s_need | unsigned(o2 >= unsigned(H32_WINDOW / 2))))) {
+          if (tid == 0) s_need = 0u;  // before rebase's barriers: a later slow-path warp sets it again after them
+          unsigned lo = ~0u;
+#pragma unroll
+          for (int j = 0; j < H32_LOADS; ++j) lo = min(min(lo, min(v[j].x, v[j].y)), min(v[j].z, v[j].w));
+          rebase(lo);
+        }
+      }
+      unsigned o3 = 0;
+#pragma unroll
+      for (int j = 0; j < H32_LOADS; ++j) o3 |= (v[j].x - base) | (v[j].y - base) | (v[j].z - base) | (v[j].w - base);
+      if (__all_sync(FULL_MASK, o3 < unsigned(H32_WINDOW))) {
+        if (has_count) {
+#pragma unroll
+          for (int j = 0; j < H32_LOADS; ++j) {
+            atomicAdd(&h32_cnt[v[j].x - base], 1u);
+            atomicAdd(&h32_cnt[v[j].y - base], 1u);
+            atomicAdd(&h32_cnt[v[j].z - base], 1u);
+            atomicAdd(&h32_cnt[v[j].w - base], 1u);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < H32_LOADS; ++j) {
+            h32_cnt[v[j].x - base] = 1u;
+            h32_cnt[v[j].y - base] = 1u;
+            h32_cnt[v[j].z - base] = 1u;
+            h32_cnt[v[j].w - base] = 1u;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < H32_LOADS; ++j) {
+          add_checked(v[j].x);
+          add_checked(v[j].y);
+          add_checked(v[j].z);
+          add_checked(v[j].w);
+        }
+        if (lane == 0) s_need = 1u;
+      }
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < H32_LOADS; ++j) v[j] = nxt[j];
+      }
+      continue;
     }
     unsigned ored = 0;
 #pragma unroll
@@ -852,6 +913,12 @@ __global__ void __launch_bounds__(H32_THREADS, TMA ? 3 : 4) agg_hist32_kernel(co
     if (!TMA && more) {
 #pragma unroll
       for (int j = 0; j < H32_LOADS; ++j) v[j] = nxt[j];
+    }
+    // the first steps run the strict protocol; by the end of the first period the table has long been cleared by
+    // everybody (ensure_table hardly waits), and from then on a warp may touch it without a CTA-wide check
+    if (DENSE && !TMA && a.relaxed && !relaxed_mode && k_step + 1 == H32_SYNC_EVERY) {
+      ensure_table();
+      relaxed_mode = true;
     }
   }
   // ---- ragged tail of the CTA's range (at most one step): row by row
@@ -2016,6 +2083,9 @@ static void launch_dense_hist(const CtxPtr& ctx, const uint32_t* key_col, int64_
   h.dense_cap = cap;  // (the kernels use meta[DM_SLOTS] <= cap)
   h.overflow = meta + DM_OVERFLOW;
   h.fused = variant != 0;
+  // FLOCKGPU_HIST_RELAXED=1: the CTA-wide window vote every H32_SYNC_EVERY steps instead of every step (A/B switch)
+  static const bool relaxed = getenv("FLOCKGPU_HIST_RELAXED") && atoi(getenv("FLOCKGPU_HIST_RELAXED")) == 1;
+  h.relaxed = relaxed ? 1 : 0;
   FG_CUDA(cudaMemsetAsync(h.slow_rows, 0, 8, ctx->stream));
   constexpr size_t h_bytes = size_t(H32_WINDOW) * 4;
   // FLOCKGPU_HIST_TMA=1 selects the bulk-copy ring instead of the register-staged loads.  Measured on q5's
@@ -2411,7 +2481,10 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
     // by (p_id, name): 2.5 M rows, 107 us of row-table build before); when the column does repeat, the general path
     // below runs as before.
     static const bool no_probe = getenv("FLOCKGPU_NO_UNIQUE_PROBE") != nullptr;
-    if (n_acc == 0 && !no_probe && n >= (int64_t(1) << 18) && n < (int64_t(1) << 32)) {
+    // (not behind an exchange over more than two ranks: a rank then holds every W-th key of the whole range, a
+    // 4096-row step spans more ids than the sliding window and the table W x the rows -- measured at N = 8, run 22:
+    // the probe overflowed after 77 us and the row table ran anyway)
+    if (n_acc == 0 && !no_probe && n >= (int64_t(1) << 18) && n < (int64_t(1) << 32) && in.partition_world <= 2) {
       int probe_col = -1;
       for (int g : group_cols)
         if (in.cols[g].dtype != FLOCKGPU_UTF8 && in.cols[g].width() == 4 && !in.cols[g].validity) {

@@ -49,8 +49,25 @@ struct JoinTable {
   unsigned* cnt;           // [cap] number of build rows with that key
   unsigned* next;          // [build rows] next build row with the same key, JOIN_EMPTY = end
   unsigned long long cap;  // power of two
+  struct JoinSlot* slots;  // KW = 4: the table proper (below); rep / head / cnt are unused, `next` holds row + 1
 };
 
+// One 4-byte key (every NEXMark join but q5's): the KEY LIVES IN THE SLOT.  A probe is one 16-byte load -- key, list
+// head and count arrive together -- where the representative-row table needs three dependent reads (rep[slot], the
+// build key column at that row, cnt[slot]) in three cache lines; the build claims a slot with one CAS that returns the
+// resident key.  ncu on q8 (profiles/r2_join_gather_ncu.md): the representative-row kernels sat at 9-25 % issue
+// utilisation with 55-140 warps stalled on those loads per issued instruction.  All-zero = empty, so the table is
+// initialised by one memset: `tag_key` carries an occupied bit above the key, `head` and next[] hold row + 1.
+struct __align__(16) JoinSlot {
+  unsigned long long tag_key;  // 0 = free, else (1 << 63) | key
+  unsigned head;               // most recently pushed build row + 1
+  unsigned cnt;                // build rows with this key
+};
+constexpr unsigned long long JOIN_TAG = 1ull << 63;
+// Capacity stays a power of two >= 2 x build rows (load 0.3 - 0.5).  A table at load 0.6 of any capacity (slot = high
+// half of hash x capacity: 67 MB instead of 134 MB for q8's 2.5 M persons, inside the L2) was measured and is SLOWER
+// (run 27: build 59 -> 83 us, count 54 -> 93 us): linear probing at that load makes 2-3 x the dependent accesses, and
+// those, not the table's footprint, are what the kernels wait for.
 // KW = 4 / 8: one fixed-width key column, read straight from JoinSide::key0 (every NEXMark join); KW = 0: the general
 // form (two packed columns, or row comparison for Utf8 / wide keys).  The general form cost ~140 lane-instructions per
 // probe row on q5 (dynamic indexing of the column table in parameter space, width and mode branches).
@@ -92,6 +109,18 @@ __global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__
     if (key_is_null(build, row)) continue;  // never enters the table: nothing can match it
     unsigned long long key;
     unsigned long long slot = side_hash<KW>(build, row, &key) & (t.cap - 1);
+    if (KW == 4) {
+      const unsigned long long want = JOIN_TAG | key;
+      while (true) {
+        unsigned long long cur = t.slots[slot].tag_key;
+        if (cur == 0ull) cur = atomicCAS(&t.slots[slot].tag_key, 0ull, want);
+        if (cur == 0ull || cur == want) break;
+        slot = (slot + 1) & (t.cap - 1);
+      }
+      t.next[row] = atomicExch(&t.slots[slot].head, unsigned(row) + 1u);
+      atomicAdd(&t.slots[slot].cnt, 1u);
+      continue;
+    }
     while (true) {
       unsigned r = t.rep[slot];
       if (r == JOIN_EMPTY) {
@@ -107,11 +136,27 @@ __global__ void __launch_bounds__(256) join_build_kernel(const __grid_constant__
 }
 
 // Slot of the key of probe row `row`, or ~0 when no build row has it.
+// (KW = 4: *head receives the list head (row + 1) and *cnt the number of build rows of the key, from the same load)
 template <int KW>
-__device__ __forceinline__ unsigned long long find_slot(const JoinSide& build, const JoinSide& probe, const JoinTable& t, int64_t row) {
+__device__ __forceinline__ unsigned long long find_slot(const JoinSide& build, const JoinSide& probe, const JoinTable& t, int64_t row, unsigned* head,
+                                                        unsigned* cnt) {
   if (key_is_null(probe, row)) return ~0ull;
   unsigned long long key;
   unsigned long long slot = side_hash<KW>(probe, row, &key) & (t.cap - 1);
+  if (KW == 4) {
+    const unsigned long long want = JOIN_TAG | key;
+    while (true) {
+      const uint4 s = *reinterpret_cast<const uint4*>(&t.slots[slot]);
+      const unsigned long long tag = ((unsigned long long)s.y << 32) | s.x;
+      if (tag == 0ull) return ~0ull;
+      if (tag == want) {
+        *head = s.z;
+        *cnt = s.w;
+        return slot;
+      }
+      slot = (slot + 1) & (t.cap - 1);
+    }
+  }
   while (true) {
     const unsigned r = t.rep[slot];
     if (r == JOIN_EMPTY) return ~0ull;
@@ -146,8 +191,9 @@ __global__ void __launch_bounds__(JC_THREADS) join_count_scan_kernel(const __gri
     for (int k = 0; k < JC_ITEMS; ++k) {
       unsigned c = 0;
       if (i0 + k < n) {
-        const unsigned long long slot = find_slot<KW>(a.build, a.probe, a.table, i0 + k);
-        if (slot != ~0ull) c = a.table.cnt[slot];
+        unsigned head = 0, in_slot = 0;
+        const unsigned long long slot = find_slot<KW>(a.build, a.probe, a.table, i0 + k, &head, &in_slot);
+        if (slot != ~0ull) c = KW == 4 ? in_slot : a.table.cnt[slot];
       }
       cnt[k] = c;
       local += c;
@@ -252,7 +298,16 @@ __global__ void __launch_bounds__(256) join_emit_kernel(const __grid_constant__ 
   for (int64_t row = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; row < a.probe.n_rows; row += int64_t(gridDim.x) * blockDim.x) {
     unsigned pos = a.off[row];
     if (a.off[row + 1] == pos) continue;
-    const unsigned long long slot = find_slot<KW>(a.build, a.probe, a.table, row);
+    unsigned head = 0, in_slot = 0;
+    const unsigned long long slot = find_slot<KW>(a.build, a.probe, a.table, row, &head, &in_slot);
+    if (KW == 4) {
+      for (unsigned r1 = head; r1 != 0u; r1 = a.table.next[r1 - 1u]) {  // row + 1 links, 0 ends the list
+        a.build_idx[pos] = r1 - 1u;
+        a.probe_idx[pos] = unsigned(row);
+        ++pos;
+      }
+      continue;
+    }
     for (unsigned r = a.table.head[slot]; r != JOIN_EMPTY; r = a.table.next[r]) {
       a.build_idx[pos] = r;
       a.probe_idx[pos] = unsigned(row);
@@ -379,12 +434,23 @@ TablePtr hash_join(const CtxPtr& ctx, const TablePtr& left_ptr, const TablePtr& 
     } else {
     unsigned long long cap = 1024;
     while (cap < 2ull * (unsigned long long)B.num_rows) cap <<= 1;
-    // rep | head | cnt in one allocation (cap words each), then next[build rows]
-    BufferPtr tbuf = alloc(ctx, size_t(cap) * 12 + size_t(B.num_rows) * 4);
-    FG_CUDA(cudaMemsetAsync(tbuf->ptr, 0xff, size_t(cap) * 8, ctx->stream));                                  // rep, head = EMPTY
-    FG_CUDA(cudaMemsetAsync(static_cast<char*>(tbuf->ptr) + size_t(cap) * 8, 0, size_t(cap) * 4, ctx->stream));  // cnt = 0
-    unsigned* w = tbuf->as<unsigned>();
-    JoinTable tab{w, w + cap, w + 2 * cap, w + 3 * cap, cap};
+    JoinTable tab{};
+    BufferPtr tbuf;
+    if (kw == 4) {
+      // 16-byte slots (key, head, count), all-zero = empty, then next[build rows]
+      tbuf = alloc(ctx, size_t(cap) * sizeof(JoinSlot) + size_t(B.num_rows) * 4);
+      FG_CUDA(cudaMemsetAsync(tbuf->ptr, 0, size_t(cap) * sizeof(JoinSlot), ctx->stream));
+      tab.slots = tbuf->as<JoinSlot>();
+      tab.next = reinterpret_cast<unsigned*>(tab.slots + cap);
+      tab.cap = cap;
+    } else {
+      // rep | head | cnt in one allocation (cap words each), then next[build rows]
+      tbuf = alloc(ctx, size_t(cap) * 12 + size_t(B.num_rows) * 4);
+      FG_CUDA(cudaMemsetAsync(tbuf->ptr, 0xff, size_t(cap) * 8, ctx->stream));                                  // rep, head = EMPTY
+      FG_CUDA(cudaMemsetAsync(static_cast<char*>(tbuf->ptr) + size_t(cap) * 8, 0, size_t(cap) * 4, ctx->stream));  // cnt = 0
+      unsigned* w = tbuf->as<unsigned>();
+      tab = JoinTable{w, w + cap, w + 2 * cap, w + 3 * cap, cap, nullptr};
+    }
     {
       LaunchTimer lt(ctx, "join_build_kernel");
       by_width([&](auto w) { join_build_kernel<decltype(w)::value><<<grid_for(ctx, B.num_rows, 256, 8), 256, 0, ctx->stream>>>(bs, tab); });

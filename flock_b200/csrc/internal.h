@@ -176,7 +176,7 @@ struct CtxCore {
   bool feed_register = false;
   // pageable sources of a copy feed are staged into a page-locked block by this many host threads, each issuing the
   // DMA of a batch as soon as it has copied it (0: hand the pageable pointer to cudaMemcpyAsync)
-  int feed_stage_threads = 4;
+  int feed_stage_threads = 8;  // run 27: 3.08 ms per 80 MB feed at 8 threads, 3.40 at 4, 4.4-5.7 at 16-32 (profiles/r2_feed_threads_run27.txt)
   // grid-wide prefix protocol of the compaction kernels: 0 = automatic (single wave when every tile is resident,
   // decoupled look-back otherwise), 1 = always decoupled look-back (flockgpu_set_option "compact_mode"; the parity
   // tests run both)

@@ -15,6 +15,7 @@ namespace {
 struct HostBatch {
   std::vector<ColInfo> infos;
   std::vector<ColRef> refs;
+  std::vector<std::vector<uint8_t>> validity;  // byte per row, like Column::validity on the device (reserved up front: refs point into it)
   int64_t rows = 0;
 };
 
@@ -22,16 +23,31 @@ HostBatch view_batch(const ArrowSchema* schema, const ArrowArray* batch) {
   FG_CHECK(schema && batch && schema->format && !strcmp(schema->format, "+s"), FLOCKGPU_ERR_INVALID, "selftest: need a struct batch");
   HostBatch hb;
   hb.rows = batch->length;
+  hb.validity.reserve(size_t(schema->n_children));
   for (int64_t c = 0; c < schema->n_children; ++c) {
     const ArrowSchema* cs = schema->children[c];
     const ArrowArray* a = batch->children[c];
     int dt = dtype_from_format(cs->format);
     FG_CHECK(dt >= 0, FLOCKGPU_ERR_UNSUPPORTED, "selftest: unsupported column format %s", cs->format);
-    FG_CHECK(a->null_count <= 0, FLOCKGPU_ERR_UNSUPPORTED, "selftest: nulls");
-    hb.infos.push_back({dt, cs->name ? cs->name : "", cs->format});
+    ColInfo info{dt, cs->name ? cs->name : "", cs->format};
     ColRef r{};
     r.dtype = dt;
     int64_t off = batch->offset + a->offset;
+    if (a->null_count != 0 && a->buffers[0]) {  // the bitmap as the import path expands it: one byte per row
+      const uint8_t* bits = static_cast<const uint8_t*>(a->buffers[0]);
+      std::vector<uint8_t> v(size_t(std::max<int64_t>(hb.rows, 1)));
+      bool any_null = false;
+      for (int64_t i = 0; i < hb.rows; ++i) {
+        v[size_t(i)] = (bits[(off + i) >> 3] >> ((off + i) & 7)) & 1u;
+        any_null |= !v[size_t(i)];
+      }
+      if (any_null) {
+        hb.validity.push_back(std::move(v));
+        r.validity = hb.validity.back().data();
+        info.has_nulls = true;
+      }
+    }
+    hb.infos.push_back(info);
     if (dt == FLOCKGPU_UTF8) {
       r.offsets = static_cast<const int32_t*>(a->buffers[1]) + off;
       r.data = a->buffers[2];

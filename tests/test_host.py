@@ -182,6 +182,33 @@ def test_truth_table_covers_and_or_not():
     assert np.array_equal(got, (t[0] & ~t[1]) | (t[2] & (t[3] | ~t[0])))
 
 
+def test_three_valued_predicates_match_arrow_kleene():
+    """NULL operands: a comparison over a NULL is NULL, AND / OR / NOT follow Kleene's tables, and FilterExec keeps the rows
+    whose predicate is TRUE.  The truth table the kernels index is built by expr_compile.cc; here
+    it runs on the host over bitmaps with a non-zero bit offset."""
+    import pyarrow.compute as pc
+    n = 300
+    rng = np.random.default_rng(3)
+    a = pa.array(rng.integers(-20, 20, n).astype(np.int32), mask=np.arange(n) % 5 == 0)
+    b_ = pa.array(rng.integers(-20, 20, n), mask=np.arange(n) % 7 == 3)
+    s_ = pa.array([None if k % 11 == 2 else ["or", "id", "ca", "wa"][k % 4] for k in range(n)])
+    full = pa.RecordBatch.from_arrays([a, b_, s_, pa.array(np.arange(n, dtype=np.int32))], names=["a", "b", "s", "id"])
+    b = full.slice(3, n - 9)                                                                   # bit offset 3 in every bitmap
+    A, B, S, I = (b.column(i) for i in range(4))
+    cases = [
+        (col(0) > 3, pc.greater(A, 3)),
+        ((col(0) > 3) | (col(1) < 0), pc.or_kleene(pc.greater(A, 3), pc.less(B, 0))),
+        ((col(0) > 3) & (col(1) < 0), pc.and_kleene(pc.greater(A, 3), pc.less(B, 0))),
+        (~((col(0) > 3) | (col(2) == "or")), pc.invert(pc.or_kleene(pc.greater(A, 3), pc.equal(S, "or")))),
+        (((col(0) > 3) & ~(col(1) < 0)) | ((col(2) == "id") & (col(3) % 2 == 0)),
+         pc.or_kleene(pc.and_kleene(pc.greater(A, 3), pc.invert(pc.less(B, 0))), pc.and_kleene(pc.equal(S, "id"), pc.equal(pc.bit_wise_and(I, 1), 0)))),
+        (col(0).cast("int64") + col(1) > 0, pc.greater(pc.add(pc.cast(A, pa.int64()), B), 0)),
+    ]
+    for e, want in cases:
+        got, _ = fb.selftest_eval_predicate(b, e)
+        assert np.array_equal(got, want.fill_null(False).to_numpy(zero_copy_only=False)), fb.E.wrap(e).tokens
+
+
 def test_value_lowering_matches_numpy():
     b = expr_batch(500, seed=2)
     c = cols(b)

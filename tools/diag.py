@@ -32,16 +32,48 @@ if what == "q5":
     for _ in range(10):
         ctx.flush_l2(); ctx.synchronize(); run().num_rows
     ctx.set_option("host_trace_dump", 1)
+elif what == "q8":
+    # host-side view of one q8 step over the per-GPU share of the 1 B-event configuration: how many times does the host
+    # wait for the device, and for how long (FLOCKGPU_HOST_TRACE=1)
+    n_p, n_a, _ = nexgen.relation_counts(125_000_000)
+    res = {"person": ctx.import_batches(nexgen.split_batches(nexgen.persons(n_p, 42, 0))),
+           "auction": ctx.import_batches(nexgen.split_batches(nexgen.auctions(n_a, 42, 0)))}
+    ec = fb.ExecutionContext(ctx, plans.q8())
+    def run():
+        ec.feed_tables([res[r] for r in plans.SOURCES["q8"]]); return ec.execute_device(0)
+    for _ in range(3): run().num_rows
+    ts, hs = [], []
+    for _ in range(20):
+        ctx.synchronize()
+        t = time.perf_counter()
+        ctx.timer_start(0); o = run(); ctx.timer_stop(0); o.num_rows
+        hs.append((time.perf_counter() - t) * 1e3)
+        ts.append(ctx.timer_ms(0))
+    print("q8 warm device ms", [round(x, 3) for x in ts])
+    print("        host ms  ", [round(x, 3) for x in hs])
+    ctx.profile_begin(); run().num_rows; print(json.dumps(ctx.profile_end()))
+    ctx.set_option("host_trace_dump", 1)
+    for _ in range(10):
+        ctx.synchronize(); run().num_rows
+    ctx.set_option("host_trace_dump", 1)
 elif what == "feed":
-    rel = nexgen.bids_chunked(10_000_000, 42)
+    # pageable feed of q2's 10 M bids: staging threads x CPU binding.  FOUR distinct host relations in rotation (320 MB:
+    # nothing stays in the CPU caches, like bench.py's e2e leg); DIAG_BIND=1 pins the process to the GPU's NUMA node
+    # BEFORE the staging threads exist (they inherit the mask)
+    import os
+    if os.environ.get("DIAG_BIND") == "1":
+        import pynvml
+        pynvml.nvmlInit(); pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(0))
+    print("cpu affinity:", len(os.sched_getaffinity(0)), "cores")
+    rels = [nexgen.bids_chunked(10_000_000, 42 + k) for k in range(4)]
     ec = fb.ExecutionContext(ctx, plans.q2())
-    src = [fb.HostRelation(rel)]
-    for thr in (0, 2, 4, 8, 16, 32, 64):
+    srcs = [[fb.HostRelation(r)] for r in rels]
+    for thr in (4, 8, 12, 16, 24, 32):
         ctx.set_option("feed_stage_threads", thr)
         ts = []
-        for _ in range(8):
+        for i in range(12):
             t = time.perf_counter()
-            ec.feed_data_sources(src); a = time.perf_counter(); r = ec.execute(); b = time.perf_counter(); ec.clean_data_sources()
+            ec.feed_data_sources(srcs[i % 4]); a = time.perf_counter(); r = ec.execute(); b = time.perf_counter(); ec.clean_data_sources()
             ts.append(((a - t) * 1e3, (b - a) * 1e3, (time.perf_counter() - t) * 1e3))
         print("stage threads", thr, "feed/exec/total ms (median)", [round(float(np.median([x[i] for x in ts[2:]])), 3) for i in range(3)])
 elif what == "partition":
