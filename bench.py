@@ -568,15 +568,31 @@ def phase_times(prof: dict) -> dict:
     return out
 
 
-def bind_to_gpu_numa_node(device: int) -> str:
-    """Pins this process to the CPU cores next to its GPU (NVML's ideal affinity: `nvidia-smi topo -m` shows GPUs 0-3 on
-    NUMA node 0 and 4-7 on node 1 on these boxes).  torchrun does not bind ranks, and a rank whose host thread sits on
-    the far socket reaches every exchange late -- its peers then wait inside exchange_place_kernel."""
+def bind_to_gpu_numa_node(device: int, dist: "Dist | None" = None) -> str:
+    """Pins this process to CPU cores next to its GPU (NVML's ideal affinity: `nvidia-smi topo -m` shows GPUs 0-3 on NUMA
+    node 0 and 4-7 on node 1 on these boxes); torchrun does not bind ranks.  With `dist`, the ranks that share a node
+    split its cores into disjoint, contiguous slices (physical cores and their hyper-thread siblings together), so that
+    no two ranks' host threads ever share a core -- what `numactl --physcpubind` would do per rank.  FLOCK_BENCH_BIND=node
+    keeps the whole node, =off leaves the process unbound."""
+    mode = os.environ.get("FLOCK_BENCH_BIND", "slice")
+    if mode == "off":
+        return "unbound (FLOCK_BENCH_BIND=off)"
     try:
         import pynvml
         pynvml.nvmlInit()
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device))
-        return f"{len(os.sched_getaffinity(0))} cores"
+        node = sorted(os.sched_getaffinity(0))
+        if dist is None or dist.world == 1 or mode == "node":
+            return f"{len(node)} cpus (node)"
+        masks = dist.gather_objects(tuple(node))
+        same = [r for r in range(dist.world) if masks[r] == masks[dist.rank]]
+        j, k = same.index(dist.rank), len(same)
+        half = len(node) // 2                         # "0-31,64-95": first half physical cores, second half their siblings
+        per = max(1, half // k)
+        mine = node[j * per:(j + 1) * per] + node[half + j * per:half + (j + 1) * per]
+        if mine:
+            os.sched_setaffinity(0, mine)
+        return f"{len(mine)} cpus (slice {j + 1} of {k} of a {len(node)}-cpu node)"
     except Exception as e:                           # affinity is a tuning aid, never a requirement
         return f"unbound ({type(e).__name__})"
 
@@ -586,7 +602,7 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
     from flock_b200 import nexgen, plans
 
     rank, world, local = dist.rank, dist.world, dist.local
-    numa = bind_to_gpu_numa_node(local)
+    numa = bind_to_gpu_numa_node(local, dist)
     ctx = fb.Context(local)
     ctx.comm_init(dist.broadcast_object(fb.Context.comm_unique_id() if rank == 0 else None), rank, world)
     alone = fb.Context(local)                       # the same share WITHOUT a communicator: what one GPU does on its own
@@ -663,7 +679,8 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
     # wait for everybody's, lay the windows out) and its own step time: rank skew shows up here, not in the kernels
     per_rank = dist.gather_objects({"rank": dist.rank, "step_ms": round(ctx.timer_ms(0) / args.steps, 5),
                                     "exchange_place_ms": round(prof.get("exchange_place_kernel", {}).get("ms", 0.0), 5),
-                                    "exchange_finish_ms": round(prof.get("exchange_finish_kernel", {}).get("ms", 0.0), 5)})
+                                    "exchange_finish_ms": round(prof.get("exchange_finish_kernel", {}).get("ms", 0.0), 5),
+                                    "kernels_us": {k: round(v["ms"] * 1e3, 1) for k, v in prof.items()}})
 
     # ---- the same share on one GPU, no communicator (what weak scaling is measured against), same protocol
     def step_alone():
@@ -709,11 +726,30 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
     # ---- q2 weak-scaled next to it (round-robin sharding, no collective)
     q2 = None
     if not args.no_queries:
-        rel = nexgen.bids_chunked(args.bids, seed=42 + 1000 * rank, columns=["auction", "price"])
-        t = alone.import_batches(rel)
+        # the protocol of the N = 1 headline: K back-to-back executions over RING distinct resident relations (> L2),
+        # CUDA events on the library stream, barrier + sync on both sides, max over ranks
+        ring = [alone.import_batches(nexgen.bids_chunked(args.bids, seed=42 + 1000 * rank + r, columns=["auction", "price"])) for r in range(RING)]
         ec2 = fb.ExecutionContext(alone, plans.q2())
-        _, rows2, ms2, best2, prof2, _ = time_plan(alone, ec2, [t], max(5, min(args.steps, 20)), dist)
-        q2 = {"ms": round(ms2, 5), "events_per_sec": world * args.bids / (ms2 * 1e-3), "bids_per_gpu": args.bids, "sharding": "round-robin, no collective"}
+
+        def q2_step(i: int):
+            ec2.feed_tables([ring[i % RING]])
+            return ec2.execute_device(0)
+        keep2 = []
+        for i in range(max(args.warmup, 3)):
+            keep2 = (keep2 + [q2_step(i)])[-2:]
+        alone.synchronize()
+        dist.barrier()
+        alone.timer_start(0)
+        for i in range(args.steps):
+            keep2 = (keep2 + [q2_step(i)])[-2:]
+        alone.timer_stop(0)
+        alone.synchronize()
+        dist.barrier()
+        keep2[-1].num_rows
+        ms2 = dist.max(alone.timer_ms(0))[0] / args.steps
+        q2 = {"ms": round(ms2, 5), "events_per_sec": world * args.bids / (ms2 * 1e-3), "bids_per_gpu": args.bids, "sharding": "round-robin, no collective",
+              "timing": f"{args.steps} back-to-back executions per rank over {RING} resident relations, max over ranks (the N = 1 headline's protocol)"}
+        del keep2, ring
         ec2.close()
     result = {
         "metric": metric, "value": events * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -2493,7 +2493,10 @@ static TablePtr hash_aggregate_impl(const CtxPtr& ctx, const TablePtr& in_ptr, i
         }
       if (probe_col >= 0) {
         constexpr int kProbeMeta = 64;  // d_scalars[64 .. 64 + DM_WORDS)
-        const unsigned long long pcap = (std::min<unsigned long long>(std::max<unsigned long long>(2ull * (unsigned long long)n, 1ull << 16), 1ull << 26) + 3) & ~3ull;
+        // capacity 4 n: behind a two-rank exchange a rank holds every second key of the WHOLE range (2 n ids plus the
+        // sampled margins); at 2 n the probe overflowed on one rank of two (run 31) and that rank then reached every
+        // exchange 105 us late.  Only the slots the device decides to use are cleared and scanned.
+        const unsigned long long pcap = (std::min<unsigned long long>(std::max<unsigned long long>(4ull * (unsigned long long)n, 1ull << 16), 1ull << 26) + 3) & ~3ull;
         BufferPtr ptable = alloc(ctx, size_t(pcap) * 4);
         unsigned long long* pmeta = ctx->d_scalars + kProbeMeta;
         FG_CUDA(cudaMemsetAsync(pmeta, 0, DM_WORDS * 8, ctx->stream));

@@ -469,14 +469,21 @@ __global__ void __launch_bounds__(PT_THREADS, 3) partition_scatter_kernel(const 
         for (unsigned i = tid; i < n16; i += PT_THREADS) reinterpret_cast<uint4*>(s_src)[i] = __ldg(aligned + i);
         __syncthreads();
       }
+      // The offsets entries are NOT stored from here: a thread owns 8 consecutive slots, so the lanes of a warp would
+      // write 4 bytes each into addresses 32 bytes apart -- 32 partial sectors per store instruction.  HBM absorbs
+      // that; NVLink sends every partial sector as a packet of its own, and with 7/8 of the rows leaving the GPU the
+      // scatter of q8's persons took 190 us at 8 ranks against 100 us at 2 (profiles/r2_bench_run22_8gpu.json).  The
+      // values go through shared memory (the source staging area is free again after the shuffle) and are written
+      // out below with consecutive lanes on consecutive slots, like the fixed-width columns.
+      int32_t offv[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int s = tid * 8 + k;
+        offv[k] = 0;
         if (s >= rows) continue;
         const unsigned p = s_pid[s];
-        const int64_t pos = int64_t(s_run[p]) + (s - int(s_seg[p]));
         const unsigned rel = s_runb[u * P + p] + (bytepos[k] - s_segb[p]);
-        dest[p].off[u][pos] = int32_t(dest[p].byte_origin[u] + (long long)rel);
+        offv[k] = int32_t(dest[p].byte_origin[u] + (long long)rel);
         if (staged) {
           const unsigned char* from = s_src + shift + (src[k] - sb0);
           unsigned char* to = s_stage + bytepos[k];
@@ -488,6 +495,9 @@ __global__ void __launch_bounds__(PT_THREADS, 3) partition_scatter_kernel(const 
         }
       }
       __syncthreads();
+      int32_t* s_offv = reinterpret_cast<int32_t*>(s_src);  // every read of the source staging area is behind the barrier
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_offv[tid * 8 + k] = offv[k];
       if (staged) {
         // a warp per destination segment: the lanes write consecutive bytes (full sectors on the wire)
         for (int p = warp; p < P; p += PT_WARPS) {
@@ -508,6 +518,15 @@ __global__ void __launch_bounds__(PT_THREADS, 3) partition_scatter_kernel(const 
         }
       }
       __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int sx = tid + k * PT_THREADS;
+        if (sx < rows) {
+          const unsigned p = s_pid[sx];
+          dest[p].off[u][int64_t(s_run[p]) + (sx - int(s_seg[p]))] = s_offv[sx];
+        }
+      }
+      __syncthreads();  // s_offv aliases the source staging area of the next column / tile
       for (int p = tid; p < P; p += PT_THREADS) s_runb[u * P + p] += s_sege[p] - s_segb[p];
     }
     __syncthreads();
@@ -624,6 +643,8 @@ PartPass partition_count_scan(const CtxPtr& ctx, const Table& in, const std::vec
   const bool fused_scan = !no_fused_scan && (1 + U) * n_parts <= PT_FUSED_SCAN_COLS;
   if (fused_scan) {
     ca.arrive = reinterpret_cast<unsigned*>(ctx->d_scalars + kPartitionArriveSlot);
+    // (the last CTA leaves the word at zero, but a launch that died half-way would not: never trust it)
+    FG_CUDA(cudaMemsetAsync(ca.arrive, 0, 8, ctx->stream));
     ca.cta_pos = ps.cta_pos->as<uint32_t>();
     ca.totals = ps.totals->as<unsigned long long>();
   }
