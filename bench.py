@@ -27,7 +27,9 @@ One JSON line on stdout (rank 0).  Keys beyond the base contract:
                adds the page-locked zero-copy feed and a cudaHostRegister-on-feed path (registration inside the timed
                region).  Byte counts come from the library (flockgpu_bytes_moved).
   roofline     dominant kernel of the headline workload: algorithmic bytes per launch / mean launch duration from
-               per-launch CUDA events (flockgpu_profile_begin/_end) against the measured HBM copy bandwidth.
+               per-launch CUDA events (flockgpu_profile_begin/_end) against the measured HBM copy bandwidth.  At N = 1
+               the K steps run twice back to back: once bare (`value`, `ms_per_step`) and once with the event pairs
+               (`roofline.kernel_ms`, `ms_per_step_instrumented`) -- the pairs cost ~3 us per 25 us step.
   cpu_baseline the CPU arm on the host cores in the same run (native threads inside liboracle.so, no Python per batch):
                all cores, target_partitions = 8 (flock/src/configs/flock.toml:113) and one thread.
 """
@@ -433,9 +435,9 @@ def run_gpu_q2(args, dist: Dist) -> dict:
         keep = (keep + [step_device(i)])[-2:]
     ctx.synchronize()
     dist.barrier()
+    # ---- timed region A: the K steps, nothing between the launches but the library's own work -> `value`
     launches0 = ctx.kernel_launches
     sampler.active.set()
-    ctx.profile_begin()
     ctx.timer_start(0)
     t_host = time.perf_counter()
     for i in range(args.steps):
@@ -444,11 +446,23 @@ def run_gpu_q2(args, dist: Dist) -> dict:
     ctx.timer_stop(0)
     ctx.synchronize()
     dist.barrier()
-    sampler.active.clear()
     dev_ms = ctx.timer_ms(0)
-    prof = ctx.profile_end()
     launches = ctx.kernel_launches - launches0
     assert keep[-1].num_rows == n_sel[(args.warmup + args.steps - 1) % RING]
+    # ---- timed region B: the same K steps again with a CUDA-event pair around every launch (flockgpu_profile_*) -> the
+    # kernel's mean duration for `roofline`.  Kept apart from A because the event pairs themselves cost ~3 us per step
+    # (27.8 vs 24.4 us per step, runs 28 / 32); `ms_per_step_instrumented` reports B next to A.
+    dist.barrier()
+    ctx.profile_begin()
+    ctx.timer_start(0)
+    for i in range(args.steps):
+        keep = (keep + [step_device(args.warmup + args.steps + i)])[-2:]
+    ctx.timer_stop(0)
+    ctx.synchronize()
+    dist.barrier()
+    sampler.active.clear()
+    dev_ms_instrumented = dist.max(ctx.timer_ms(0))[0]
+    prof = ctx.profile_end()
     del keep
     dev_ms = dist.max(dev_ms)[0]
 
@@ -533,7 +547,8 @@ def run_gpu_q2(args, dist: Dist) -> dict:
         "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
         "notes": {"sharding": "one GPU", "cache": f"inputs rotate over {RING} resident relations ({RING} x {8 * args.bids / 1e6:.0f} MB > 126 MB L2)",
                   "selectivity": mean_sel / args.bids},
-        "e2e": e2e, "gpu_launches": int(launches), "host_enqueue_us_per_step": round(host_us, 2), "kernels": prof, "clocks": clocks, "roofline": roofline,
+        "e2e": e2e, "gpu_launches": int(launches), "host_enqueue_us_per_step": round(host_us, 2),
+        "ms_per_step_instrumented": dev_ms_instrumented / args.steps, "kernels": prof, "clocks": clocks, "roofline": roofline,
         "stream_events_per_sec": world * args.bids * (50 / 46) * args.steps / (dev_ms * 1e-3),
     }
     ec.close()
