@@ -6,7 +6,8 @@
 // partition = hash % n -> per-partition index lists -> arrow `take` of every column.  Rows keep their
 // input order inside a partition.
 //
-// Here: count -> scan -> place -> scatter, four launches whatever n is; the n output tables are VIEWS of one
+// Here: count (+ scan in its last CTA for up to 64 histogram columns, else a scan launch) -> place -> scatter, three or
+// four launches whatever n is; the n output tables are VIEWS of one
 // partition-ordered set of buffers (every partition starts on a 16-byte boundary so that vector loads keep working).
 #include "partition.h"
 

@@ -4,14 +4,18 @@
 // One pass over the relation, whatever the number of partitions (round 1 made one compaction pass and one take() per
 // destination: 165 launches on rank 0 for q8 at 8 GPUs):
 //   partition_count_kernel    row -> destination byte (the routing function), per-CTA histograms of rows and of the
-//                             bytes of every Utf8 column
-//   partition_scan_kernel     per destination: exclusive scan of the histograms over the CTAs
+//                             bytes of every Utf8 column (<= 8 destinations: eight 8-bit counters in one register);
+//                             with few destinations (an exchange) the CTA that arrives last also scans
+//   partition_scan_kernel     per destination: exclusive scan of the histograms over the CTAs -- a launch of its own
+//                             only for many destinations (the 256-way passes of the radix sort)
 //   <place>                   decides where this source's rows of every destination go (PartDest): partition.cu lays
 //                             the partitions out one behind the other in local buffers, exchange.cu agrees the
 //                             layout with the peers and points into their windows
 //   partition_scatter_kernel  2048 rows at a time are ordered by destination in shared memory (stable) and written
 //                             out segment by segment: a destination receives contiguous, coalesced runs of rows
-//                             (fixed-width values, Utf8 offsets and the string bytes staged through shared memory)
+//                             (fixed-width values; the string bytes staged through shared memory; the Utf8 offsets
+//                             through shared memory too, so that consecutive lanes store consecutive entries --
+//                             partial-sector stores are what NVLink pays for)
 #pragma once
 
 #include "internal.h"
