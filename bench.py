@@ -535,11 +535,24 @@ def run_gpu_q2(args, dist: Dist) -> dict:
             except Exception:
                 pass
     if k and k["launches"]:
-        k_ms = k["ms"] / k["launches"]
+        # Two CUDA-event measurements of the kernel's average launch duration, both on the launching stream:
+        #   back to back  region A / K: the region holds exactly K launches of this kernel and nothing else (one launch per
+        #                 step, `gpu_launches` == `steps`), so its length / K bounds a launch from above, gaps included;
+        #   event pairs   region B: an event pair around every launch -- what an isolated launch costs; the pairs
+        #                 serialise the launches and read ~2.5 us longer (25.1 vs 22.6 us, run 34; ncu's cold, serialised
+        #                 launch: 24.3 us).
+        # `achieved` / `frac` use the back-to-back figure (the sustained rate the workload actually runs at, the same
+        # measurement as `value`); the event-pair figure stays beside it.
+        k_pairs_ms = k["ms"] / k["launches"]
+        one_per_step = launches == args.steps
+        k_ms = min(k_pairs_ms, dev_ms / args.steps) if one_per_step else k_pairs_ms
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        pairs = alg_bytes / (k_pairs_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": traffic, "traffic_source": tsrc, "kernel": "filter_compact_kernel", "kernel_ms": round(k_ms, 5), "launches_timed": k["launches"],
-                    "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src}
+                    "traffic": traffic, "traffic_source": tsrc, "kernel": "filter_compact_kernel", "kernel_ms": round(k_ms, 5),
+                    "kernel_ms_source": "timed region / launches (back to back)" if k_ms < k_pairs_ms else "event pair around every launch",
+                    "event_pairs": {"kernel_ms": round(k_pairs_ms, 5), "achieved": round(pairs, 1), "frac": round(pairs / peak, 4)},
+                    "launches_timed": k["launches"], "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src}
 
     result = {
         "metric": metric, "value": world * args.bids * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,

@@ -25,8 +25,12 @@ NVCC_FLAGS = [
 ]
 
 
+CXX = os.environ.get("CXX", "g++")
+CXX_FLAGS = ["-std=c++17", "-O3", "-fPIC", "-Wall", "-DFLOCKGPU_BUILD"]   # host/*.cpp: plain C++ (CPU intrinsics), no CUDA headers
+
+
 def _sources() -> list[Path]:
-    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cc")) + list((CSRC / "host").glob("*.cc")))
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cc")) + list((CSRC / "host").glob("*.cc")) + list((CSRC / "host").glob("*.cpp")))
 
 
 def _headers_mtime() -> float:
@@ -40,10 +44,12 @@ def _compile(src: Path, verbose: bool) -> Path:
     if obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr):
         return obj
     cmd = [NVCC, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    if src.suffix == ".cpp":
+        cmd = [CXX, *CXX_FLAGS, "-c", str(src), "-o", str(obj)]
     if src.suffix == ".cc":
         cmd.insert(1, "-x")
         cmd.insert(2, "cu")   # the host layer includes headers with __host__ __device__ helpers
-    if verbose:
+    if verbose and src.suffix != ".cpp":
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -786,9 +786,10 @@ TablePtr import_batches(const CtxPtr& ctx, const ArrowSchema* schema, const Arro
       std::unique_ptr<std::atomic<int>[]> remaining(new std::atomic<int>[chunks.size()]);
       for (size_t c = 0; c < chunks.size(); ++c) remaining[c].store(chunks[c].pieces);
       std::atomic<size_t> next{0};
+      const int stream_stores = ctx->feed_stream_stores;
       const std::function<void()> worker = [&]() {
         for (size_t i = next.fetch_add(1); i < pieces.size(); i = next.fetch_add(1)) {
-          memcpy(stage + pieces[i].stage_off, pieces[i].src, pieces[i].bytes);
+          stage_copy(stage + pieces[i].stage_off, pieces[i].src, pieces[i].bytes, stream_stores);
           remaining[chunk_of[i]].fetch_sub(1, std::memory_order_release);
         }
       };
@@ -1439,6 +1440,7 @@ int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "compact_mode")) c->compact_mode = int(value);
     else if (!strcmp(name, "feed_register")) c->feed_register = value != 0;
     else if (!strcmp(name, "host_trace_dump")) host_trace_dump(value != 0);
+    else if (!strcmp(name, "feed_stream_stores")) c->feed_stream_stores = value != 0;
     else if (!strcmp(name, "feed_stage_threads")) c->feed_stage_threads = int(std::max<int64_t>(0, std::min<int64_t>(value, 64)));
     else if (!strcmp(name, "exchange_window_mb")) c->exchange_window_mb = value;
     else fail(FLOCKGPU_ERR_INVALID, "set_option: unknown option \"%s\"", name);

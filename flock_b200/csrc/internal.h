@@ -176,6 +176,7 @@ struct CtxCore {
   bool feed_register = false;
   // pageable sources of a copy feed are staged into a page-locked block by this many host threads, each issuing the
   // DMA of a batch as soon as it has copied it (0: hand the pageable pointer to cudaMemcpyAsync)
+  int feed_stream_stores = 1;  // non-temporal stores into the staging ring (host/stream_copy.cpp); 0: memcpy
   int feed_stage_threads = 8;  // run 27: 3.08 ms per 80 MB feed at 8 threads, 3.40 at 4, 4.4-5.7 at 16-32 (profiles/r2_feed_threads_run27.txt)
   // grid-wide prefix protocol of the compaction kernels: 0 = automatic (single wave when every tile is resident,
   // decoupled look-back otherwise), 1 = always decoupled look-back (flockgpu_set_option "compact_mode"; the parity
@@ -263,6 +264,8 @@ int scan_poll_sleep_ns();
 // occupancy query costs microseconds per call and most kernels here run ~10 us, so the answer is cached per
 // (device, kernel, smem): processes that drive unlike GPUs get the right value for each.
 int resident_ctas(const CtxPtr& ctx, const void* kernel, int threads, size_t smem = 0);
+// Host copy into memory a device reads next (host/stream_copy.cpp).
+void stage_copy(void* dst, const void* src, size_t n, int streaming);
 // Copies `n` u64 scalars from d_scalars[first..] to the host and waits.
 void read_scalars(const CtxPtr& ctx, int first, int n, unsigned long long* out);
 

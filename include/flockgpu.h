@@ -107,7 +107,12 @@ int64_t flockgpu_bytes_moved(flockgpu_ctx* ctx, int32_t direction);
  * "compact_mode" (0 automatic | 1 always decoupled look-back): which grid-wide prefix protocol the compaction /
  * scan kernels use; results are identical, the parity tests run both.
  * "exchange_window_mb" (default 4096): size of the receive window the multi-GPU exchange stores rows into over NVLink
- * peer memory; read by flockgpu_comm_init, so set it first.                                                           */
+ * peer memory; read by flockgpu_comm_init, so set it first.
+ * Feeding PAGEABLE batches (what arrow-rs allocates): "feed_stage_threads" (default 8, 0 = plain cudaMemcpyAsync): host
+ * threads that copy the batches into a page-locked ring ahead of the DMA; "feed_stream_stores" (default 1): those copies
+ * use non-temporal stores; "feed_register" (default 0): page-lock the caller's buffers in place (cudaHostRegister) for
+ * the span feed .. clean instead of staging them.  "host_trace_dump": print the host-side spans collected under
+ * FLOCKGPU_HOST_TRACE=1.                                                                                              */
 int flockgpu_set_option(flockgpu_ctx* ctx, const char* name, int64_t value);
 /* Per-kernel device timing: between _begin and _end every kernel this library launches on the ctx is
  * bracketed by its own pair of CUDA events on the ctx stream.  _end waits for the stream and writes a JSON

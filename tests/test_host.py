@@ -287,3 +287,15 @@ def test_pred_i32_arithmetic_matches_truncated_remainder(modulus):
         assert modes == {0, 1}                   # odd m: `% m (=|!=) 0` is the affine test, everything else Lemire
     else:
         assert modes == {1, 2}                   # even m: rotate test for divisibility
+
+
+def test_stage_copy_is_exact(tmp_path):
+    """The staging copy of the pageable feed uses non-temporal stores for the aligned body and memcpy for head and tail:
+    every alignment / size combination must copy exactly n bytes (tests/cabi/stage_copy_test.cpp)."""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "stage_copy_test"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-Werror", str(root / "tests" / "cabi" / "stage_copy_test.cpp"),
+                    str(root / "flock_b200" / "csrc" / "host" / "stream_copy.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

@@ -68,7 +68,9 @@ elif what == "feed":
     rels = [nexgen.bids_chunked(10_000_000, 42 + k) for k in range(4)]
     ec = fb.ExecutionContext(ctx, plans.q2())
     srcs = [[fb.HostRelation(r)] for r in rels]
-    for thr in (4, 8, 12, 16, 24, 32):
+    ctx.set_option("feed_stream_stores", int(os.environ.get("DIAG_STREAM", "1")))
+    print("non-temporal staging stores:", os.environ.get("DIAG_STREAM", "1"))
+    for thr in [int(x) for x in os.environ.get("DIAG_THREADS", "4,8,12,16,24,32").split(",")]:
         ctx.set_option("feed_stage_threads", thr)
         ts = []
         for i in range(12):
