@@ -99,6 +99,11 @@ class ClockSampler(threading.Thread):
         self._stop_evt = threading.Event()
         self.active = threading.Event()
         self.ok = False
+        # seconds between samples: 2 ms while the short device-resident regions run (a K = 200 region lasts ~5 ms); the
+        # host-buffer legs last 100+ ms and are sampled every 20 ms -- NVML queries take driver locks and the sampling
+        # thread takes the interpreter lock, both of which the host side of an e2e step would otherwise wait for
+        # (execute + export read 0.40 ms per step under 2 ms sampling against 0.07 ms without a sampler, run 37)
+        self.interval = 0.002
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -129,7 +134,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
                 except Exception:
                     pass
-            time.sleep(0.002)
+            time.sleep(self.interval)
 
     def stop(self) -> dict:
         self._stop_evt.set()
@@ -477,6 +482,7 @@ def run_gpu_q2(args, dist: Dist) -> dict:
             ec.clean_data_sources()
         dist.barrier()
         h0, d0 = ctx.bytes_moved()
+        sampler.interval = 0.02
         sampler.active.set()
         ctx.timer_start(1)
         t_wall = time.perf_counter()
@@ -635,6 +641,7 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
     ctx.comm_init(dist.broadcast_object(fb.Context.comm_unique_id() if rank == 0 else None), rank, world)
     alone = fb.Context(local)                       # the same share WITHOUT a communicator: what one GPU does on its own
     sampler = ClockSampler(local)
+    sampler.interval = float(os.environ.get("FLOCK_BENCH_SAMPLE_MS", "2")) * 1e-3
     sampler.start()
     metric, config = workload_config(world, args.bids)
     peak, peak_src = measured_peak_gbs()
@@ -735,6 +742,7 @@ def run_gpu_q8(args, dist: Dist) -> dict | None:
     e2e_steps = max(3, min(args.steps if args.e2e_steps is None else args.e2e_steps, 20))
     dist.barrier()
     h0, d0 = ctx.bytes_moved()
+    sampler.interval = 0.02
     sampler.active.set()
     t_wall = time.perf_counter()
     for _ in range(e2e_steps):

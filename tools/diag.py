@@ -78,6 +78,15 @@ elif what == "feed":
             ec.feed_data_sources(srcs[i % 4]); a = time.perf_counter(); r = ec.execute(); b = time.perf_counter(); ec.clean_data_sources()
             ts.append(((a - t) * 1e3, (b - a) * 1e3, (time.perf_counter() - t) * 1e3))
         print("stage threads", thr, "feed/exec/total ms (median)", [round(float(np.median([x[i] for x in ts[2:]])), 3) for i in range(3)])
+    # where does execute() spend its time once the relation is resident?  launch -> survivor count -> export -> release
+    parts = []
+    for i in range(12):
+        ec.feed_data_sources(srcs[i % 4])
+        t0 = time.perf_counter(); tab = ec.execute_device(0); t1 = time.perf_counter(); n = tab.num_rows; t2 = time.perf_counter()
+        b = tab.to_batch(); t3 = time.perf_counter(); del b, tab; t4 = time.perf_counter()
+        ec.clean_data_sources()
+        parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3))
+    print("execute_device / num_rows wait / to_batch (export) / release  ms (median)", [round(float(np.median([x[i] for x in parts[2:]])), 4) for i in range(4)], "rows", n)
 elif what == "partition":
     n_p, n_a, _ = nexgen.relation_counts(125_000_000)
     tabs = {"persons(p_id,name)": (ctx.import_batches(nexgen.split_batches(nexgen.persons(n_p, 42, 0, ["p_id", "name"]))), [0]),
