@@ -831,7 +831,8 @@ def run_reference(args) -> dict | None:
         for label, parts, threads in (("all_cores", min(cores, len(batches)), cores), ("target_partitions_8", 8, min(8, cores)), ("single_thread", 1, 1)):
             tbl, times = oracle.q2_collect(batches, parts, threads, repeat=max(args.warmup, 1) + args.steps)
             times = times[max(args.warmup, 1):]
-            figures[label] = {"value": args.bids * len(times) / sum(times), "ms_per_step": sum(times) * 1e3 / len(times), "partitions": parts, "threads": threads}
+            figures[label] = {"value": args.bids * len(times) / sum(times), "ms_per_step": sum(times) * 1e3 / len(times),
+                              "ms_median": statistics.median(times) * 1e3, "ms_best": min(times) * 1e3, "partitions": parts, "threads": threads}
         au = np.concatenate([b["auction"].to_numpy() for b in batches])
         assert tbl.num_rows == int((np.fmod(au.astype(np.int64), 123) == 0).sum())
         # a second CPU reference point: the same query on Arrow C++'s compute kernels through Acero -- the
