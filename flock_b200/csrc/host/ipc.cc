@@ -29,7 +29,7 @@ struct Fb {
   size_t n;
   template <typename T>
   T rd(size_t at) const {
-    FG_CHECK(at + sizeof(T) <= n, FLOCKGPU_ERR_INVALID, "IPC header: truncated flatbuffer (offset %zu of %zu)", at, n);
+    FG_CHECK(at <= n && sizeof(T) <= n - at, FLOCKGPU_ERR_INVALID, "IPC header: truncated or corrupt flatbuffer (offset %zu of %zu)", at, n);
     T v;
     memcpy(&v, p + at, sizeof(T));
     return v;
@@ -135,26 +135,33 @@ std::vector<uint8_t> build_record_batch_message(int64_t length, const std::vecto
 
 }  // namespace
 
-TablePtr import_ipc_frames(const CtxPtr& ctx, const ArrowSchema* schema, const uint8_t* const* headers, const int64_t* header_lens,
-                           const uint8_t* const* bodies, const int64_t* body_lens, int n_frames, const int* projection, int n_projection) {
+// Arrow C arrays whose buffers point INTO the frames' bodies: pure host work, no device, no context -- every offset and
+// length a frame claims is checked against the bytes it came with before anything dereferences them.
+struct IpcFrame {
+  ArrowArray top;
+  std::vector<ArrowArray> kids;
+  std::vector<ArrowArray*> kid_ptrs;
+  std::vector<std::vector<const void*>> bufs;
+  const void* top_buf[1] = {nullptr};
+};
+struct IpcFrames {
+  std::vector<std::unique_ptr<IpcFrame>> frames;
+  std::vector<const ArrowArray*> tops;
+};
+
+IpcFrames view_ipc_frames(const ArrowSchema* schema, const uint8_t* const* headers, const int64_t* header_lens, const uint8_t* const* bodies,
+                          const int64_t* body_lens, int n_frames) {
   FG_CHECK(schema && schema->format && !strcmp(schema->format, "+s"), FLOCKGPU_ERR_INVALID, "table_import_ipc: schema must be a struct (\"+s\")");
   FG_CHECK(n_frames >= 0 && (n_frames == 0 || (headers && header_lens && bodies && body_lens)), FLOCKGPU_ERR_INVALID, "table_import_ipc: bad frame list");
   const int64_t n_fields = schema->n_children;
-  // Arrow C arrays whose buffers point into the bodies
-  struct Frame {
-    ArrowArray top;
-    std::vector<ArrowArray> kids;
-    std::vector<ArrowArray*> kid_ptrs;
-    std::vector<std::vector<const void*>> bufs;
-    const void* top_buf[1] = {nullptr};
-  };
-  std::vector<std::unique_ptr<Frame>> frames;
-  std::vector<const ArrowArray*> tops;
+  IpcFrames out;
   for (int f = 0; f < n_frames; ++f) {
+    FG_CHECK(body_lens[f] >= 0 && (body_lens[f] == 0 || bodies[f]), FLOCKGPU_ERR_INVALID, "table_import_ipc: frame %d has no body", f);
     const FrameLayout L = parse_record_batch_message(headers[f], header_lens[f]);
     FG_CHECK(int64_t(L.nodes.size()) == n_fields, FLOCKGPU_ERR_INVALID, "table_import_ipc: frame %d describes %zu fields, the schema has %lld", f, L.nodes.size(),
              (long long)n_fields);
-    auto fr = std::make_unique<Frame>();
+    FG_CHECK(L.length >= 0 && L.length < (int64_t(1) << 31), FLOCKGPU_ERR_INVALID, "table_import_ipc: frame %d: batch length %lld", f, (long long)L.length);
+    auto fr = std::make_unique<IpcFrame>();
     fr->kids.resize(size_t(n_fields));
     fr->bufs.resize(size_t(n_fields));
     size_t next = 0;
@@ -170,14 +177,39 @@ TablePtr import_ipc_frames(const CtxPtr& ctx, const ArrowSchema* schema, const u
       a.null_count = L.nodes[size_t(c)].second;
       FG_CHECK(a.length == L.length, FLOCKGPU_ERR_INVALID, "table_import_ipc: frame %d: field length %lld differs from the batch length %lld", f,
                (long long)a.length, (long long)L.length);
+      FG_CHECK(a.null_count >= 0 && a.null_count <= a.length, FLOCKGPU_ERR_INVALID, "table_import_ipc: frame %d: null count %lld of %lld rows", f,
+               (long long)a.null_count, (long long)a.length);
       for (size_t b = 0; b < want; ++b) {
         const auto& ext = L.buffers[next + b];
-        FG_CHECK(ext.first >= 0 && ext.second >= 0 && ext.first + ext.second <= body_lens[f], FLOCKGPU_ERR_INVALID,
+        FG_CHECK(ext.first >= 0 && ext.second >= 0 && ext.first <= body_lens[f] && ext.second <= body_lens[f] - ext.first, FLOCKGPU_ERR_INVALID,
                  "table_import_ipc: frame %d: buffer [%lld, +%lld) outside the %lld-byte body", f, (long long)ext.first, (long long)ext.second,
                  (long long)body_lens[f]);
         // a zero-length validity buffer means "no nulls"; zero-length data buffers of empty batches still get an address
         const bool absent = ext.second == 0 && b == 0;
         fr->bufs[size_t(c)].push_back(absent ? nullptr : static_cast<const void*>(bodies[f] + ext.first));
+      }
+      // every buffer holds what `length` rows need (a frame that claims more rows than it carries would be read past its end)
+      const auto& validity = L.buffers[next];
+      FG_CHECK(validity.second == 0 ? a.null_count == 0 : validity.second >= (a.length + 7) / 8, FLOCKGPU_ERR_INVALID,
+               "table_import_ipc: frame %d, column \"%s\": validity bitmap of %lld bytes for %lld rows with %lld nulls", f, schema->children[c]->name,
+               (long long)validity.second, (long long)a.length, (long long)a.null_count);
+      if (dt == FLOCKGPU_UTF8) {
+        const auto& offs = L.buffers[next + 1];
+        const auto& data = L.buffers[next + 2];
+        if (a.length > 0) {
+          FG_CHECK(offs.second >= (a.length + 1) * 4, FLOCKGPU_ERR_INVALID, "table_import_ipc: frame %d, column \"%s\": offsets buffer of %lld bytes for %lld rows", f,
+                   schema->children[c]->name, (long long)offs.second, (long long)a.length);
+          int32_t first, last;
+          memcpy(&first, bodies[f] + offs.first, 4);
+          memcpy(&last, bodies[f] + offs.first + a.length * 4, 4);
+          FG_CHECK(first >= 0 && last >= first && int64_t(last) <= data.second, FLOCKGPU_ERR_INVALID,
+                   "table_import_ipc: frame %d, column \"%s\": offsets [%d, %d] outside the %lld value bytes", f, schema->children[c]->name, first, last,
+                   (long long)data.second);
+        }
+      } else {
+        const auto& data = L.buffers[next + 1];
+        FG_CHECK(data.second >= a.length * int64_t(dtype_width(dt)), FLOCKGPU_ERR_INVALID, "table_import_ipc: frame %d, column \"%s\": %lld value bytes for %lld rows", f,
+                 schema->children[c]->name, (long long)data.second, (long long)a.length);
       }
       next += want;
       a.n_buffers = int64_t(want);
@@ -190,10 +222,10 @@ TablePtr import_ipc_frames(const CtxPtr& ctx, const ArrowSchema* schema, const u
     fr->top.buffers = fr->top_buf;
     fr->top.n_children = n_fields;
     fr->top.children = fr->kid_ptrs.data();
-    tops.push_back(&fr->top);
-    frames.push_back(std::move(fr));
+    out.tops.push_back(&fr->top);
+    out.frames.push_back(std::move(fr));
   }
-  return import_batches(ctx, schema, tops.data(), n_frames, projection, n_projection, ctx->feed_zero_copy);
+  return out;
 }
 
 // One frame for rows [row_begin, row_begin + row_count) of `t`.  The two blocks are malloc'ed (flockgpu_ipc_free).
@@ -322,11 +354,14 @@ int flockgpu_table_import_ipc(flockgpu_ctx* ctx, const struct ArrowSchema* schem
                               const uint8_t* const* bodies, const int64_t* body_lens, int32_t n_frames, const int32_t* projection, int32_t n_projection,
                               flockgpu_table** out) {
   return guarded([&] {
-    auto c = core_of(ctx);
     FG_CHECK(out, FLOCKGPU_ERR_INVALID, "table_import_ipc: null out pointer");
+    // the frames are checked before the context is even looked at: a malformed payload is an INVALID error whatever
+    // the state of the device (and CPU-only CI can exercise the checks: tests/test_host.py)
+    const IpcFrames view = view_ipc_frames(schema, headers, header_lens, bodies, body_lens, n_frames);
+    auto c = core_of(ctx);
     std::lock_guard<std::recursive_mutex> g(c->mu);
     FG_CUDA(cudaSetDevice(c->device));
-    *out = wrap_table(import_ipc_frames(c, schema, headers, header_lens, bodies, body_lens, n_frames, projection, n_projection));
+    *out = wrap_table(import_batches(c, schema, view.tops.data(), n_frames, projection, n_projection, c->feed_zero_copy));
   });
 }
 

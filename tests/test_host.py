@@ -299,3 +299,60 @@ def test_stage_copy_is_exact(tmp_path):
                     str(root / "flock_b200" / "csrc" / "host" / "stream_copy.cpp"), "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+def _import_ipc_without_a_device(schema: pa.Schema, frames) -> str:
+    """flockgpu_table_import_ipc with a NULL context: the frames are validated BEFORE the context is looked at, so the error
+    message tells whether validation passed ("null context handle") or what was wrong with the payload."""
+    keep = [(pa.py_buffer(h), pa.py_buffer(b)) for h, b in frames]
+    n = len(keep)
+    hp = (C.c_void_p * max(n, 1))(*[h.address for h, _ in keep])
+    hl = (C.c_int64 * max(n, 1))(*[h.size for h, _ in keep])
+    bp = (C.c_void_p * max(n, 1))(*[b.address for _, b in keep])
+    bl = (C.c_int64 * max(n, 1))(*[b.size for _, b in keep])
+    c_schema = _ffi.ArrowSchema()
+    schema._export_to_c(C.addressof(c_schema))
+    out = C.c_void_p()
+    try:
+        rc = _ffi.lib.flockgpu_table_import_ipc(None, C.byref(c_schema), hp, hl, bp, bl, n, None, 0, C.byref(out))
+    finally:
+        if c_schema.release:
+            C.CFUNCTYPE(None, C.c_void_p)(c_schema.release)(C.addressof(c_schema))
+    assert rc == _ffi.ERR_INVALID or rc == _ffi.ERR_UNSUPPORTED, rc
+    return _ffi.lib.flockgpu_last_error().decode()
+
+
+def test_ipc_frames_are_validated_before_anything_reads_them():
+    """A payload frame is untrusted input (flock/src/runtime/payload.rs:161-192 hands over what arrived in the Lambda
+    event): lengths, offsets and buffer extents are checked against the bytes that came with them, on the host, before a
+    device is involved."""
+    import struct
+    b = pa.RecordBatch.from_arrays([pa.array(np.arange(1000, dtype=np.int32)), pa.array(["s%d" % (i % 17) for i in range(1000)]),
+                                    pa.array(np.arange(1000, dtype=np.int64), mask=np.arange(1000) % 3 == 0)], names=["a", "s", "v"])
+    frame = lambda batch: (lambda m: (m.metadata.to_pybytes(), m.body.to_pybytes()))(pa.ipc.read_message(batch.serialize()))
+    header, body = frame(b)
+    ok = "null context handle"
+    assert _import_ipc_without_a_device(b.schema, [(header, body)]) == ok
+    assert _import_ipc_without_a_device(b.schema, [frame(b.slice(3, 200)), frame(b.slice(0, 0)), frame(b.slice(203))]) == ok
+    # a body shorter than the buffers the header lists
+    assert "outside the" in _import_ipc_without_a_device(b.schema, [(header, body[:len(body) // 2])])
+    # a header cut short / garbage
+    assert "flatbuffer" in _import_ipc_without_a_device(b.schema, [(header[:40], body)]) or "IPC header" in _import_ipc_without_a_device(b.schema, [(header[:40], body)])
+    assert "IPC header" in _import_ipc_without_a_device(b.schema, [(b"\xff" * 64, body)])
+    # a frame of another schema: fewer fields, or a narrower column where a wider one is declared
+    assert "fields" in _import_ipc_without_a_device(b.schema, [frame(b.select(["a", "s"]))])
+    wide = pa.schema([pa.field("a", pa.int64()), b.schema.field("s"), b.schema.field("v")])
+    assert "value bytes" in _import_ipc_without_a_device(wide, [(header, body)])
+    # Utf8 offsets that point past the value bytes: patch the LAST offset of column s inside the body
+    off = np.frombuffer(pa.ipc.read_record_batch(pa.ipc.read_message(b.serialize()), b.schema).column(1).buffers()[1], dtype=np.int32)
+    needle = struct.pack("<i", int(off[1000]))
+    at = body.rfind(needle, 0, body.find(b"s0s1s2"))           # the offsets buffer sits right before the value bytes
+    assert at > 0
+    broken = body[:at] + struct.pack("<i", 1 << 30) + body[at + 4:]
+    assert "offsets" in _import_ipc_without_a_device(b.schema, [(header, broken)])
+    # a dictionary / schema message is not a data frame
+    sink = pa.BufferOutputStream()
+    with pa.ipc.new_stream(sink, b.schema):
+        pass
+    schema_msg = pa.ipc.read_message(sink.getvalue())
+    assert "message type" in _import_ipc_without_a_device(b.schema, [(schema_msg.metadata.to_pybytes(), b"")])
