@@ -448,6 +448,35 @@ def q2_collect(batches: list[pa.RecordBatch], n_partitions: int, n_threads: int,
     return tbl, times
 
 
+def q8_collect(persons: list[pa.RecordBatch], auctions: list[pa.RecordBatch], n_partitions: int, n_threads: int, repeat: int = 1):
+    """NEXMark q8 over one window by the native partition-parallel pipeline (orc_q8_collect: Partial DISTINCT per input
+    partition -> hash repartition -> FinalPartitioned DISTINCT -> partitioned join; native threads, no Python per batch).
+    Returns (result table (p_id, name), seconds per call as a list of `repeat` wall times)."""
+    import time
+    fn = lib().orc_q8_collect
+    fn.restype = C.c_int64
+    persons = [b for b in persons if b.num_rows]
+    auctions = [b for b in auctions if b.num_rows]
+    npb, nab = len(persons), len(auctions)
+    pid = (C.c_void_p * max(npb, 1))(*[b.column("p_id").buffers()[1].address + 4 * b.column("p_id").offset for b in persons])
+    noff = (C.c_void_p * max(npb, 1))(*[b.column("name").buffers()[1].address + 4 * b.column("name").offset for b in persons])
+    ndat = (C.c_void_p * max(npb, 1))(*[(b.column("name").buffers()[2].address if b.column("name").buffers()[2] is not None else 0) for b in persons])
+    prow = (C.c_int64 * max(npb, 1))(*[b.num_rows for b in persons])
+    sel = (C.c_void_p * max(nab, 1))(*[b.column("seller").buffers()[1].address + 4 * b.column("seller").offset for b in auctions])
+    arow = (C.c_int64 * max(nab, 1))(*[b.num_rows for b in auctions])
+    rows = sum(b.num_rows for b in persons)
+    nbytes = sum(b.column("name").buffers()[2].size if b.column("name").buffers()[2] is not None else 0 for b in persons)
+    out_pid, out_off, out_dat = np.empty(max(rows, 1), np.int32), np.empty(rows + 1, np.int32), np.empty(max(nbytes, 1), np.uint8)
+    times, m = [], 0
+    for _ in range(max(repeat, 1)):
+        t = time.perf_counter()
+        m = fn(pid, noff, ndat, prow, C.c_int32(npb), sel, arow, C.c_int32(nab), C.c_int32(n_partitions), C.c_int32(n_threads),
+               out_pid.ctypes.data_as(C.c_void_p), out_off.ctypes.data_as(C.c_void_p), out_dat.ctypes.data_as(C.c_void_p))
+        times.append(time.perf_counter() - t)
+    names = pa.Array.from_buffers(pa.utf8(), m, [None, pa.py_buffer(out_off[:m + 1].tobytes()), pa.py_buffer(out_dat[:int(out_off[m]) if m else 0].tobytes())])
+    return pa.table({"p_id": pa.array(out_pid[:m]), "name": names}), times
+
+
 def _schema_from_json(s: dict) -> pa.Schema:
     def ty(t):
         if isinstance(t, dict):

@@ -571,4 +571,161 @@ int64_t orc_q2_collect(const int32_t* const* auction, const int32_t* const* pric
   return total;
 }
 
+
+// ---- the N > 1 CPU arm of bench.py: NEXMark q8 over one rank's share, executed natively the way the plan runs ----------
+// Plan (benchmarks/src/nexmark/query/q8.sql, q8_plan.fmt; shapes planner.rs:152-171, stage.rs:535-543, :597-601):
+//   P = DISTINCT (p_id, name) over person, A = DISTINCT seller over auction, P JOIN A ON p_id = seller -> (p_id, name).
+//   Each DISTINCT is HashAggregate(Partial) per input partition -> RepartitionExec(Hash) -> HashAggregate(FinalPartitioned);
+//   the join is Partitioned on the same routing.  Input batches are dealt round-robin to n_partitions input partitions
+//   (RepartitionExec(RoundRobinBatch)); a pool of native threads draws the partitions of each phase from a counter.
+// Output: p_id / name (offsets + bytes) of the join result, partitions in order; returns the row count.
+}  // extern "C" (the helpers below are templates)
+namespace {
+
+struct RowRef {
+  int32_t batch, row;
+};
+inline uint64_t q8_mix(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+// open-addressing set of row references; equality and hash are supplied by the caller
+template <class Hash, class Eq>
+struct RefSet {
+  std::vector<int64_t> slot;  // (batch << 32) | row, -1 = free
+  uint64_t mask;
+  Hash hash;
+  Eq eq;
+  RefSet(size_t n, Hash h, Eq e) : hash(h), eq(e) {
+    size_t cap = 16;
+    while (cap < 2 * n) cap <<= 1;
+    slot.assign(cap, -1);
+    mask = cap - 1;
+  }
+  // true when (b, r) was new
+  bool insert(int32_t b, int32_t r) {
+    uint64_t i = hash(b, r) & mask;
+    while (true) {
+      const int64_t cur = slot[i];
+      if (cur < 0) {
+        slot[i] = (int64_t(b) << 32) | uint32_t(r);
+        return true;
+      }
+      if (eq(int32_t(cur >> 32), int32_t(cur & 0xffffffff), b, r)) return false;
+      i = (i + 1) & mask;
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int64_t orc_q8_collect(const int32_t* const* p_id, const int32_t* const* name_off, const uint8_t* const* name_data, const int64_t* p_rows, int32_t n_p_batches,
+                       const int32_t* const* seller, const int64_t* a_rows, int32_t n_a_batches, int32_t n_partitions, int32_t n_threads, int32_t* out_pid,
+                       int32_t* out_name_off, uint8_t* out_name_data) {
+  const int32_t P = std::max(1, n_partitions);
+  const int32_t T = std::max(1, std::min(n_threads, P));
+  auto run = [&](auto&& task) {
+    std::atomic<int32_t> next{0};
+    auto worker = [&]() {
+      for (int32_t p = next.fetch_add(1); p < P; p = next.fetch_add(1)) task(p);
+    };
+    std::vector<std::thread> pool;
+    for (int32_t t = 1; t < T; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
+  };
+  auto name_len = [&](int32_t b, int32_t r) { return name_off[b][r + 1] - name_off[b][r]; };
+  auto p_hash = [&](int32_t b, int32_t r) {
+    uint64_t h = q8_mix(uint32_t(p_id[b][r]));
+    const uint8_t* s = name_data[b] + name_off[b][r];
+    for (int32_t i = 0, n = name_len(b, r); i < n; ++i) h = (h ^ s[i]) * 0x100000001b3ull;
+    return q8_mix(h);
+  };
+  auto p_eq = [&](int32_t b1, int32_t r1, int32_t b2, int32_t r2) {
+    if (p_id[b1][r1] != p_id[b2][r2]) return false;
+    const int32_t n = name_len(b1, r1);
+    return n == name_len(b2, r2) && !memcmp(name_data[b1] + name_off[b1][r1], name_data[b2] + name_off[b2][r2], size_t(n));
+  };
+  auto route = [&](int32_t key) { return int32_t((q8_mix(uint32_t(key)) >> 32) * uint64_t(P) >> 32); };
+  // ---- phase 1: Partial DISTINCT per input partition, then the hash repartition of its groups
+  const size_t np = size_t(P);
+  std::vector<std::vector<std::vector<RowRef>>> p_parts{np, std::vector<std::vector<RowRef>>{np}};   // [source][destination]
+  std::vector<std::vector<std::vector<int32_t>>> a_parts{np, std::vector<std::vector<int32_t>>{np}};
+  run([&](int32_t p) {
+    size_t rows = 0;
+    for (int32_t b = p; b < n_p_batches; b += P) rows += size_t(p_rows[b]);
+    RefSet<decltype(p_hash), decltype(p_eq)> groups(rows, p_hash, p_eq);
+    for (int32_t b = p; b < n_p_batches; b += P)
+      for (int32_t r = 0; r < int32_t(p_rows[b]); ++r)
+        if (groups.insert(b, r)) p_parts[size_t(p)][size_t(route(p_id[b][r]))].push_back(RowRef{b, r});
+    size_t arows = 0;
+    for (int32_t b = p; b < n_a_batches; b += P) arows += size_t(a_rows[b]);
+    size_t cap = 16;
+    while (cap < 2 * arows) cap <<= 1;
+    std::vector<int64_t> set(cap, -1);
+    for (int32_t b = p; b < n_a_batches; b += P)
+      for (int64_t r = 0; r < a_rows[b]; ++r) {
+        const int32_t k = seller[b][r];
+        uint64_t i = q8_mix(uint32_t(k)) & (cap - 1);
+        while (set[i] >= 0 && int32_t(set[i]) != k) i = (i + 1) & (cap - 1);
+        if (set[i] < 0) {
+          set[i] = int64_t(uint32_t(k));
+          a_parts[size_t(p)][size_t(route(k))].push_back(k);
+        }
+      }
+  });
+  // ---- phase 2: FinalPartitioned DISTINCTs of one output partition, then its join (build P, probe A: probe = membership)
+  std::vector<std::vector<int32_t>> o_pid{np}, o_len{np};
+  std::vector<std::vector<uint8_t>> o_bytes{np};
+  run([&](int32_t q) {
+    size_t n_p = 0, n_a = 0;
+    for (int32_t p = 0; p < P; ++p) {
+      n_p += p_parts[size_t(p)][size_t(q)].size();
+      n_a += a_parts[size_t(p)][size_t(q)].size();
+    }
+    size_t cap = 16;
+    while (cap < 2 * n_a) cap <<= 1;
+    std::vector<int64_t> sellers(cap, -1);
+    for (int32_t p = 0; p < P; ++p)
+      for (int32_t k : a_parts[size_t(p)][size_t(q)]) {
+        uint64_t i = q8_mix(uint32_t(k)) & (cap - 1);
+        while (sellers[i] >= 0 && int32_t(sellers[i]) != k) i = (i + 1) & (cap - 1);
+        sellers[i] = int64_t(uint32_t(k));
+      }
+    RefSet<decltype(p_hash), decltype(p_eq)> groups(n_p, p_hash, p_eq);
+    for (int32_t p = 0; p < P; ++p)
+      for (const RowRef& ref : p_parts[size_t(p)][size_t(q)]) {
+        if (!groups.insert(ref.batch, ref.row)) continue;
+        const int32_t k = p_id[ref.batch][ref.row];
+        uint64_t i = q8_mix(uint32_t(k)) & (cap - 1);
+        while (sellers[i] >= 0 && int32_t(sellers[i]) != k) i = (i + 1) & (cap - 1);
+        if (sellers[i] < 0) continue;
+        o_pid[size_t(q)].push_back(k);
+        const int32_t n = name_len(ref.batch, ref.row);
+        o_len[size_t(q)].push_back(n);
+        const uint8_t* sp = name_data[ref.batch] + name_off[ref.batch][ref.row];
+        o_bytes[size_t(q)].insert(o_bytes[size_t(q)].end(), sp, sp + n);
+      }
+  });
+  // ---- collect: the partitions one behind the other
+  int64_t rows = 0, bytes = 0;
+  out_name_off[0] = 0;
+  for (int32_t q = 0; q < P; ++q) {
+    std::copy(o_pid[size_t(q)].begin(), o_pid[size_t(q)].end(), out_pid + rows);
+    for (size_t i = 0; i < o_len[size_t(q)].size(); ++i) {
+      bytes += o_len[size_t(q)][i];
+      out_name_off[rows + int64_t(i) + 1] = int32_t(bytes);
+    }
+    std::copy(o_bytes[size_t(q)].begin(), o_bytes[size_t(q)].end(), out_name_data + (bytes - int64_t(o_bytes[size_t(q)].size())));
+    rows += int64_t(o_pid[size_t(q)].size());
+  }
+  return rows;
+}
+
 }  // extern "C"

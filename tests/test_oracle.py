@@ -202,3 +202,31 @@ def _digest(t: pa.Table) -> str:
     import hashlib
     rows = json.dumps(t.to_pylist(), default=str, sort_keys=True)
     return hashlib.sha256(rows.encode()).hexdigest()
+
+
+def test_native_q8_arm_matches_the_plan_executor_and_an_independent_reference():
+    """bench.py's N > 1 CPU arm (oracle.q8_collect -> orc_q8_collect: native threads, Partial DISTINCT -> hash repartition ->
+    FinalPartitioned DISTINCT -> partitioned join) against (a) the plan executor running the reference's q8 plan JSON and
+    (b) pyarrow's group_by / is_in on inputs with duplicate rows and equal ids under different names."""
+    import pyarrow.compute as pc
+    ev = nexgen.generate(200_000, seed=21, batch_rows=4096)
+    want = oracle.execute_plan(plans.q8(), [[ev[r]] for r in plans.SOURCES["q8"]])
+    for parts, threads in ((1, 1), (4, 2), (8, 8), (13, 3)):
+        got, times = oracle.q8_collect(ev["person"], ev["auction"], parts, threads, repeat=2)
+        assert len(times) == 2
+        oracle.assert_tables_equal(got, want)
+    rng = np.random.default_rng(3)
+    n = 30_000
+    pid = rng.integers(0, 12_000, n).astype(np.int32)
+    names = np.array(["n%d" % (k % 7) for k in rng.integers(0, 1000, n)])
+    persons = [pa.RecordBatch.from_arrays([pa.array(pid[i:i + 4096]), pa.array(names[i:i + 4096])], names=["p_id", "name"]) for i in range(0, n, 4096)]
+    sel = rng.integers(0, 18_000, 50_000).astype(np.int32)
+    auctions = [pa.RecordBatch.from_arrays([pa.array(sel[i:i + 8192])], names=["seller"]) for i in range(0, 50_000, 8192)]
+    distinct = pa.Table.from_batches(persons).group_by(["p_id", "name"], use_threads=False).aggregate([])
+    ref = distinct.filter(pc.is_in(distinct["p_id"], value_set=pa.array(np.unique(sel)))).select(["p_id", "name"])
+    for parts, threads in ((1, 1), (8, 4)):
+        got, _ = oracle.q8_collect(persons, auctions, parts, threads)
+        assert got.num_rows == ref.num_rows and got.num_rows < n
+        oracle.assert_tables_equal(got, ref)
+    assert oracle.q8_collect([persons[0].slice(0, 0)], auctions, 4, 2)[0].num_rows == 0
+    assert oracle.q8_collect(persons, [auctions[0].slice(0, 0)], 4, 2)[0].num_rows == 0
