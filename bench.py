@@ -854,6 +854,27 @@ def run_reference(args) -> dict | None:
                                       "note": "Arrow C++ compute kernels via Acero (pyarrow %s): a SIMD CPU engine, not the reference's DataFusion; not the headline" % pa.__version__}
         except Exception as e:                       # a reference point, never a requirement
             figures["arrow_acero"] = {"value": None, "note": f"failed: {e!r}"[:200]}
+        # ---- the other BASELINE configurations on the same host cores (the CPU side of the GPU arm's `queries`): q5 over
+        # 100 M bids and q8 over the one-GPU share of 1 B events, native threads, all cores and target_partitions = 8
+        by_query = {}
+        if not args.no_queries:
+            def arm(fn, events):
+                out = {}
+                for label, parts, threads in (("all_cores", cores, cores), ("target_partitions_8", 8, min(8, cores))):
+                    res, ts = fn(parts, threads, 1 + max(1, min(args.steps, 3)))
+                    ts = ts[1:]
+                    out[label] = {"events_per_sec": events * len(ts) / sum(ts), "ms": sum(ts) * 1e3 / len(ts), "ms_best": min(ts) * 1e3, "partitions": parts,
+                                  "threads": threads, "rows_out": res.num_rows}
+                return out
+            try:
+                q5_bids = nexgen.bids_chunked(100_000_000, seed=42, columns=["auction"])
+                by_query["q5"] = arm(lambda p, t, r: oracle.q5_collect(q5_bids, p, t, repeat=r), 100_000_000)
+                del q5_bids
+                q8_p, q8_a = q8_slice(0)
+                by_query["q8"] = arm(lambda p, t, r: oracle.q8_collect(q8_p, q8_a, p, t, repeat=r), EVENTS_PER_GPU)
+                del q8_p, q8_a
+            except Exception as e:                   # reference points beside `queries`, never a requirement
+                by_query["error"] = repr(e)[:300]
         best = max((k for k in figures if k != "arrow_acero"), key=lambda k: figures[k]["value"])
         value, ms = figures[best]["value"], figures[best]["ms_per_step"]
         sample = (f"all {args.bids} bids per step, {args.steps} steps; native threads inside liboracle.so (orc_q2_collect), one task per partition; "
@@ -862,7 +883,7 @@ def run_reference(args) -> dict | None:
         rows_out = tbl.num_rows
     else:
         persons, auctions = q8_slice(0)
-        figures = {}
+        figures, by_query = {}, {}
         n_steps = max(1, min(args.steps, 10))
         for label, parts, threads in (("all_cores", cores, cores), ("target_partitions_8", 8, min(8, cores)), ("single_thread", 1, 1)):
             out, times = oracle.q8_collect(persons, auctions, parts, threads, repeat=1 + (n_steps if threads > 1 else min(n_steps, 2)))
@@ -879,7 +900,8 @@ def run_reference(args) -> dict | None:
     return {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32" if config["query"] == "q2" else "int32+utf8",
             "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample, "figures": figures, "host_cores": cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample, "figures": figures, "host_cores": cores,
+                             **({"queries": by_query} if by_query else {})},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "rows_out": rows_out}
 
@@ -888,6 +910,8 @@ def cpu_baseline(args, world: int, steps: int = 5) -> dict:
     """The CPU arm timed beside the GPU run: `bench.py --impl reference` in a child process, a bounded sample."""
     import subprocess
     cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", str(world), "--steps", str(steps), "--warmup", "1", "--bids", str(args.bids)]
+    if args.no_queries:
+        cmd.append("--no-queries")
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
     if world > 1:
         env["WORLD_SIZE"] = str(world)

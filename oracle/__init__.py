@@ -477,6 +477,27 @@ def q8_collect(persons: list[pa.RecordBatch], auctions: list[pa.RecordBatch], n_
     return pa.table({"p_id": pa.array(out_pid[:m]), "name": names}), times
 
 
+def q5_collect(bids: list[pa.RecordBatch], n_partitions: int, n_threads: int, repeat: int = 1):
+    """NEXMark q5 over one window by the native partition-parallel pipeline (orc_q5_collect).  Returns (table (auction, num),
+    seconds per call)."""
+    import time
+    fn = lib().orc_q5_collect
+    fn.restype = C.c_int64
+    bids = [b for b in bids if b.num_rows]
+    n = len(bids)
+    au = (C.c_void_p * max(n, 1))(*[b.column("auction").buffers()[1].address + 4 * b.column("auction").offset for b in bids])
+    rows = (C.c_int64 * max(n, 1))(*[b.num_rows for b in bids])
+    cap = 1 << 16
+    out_a, out_n = np.empty(cap, np.int32), np.empty(cap, np.uint64)
+    times, m = [], 0
+    for _ in range(max(repeat, 1)):
+        t = time.perf_counter()
+        m = fn(au, rows, C.c_int32(n), C.c_int32(n_partitions), C.c_int32(n_threads), out_a.ctypes.data_as(C.c_void_p), out_n.ctypes.data_as(C.c_void_p),
+               C.c_int64(cap))
+        times.append(time.perf_counter() - t)
+    return pa.table({"auction": pa.array(out_a[:m]), "num": pa.array(out_n[:m])}), times
+
+
 def _schema_from_json(s: dict) -> pa.Schema:
     def ty(t):
         if isinstance(t, dict):

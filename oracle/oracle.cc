@@ -728,4 +728,99 @@ int64_t orc_q8_collect(const int32_t* const* p_id, const int32_t* const* name_of
   return rows;
 }
 
+
+// ---- NEXMark q5 over one window, natively (the CPU figure beside bench.py's `queries.q5`) -------------------------------------
+// Plan (benchmarks/src/nexmark/query/q5.sql, q5_plan.fmt; shapes stage.rs:535-543, :597-601): AuctionBids = COUNT(*) GROUP BY
+// auction as HashAggregate(Partial) per input partition -> RepartitionExec(Hash[auction]) -> HashAggregate(FinalPartitioned);
+// MaxBids = MAX(num) over it; join num = maxn.  The duplicated COUNT subtree of the reference plan is evaluated once
+// (SURVEY.md 8d allows the CSE).  Output: every (auction, num) with num = MAX(num); returns the row count.
+int64_t orc_q5_collect(const int32_t* const* auction, const int64_t* rows, int32_t n_batches, int32_t n_partitions, int32_t n_threads, int32_t* out_auction,
+                       uint64_t* out_num, int64_t out_capacity) {
+  const int32_t P = std::max(1, n_partitions);
+  const int32_t T = std::max(1, std::min(n_threads, P));
+  const size_t np = size_t(P);
+  auto run = [&](auto&& task) {
+    std::atomic<int32_t> next{0};
+    auto worker = [&]() {
+      for (int32_t p = next.fetch_add(1); p < P; p = next.fetch_add(1)) task(p);
+    };
+    std::vector<std::thread> pool;
+    for (int32_t t = 1; t < T; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
+  };
+  auto mix = [](uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+  };
+  struct Counts {  // open addressing, key = auction, grows by doubling
+    std::vector<int64_t> key;  // -1 = free
+    std::vector<uint64_t> cnt;
+    size_t used = 0;
+    Counts() : key(1024, -1), cnt(1024, 0) {}
+  };
+  auto add = [&](Counts& c, int32_t k, uint64_t n, auto&& self) -> void {
+    if (2 * (c.used + 1) > c.key.size()) {
+      Counts bigger;
+      bigger.key.assign(c.key.size() * 4, -1);
+      bigger.cnt.assign(c.key.size() * 4, 0);
+      for (size_t i = 0; i < c.key.size(); ++i)
+        if (c.key[i] >= 0) self(bigger, int32_t(c.key[i]), c.cnt[i], self);
+      c = std::move(bigger);
+    }
+    uint64_t i = mix(uint32_t(k)) & (c.key.size() - 1);
+    while (c.key[i] >= 0 && int32_t(c.key[i]) != k) i = (i + 1) & (c.key.size() - 1);
+    if (c.key[i] < 0) {
+      c.key[i] = int64_t(uint32_t(k));
+      ++c.used;
+    }
+    c.cnt[i] += n;
+  };
+  auto route = [&](int32_t key) { return int32_t((mix(uint32_t(key)) >> 32) * uint64_t(P) >> 32); };
+  // phase 1: Partial COUNT per input partition, its groups routed by hash(auction)
+  std::vector<std::vector<std::vector<std::pair<int32_t, uint64_t>>>> parts{np, std::vector<std::vector<std::pair<int32_t, uint64_t>>>{np}};
+  run([&](int32_t p) {
+    Counts c;
+    for (int32_t b = p; b < n_batches; b += P)
+      for (int64_t r = 0; r < rows[b]; ++r) add(c, auction[b][r], 1, add);
+    for (size_t i = 0; i < c.key.size(); ++i)
+      if (c.key[i] >= 0) parts[size_t(p)][size_t(route(int32_t(c.key[i])))].emplace_back(int32_t(c.key[i]), c.cnt[i]);
+  });
+  // phase 2: FinalPartitioned COUNT per output partition; its MAX
+  std::vector<Counts> finals{np};
+  std::vector<uint64_t> part_max(np, 0);
+  run([&](int32_t q) {
+    Counts& c = finals[size_t(q)];
+    for (int32_t p = 0; p < P; ++p)
+      for (const auto& kv : parts[size_t(p)][size_t(q)]) add(c, kv.first, kv.second, add);
+    uint64_t m = 0;
+    for (size_t i = 0; i < c.key.size(); ++i)
+      if (c.key[i] >= 0) m = std::max(m, c.cnt[i]);
+    part_max[size_t(q)] = m;
+  });
+  // MaxBids (Partial MAX per partition above, Final here) and the join num = maxn
+  uint64_t maxn = 0;
+  bool any = false;
+  for (int32_t q = 0; q < P; ++q) {
+    maxn = std::max(maxn, part_max[size_t(q)]);
+    any = any || finals[size_t(q)].used > 0;
+  }
+  int64_t out = 0;
+  if (any)
+    for (int32_t q = 0; q < P; ++q) {
+      const Counts& c = finals[size_t(q)];
+      for (size_t i = 0; i < c.key.size(); ++i)
+        if (c.key[i] >= 0 && c.cnt[i] == maxn && out < out_capacity) {
+          out_auction[out] = int32_t(c.key[i]);
+          out_num[out] = c.cnt[i];
+          ++out;
+        }
+    }
+  return out;
+}
+
 }  // extern "C"

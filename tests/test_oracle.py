@@ -230,3 +230,23 @@ def test_native_q8_arm_matches_the_plan_executor_and_an_independent_reference():
         oracle.assert_tables_equal(got, ref)
     assert oracle.q8_collect([persons[0].slice(0, 0)], auctions, 4, 2)[0].num_rows == 0
     assert oracle.q8_collect(persons, [auctions[0].slice(0, 0)], 4, 2)[0].num_rows == 0
+
+
+def test_native_q5_arm_matches_bincount_and_the_plan_executor():
+    """oracle.q5_collect (orc_q5_collect: Partial COUNT per input partition -> hash repartition -> FinalPartitioned COUNT ->
+    MAX -> join num = maxn) against numpy.bincount (ties included) and against the plan executor on the reference's q5 plan."""
+    bids = nexgen.bids_chunked(1_000_000, 42, ["auction"])
+    au = np.concatenate([b["auction"].to_numpy() for b in bids])
+    cnt = np.bincount(au)
+    winners = np.nonzero(cnt == cnt.max())[0]
+    for parts, threads in ((1, 1), (8, 8), (13, 4)):
+        got, times = oracle.q5_collect(bids, parts, threads, repeat=2)
+        assert len(times) == 2 and sorted(got["auction"].to_pylist()) == winners.tolist() and set(got["num"].to_pylist()) == {int(cnt.max())}
+    ties = [pa.RecordBatch.from_arrays([pa.array(np.array([5, 5, 7, 7, 9], np.int32))], names=["auction"])]
+    got, _ = oracle.q5_collect(ties, 4, 2)
+    assert sorted(zip(got["auction"].to_pylist(), got["num"].to_pylist())) == [(5, 2), (7, 2)]
+    assert oracle.q5_collect([ties[0].slice(0, 0)], 4, 2)[0].num_rows == 0
+    ev = nexgen.generate(200_000, seed=5, batch_rows=4096)
+    want = oracle.execute_plan(plans.q5(), [[ev[r]] for r in plans.SOURCES["q5"]])
+    got, _ = oracle.q5_collect(ev["bid"], 8, 4)
+    oracle.assert_tables_equal(got, want, check_names=False)
