@@ -867,6 +867,12 @@ def run_reference(args) -> dict | None:
                                   "threads": threads, "rows_out": res.num_rows}
                 return out
             try:
+                q1_bids = nexgen.bids_chunked(BATCH_ROWS, seed=42)                     # configs[0]: one 64 Ki-row bid batch
+                by_query["q1"] = arm(lambda p, t, r: ((lambda res, ts: (pa.Table.from_batches(res), ts))(*oracle.q1_collect(q1_bids, p, t, repeat=r))), BATCH_ROWS)
+                ev3 = nexgen.generate(10_000_000, seed=42, relations=("person", "auction"),
+                                      columns={"person": ["p_id", "name", "city", "state"], "auction": ["a_id", "seller", "category"]})
+                by_query["q3"] = arm(lambda p, t, r: oracle.q3_collect(ev3["auction"], ev3["person"], p, t, repeat=r), 10_000_000)
+                del ev3
                 q5_bids = nexgen.bids_chunked(100_000_000, seed=42, columns=["auction"])
                 by_query["q5"] = arm(lambda p, t, r: oracle.q5_collect(q5_bids, p, t, repeat=r), 100_000_000)
                 del q5_bids

@@ -498,6 +498,73 @@ def q5_collect(bids: list[pa.RecordBatch], n_partitions: int, n_threads: int, re
     return pa.table({"auction": pa.array(out_a[:m]), "num": pa.array(out_n[:m])}), times
 
 
+def _col_ptrs(batches, name, width=4):
+    return (C.c_void_p * max(len(batches), 1))(*[b.column(name).buffers()[1].address + width * b.column(name).offset for b in batches])
+
+
+def _utf8_ptrs(batches, name):
+    offs = (C.c_void_p * max(len(batches), 1))(*[b.column(name).buffers()[1].address + 4 * b.column(name).offset for b in batches])
+    data = (C.c_void_p * max(len(batches), 1))(*[(b.column(name).buffers()[2].address if b.column(name).buffers()[2] is not None else 0) for b in batches])
+    return offs, data
+
+
+def q1_collect(bids: list[pa.RecordBatch], n_partitions: int, n_threads: int, repeat: int = 1):
+    """NEXMark q1 natively (orc_q1_collect): the computed column 0.908 * CAST(price AS Float64) batch by batch, the pass-through
+    columns shared like the reference's Arc clones.  Returns (list of result batches, seconds per call)."""
+    import time
+    fn = lib().orc_q1_collect
+    fn.restype = None
+    n = len(bids)
+    price = _col_ptrs(bids, "price")
+    rows = (C.c_int64 * max(n, 1))(*[b.num_rows for b in bids])
+    outs = [np.empty(b.num_rows, np.float64) for b in bids]
+    optr = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+    times = []
+    for _ in range(max(repeat, 1)):
+        t = time.perf_counter()
+        fn(price, rows, C.c_int32(n), C.c_int32(n_partitions), C.c_int32(n_threads), optr)
+        times.append(time.perf_counter() - t)
+    res = [pa.RecordBatch.from_arrays([b.column("auction"), b.column("bidder"), pa.array(o), b.column("b_date_time")], names=["auction", "bidder", "price", "b_date_time"])
+           for b, o in zip(bids, outs)]
+    return res, times
+
+
+def q3_collect(auctions: list[pa.RecordBatch], persons: list[pa.RecordBatch], n_partitions: int, n_threads: int, repeat: int = 1):
+    """NEXMark q3 natively (orc_q3_collect: the two filters -> hash repartition on the join key -> partitioned hash join ->
+    projection).  Returns (table (name, city, state, a_id), seconds per call)."""
+    import time
+    fn = lib().orc_q3_collect
+    fn.restype = C.c_int64
+    auctions = [b for b in auctions if b.num_rows]
+    persons = [b for b in persons if b.num_rows]
+    na, npb = len(auctions), len(persons)
+    a_id, a_sel, a_cat = _col_ptrs(auctions, "a_id"), _col_ptrs(auctions, "seller"), _col_ptrs(auctions, "category")
+    a_rows = (C.c_int64 * max(na, 1))(*[b.num_rows for b in auctions])
+    p_id = _col_ptrs(persons, "p_id")
+    (n_o, n_d), (c_o, c_d), (s_o, s_d) = _utf8_ptrs(persons, "name"), _utf8_ptrs(persons, "city"), _utf8_ptrs(persons, "state")
+    p_rows = (C.c_int64 * max(npb, 1))(*[b.num_rows for b in persons])
+    cap = max(1024, 2 * sum(b.num_rows for b in auctions))
+    while True:
+        bcap = cap * 48
+        o_a = np.empty(cap, np.int32)
+        o_no, o_co, o_so = (np.empty(cap + 1, np.int32) for _ in range(3))
+        o_n, o_c, o_s = (np.empty(bcap, np.uint8) for _ in range(3))
+        times, m = [], 0
+        for _ in range(max(repeat, 1)):
+            t = time.perf_counter()
+            m = fn(a_id, a_sel, a_cat, a_rows, C.c_int32(na), p_id, n_o, n_d, c_o, c_d, s_o, s_d, p_rows, C.c_int32(npb), C.c_int32(n_partitions), C.c_int32(n_threads),
+                   o_a.ctypes.data_as(C.c_void_p), o_no.ctypes.data_as(C.c_void_p), o_n.ctypes.data_as(C.c_void_p), o_co.ctypes.data_as(C.c_void_p),
+                   o_c.ctypes.data_as(C.c_void_p), o_so.ctypes.data_as(C.c_void_p), o_s.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.c_int64(bcap))
+            times.append(time.perf_counter() - t)
+            if m < 0:
+                break
+        if m >= 0:
+            break
+        cap *= 4
+    utf8 = lambda off, dat: pa.Array.from_buffers(pa.utf8(), m, [None, pa.py_buffer(off[:m + 1].tobytes()), pa.py_buffer(dat[:int(off[m]) if m else 0].tobytes())])
+    return pa.table({"name": utf8(o_no, o_n), "city": utf8(o_co, o_c), "state": utf8(o_so, o_s), "a_id": pa.array(o_a[:m])}), times
+
+
 def _schema_from_json(s: dict) -> pa.Schema:
     def ty(t):
         if isinstance(t, dict):

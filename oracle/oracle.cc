@@ -823,4 +823,140 @@ int64_t orc_q5_collect(const int32_t* const* auction, const int64_t* rows, int32
   return out;
 }
 
+
+// ---- NEXMark q1 natively: ProjectionExec [auction, bidder, 0.908 * CAST(price AS Float64), b_date_time] (planner.rs:90-92).
+// The pass-through columns are Arc clones in the reference; the work is the computed column, batch by batch, the batches
+// dealt round-robin to n_partitions tasks.  out_price[b] receives batch b's Float64 column.
+void orc_q1_collect(const int32_t* const* price, const int64_t* rows, int32_t n_batches, int32_t n_partitions, int32_t n_threads, double* const* out_price) {
+  const int32_t P = std::max(1, n_partitions);
+  const int32_t T = std::max(1, std::min(n_threads, P));
+  std::atomic<int32_t> next{0};
+  auto worker = [&]() {
+    for (int32_t p = next.fetch_add(1); p < P; p = next.fetch_add(1))
+      for (int32_t b = p; b < n_batches; b += P) {
+        const int32_t* in = price[b];
+        double* out = out_price[b];
+        for (int64_t r = 0; r < rows[b]; ++r) out[r] = 0.908 * double(in[r]);
+      }
+  };
+  std::vector<std::thread> pool;
+  for (int32_t t = 1; t < T; ++t) pool.emplace_back(worker);
+  worker();
+  for (std::thread& t : pool) t.join();
+}
+
+// ---- NEXMark q3 natively (planner.rs:151-171): auction' = FilterExec(category = 10) over (a_id, seller, category), person' =
+// FilterExec(state = 'or' OR 'id' OR 'ca') over (p_id, name, city, state); both hash-repartitioned on the join key; per
+// partition HashJoinExec(build auction', probe person') on seller = p_id; ProjectionExec -> (name, city, state, a_id).
+// Strings are (offsets, bytes) pairs per batch.  Output columns are written one partition behind the other; returns rows,
+// or -1 when the output does not fit out_capacity rows / out_bytes_capacity bytes per string column.
+int64_t orc_q3_collect(const int32_t* const* a_id, const int32_t* const* a_seller, const int32_t* const* a_category, const int64_t* a_rows, int32_t n_a_batches,
+                       const int32_t* const* p_id, const int32_t* const* name_off, const uint8_t* const* name_dat, const int32_t* const* city_off,
+                       const uint8_t* const* city_dat, const int32_t* const* state_off, const uint8_t* const* state_dat, const int64_t* p_rows,
+                       int32_t n_p_batches, int32_t n_partitions, int32_t n_threads, int32_t* out_a_id, int32_t* out_name_off, uint8_t* out_name,
+                       int32_t* out_city_off, uint8_t* out_city, int32_t* out_state_off, uint8_t* out_state, int64_t out_capacity, int64_t out_bytes_capacity) {
+  const int32_t P = std::max(1, n_partitions);
+  const int32_t T = std::max(1, std::min(n_threads, P));
+  const size_t np = size_t(P);
+  auto run = [&](auto&& task) {
+    std::atomic<int32_t> next{0};
+    auto worker = [&]() {
+      for (int32_t p = next.fetch_add(1); p < P; p = next.fetch_add(1)) task(p);
+    };
+    std::vector<std::thread> pool;
+    for (int32_t t = 1; t < T; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
+  };
+  auto mix = [](uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+  };
+  auto route = [&](int32_t key) { return int32_t((mix(uint32_t(key)) >> 32) * uint64_t(P) >> 32); };
+  struct Ref {
+    int32_t batch, row;
+  };
+  // phase 1: the two filters, survivors routed by hash(join key)
+  std::vector<std::vector<std::vector<Ref>>> a_parts{np, std::vector<std::vector<Ref>>{np}}, p_parts{np, std::vector<std::vector<Ref>>{np}};
+  run([&](int32_t p) {
+    for (int32_t b = p; b < n_a_batches; b += P)
+      for (int32_t r = 0; r < int32_t(a_rows[b]); ++r)
+        if (int64_t(a_category[b][r]) == 10) a_parts[size_t(p)][size_t(route(a_seller[b][r]))].push_back(Ref{b, r});
+    for (int32_t b = p; b < n_p_batches; b += P)
+      for (int32_t r = 0; r < int32_t(p_rows[b]); ++r) {
+        const int32_t lo = state_off[b][r], n = state_off[b][r + 1] - lo;
+        const uint8_t* st = state_dat[b] + lo;
+        const bool keep = n == 2 && ((st[0] == 'o' && st[1] == 'r') || (st[0] == 'i' && st[1] == 'd') || (st[0] == 'c' && st[1] == 'a'));
+        if (keep) p_parts[size_t(p)][size_t(route(p_id[b][r]))].push_back(Ref{b, r});
+      }
+  });
+  // phase 2: per partition, build on auction' (seller -> chain of rows), probe with person' in order
+  struct Out {
+    std::vector<int32_t> a, name_len, city_len, state_len;
+    std::vector<uint8_t> name, city, state;
+  };
+  std::vector<Out> outs{np};
+  run([&](int32_t q) {
+    std::vector<Ref> build;
+    for (int32_t p = 0; p < P; ++p) build.insert(build.end(), a_parts[size_t(p)][size_t(q)].begin(), a_parts[size_t(p)][size_t(q)].end());
+    size_t cap = 16;
+    while (cap < 2 * build.size()) cap <<= 1;
+    std::vector<int32_t> head(cap, -1), nxt(build.size(), -1);
+    std::vector<int64_t> key(cap, -1);
+    for (size_t i = 0; i < build.size(); ++i) {
+      const int32_t k = a_seller[build[i].batch][build[i].row];
+      uint64_t s = mix(uint32_t(k)) & (cap - 1);
+      while (key[s] >= 0 && int32_t(key[s]) != k) s = (s + 1) & (cap - 1);
+      key[s] = int64_t(uint32_t(k));
+      nxt[i] = head[s];
+      head[s] = int32_t(i);
+    }
+    Out& o = outs[size_t(q)];
+    auto put = [](std::vector<uint8_t>& bytes, std::vector<int32_t>& lens, const int32_t* off, const uint8_t* dat, int32_t r) {
+      const int32_t n = off[r + 1] - off[r];
+      lens.push_back(n);
+      bytes.insert(bytes.end(), dat + off[r], dat + off[r] + n);
+    };
+    for (int32_t p = 0; p < P; ++p)
+      for (const Ref& ref : p_parts[size_t(p)][size_t(q)]) {
+        const int32_t k = p_id[ref.batch][ref.row];
+        uint64_t s = mix(uint32_t(k)) & (cap - 1);
+        while (key[s] >= 0 && int32_t(key[s]) != k) s = (s + 1) & (cap - 1);
+        if (key[s] < 0) continue;
+        for (int32_t i = head[s]; i >= 0; i = nxt[size_t(i)]) {
+          o.a.push_back(a_id[build[size_t(i)].batch][build[size_t(i)].row]);
+          put(o.name, o.name_len, name_off[ref.batch], name_dat[ref.batch], ref.row);
+          put(o.city, o.city_len, city_off[ref.batch], city_dat[ref.batch], ref.row);
+          put(o.state, o.state_len, state_off[ref.batch], state_dat[ref.batch], ref.row);
+        }
+      }
+  });
+  int64_t rows = 0;
+  int64_t nb = 0, cb = 0, sb = 0;
+  out_name_off[0] = out_city_off[0] = out_state_off[0] = 0;
+  for (int32_t q = 0; q < P; ++q) {
+    const Out& o = outs[size_t(q)];
+    if (rows + int64_t(o.a.size()) > out_capacity) return -1;  // the caller retries with more room
+    if (nb + int64_t(o.name.size()) > out_bytes_capacity || cb + int64_t(o.city.size()) > out_bytes_capacity || sb + int64_t(o.state.size()) > out_bytes_capacity) return -1;
+    std::copy(o.a.begin(), o.a.end(), out_a_id + rows);
+    std::copy(o.name.begin(), o.name.end(), out_name + nb);
+    std::copy(o.city.begin(), o.city.end(), out_city + cb);
+    std::copy(o.state.begin(), o.state.end(), out_state + sb);
+    for (size_t i = 0; i < o.a.size(); ++i) {
+      nb += o.name_len[i];
+      cb += o.city_len[i];
+      sb += o.state_len[i];
+      out_name_off[rows + int64_t(i) + 1] = int32_t(nb);
+      out_city_off[rows + int64_t(i) + 1] = int32_t(cb);
+      out_state_off[rows + int64_t(i) + 1] = int32_t(sb);
+    }
+    rows += int64_t(o.a.size());
+  }
+  return rows;
+}
+
 }  // extern "C"

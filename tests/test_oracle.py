@@ -250,3 +250,26 @@ def test_native_q5_arm_matches_bincount_and_the_plan_executor():
     want = oracle.execute_plan(plans.q5(), [[ev[r]] for r in plans.SOURCES["q5"]])
     got, _ = oracle.q5_collect(ev["bid"], 8, 4)
     oracle.assert_tables_equal(got, want, check_names=False)
+
+
+def test_native_q1_and_q3_arms_match_the_plan_executor():
+    """oracle.q1_collect / q3_collect (the CPU figures beside bench.py's `queries`) against the plan executor on the
+    reference's plans; q3 also on a toy input where equal join keys on both sides give the cross product."""
+    ev = nexgen.generate(400_000, seed=42, batch_rows=8192)
+    want = oracle.execute_plan(plans.q3(), [[ev[r]] for r in plans.SOURCES["q3"]])
+    for parts, threads in ((1, 1), (8, 4), (13, 8)):
+        got, times = oracle.q3_collect(ev["auction"], ev["person"], parts, threads, repeat=2)
+        assert len(times) == 2
+        oracle.assert_tables_equal(got, want)
+    a = pa.RecordBatch.from_arrays([pa.array([1, 2, 3, 4], pa.int32()), pa.array([7, 7, 8, 9], pa.int32()), pa.array([10, 10, 11, 10], pa.int32())],
+                                   names=["a_id", "seller", "category"])
+    p = pa.RecordBatch.from_arrays([pa.array([7, 7, 9, 8], pa.int32()), pa.array(["x", "y", "z", "w"]), pa.array(["c1", "c2", "c3", "c4"]),
+                                    pa.array(["or", "id", "wa", "ca"])], names=["p_id", "name", "city", "state"])
+    got, _ = oracle.q3_collect([a], [p], 4, 2)
+    assert sorted(zip(got["name"].to_pylist(), got["a_id"].to_pylist())) == [("x", 1), ("x", 2), ("y", 1), ("y", 2)]
+    assert oracle.q3_collect([a.slice(0, 0)], [p], 4, 2)[0].num_rows == 0
+    res, _ = oracle.q1_collect(ev["bid"], 8, 4)
+    oracle.assert_tables_equal(pa.Table.from_batches(res), oracle.execute_plan(plans.q1(), [[ev["bid"]]]))
+    price = np.concatenate([b["price"].to_numpy() for b in ev["bid"]])
+    got = np.concatenate([b["price"].to_numpy() for b in res])
+    assert np.array_equal(got.view(np.int64), (np.float64(0.908) * price.astype(np.float64)).view(np.int64))      # one IEEE rounding
