@@ -37,11 +37,15 @@ fn last_error() -> DataFusionError {
 }
 
 /// One GPU context per process (a Lambda instance handles one event at a time, cloud_context.rs:22).
+/// The handle is an opaque pointer into the library, which serialises calls on a context with its own mutex: it may
+/// cross threads (spawn_blocking) -- `Send` and `Copy` are asserted here, once, instead of at every use.
+#[derive(Clone, Copy)]
 struct Gpu(*mut ffi::flockgpu_ctx);
 unsafe impl Send for Gpu {}
+unsafe impl Sync for Gpu {}
 static GPU: Mutex<Option<Gpu>> = Mutex::new(None);
 
-fn gpu() -> Result<*mut ffi::flockgpu_ctx> {
+fn gpu() -> Result<Gpu> {
     let mut g = GPU.lock().unwrap();
     if g.is_none() {
         let mut ctx = std::ptr::null_mut();
@@ -50,7 +54,7 @@ fn gpu() -> Result<*mut ffi::flockgpu_ctx> {
         }
         *g = Some(Gpu(ctx));
     }
-    Ok(g.as_ref().unwrap().0)
+    Ok(*g.as_ref().unwrap())
 }
 
 /// A physical (sub-)plan executed on the GPU.
@@ -113,7 +117,7 @@ impl ExecutionPlan for GpuPlanExec {
 
     async fn execute(&self, partition: usize) -> Result<SendableRecordBatchStream> {
         assert_eq!(partition, 0);
-        let ctx = gpu()?;
+        let gpu = gpu()?;
         let json = CString::new(serde_json::to_string(&self.plan).map_err(|e| DataFusionError::Execution(e.to_string()))?).unwrap();
         // 1. drain the MemoryExec leaves (they were filled by feed_data_sources)
         let mut per_leaf: Vec<Vec<RecordBatch>> = vec![];
@@ -124,6 +128,7 @@ impl ExecutionPlan for GpuPlanExec {
         let schema = self.schema();
         // 2. the blocking GPU call runs off the async executor
         let batches = tokio::task::spawn_blocking(move || -> Result<Option<Vec<RecordBatch>>> {
+            let ctx = gpu.0;
             let mut ec = std::ptr::null_mut();
             if unsafe { ffi::flock_context_unmarshal(ctx, json.as_ptr(), &mut ec) } != 0 {
                 return Err(last_error());
